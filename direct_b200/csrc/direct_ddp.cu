@@ -1,0 +1,484 @@
+// direct_ddp.cu -- kernels + C-ABI of libdirect_ddp_b200.so (include/direct_ddp.h).
+//
+// One persistent kernel per call: every warp pulls trajectory indices from an atomic work queue and
+// runs the complete polyCurveGeneration-equivalent solve (ipddp_solver.h) for each, both stages of the
+// node's two-stage protocol back to back when asked.  No host round trips, no CPU fallback.
+// Built for sm_100a only (see direct_b200/build.py).
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/direct_ddp.h"
+#include "ipddp_solver.h"
+
+namespace {
+
+using ddp::SolveArgs;
+
+template <class R>
+__global__ void __launch_bounds__(128, 3) ipddp_solve_kernel(SolveArgs A, const R *__restrict__ tabs_g) {
+    extern __shared__ __align__(16) unsigned char smraw[];
+    R *sm_all = reinterpret_cast<R *>(smraw);
+    R *tabs = sm_all;  // 360 table entries shared by the block
+    for (int i = threadIdx.x; i < 360; i += blockDim.x) tabs[i] = tabs_g[i];
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int per_warp = ddp::smem_elems_per_warp(A.PM);
+    R *sm = sm_all + 360 + warp * per_warp;
+    const long long slot = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+    R *ws = reinterpret_cast<R *>(A.ws) + slot * A.ws_stride;
+    while (true) {
+        unsigned int b = 0;
+        if (lane == 0) b = atomicAdd(A.counter, 1u);
+        b = __shfl_sync(0xffffffffu, b, 0);
+        if (b >= (unsigned int)A.B) break;
+        if (A.two_stage) ddp::solve_one<R>(A, 0, (int)b, sm, tabs, ws, lane);
+        ddp::solve_one<R>(A, A.two_stage ? 1 : 0, (int)b, sm, tabs, ws, lane);
+    }
+}
+
+// initTimeAllocation, teach_repeat_planner.cpp:583-639 (v0 = 0): one thread per segment.
+__global__ void time_allocation_kernel(int B, int N, const double *start, const double *end, const double *seeds,
+                                       double vel, double accl, double *durations) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)B * N) return;
+    const int b = (int)(idx / N), k = (int)(idx % N);
+    double p0[3], p1[3];
+    for (int a = 0; a < 3; a++) {
+        p0[a] = (k == 0) ? start[(long long)b * 3 + a] : seeds[((long long)b * N + k) * 3 + a];
+        p1[a] = (k == N - 1) ? end[(long long)b * 3 + a] : seeds[((long long)b * N + k + 1) * 3 + a];
+    }
+    const double d0 = p1[0] - p0[0], d1 = p1[1] - p0[1], d2 = p1[2] - p0[2];
+    const double D = sqrt(d0 * d0 + d1 * d1 + d2 * d2);
+    const double V0 = 0.0 * (d0 / D) + 0.0 * (d1 / D) + 0.0 * (d2 / D);
+    const double aV0 = fabs(V0);
+    const double acct = (vel - V0) / accl * ((vel > V0) ? 1 : -1);
+    const double accd = V0 * acct + (accl * acct * acct / 2) * ((vel > V0) ? 1 : -1);
+    const double dcct = vel / accl, dccd = accl * dcct * dcct / 2;
+    double dt;
+    if (D < aV0 * aV0 / (2 * accl)) {
+        dt = ((V0 < 0) ? 2.0 * aV0 / accl : 0.0) + aV0 / accl;
+    } else if (D < accd + dccd) {
+        const double t1 = (V0 < 0) ? 2.0 * aV0 / accl : 0.0;
+        const double t2 = (-aV0 + sqrt(aV0 * aV0 + accl * D - aV0 * aV0 / 2)) / accl;
+        dt = t1 + t2 + (aV0 + accl * t2) / accl;
+    } else {
+        dt = acct + (D - accd - dccd) / vel + dcct;
+    }
+    durations[idx] = dt;
+}
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+}  // namespace
+
+struct direct_ddp_handle_s {
+    direct_ddp_opts opts;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    std::string err;
+    direct_ddp_stats stats;
+    // grow-only device buffers
+    DevBuf planes, nplanes, durations, seeds, x0, xd, init_bez, infeas;
+    DevBuf o_int[2], o_cost[2], o_xf[2], o_pc[2], o_bz[2], o_pt[2], o_jk[2], o_st[2];
+    DevBuf ws, counter, tabs, bez_tmp, time_tmp, trace, trace_len, scratch_i;
+    const long long *last_stats_dev = nullptr;  // device [B][4] of the last solve (stage 1 / single)
+    const long long *last_stats_dev0 = nullptr; // stage 0 when two-stage
+    int last_B = 0;
+    bool stats_valid = false;
+};
+
+namespace {
+
+typedef direct_ddp_handle_s H;
+
+bool cuda_ok(H *h, cudaError_t e, const char *what) {
+    if (e == cudaSuccess) return true;
+    h->err = std::string(what) + ": " + cudaGetErrorString(e);
+    return false;
+}
+#define CK(call)                                                 \
+    do {                                                         \
+        if (!cuda_ok(h, (call), #call)) return DIRECT_DDP_ERR_CUDA; \
+    } while (0)
+
+int ensure(H *h, DevBuf &b, size_t bytes) {
+    if (bytes == 0) bytes = 16;
+    if (b.cap >= bytes) return 0;
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr; b.cap = 0;
+    if (!cuda_ok(h, cudaMalloc(&b.p, bytes), "cudaMalloc")) return DIRECT_DDP_ERR_NOMEM;
+    b.cap = bytes;
+    return 0;
+}
+
+int validate(H *h, const direct_ddp_batch *in) {
+    if (!in) { h->err = "batch is NULL"; return DIRECT_DDP_ERR_ARG; }
+    if (in->B <= 0 || in->N <= 0) { h->err = "B and N must be positive"; return DIRECT_DDP_ERR_ARG; }
+    if (in->P_max < 0 || in->P_max > DIRECT_DDP_MAX_PLANES) { h->err = "P_max must be in [0, 32]"; return DIRECT_DDP_ERR_ARG; }
+    if (!in->planes || !in->nplanes || !in->durations || !in->x0 || !in->xd) { h->err = "missing input pointer"; return DIRECT_DDP_ERR_ARG; }
+    return 0;
+}
+int validate_cfg(H *h, int time_power, int line_init, int iter_max) {
+    if (time_power != 1 && time_power != 2) { h->err = "time_power must be 1 or 2"; return DIRECT_DDP_ERR_ARG; }
+    if (iter_max < 0) { h->err = "iter_max must be >= 0"; return DIRECT_DDP_ERR_ARG; }
+    if (line_init) { h->err = "line_init_flag is not supported by the device path yet"; return DIRECT_DDP_ERR_UNSUPPORTED; }
+    return 0;
+}
+
+template <class R> int upload_tables(H *h) {
+    std::vector<R> t(360);
+    const ddp::BasisTables &bt = ddp::basis_tables();
+    for (int m = 0; m < 2; m++)
+        for (int e = 0; e < 90; e++) { t[m * 180 + e] = (R)bt.val[m][e]; t[m * 180 + 90 + e] = (R)bt.dt[e]; }
+    int st = ensure(h, h->tabs, 360 * sizeof(R));
+    if (st) return st;
+    CK(cudaMemcpyAsync(h->tabs.p, t.data(), 360 * sizeof(R), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+// Launch the persistent solve kernel on device-resident arguments.
+template <class R> int launch(H *h, SolveArgs &A, cudaStream_t s) {
+    const int wpb = h->opts.warps_per_block > 0 ? h->opts.warps_per_block : 4;
+    const int threads = wpb * 32;
+    if (threads > 128) { h->err = "warps_per_block must be <= 4"; return DIRECT_DDP_ERR_ARG; }
+    const size_t smem = (size_t)(360 + wpb * ddp::smem_elems_per_warp(A.PM)) * sizeof(R);
+    auto kern = ipddp_solve_kernel<R>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
+    if (per_sm < 1) { h->err = "kernel does not fit on an SM (shared memory)"; return DIRECT_DDP_ERR_CUDA; }
+    if (h->opts.blocks_per_sm > 0 && per_sm > h->opts.blocks_per_sm) per_sm = h->opts.blocks_per_sm;
+    long long grid = (long long)per_sm * h->sm_count;
+    const long long need = (A.B + wpb - 1) / wpb;
+    if (grid > need) grid = need;
+    int max_iter = A.cfg[0].iter_max;
+    if (A.two_stage && A.cfg[1].iter_max > max_iter) max_iter = A.cfg[1].iter_max;
+    A.fcap = max_iter + 2;
+    const ddp::WsLay wl = ddp::ws_layout(A.N, A.PM, A.fcap);
+    A.ws_stride = wl.total;
+    const size_t ws_bytes = (size_t)grid * wpb * wl.total * sizeof(R);
+    if (h->ws.cap < ws_bytes) {
+        int st = ensure(h, h->ws, ws_bytes);
+        if (st) return st;
+        CK(cudaMemsetAsync(h->ws.p, 0, ws_bytes, s));
+    }
+    A.ws = h->ws.p;
+    int st = ensure(h, h->counter, 16);
+    if (st) return st;
+    CK(cudaMemsetAsync(h->counter.p, 0, 16, s));
+    A.counter = (unsigned int *)h->counter.p;
+    if (h->opts.trace) {
+        if ((st = ensure(h, h->trace, 512 * 12 * sizeof(double)))) return st;
+        if ((st = ensure(h, h->trace_len, 16))) return st;
+        CK(cudaMemsetAsync(h->trace_len.p, 0, 16, s));
+        A.trace = (double *)h->trace.p; A.trace_cap = 512; A.trace_len = (int *)h->trace_len.p;
+    }
+    CK(cudaEventRecord(h->ev[2], s));
+    kern<<<(unsigned)grid, threads, smem, s>>>(A, (const R *)h->tabs.p);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(h->ev[3], s));
+    h->stats.kernel_launches = 1;
+    h->stats.grid_blocks = (int)grid; h->stats.block_threads = threads;
+    h->stats.smem_bytes_per_block = (int)smem; h->stats.workspace_slots = (int)(grid * wpb);
+    return 0;
+}
+
+void fill_cfg(ddp::StageCfg &c, double ws, double wt, double wtime, int iters, int tp, int zero, int line, int minvo, int inf) {
+    c.w_snap = ws; c.w_terminal = wt; c.w_time = wtime; c.iter_max = iters; c.time_power = tp;
+    c.zero_init = zero; c.line_init = line; c.minvo = minvo; c.infeas_all = inf;
+}
+
+void fill_out(ddp::OutPtrs &O, const direct_ddp_result *r) {
+    memset(&O, 0, sizeof O);
+    if (!r) return;
+    O.rtn = r->rtn; O.infeas_out = r->infeas_out; O.line_failed_out = r->line_failed_out; O.iters = r->iters;
+    O.cost = r->cost; O.x_final = r->x_final; O.poly_coeff = r->poly_coeff; O.bez_coeff = r->bez_coeff;
+    O.poly_time = r->poly_time; O.jerk = r->jerk; O.stats = (long long *)r->stats;
+}
+
+// Core: everything device-resident.  `ts` NULL = single stage using the batch's own scalars.
+int solve_device(H *h, const direct_ddp_batch *in, const direct_ddp_two_stage *ts, const direct_ddp_result *out0,
+                 const direct_ddp_result *out1, cudaStream_t s) {
+    int st = validate(h, in);
+    if (st) return st;
+    if (!out1) { h->err = "result is NULL"; return DIRECT_DDP_ERR_ARG; }
+    SolveArgs A;
+    memset(&A, 0, sizeof A);
+    A.B = in->B; A.N = in->N; A.PM = in->P_max;
+    A.planes = in->planes; A.nplanes = in->nplanes; A.durations = in->durations; A.seeds = in->seeds;
+    A.x0 = in->x0; A.xd = in->xd; A.max_vel = in->max_vel; A.max_acc = in->max_acc;
+    if (ts) {
+        if ((st = validate_cfg(h, ts->time_power, 0, ts->iter_max0))) return st;
+        if ((st = validate_cfg(h, ts->time_power, 0, ts->iter_max))) return st;
+        A.two_stage = 1;
+        // teach_repeat_planner.cpp:895-897 and :918-921
+        fill_cfg(A.cfg[0], ts->w_snap0, ts->w_terminal0, ts->w_time0, ts->iter_max0, ts->time_power, 1, 0, 0, 1);
+        fill_cfg(A.cfg[1], ts->w_snap, ts->w_terminal, ts->w_time, ts->iter_max, ts->time_power, 0, 0, 0, 0);
+        fill_out(A.out[0], out0);
+        fill_out(A.out[1], out1);
+        if ((st = ensure(h, h->bez_tmp, (size_t)in->B * in->N * 18 * sizeof(double)))) return st;
+        if ((st = ensure(h, h->time_tmp, (size_t)in->B * in->N * sizeof(double)))) return st;
+        A.bez_tmp = (double *)h->bez_tmp.p; A.time_tmp = (double *)h->time_tmp.p;
+        if (!A.out[0].rtn || !A.out[0].infeas_out) {  // stage 1 needs stage 0's rtn and infeas
+            if ((st = ensure(h, h->scratch_i, (size_t)in->B * 2 * sizeof(int32_t)))) return st;
+            if (!A.out[0].rtn) A.out[0].rtn = (int32_t *)h->scratch_i.p;
+            if (!A.out[0].infeas_out) A.out[0].infeas_out = (int32_t *)h->scratch_i.p + in->B;
+        }
+    } else {
+        if ((st = validate_cfg(h, in->time_power, in->line_init, in->iter_max))) return st;
+        A.two_stage = 0;
+        A.init_bez = in->init_bez; A.infeas = in->infeas;
+        fill_cfg(A.cfg[0], in->w_snap, in->w_terminal, in->w_time, in->iter_max, in->time_power, in->zero_init,
+                 in->line_init, in->minvo, in->infeas_all);
+        fill_out(A.out[1], out1);
+    }
+    // statistics are always collected (roofline accounting): use internal buffers when the caller has none
+    for (int k = ts ? 0 : 1; k < 2; k++) {
+        if (!A.out[k].stats) {
+            if ((st = ensure(h, h->o_st[k], (size_t)in->B * 4 * sizeof(long long)))) return st;
+            A.out[k].stats = (long long *)h->o_st[k].p;
+        }
+    }
+    h->last_stats_dev = A.out[1].stats;
+    h->last_stats_dev0 = ts ? A.out[0].stats : nullptr;
+    h->last_B = in->B;
+    h->stats_valid = false;
+    if (h->opts.precision == DIRECT_DDP_FP32) return launch<float>(h, A, s);
+    return launch<double>(h, A, s);
+}
+
+// Device mirror of a host result: allocate what the caller asked for.
+int mirror_result(H *h, int k, const direct_ddp_result *host, int B, int N, direct_ddp_result *dev) {
+    memset(dev, 0, sizeof *dev);
+    if (!host) return 0;
+    int st;
+    if ((st = ensure(h, h->o_int[k], (size_t)B * 4 * sizeof(int32_t)))) return st;
+    int32_t *ip = (int32_t *)h->o_int[k].p;
+    dev->rtn = ip; dev->infeas_out = ip + B; dev->line_failed_out = ip + 2 * B; dev->iters = ip + 3 * B;
+    if ((st = ensure(h, h->o_cost[k], (size_t)B * 8))) return st;
+    dev->cost = (double *)h->o_cost[k].p;
+    if ((st = ensure(h, h->o_xf[k], (size_t)B * 9 * 8))) return st;
+    dev->x_final = (double *)h->o_xf[k].p;
+    if (host->poly_coeff) { if ((st = ensure(h, h->o_pc[k], (size_t)B * N * 18 * 8))) return st; dev->poly_coeff = (double *)h->o_pc[k].p; }
+    if (host->bez_coeff) { if ((st = ensure(h, h->o_bz[k], (size_t)B * N * 18 * 8))) return st; dev->bez_coeff = (double *)h->o_bz[k].p; }
+    if (host->poly_time) { if ((st = ensure(h, h->o_pt[k], (size_t)B * N * 8))) return st; dev->poly_time = (double *)h->o_pt[k].p; }
+    if (host->jerk) { if ((st = ensure(h, h->o_jk[k], (size_t)B * N * 8))) return st; dev->jerk = (double *)h->o_jk[k].p; }
+    if ((st = ensure(h, h->o_st[k], (size_t)B * 4 * 8))) return st;
+    dev->stats = (int64_t *)h->o_st[k].p;
+    return 0;
+}
+
+int download_result(H *h, const direct_ddp_result *host, const direct_ddp_result *dev, int B, int N, cudaStream_t s,
+                    int64_t *bytes) {
+    if (!host) return 0;
+#define DL(field, n)                                                                                         \
+    if (host->field && dev->field) {                                                                         \
+        CK(cudaMemcpyAsync(host->field, dev->field, (size_t)(n), cudaMemcpyDeviceToHost, s));                \
+        *bytes += (int64_t)(n);                                                                              \
+    }
+    DL(rtn, (size_t)B * 4) DL(infeas_out, (size_t)B * 4) DL(line_failed_out, (size_t)B * 4) DL(iters, (size_t)B * 4)
+    DL(cost, (size_t)B * 8) DL(x_final, (size_t)B * 72) DL(poly_coeff, (size_t)B * N * 144)
+    DL(bez_coeff, (size_t)B * N * 144) DL(poly_time, (size_t)B * N * 8) DL(jerk, (size_t)B * N * 8)
+    DL(stats, (size_t)B * 32)
+#undef DL
+    return 0;
+}
+
+int solve_host(H *h, const direct_ddp_batch *in, const direct_ddp_two_stage *ts, direct_ddp_result *out0,
+               direct_ddp_result *out1) {
+    int st = validate(h, in);
+    if (st) return st;
+    if (!out1) { h->err = "result is NULL"; return DIRECT_DDP_ERR_ARG; }
+    CK(cudaSetDevice(h->opts.device));
+    cudaStream_t s = h->stream;
+    const int B = in->B, N = in->N, PM = in->P_max;
+    direct_ddp_batch d = *in;
+    int64_t h2d = 0, d2h = 0;
+    CK(cudaEventRecord(h->ev[0], s));
+#define UP(buf, field, bytes, type)                                                                          \
+    if (in->field) {                                                                                         \
+        if ((st = ensure(h, h->buf, (size_t)(bytes)))) return st;                                            \
+        CK(cudaMemcpyAsync(h->buf.p, in->field, (size_t)(bytes), cudaMemcpyHostToDevice, s));                \
+        d.field = (const type *)h->buf.p;                                                                    \
+        h2d += (int64_t)(bytes);                                                                             \
+    }
+    UP(planes, planes, (size_t)B * N * PM * 32, double)
+    UP(nplanes, nplanes, (size_t)B * N * 4, int32_t)
+    UP(durations, durations, (size_t)B * N * 8, double)
+    UP(x0, x0, (size_t)B * 72, double)
+    UP(xd, xd, (size_t)B * 72, double)
+    if (!ts) {
+        UP(init_bez, init_bez, (size_t)B * N * 144, double)
+        UP(infeas, infeas, (size_t)B * 4, int32_t)
+    }
+    d.seeds = nullptr;  // only line_init reads seeds
+#undef UP
+    CK(cudaEventRecord(h->ev[1], s));
+    direct_ddp_result dev0, dev1;
+    if ((st = mirror_result(h, 0, ts ? out0 : nullptr, B, N, &dev0))) return st;
+    if ((st = mirror_result(h, 1, out1, B, N, &dev1))) return st;
+    if ((st = solve_device(h, &d, ts, (ts && out0) ? &dev0 : nullptr, &dev1, s))) return st;
+    CK(cudaEventRecord(h->ev[4], s));
+    if (ts && out0 && (st = download_result(h, out0, &dev0, B, N, s, &d2h))) return st;
+    if ((st = download_result(h, out1, &dev1, B, N, s, &d2h))) return st;
+    CK(cudaEventRecord(h->ev[5], s));
+    CK(cudaStreamSynchronize(s));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, h->ev[0], h->ev[1])); h->stats.h2d_ms = ms;
+    CK(cudaEventElapsedTime(&ms, h->ev[2], h->ev[3])); h->stats.kernel_ms = ms;
+    CK(cudaEventElapsedTime(&ms, h->ev[4], h->ev[5])); h->stats.d2h_ms = ms;
+    h->stats.h2d_bytes = h2d; h->stats.d2h_bytes = d2h;
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int direct_ddp_version(void) { return DIRECT_DDP_VERSION; }
+
+int direct_ddp_create(const direct_ddp_opts *opts, direct_ddp_handle *out) {
+    if (!out) return DIRECT_DDP_ERR_ARG;
+    *out = nullptr;
+    H *h = new H();
+    memset(&h->opts, 0, sizeof h->opts);
+    if (opts) h->opts = *opts;
+    memset(&h->stats, 0, sizeof h->stats);
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0 || h->opts.device < 0 || h->opts.device >= ndev) {
+        // No CPU fallback: the handle is returned so the caller can read the error text, every solve fails.
+        h->err = std::string("no usable CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "bad ordinal");
+        h->sm_count = 0;
+        *out = h;
+        return DIRECT_DDP_ERR_CUDA;
+    }
+    cudaDeviceProp prop;
+    if (cudaSetDevice(h->opts.device) != cudaSuccess || cudaGetDeviceProperties(&prop, h->opts.device) != cudaSuccess) {
+        h->err = "cudaSetDevice/cudaGetDeviceProperties failed";
+        *out = h;
+        return DIRECT_DDP_ERR_CUDA;
+    }
+    h->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { h->err = "stream"; *out = h; return DIRECT_DDP_ERR_CUDA; }
+    for (int i = 0; i < 6; i++) cudaEventCreate(&h->ev[i]);
+    int st = h->opts.precision == DIRECT_DDP_FP32 ? upload_tables<float>(h) : upload_tables<double>(h);
+    *out = h;
+    return st;
+}
+
+void direct_ddp_destroy(direct_ddp_handle h) {
+    if (!h) return;
+    if (h->sm_count > 0) {
+        cudaSetDevice(h->opts.device);
+        DevBuf *bufs[] = {&h->planes, &h->nplanes, &h->durations, &h->seeds, &h->x0, &h->xd, &h->init_bez, &h->infeas,
+                          &h->ws, &h->counter, &h->tabs, &h->bez_tmp, &h->time_tmp, &h->trace, &h->trace_len, &h->scratch_i};
+        for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
+        for (int k = 0; k < 2; k++) {
+            DevBuf *ob[] = {&h->o_int[k], &h->o_cost[k], &h->o_xf[k], &h->o_pc[k], &h->o_bz[k], &h->o_pt[k], &h->o_jk[k], &h->o_st[k]};
+            for (DevBuf *b : ob) if (b->p) cudaFree(b->p);
+        }
+        for (int i = 0; i < 6; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+        if (h->stream) cudaStreamDestroy(h->stream);
+    }
+    delete h;
+}
+
+const char *direct_ddp_last_error(direct_ddp_handle h) { return h ? h->err.c_str() : "null handle"; }
+
+#define REQUIRE_DEVICE(h)                                                      \
+    if (!(h)) return DIRECT_DDP_ERR_ARG;                                       \
+    if ((h)->sm_count <= 0) { if ((h)->err.empty()) (h)->err = "no CUDA device"; return DIRECT_DDP_ERR_CUDA; }
+
+int direct_ddp_solve_batch(direct_ddp_handle h, const direct_ddp_batch *in, direct_ddp_result *out) {
+    REQUIRE_DEVICE(h)
+    return solve_host(h, in, nullptr, nullptr, out);
+}
+
+int direct_ddp_solve_two_stage(direct_ddp_handle h, const direct_ddp_batch *in, const direct_ddp_two_stage *ts,
+                               direct_ddp_result *out0, direct_ddp_result *out1) {
+    REQUIRE_DEVICE(h)
+    if (!ts) { h->err = "two_stage options are NULL"; return DIRECT_DDP_ERR_ARG; }
+    return solve_host(h, in, ts, out0, out1);
+}
+
+int direct_ddp_solve_batch_device(direct_ddp_handle h, const direct_ddp_batch *in, direct_ddp_result *out, void *stream) {
+    REQUIRE_DEVICE(h)
+    CK(cudaSetDevice(h->opts.device));
+    return solve_device(h, in, nullptr, nullptr, out, (cudaStream_t)stream);
+}
+
+int direct_ddp_solve_two_stage_device(direct_ddp_handle h, const direct_ddp_batch *in, const direct_ddp_two_stage *ts,
+                                      direct_ddp_result *out0, direct_ddp_result *out1, void *stream) {
+    REQUIRE_DEVICE(h)
+    if (!ts) { h->err = "two_stage options are NULL"; return DIRECT_DDP_ERR_ARG; }
+    CK(cudaSetDevice(h->opts.device));
+    return solve_device(h, in, ts, out0, out1, (cudaStream_t)stream);
+}
+
+int direct_ddp_time_allocation_device(direct_ddp_handle h, int B, int N, const double *start, const double *end,
+                                      const double *seeds, double max_vel, double max_acc, double *durations, void *stream) {
+    REQUIRE_DEVICE(h)
+    if (B <= 0 || N <= 0 || !start || !end || !seeds || !durations) { h->err = "bad argument"; return DIRECT_DDP_ERR_ARG; }
+    CK(cudaSetDevice(h->opts.device));
+    const long long n = (long long)B * N;
+    time_allocation_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(B, N, start, end, seeds, max_vel, max_acc, durations);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int direct_ddp_last_stats(direct_ddp_handle h, direct_ddp_stats *out) {
+    REQUIRE_DEVICE(h)
+    if (!out) return DIRECT_DDP_ERR_ARG;
+    if (!h->stats_valid && h->last_stats_dev && h->last_B > 0) {
+        CK(cudaSetDevice(h->opts.device));
+        CK(cudaDeviceSynchronize());
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]) == cudaSuccess) h->stats.kernel_ms = ms;
+        std::vector<long long> tmp((size_t)h->last_B * 4);
+        long long tot[4] = {0, 0, 0, 0};
+        for (int pass = 0; pass < 2; pass++) {
+            const long long *src = pass == 0 ? h->last_stats_dev : h->last_stats_dev0;
+            if (!src) continue;
+            CK(cudaMemcpy(tmp.data(), src, tmp.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+            for (int i = 0; i < h->last_B; i++) for (int k = 0; k < 4; k++) tot[k] += tmp[(size_t)i * 4 + k];
+        }
+        h->stats.bwd_sweeps = tot[0]; h->stats.bwd_knots = tot[1]; h->stats.fwd_trials = tot[2]; h->stats.fwd_knots = tot[3];
+        h->stats_valid = true;
+    }
+    *out = h->stats;
+    return 0;
+}
+
+int direct_ddp_last_trace(direct_ddp_handle h, direct_ddp_trace_row *rows, int cap, int *len) {
+    REQUIRE_DEVICE(h)
+    if (!rows || !len) return DIRECT_DDP_ERR_ARG;
+    *len = 0;
+    if (!h->opts.trace || !h->trace.p) return 0;
+    CK(cudaSetDevice(h->opts.device));
+    CK(cudaDeviceSynchronize());
+    int n = 0;
+    CK(cudaMemcpy(&n, h->trace_len.p, sizeof(int), cudaMemcpyDeviceToHost));
+    if (n > cap) n = cap;
+    std::vector<double> t((size_t)n * 12 + 1);
+    if (n > 0) CK(cudaMemcpy(t.data(), h->trace.p, (size_t)n * 12 * sizeof(double), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n; i++) {
+        const double *r = &t[(size_t)i * 12];
+        rows[i].cost = r[0]; rows[i].costq = r[1]; rows[i].logcost = r[2]; rows[i].err = r[3]; rows[i].mu = r[4];
+        rows[i].reg = r[5]; rows[i].stepsize = r[6]; rows[i].opterr = r[7];
+        rows[i].step = (int)r[8]; rows[i].fp_failed = (int)r[9]; rows[i].n_bwd = (int)r[10]; rows[i].pad = 0;
+    }
+    *len = n;
+    return 0;
+}
+
+}  // extern "C"

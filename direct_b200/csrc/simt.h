@@ -1,0 +1,126 @@
+// simt.h -- the thin layer the warp-per-trajectory solver is written against.
+//
+// The solver (ipddp_solver.h) is warp-synchronous code: 32 lanes own one trajectory, per-lane values
+// live in registers (Reg<>), lanes talk through a per-warp shared-memory scratch separated by
+// WARP_SYNC(), plus a handful of shuffle collectives.  Built by nvcc this maps 1:1 onto sm_100a SIMT.
+// Built with -DDDP_EMULATE by a host compiler the same source runs the 32 lanes of each phase one
+// after the other (FOR_LANES becomes a loop, Reg<> grows a lane dimension), which is how the kernel
+// logic is debugged in a container without a GPU (tools/emulate.cpp, never shipped in the library).
+#ifndef DIRECT_B200_SIMT_H_
+#define DIRECT_B200_SIMT_H_
+
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__) && !defined(DDP_EMULATE)
+#define DDP_GPU 1
+#define DDP_DEVICE __device__ __forceinline__
+#define DDP_DEVICE_NOINLINE __device__ __noinline__
+#define DDP_HD __host__ __device__ inline
+#define FOR_LANES(lane) for (int lane = lane_, once_ = 1; once_; once_ = 0)
+#define WARP_SYNC() __syncwarp()
+#define DDP_UNROLL _Pragma("unroll")
+#else
+#define DDP_GPU 0
+#define DDP_DEVICE inline
+#define DDP_DEVICE_NOINLINE inline
+#define DDP_HD inline
+#define FOR_LANES(lane) for (int lane = 0; lane < 32; ++lane)
+#define WARP_SYNC() ((void)0)
+#define DDP_UNROLL
+#endif
+
+namespace ddp {
+
+// Per-lane register array: N values in every lane.
+template <class T, int N> struct Reg {
+#if DDP_GPU
+    T v[N];
+    DDP_DEVICE T &operator()(int, int i) { return v[i]; }
+    DDP_DEVICE const T &operator()(int, int i) const { return v[i]; }
+#else
+    T v[32][N];
+    T &operator()(int lane, int i) { return v[lane][i]; }
+    const T &operator()(int lane, int i) const { return v[lane][i]; }
+#endif
+};
+
+#if DDP_GPU
+DDP_DEVICE double shfl_xor(double x, int m) { return __shfl_xor_sync(0xffffffffu, x, m); }
+DDP_DEVICE float shfl_xor(float x, int m) { return __shfl_xor_sync(0xffffffffu, x, m); }
+DDP_DEVICE double shfl_idx(double x, int s) { return __shfl_sync(0xffffffffu, x, s); }
+DDP_DEVICE float shfl_idx(float x, int s) { return __shfl_sync(0xffffffffu, x, s); }
+#endif
+
+// Butterfly all-reduce over the warp, element i of r; every lane ends with the same value, returned.
+// The emulation reproduces the butterfly's association order so both builds round identically.
+template <class T, int N> DDP_DEVICE T warp_sum(Reg<T, N> &r, int i, int lane_) {
+#if DDP_GPU
+    T x = r.v[i];
+    DDP_UNROLL
+    for (int m = 16; m >= 1; m >>= 1) x += shfl_xor(x, m);
+    (void)lane_;
+    return x;
+#else
+    (void)lane_;
+    T t[32];
+    for (int l = 0; l < 32; l++) t[l] = r.v[l][i];
+    for (int m = 16; m >= 1; m >>= 1) {
+        T u[32];
+        for (int l = 0; l < 32; l++) u[l] = t[l] + t[l ^ m];
+        for (int l = 0; l < 32; l++) t[l] = u[l];
+    }
+    return t[0];
+#endif
+}
+template <class T, int N> DDP_DEVICE T warp_max(Reg<T, N> &r, int i, int lane_) {
+#if DDP_GPU
+    T x = r.v[i];
+    DDP_UNROLL
+    for (int m = 16; m >= 1; m >>= 1) { T y = shfl_xor(x, m); x = (y > x || y != y) ? y : x; }
+    (void)lane_;
+    return x;
+#else
+    (void)lane_;
+    T x = r.v[0][i];
+    int nan = 0;
+    for (int l = 0; l < 32; l++) { T y = r.v[l][i]; if (y != y) nan = 1; if (y > x) x = y; }
+    return nan ? (T)NAN : x;
+#endif
+}
+// Value of element i held by lane `src` (warp-uniform result).
+template <class T, int N> DDP_DEVICE T warp_bcast(const Reg<T, N> &r, int i, int src, int lane_) {
+#if DDP_GPU
+    (void)lane_;
+    return shfl_idx(r.v[i], src);
+#else
+    (void)lane_;
+    return r.v[src][i];
+#endif
+}
+template <int N> DDP_DEVICE bool warp_any(const Reg<int, N> &r, int i, int lane_) {
+#if DDP_GPU
+    (void)lane_;
+    return __any_sync(0xffffffffu, r.v[i]) != 0;
+#else
+    (void)lane_;
+    for (int l = 0; l < 32; l++) if (r.v[l][i]) return true;
+    return false;
+#endif
+}
+
+DDP_DEVICE double rlog(double x) { return log(x); }
+DDP_DEVICE float rlog(float x) { return logf(x); }
+DDP_DEVICE double rsqrt_(double x) { return sqrt(x); }
+DDP_DEVICE float rsqrt_(float x) { return sqrtf(x); }
+DDP_DEVICE double rabs(double x) { return fabs(x); }
+DDP_DEVICE float rabs(float x) { return fabsf(x); }
+DDP_DEVICE double rpow(double x, double y) { return pow(x, y); }
+DDP_DEVICE float rpow(float x, float y) { return powf(x, y); }
+template <class T> DDP_DEVICE T rmax(T a, T b) { return (a < b) ? b : a; }   // std::max(a, b)
+template <class T> DDP_DEVICE T rmin(T a, T b) { return (b < a) ? b : a; }   // std::min(a, b)
+// max that propagates like Eigen's lpNorm<Infinity> over finite data; NaN in b is kept.
+template <class T> DDP_DEVICE T amax(T a, T b) { return (b > a || b != b) ? b : a; }
+
+}  // namespace ddp
+#endif
