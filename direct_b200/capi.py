@@ -110,7 +110,7 @@ class HostResult:
         self.bez_coeff = np.zeros((B, N, 18))
         self.poly_time = np.zeros((B, N))
         self.jerk = np.zeros((B, N))
-        self.stats = np.zeros((B, 4), np.int64)
+        self.stats = np.zeros((B, 8), np.int64)
 
     def c_struct(self) -> ResultC:
         return ResultC(*[getattr(self, n).ctypes.data for n, _ in ResultC._fields_])

@@ -244,7 +244,7 @@ int solve_device(H *h, const direct_ddp_batch *in, const direct_ddp_two_stage *t
     // statistics are always collected (roofline accounting): use internal buffers when the caller has none
     for (int k = ts ? 0 : 1; k < 2; k++) {
         if (!A.out[k].stats) {
-            if ((st = ensure(h, h->o_st[k], (size_t)in->B * 4 * sizeof(long long)))) return st;
+            if ((st = ensure(h, h->o_st[k], (size_t)in->B * 8 * sizeof(long long)))) return st;
             A.out[k].stats = (long long *)h->o_st[k].p;
         }
     }
@@ -272,7 +272,7 @@ int mirror_result(H *h, int k, const direct_ddp_result *host, int B, int N, dire
     if (host->bez_coeff) { if ((st = ensure(h, h->o_bz[k], (size_t)B * N * 18 * 8))) return st; dev->bez_coeff = (double *)h->o_bz[k].p; }
     if (host->poly_time) { if ((st = ensure(h, h->o_pt[k], (size_t)B * N * 8))) return st; dev->poly_time = (double *)h->o_pt[k].p; }
     if (host->jerk) { if ((st = ensure(h, h->o_jk[k], (size_t)B * N * 8))) return st; dev->jerk = (double *)h->o_jk[k].p; }
-    if ((st = ensure(h, h->o_st[k], (size_t)B * 4 * 8))) return st;
+    if ((st = ensure(h, h->o_st[k], (size_t)B * 8 * 8))) return st;
     dev->stats = (int64_t *)h->o_st[k].p;
     return 0;
 }
@@ -288,7 +288,7 @@ int download_result(H *h, const direct_ddp_result *host, const direct_ddp_result
     DL(rtn, (size_t)B * 4) DL(infeas_out, (size_t)B * 4) DL(line_failed_out, (size_t)B * 4) DL(iters, (size_t)B * 4)
     DL(cost, (size_t)B * 8) DL(x_final, (size_t)B * 72) DL(poly_coeff, (size_t)B * N * 144)
     DL(bez_coeff, (size_t)B * N * 144) DL(poly_time, (size_t)B * N * 8) DL(jerk, (size_t)B * N * 8)
-    DL(stats, (size_t)B * 32)
+    DL(stats, (size_t)B * 64)
 #undef DL
     return 0;
 }
@@ -444,13 +444,13 @@ int direct_ddp_last_stats(direct_ddp_handle h, direct_ddp_stats *out) {
         CK(cudaDeviceSynchronize());
         float ms = 0;
         if (cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]) == cudaSuccess) h->stats.kernel_ms = ms;
-        std::vector<long long> tmp((size_t)h->last_B * 4);
+        std::vector<long long> tmp((size_t)h->last_B * 8);
         long long tot[4] = {0, 0, 0, 0};
         for (int pass = 0; pass < 2; pass++) {
             const long long *src = pass == 0 ? h->last_stats_dev : h->last_stats_dev0;
             if (!src) continue;
             CK(cudaMemcpy(tmp.data(), src, tmp.size() * sizeof(long long), cudaMemcpyDeviceToHost));
-            for (int i = 0; i < h->last_B; i++) for (int k = 0; k < 4; k++) tot[k] += tmp[(size_t)i * 4 + k];
+            for (int i = 0; i < h->last_B; i++) for (int k = 0; k < 4; k++) tot[k] += tmp[(size_t)i * 8 + k];
         }
         h->stats.bwd_sweeps = tot[0]; h->stats.bwd_knots = tot[1]; h->stats.fwd_trials = tot[2]; h->stats.fwd_knots = tot[3];
         h->stats_valid = true;

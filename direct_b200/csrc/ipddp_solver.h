@@ -165,6 +165,14 @@ DDP_HD WsLay ws_layout(int N, int PM, int fcap) {
     return w;
 }
 
+DDP_DEVICE long long ddp_clock() {
+#if DDP_GPU
+    return clock64();
+#else
+    return 0;
+#endif
+}
+
 // z-space index of monomial coefficient (l, axis): z = [u(0..8), T(9), x(10..18)].
 DDP_DEVICE int zidx(int l, int a) { return l < 3 ? 10 + 3 * l + a : 3 * (l - 3) + a; }
 
@@ -181,6 +189,7 @@ template <class R> struct Traj {
     R mu, tol, reg, reg_base, opterr, cost, costq, logcost, err, stepsize;
     int step, failed, bfailed, nfilter;
     long long n_bwd_sweeps, n_bwd_knots, n_fwd_trials, n_fwd_knots;
+    long long cyc_bwd, cyc_fwd, cyc_t0;  // clock64 accounting (0 in the emulation)
 };
 
 // Row slots of a lane: 0..5 corridor rows (control point j = slot, plane = lane), 6 = fixed "+" row,
@@ -304,6 +313,7 @@ template <class R> DDP_DEVICE_NOINLINE void backward_pass(Traj<R> &t) {
     const int lane_ = t.lane_;
     const Lay L(t.PM);
     R *sm = t.sm;
+    const long long clk0 = ddp_clock();
     t.n_bwd_sweeps++;
     // regularisation schedule, ddp.cpp:452-474
     if (t.failed || t.bfailed) t.reg = t.reg + R(1);
@@ -592,6 +602,7 @@ template <class R> DDP_DEVICE_NOINLINE void backward_pass(Traj<R> &t) {
         if (fail) {  // ddp.cpp:546-551 / :595-600
             t.bfailed = 1;
             t.opterr = R(INFINITY);
+            t.cyc_bwd += ddp_clock() - clk0;
             return;
         }
         // ---- phase G: gains [ku | Ku] = -(L L^T)^-1 [Qu | Qux] (ddp.cpp:561-564 / :607-609) -----------
@@ -658,6 +669,7 @@ template <class R> DDP_DEVICE_NOINLINE void backward_pass(Traj<R> &t) {
     t.bfailed = 0;
     const R e0 = warp_max(errs, 0, lane_), e1 = warp_max(errs, 1, lane_), e2 = warp_max(errs, 2, lane_);
     t.opterr = rmax(rmax(e0, t.infeas ? e2 : R(0)), e1);  // ddp.cpp:641
+    t.cyc_bwd += ddp_clock() - clk0;
 }
 
 // =============================================================================================
@@ -935,6 +947,7 @@ template <class R> DDP_DEVICE_NOINLINE bool any_violation(Traj<R> &t, R thresh, 
 // Line search with the filter (ddp.cpp:647-778).
 template <class R> DDP_DEVICE_NOINLINE void forward_pass(Traj<R> &t) {
     const int lane_ = t.lane_;
+    const long long clk0 = ddp_clock();
     const R tau = rmax(R(0.99), R(1) - t.mu);
     bool failed = true;
     RollOut<R> ro;
@@ -985,6 +998,7 @@ template <class R> DDP_DEVICE_NOINLINE void forward_pass(Traj<R> &t) {
         if (t.infeas) { tmp = t.y; t.y = t.yn; t.yn = tmp; }
         t.stepsize = stepsize; t.step = step; t.failed = 0;
     }
+    t.cyc_fwd += ddp_clock() - clk0;
 }
 
 // =============================================================================================
@@ -1010,6 +1024,7 @@ template <class R> DDP_DEVICE_NOINLINE void solve_one(const SolveArgs &A, int st
     t.tol = R(1.0e-7);                                 // ddp.cpp:43
     t.reg_base = cfg.zero_init ? R(1.6) : R(4.0);      // ddp.cpp:60-61
     t.n_bwd_sweeps = t.n_bwd_knots = t.n_fwd_trials = t.n_fwd_knots = 0;
+    t.cyc_bwd = t.cyc_fwd = 0; t.cyc_t0 = ddp_clock();
     const bool from_stage0 = (A.two_stage && st == 1);
     int infeas_in;
     if (from_stage0) infeas_in = A.out[0].infeas_out ? A.out[0].infeas_out[b] : 1;
@@ -1136,8 +1151,9 @@ template <class R> DDP_DEVICE_NOINLINE void solve_one(const SolveArgs &A, int st
             if (O.iters) O.iters[b] = iter;
             if (O.cost) O.cost[b] = (double)t.cost;
             if (O.stats) {
-                O.stats[(long long)b * 4 + 0] = t.n_bwd_sweeps; O.stats[(long long)b * 4 + 1] = t.n_bwd_knots;
-                O.stats[(long long)b * 4 + 2] = t.n_fwd_trials; O.stats[(long long)b * 4 + 3] = t.n_fwd_knots;
+                long long *S = O.stats + (long long)b * 8;
+                S[0] = t.n_bwd_sweeps; S[1] = t.n_bwd_knots; S[2] = t.n_fwd_trials; S[3] = t.n_fwd_knots;
+                S[4] = t.cyc_bwd; S[5] = t.cyc_fwd; S[6] = ddp_clock() - t.cyc_t0; S[7] = 0;
             }
         }
         if (lane < 9 && O.x_final) O.x_final[(long long)b * 9 + lane] = (double)t.xu[(long long)N * 20 + 10 + lane];

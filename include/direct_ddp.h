@@ -87,7 +87,8 @@ typedef struct direct_ddp_batch {
  *   poly_time      getPolyTime()   [N]
  *   jerk           per-segment jerk cost; getJerkCost() is its sum
  *   x_final        fp.x.back(); getTerminalNorm() = |x_final - xd|^2
- *   stats          [B][4] backward sweeps, backward knots, line-search rollouts, rollout knots
+ *   stats          [B][8] backward sweeps, backward knots, line-search rollouts, rollout knots,
+ *                  SM cycles in backward passes, in line searches, in the whole solve, reserved
  */
 typedef struct direct_ddp_result {
     int32_t *rtn, *infeas_out, *line_failed_out, *iters;
@@ -97,7 +98,7 @@ typedef struct direct_ddp_result {
     double *bez_coeff;  /* [B][N][18]  */
     double *poly_time;  /* [B][N]      */
     double *jerk;       /* [B][N]      */
-    int64_t *stats;     /* [B][4]      */
+    int64_t *stats;     /* [B][8]      */
 } direct_ddp_result;
 
 /* The node's two-stage protocol, teach_repeat_planner.cpp:853-951 (fastTrajPlanning): stage 0 =

@@ -25,7 +25,7 @@ typedef struct {
     int *rtn, *infeas_out, *line_failed_out, *iters; /* [B] */
     double *cost, *x_final;                          /* [B], [B][9] */
     double *poly_coeff, *bez_coeff, *poly_time, *jerk; /* [B][N][18] x2, [B][N] x2 */
-    long *stats;                                     /* [B][4]: bwd sweeps, bwd knots, fwd trials, fwd knots */
+    long *stats;                                     /* [B][8]: bwd sweeps, bwd knots, fwd trials, fwd knots, 4 x reserved (0) */
 } oracle_out;
 
 static void fill_problem(const oracle_batch *b, int i, ipddp_problem *p) {
@@ -61,8 +61,9 @@ static void store_result(const oracle_out *o, int i, const ipddp_result *r) {
     if (o->cost) o->cost[i] = r->cost;
     if (o->x_final) memcpy(o->x_final + (size_t)i * 9, r->x_final, 72);
     if (o->stats) {
-        o->stats[(size_t)i * 4 + 0] = r->n_bwd_sweeps; o->stats[(size_t)i * 4 + 1] = r->n_bwd_knots;
-        o->stats[(size_t)i * 4 + 2] = r->n_fwd_trials; o->stats[(size_t)i * 4 + 3] = r->n_fwd_knots;
+        long *S = o->stats + (size_t)i * 8;
+        S[0] = r->n_bwd_sweeps; S[1] = r->n_bwd_knots; S[2] = r->n_fwd_trials; S[3] = r->n_fwd_knots;
+        S[4] = S[5] = S[6] = S[7] = 0;
     }
 }
 

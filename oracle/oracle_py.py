@@ -103,7 +103,7 @@ class Result:
         self.bez_coeff = np.zeros((B, N, 18))
         self.poly_time = np.zeros((B, N))
         self.jerk = np.zeros((B, N))
-        self.stats = np.zeros((B, 4), np.int64)
+        self.stats = np.zeros((B, 8), np.int64)
 
     def c_struct(self):
         return _Out(_p(self.rtn, _ip), _p(self.infeas_out, _ip), _p(self.line_failed_out, _ip), _p(self.iters, _ip),
