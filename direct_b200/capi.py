@@ -60,7 +60,7 @@ class TraceRow(C.Structure):
 EXPORTS = ["direct_ddp_version", "direct_ddp_create", "direct_ddp_destroy", "direct_ddp_last_error",
            "direct_ddp_solve_batch", "direct_ddp_solve_batch_device", "direct_ddp_solve_two_stage",
            "direct_ddp_solve_two_stage_device", "direct_ddp_time_allocation_device", "direct_ddp_last_stats",
-           "direct_ddp_last_trace"]
+           "direct_ddp_last_trace", "direct_ddp_measure_fma_peak"]
 
 _lib = None
 
@@ -88,6 +88,7 @@ def load_library(build_if_missing: bool = True):
                                                           C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_void_p]
         lib.direct_ddp_last_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
         lib.direct_ddp_last_trace.argtypes = [C.c_void_p, C.POINTER(TraceRow), C.c_int, C.POINTER(C.c_int)]
+        lib.direct_ddp_measure_fma_peak.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]
         _lib = lib
     return _lib
 
@@ -212,6 +213,11 @@ class Solver:
         s = Stats()
         self._check(self.lib.direct_ddp_last_stats(self.h, C.byref(s)))
         return s
+
+    def fma_peak_tflops(self, precision: str) -> float:
+        v = C.c_double(0.0)
+        self._check(self.lib.direct_ddp_measure_fma_peak(self.h, {"fp64": 0, "fp32": 1}[precision], C.byref(v)))
+        return v.value
 
     def trace(self, cap: int = 512):
         rows = (TraceRow * cap)()

@@ -71,6 +71,17 @@ __global__ void time_allocation_kernel(int B, int N, const double *start, const 
     durations[idx] = dt;
 }
 
+// Register-resident FMA throughput probe: the measured denominator of the FMA roofline (MEASURED_PEAKS.json
+// only carries HBM and bf16 tensor numbers).  8 independent chains per thread, 2 flops per FMA.
+template <class R> __global__ void fma_peak_kernel(R *out, int iters, R a, R b) {
+    R x0 = a + threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; i++) {
+        x0 = x0 * a + b; x1 = x1 * a + b; x2 = x2 * a + b; x3 = x3 * a + b;
+        x4 = x4 * a + b; x5 = x5 * a + b; x6 = x6 * a + b; x7 = x7 * a + b;
+    }
+    if (x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7 == R(12345.678)) out[0] = x0;
+}
+
 struct DevBuf {
     void *p = nullptr;
     size_t cap = 0;
@@ -433,6 +444,29 @@ int direct_ddp_time_allocation_device(direct_ddp_handle h, int B, int N, const d
     const long long n = (long long)B * N;
     time_allocation_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(B, N, start, end, seeds, max_vel, max_acc, durations);
     CK(cudaGetLastError());
+    return 0;
+}
+
+int direct_ddp_measure_fma_peak(direct_ddp_handle h, int precision, double *tflops) {
+    REQUIRE_DEVICE(h)
+    if (!tflops) return DIRECT_DDP_ERR_ARG;
+    CK(cudaSetDevice(h->opts.device));
+    int st = ensure(h, h->scratch_i, 64);
+    if (st) return st;
+    const int iters = 4096, blocks = h->sm_count * 8, threads = 512;
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; rep++) {
+        CK(cudaEventRecord(h->ev[0], h->stream));
+        if (precision == DIRECT_DDP_FP32) fma_peak_kernel<float><<<blocks, threads, 0, h->stream>>>((float *)h->scratch_i.p, iters, 0.999f, 0.001f);
+        else fma_peak_kernel<double><<<blocks, threads, 0, h->stream>>>((double *)h->scratch_i.p, iters, 0.999, 0.001);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(h->ev[1], h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
+        if (ms < best) best = ms;
+    }
+    *tflops = 2.0 * 8.0 * (double)iters * blocks * threads / (best * 1e-3) / 1e12;
     return 0;
 }
 

@@ -152,6 +152,9 @@ int direct_ddp_time_allocation_device(direct_ddp_handle h, int B, int N, const d
                                       double max_vel, double max_acc, double *durations, void *stream);
 
 int direct_ddp_last_stats(direct_ddp_handle h, direct_ddp_stats *out);
+/* Register-resident FMA throughput of the device (TFLOP/s, 2 flops per FMA) for DIRECT_DDP_FP64 or
+ * DIRECT_DDP_FP32: the measured denominator of the FMA roofline bench.py reports. */
+int direct_ddp_measure_fma_peak(direct_ddp_handle h, int precision, double *tflops);
 /* Per-iteration trace of trajectory 0 of the last (stage-1 or single) solve when opts.trace != 0. */
 int direct_ddp_last_trace(direct_ddp_handle h, direct_ddp_trace_row *rows, int cap, int *len);
 
