@@ -43,6 +43,69 @@ def oracle():
     return O
 
 
+# ---------------------------------------------------------------------------------------------------------
+# Conditioning screen.  The reference algorithm takes discrete decisions (line-search step index, filter
+# acceptance, Cholesky failure -> regularisation, early exits) inside a nonlinear iteration that amplifies
+# perturbations by ~10x per iteration while it struggles at high regularisation (DESIGN.md "Parity").  On a
+# few per cent of the synthetic corridors a 1-ulp change of the INPUTS therefore moves the reference's own
+# outputs by far more than 1e-5 -- the oracle built with -ffp-contract=fast disagrees with itself on those,
+# and so would the reference rebuilt with other compiler flags.  No implementation with a different rounding
+# sequence can promise 1e-5 there.  The screen below finds them with the oracle alone: a trajectory is
+# "conditioned" when four 2^-48-relative input perturbations leave every oracle output within 1e-7 relative
+# and every discrete outcome unchanged.  Parity (<= 1e-5, identical rtn / iteration counts) is asserted on
+# ALL conditioned trajectories; the others are checked for validity of what is returned.
+# ---------------------------------------------------------------------------------------------------------
+PERTURB_EPS = 2.0 ** -48
+SCREEN_TOL = 1e-7
+
+
+def _row_rel(a, b):
+    a = np.asarray(a, dtype=np.float64).reshape(len(a), -1)
+    b = np.asarray(b, dtype=np.float64).reshape(len(b), -1)
+    return np.max(np.abs(a - b), axis=1) / np.maximum(1e-300, np.max(np.abs(b), axis=1))
+
+
+def results_differ(a, b, tol, fields=OUT_FIELDS):
+    """Per-trajectory bool: discrete outcome or any output field of Result `a` differs from `b` by > tol."""
+    d = (a.rtn != b.rtn) | (a.iters != b.iters) | (a.infeas_out != b.infeas_out)
+    for f in fields:
+        d |= _row_rel(getattr(a, f), getattr(b, f)) > tol
+    return d
+
+
+def perturbed_batches(pb):
+    from direct_b200.problems import ProblemBatch
+    e = PERTURB_EPS
+    mk = lambda **kw: ProblemBatch(**{**{f: getattr(pb, f) for f in ("B", "N", "P_max", "planes", "nplanes", "durations",
+                                                                       "seeds", "x0", "xd", "max_vel", "max_acc")}, **kw})
+    return [mk(durations=pb.durations * (1 + e)), mk(durations=pb.durations * (1 - e)),
+            mk(x0=pb.x0 * (1 + e), xd=pb.xd * (1 - e)), mk(planes=np.ascontiguousarray(pb.planes * (1 + e)))]
+
+
+def conditioned_mask_two_stage(oracle, pb, base=None, nthreads=None):
+    """(mask, (a0, a1)): trajectories on which the oracle's two-stage result is insensitive to 1-ulp inputs."""
+    nt = nthreads or oracle.max_threads()
+    a0, a1 = base if base is not None else oracle.two_stage_batch(pb, nthreads=nt)
+    ok = np.ones(pb.B, dtype=bool)
+    for q in perturbed_batches(pb):
+        p0, p1 = oracle.two_stage_batch(q, nthreads=nt)
+        ok &= ~results_differ(p0, a0, SCREEN_TOL) & ~results_differ(p1, a1, SCREEN_TOL)
+    return ok, (a0, a1)
+
+
+def assert_valid_result(pb, r):
+    """What must hold for every returned trajectory, conditioned or not."""
+    assert set(np.unique(r.rtn)).issubset({0, 1, 2, -3, -4})
+    assert np.isfinite(r.cost).all() and np.isfinite(r.poly_coeff).all() and np.isfinite(r.bez_coeff).all()
+    done = np.isin(r.rtn, (1, 2))
+    if done.any():   # exits 1 and 2 need every c < 2e-4 where c already carries the -2e-4 margin (ddp_optimizer.cpp:346-378,
+        # :1281-1283; hazard H8): control points are at most 4e-4 outside their polytope
+        cp = r.bez_coeff.reshape(pb.B, pb.N, 3, 6) * r.poly_time[:, :, None, None]
+        val = np.einsum("bnpa,bnaj->bnpj", pb.planes[..., :3], cp) + pb.planes[..., 3:4]
+        assert (val[done] < 4e-4 + 1e-9).all()
+        assert (r.poly_time[done] > 0.3).all()
+
+
 def has_gpu():
     try:
         import torch
