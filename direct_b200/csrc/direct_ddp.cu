@@ -14,12 +14,19 @@
 #include "../../include/direct_ddp.h"
 #include "ipddp_solver.h"
 
+#ifndef DDP_MAX_THREADS
+#define DDP_MAX_THREADS 64   // two trajectories (warps) per CTA
+#endif
+#ifndef DDP_MIN_BLOCKS
+#define DDP_MIN_BLOCKS 4     // => <= 255 registers/thread available, >= 8 resident trajectories per SM
+#endif
+
 namespace {
 
 using ddp::SolveArgs;
 
 template <class R>
-__global__ void __launch_bounds__(128, 3) ipddp_solve_kernel(SolveArgs A, const R *__restrict__ tabs_g) {
+__global__ void __launch_bounds__(DDP_MAX_THREADS, DDP_MIN_BLOCKS) ipddp_solve_kernel(SolveArgs A, const R *__restrict__ tabs_g) {
     extern __shared__ __align__(16) unsigned char smraw[];
     R *sm_all = reinterpret_cast<R *>(smraw);
     R *tabs = sm_all;  // 360 table entries shared by the block
@@ -140,7 +147,7 @@ int validate(H *h, const direct_ddp_batch *in) {
 int validate_cfg(H *h, int time_power, int line_init, int iter_max) {
     if (time_power != 1 && time_power != 2) { h->err = "time_power must be 1 or 2"; return DIRECT_DDP_ERR_ARG; }
     if (iter_max < 0) { h->err = "iter_max must be >= 0"; return DIRECT_DDP_ERR_ARG; }
-    if (line_init) { h->err = "line_init_flag is not supported by the device path yet"; return DIRECT_DDP_ERR_UNSUPPORTED; }
+    (void)line_init;
     return 0;
 }
 
@@ -158,9 +165,9 @@ template <class R> int upload_tables(H *h) {
 
 // Launch the persistent solve kernel on device-resident arguments.
 template <class R> int launch(H *h, SolveArgs &A, cudaStream_t s) {
-    const int wpb = h->opts.warps_per_block > 0 ? h->opts.warps_per_block : 4;
+    const int wpb = h->opts.warps_per_block > 0 ? h->opts.warps_per_block : DDP_MAX_THREADS / 32;
     const int threads = wpb * 32;
-    if (threads > 128) { h->err = "warps_per_block must be <= 4"; return DIRECT_DDP_ERR_ARG; }
+    if (threads > DDP_MAX_THREADS) { h->err = "warps_per_block exceeds the kernel's launch bound"; return DIRECT_DDP_ERR_ARG; }
     const size_t smem = (size_t)(360 + wpb * ddp::smem_elems_per_warp(A.PM)) * sizeof(R);
     auto kern = ipddp_solve_kernel<R>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -331,7 +338,10 @@ int solve_host(H *h, const direct_ddp_batch *in, const direct_ddp_two_stage *ts,
         UP(init_bez, init_bez, (size_t)B * N * 144, double)
         UP(infeas, infeas, (size_t)B * 4, int32_t)
     }
-    d.seeds = nullptr;  // only line_init reads seeds
+    if (!ts && in->line_init) {  // only line_init reads the seeds (ddp_optimizer.cpp:195-247)
+        if (!in->seeds) { h->err = "line_init needs seeds"; return DIRECT_DDP_ERR_ARG; }
+        UP(seeds, seeds, (size_t)B * N * 24, double)
+    } else d.seeds = nullptr;
 #undef UP
     CK(cudaEventRecord(h->ev[1], s));
     direct_ddp_result dev0, dev1;

@@ -1,4 +1,4 @@
-// ipddp_solver.h -- warp-per-trajectory interior-point DDP (IPDDP) solve for sm_100a.
+// ipddp_solver.h -- warp-per-trajectory interior-point DDP (IPDDP) solve for sm_100a (v2).
 //
 // One warp owns one trajectory for its whole solve: setup, initial rollout, the outer barrier loop,
 // backward Riccati/IP sweeps, filter line search and output conversion all run inside one kernel
@@ -7,16 +7,27 @@
 //     polyCurveGeneration :5-438, backwardpass :440-644, forwardpass :647-778, bez2polyFunc :782,
 //     poly2bezFunc :799, computenextx :1062, computecminvo :1132, computeq :1294,
 //     computeall :1309-1368 + :1455-1604, initialroll :1608, finalroll :1624, resetfilter :1636
-// re-designed rather than ported:
-//   * no Jacobian is ever materialised: every constraint row is (basis row beta_g(T)) (x) (direction n)
-//     plus a d/dT entry, so c, J*v, J^T*w and J^T D J are evaluated from 15 "row groups"
-//     (6 position control points, 5 velocity, 4 acceleration) and the polytope planes;
-//   * lane <-> plane for the 6P corridor rows, lane <-> (group, axis) for the 55 fixed rows;
-//   * the 19x19 Hessian of Q in z = [u(10); x(9)] (plus the gradient as a 20th row/column) is held one
-//     column per lane; ten right-looking Cholesky pivots over the u block leave V_xx, V_x in the
-//     trailing block (a Schur complement) and the gains come from one back-substitution per lane;
-//   * per-knot state (x,u,s,y, gains) streams through a per-warp workspace slot in global memory,
-//     c and the slack gains ks,Ks,ky,Ky are recomputed on the fly instead of being stored.
+// re-designed rather than ported.  The batch is heavy-tailed (a few trajectories need 10-15x the mean
+// work), so the kernel time is the critical path of the longest solves: everything is organised to keep
+// the per-knot dependent chain of ONE warp short.
+//   * Two kinds of phases.  KNOT-PARALLEL phases (lane <-> knot, no communication between lanes):
+//     `linearize` (everything of the backward pass that does not depend on the Riccati recursion: constraint
+//     values, interior-point weights, the constraint + stage-cost part of the Hessian/gradient of Q),
+//     `evaluate_trial` (slack/dual updates, fraction-to-boundary tests, barrier cost of a line-search
+//     trial), `scan_constraints` (filter reset, feasibility count).  SEQUENTIAL phases (lane <-> matrix
+//     column / state element): `riccati` (dynamics term, ten Cholesky pivots, gains, value backup) and
+//     the closed-loop state rollout inside `forward_trial`.
+//   * No Jacobian is ever materialised: every constraint row is (basis row beta_g(T)) (x) (direction n)
+//     plus a d/dT entry, so c, J*v, J^T*w and J^T D J come from 15 "row groups" (6 position control
+//     points, 5 velocity, 4 acceleration) and the polytope planes.  J^T D J = sum_g (beta_g beta_g^T) (x) M_g
+//     with 3x3 blocks M_g; only the 126 + 38 distinct entries are formed.
+//   * The 19x19 Hessian of Q in z = [u(10); x(9)] plus the gradient as 20th row/column is held one column
+//     per lane; ten right-looking Cholesky pivots over the u block (pivot broadcast by shuffle, multiplier
+//     row through shared memory, next pivot's diagonal sent ahead of the rank-1 update) leave V_xx, V_x
+//     in the trailing block (a Schur complement); the gains come from one back-substitution per lane.
+//   * Per-knot state streams through a per-warp workspace slot in global memory (row arrays stored
+//     [row][knot] so lane <-> knot accesses coalesce); c and the slack gains ks,Ks,ky,Ky are recomputed
+//     on the fly instead of being stored.
 // Arithmetic is re-associated with respect to the reference (documented in DESIGN.md), so results
 // agree with the oracle to rounding, not bit for bit.
 //
@@ -114,52 +125,52 @@ struct SolveArgs {
     int *trace_len;
 };
 
-// Shared-memory layout of one warp's scratch, in elements of Real.
+// ---------------------------------------------------------------------------------------------
+// Per-warp shared-memory scratch (elements of Real).  Independent of the number of planes: the
+// knot-parallel phases read planes straight from global memory (each lane its own knot).
+// ---------------------------------------------------------------------------------------------
 struct Lay {
-    int PM;
-    DDP_DEVICE explicit Lay(int pm) : PM(pm) {}
-    enum { BS = 0, BDT = 90, ZO = 180, ZN = 200, KC = 220, VXX = 320, VX = 404, XD = 416, PL = 428 };
-    DDP_DEVICE int cend() const { return 428 + 4 * PM; }
-    // backward-only region
-    DDP_DEVICE int FG() const { return cend(); }
-    DDP_DEVICE int FT() const { return cend() + 20; }
-    DDP_DEVICE int RR() const { return cend() + 32; }
-    DDP_DEVICE int TT9() const { return cend() + 52; }
-    DDP_DEVICE int TRB() const { return cend() + 64; }
-    DDP_DEVICE int G() const { return cend() + 154; }
-    DDP_DEVICE int X() const { return cend() + 326; }
-    DDP_DEVICE int XT() const { return cend() + 346; }
-    DDP_DEVICE int XI() const { return cend() + 366; }
-    DDP_DEVICE int LF() const { return cend() + 378; }
-    DDP_DEVICE int W() const { return cend() + 578; }
-    DDP_DEVICE int BV() const { return cend() + 578 + 30 * PM; }
-    // forward-only region (aliases the backward one)
-    DDP_DEVICE int BSN() const { return cend(); }
-    DDP_DEVICE int TRF() const { return cend() + 90; }
-    DDP_DEVICE int V1() const { return cend() + 318; }
-    DDP_DEVICE int V2() const { return cend() + 338; }
-    DDP_DEVICE int DX() const { return cend() + 358; }
-    DDP_DEVICE int FGN() const { return cend() + 370; }
-    DDP_DEVICE int total() const { return cend() + 578 + 40 * PM; }
+    enum {
+        XD = 0,     // desired terminal state (9)
+        S1 = 10,    // value-function Hessian as left by the Schur complement, S1[a*10+b] = S[a][b]
+        S2 = 100,   // the same transposed, S2[b*10+a] = S[a][b]; V = (S + S^T)/2 is formed by the reader
+        VX = 190,   // V_x (9)
+        MB = 200,   // Cholesky multiplier rows, MB[p*20+r] = L[r][p]  (10 x 20)
+        XT = 400,   // row T of every column, for the T column (20)
+        XH = 420,   // fT[p] * (V fT)[p]  (9)
+        KC = 430,   // gains of the current knot, KC[p*10+qc], qc 0 = ku, 1..9 = Ku columns
+        ZN = 530,   // rollout broadcast: new [u(10); x(9)] (20)
+        DX = 550,   // rollout broadcast: xnew - xold (9)
+        FL = 560,   // filter decision (2)
+        MSC = 564,  // per-lane 3x3 blocks M_g of the linearisation: MSC[e*32+lane], e < 63
+        TOTAL = 564 + 63 * 32
+    };
 };
-DDP_HD int smem_elems_per_warp(int pm) { return 428 + 4 * pm + 578 + 40 * pm; }
+DDP_HD int smem_elems_per_warp(int /*pm*/) { return Lay::TOTAL; }
 
-// Workspace slot layout (elements of Real).
+// Workspace slot layout (elements of Real).  Row arrays (s, y and their trial copies) are stored
+// [row slot][knot] with the knot index padded to a multiple of 32, so lane <-> knot accesses coalesce.
+// Row slots: corridor row (control point j, plane k) -> j*PM+k; then +v (15), -v (15), +a (12), -a (12), time.
 struct WsLay {
-    long long xu, xun, s, sn, y, yn, K, filt, total;
-    int MCS;
+    long long xu, xun, K, kdx, aux, H, s, sn, y, yn, filt, total;
+    int MCS, NP;
 };
 DDP_HD WsLay ws_layout(int N, int PM, int fcap) {
     WsLay w;
-    w.MCS = (6 * PM + 55 + 3) & ~3;
+    w.MCS = 6 * PM + 55;
+    w.NP = (N + 31) & ~31;
     long long o = 0;
     w.xu = o; o += (long long)(N + 1) * 20;
     w.xun = o; o += (long long)(N + 1) * 20;
-    w.s = o; o += (long long)N * w.MCS;
-    w.sn = o; o += (long long)N * w.MCS;
-    w.y = o; o += (long long)N * w.MCS;
-    w.yn = o; o += (long long)N * w.MCS;
     w.K = o; o += (long long)N * 100;
+    w.kdx = o; o += (long long)N * 10;
+    w.aux = o; o += (long long)N * 12;
+    o = (o + 1) & ~1LL;
+    w.H = o; o += (long long)N * 400;
+    w.s = o; o += (long long)w.MCS * w.NP;
+    w.sn = o; o += (long long)w.MCS * w.NP;
+    w.y = o; o += (long long)w.MCS * w.NP;
+    w.yn = o; o += (long long)w.MCS * w.NP;
     w.filt = o; o += 2LL * fcap;
     w.total = (o + 15) & ~15LL;
     return w;
@@ -174,15 +185,17 @@ DDP_DEVICE long long ddp_clock() {
 }
 
 // z-space index of monomial coefficient (l, axis): z = [u(0..8), T(9), x(10..18)].
-DDP_DEVICE int zidx(int l, int a) { return l < 3 ? 10 + 3 * l + a : 3 * (l - 3) + a; }
+DDP_DEVICE constexpr int zidx(int l, int a) { return l < 3 ? 10 + 3 * l + a : 3 * (l - 3) + a; }
+// index of the unordered pair (la <= lb) of monomial orders, 0..20
+DDP_DEVICE constexpr int pidx(int la, int lb) { return la * 6 + lb - (la * (la + 1)) / 2; }
 
 template <class R> struct Traj {
-    int N, PM, MCS, lane_;
+    int N, PM, NP, MCS, lane_;
     const double *planes;
     const int32_t *nplanes;
     R *sm;
-    const R *tab;  // [0..89] value table (chosen basis), [90..179] dt table
-    R *xu, *xun, *s, *sn, *y, *yn, *K, *filt;
+    const R *tab;  // [0..89] value table (chosen basis), [90..179] d/dT table
+    R *xu, *xun, *K, *kdx, *aux, *H, *s, *sn, *y, *yn, *filt;
     int fcap;
     R max_vel, max_acc, w_snap, w_terminal, w_time, margin;
     int time_power, infeas, zero_init, line_init;
@@ -192,420 +205,496 @@ template <class R> struct Traj {
     long long cyc_bwd, cyc_fwd, cyc_t0;  // clock64 accounting (0 in the emulation)
 };
 
-// Row slots of a lane: 0..5 corridor rows (control point j = slot, plane = lane), 6 = fixed "+" row,
-// 7 = fixed "-" row.  Fixed lanes: 0..14 velocity (group 6+f/3, axis f%3), 15..26 acceleration,
-// 27 the time row -T + 0.3 <= 0.  Reference row order (ddp.cpp:1181-1187, :1238, :1276, :1279).
-DDP_DEVICE int row_index(int slot, int lane, int P) {
-    if (slot < 6) return slot * P + lane;
-    const int b = 6 * P;
-    if (slot == 6) return lane < 15 ? b + lane : (lane < 27 ? b + 30 + (lane - 15) : b + 54);
-    return lane < 15 ? b + 15 + lane : b + 42 + (lane - 15);
+// ---------------------------------------------------------------------------------------------
+// Model pieces shared by the phases (all per-lane, no communication).
+// ---------------------------------------------------------------------------------------------
+// Powers of the segment time by repeated multiplication like the reference's Tkv (ddp.cpp:1148-1160).
+template <class R> DDP_DEVICE void time_powers(R T, R *tp) {
+    tp[0] = R(1); tp[1] = T; tp[2] = tp[1] * T; tp[3] = tp[2] * T; tp[4] = tp[3] * T; tp[5] = tp[4] * T;
 }
-DDP_DEVICE bool row_valid(int slot, int lane, int P) {
-    if (slot < 6) return lane < P;
-    if (slot == 6) return lane < 28;
-    return lane < 27;
-}
-
-template <class R> DDP_DEVICE void load_rows(const R *src, int P, Reg<R, 8> &dst, int lane_) {
-    FOR_LANES(lane) {
-        DDP_UNROLL
-        for (int q = 0; q < 8; q++) dst(lane, q) = row_valid(q, lane, P) ? src[row_index(q, lane, P)] : R(1);
-    }
-}
-template <class R> DDP_DEVICE void store_rows(R *dst, int P, const Reg<R, 8> &src, int lane_) {
-    FOR_LANES(lane) {
-        DDP_UNROLL
-        for (int q = 0; q < 8; q++)
-            if (row_valid(q, lane, P)) dst[row_index(q, lane, P)] = src(lane, q);
-    }
-}
-
-// T-scaled basis rows: Bs[g*6+l] = tab[g][l] * T^(l-shift_g) * Ek_inv[l]  (ddp.cpp:1148-1160, :1203-1209,
-// :1240-1247; Ek_inv = {1,1,1/2} folded in, ddp.cpp:1138-1143), Bdt likewise from the d/dT table
-// (ddp.cpp:1543-1560).  Powers are formed by repeated multiplication like the reference's Tkv.
-template <class R> DDP_DEVICE void scale_tables(const R *tab, R T, R *Bs, R *Bdt, int lane) {
-    R tp1 = T, tp2 = tp1 * T, tp3 = tp2 * T, tp4 = tp3 * T, tp5 = tp4 * T;
+// T-scaled basis row of group g: b[l] = tab[g][l] * T^(l-SHIFT-DER) * Ek_inv[l] (ddp.cpp:1148-1160, :1203-1209,
+// :1240-1247; Ek_inv = {1,1,1/2} folded in, ddp.cpp:1138-1143).  SHIFT = 0/1/2 for position / velocity /
+// acceleration control points, DER = 1 for the d/dT tables (ddp.cpp:1543-1560).
+template <class R, int SHIFT, int DER> DDP_DEVICE void basis_row(const R *tab, int g, const R *tp, R *b) {
     DDP_UNROLL
-    for (int q = 0; q < 6; q++) {
-        int e = lane + 32 * q;
-        if (e >= 180) break;
-        if (e >= 90 && Bdt == nullptr) break;
-        int ee = e >= 90 ? e - 90 : e;
-        int g = ee / 6, l = ee - 6 * g;
-        int k = l - (g < 6 ? 0 : (g < 11 ? 1 : 2)) - (e >= 90 ? 1 : 0);
-        R pw = k <= 0 ? R(1) : (k == 1 ? tp1 : (k == 2 ? tp2 : (k == 3 ? tp3 : (k == 4 ? tp4 : tp5))));
-        R v = tab[e] * pw;
+    for (int l = 0; l < 6; l++) {
+        const int k = l - SHIFT - DER;
+        R v = tab[DER * 90 + g * 6 + l];
+        if (k > 0) v = v * tp[k];
         if (l == 2) v = v * R(0.5);
-        if (e >= 90) Bdt[ee] = v; else Bs[ee] = v;
+        b[l] = v;
     }
 }
-
-// dst[g*3+a] = sum_l B[g*6+l] * v[zidx(l,a)]  for the 45 (group, axis) pairs.
-template <class R> DDP_DEVICE void transform45(const R *B, const R *v, R *dst, int lane) {
+// (row b) . (coefficients of axis a of vector v in z layout); terms below order LMIN are structurally zero.
+template <class R, int LMIN> DDP_DEVICE R dot_axis(const R *b, const R *v, int a) {
+    R acc = R(0);
     DDP_UNROLL
-    for (int q = 0; q < 2; q++) {
-        int o = lane + 32 * q;
-        if (o < 45) {
-            int g = o / 3, a = o - 3 * g;
-            R acc = R(0);
-            DDP_UNROLL
-            for (int l = 0; l < 6; l++) acc += B[g * 6 + l] * v[zidx(l, a)];
-            dst[o] = acc;
-        }
-    }
+    for (int l = LMIN; l < 6; l++) acc += b[l] * v[zidx(l, 0) + a];
+    return acc;
 }
 
-// F, G of the segment dynamics x+ = (F (x) I3) x + (G (x) I3) u[0:9], ddp.cpp:862-871.  FG[o*6+l].
-template <class R> DDP_DEVICE R fg_entry(int o, int l, R T) {
-    R T2 = T * T, T3 = T2 * T, T4 = T3 * T, T5 = T4 * T;
-    switch (o * 6 + l) {
-        case 0: return R(1); case 1: return T; case 2: return T2 / R(2); case 3: return T3; case 4: return T4; case 5: return T5;
-        case 6: return R(0); case 7: return R(1); case 8: return T; case 9: return R(3) * T2; case 10: return R(4) * T3; case 11: return R(5) * T4;
-        case 12: return R(0); case 13: return R(0); case 14: return R(1); case 15: return R(6) * T; case 16: return R(12) * T2;
-        default: return R(20) * T3;
-    }
+// F, G of the segment dynamics x+ = (F (x) I3) x + (G (x) I3) u[0:9], ddp.cpp:862-871.  fg[o*6+l].
+template <class R> DDP_DEVICE void fg_matrix(const R *tp, R *fg) {
+    fg[0] = R(1); fg[1] = tp[1]; fg[2] = tp[2] / R(2); fg[3] = tp[3]; fg[4] = tp[4]; fg[5] = tp[5];
+    fg[6] = R(0); fg[7] = R(1); fg[8] = tp[1]; fg[9] = R(3) * tp[2]; fg[10] = R(4) * tp[3]; fg[11] = R(5) * tp[4];
+    fg[12] = R(0); fg[13] = R(0); fg[14] = R(1); fg[15] = R(6) * tp[1]; fg[16] = R(12) * tp[2]; fg[17] = R(20) * tp[3];
 }
-// d/dT of the above, ddp.cpp:930-935.
-template <class R> DDP_DEVICE R fgp_entry(int o, int l, R T) {
-    R T2 = T * T, T3 = T2 * T, T4 = T3 * T;
-    switch (o * 6 + l) {
-        case 1: return R(1); case 2: return T; case 3: return R(3) * T2; case 4: return R(4) * T3; case 5: return R(5) * T4;
-        case 8: return R(1); case 9: return R(6) * T; case 10: return R(12) * T2; case 11: return R(20) * T3;
-        case 15: return R(6); case 16: return R(24) * T; case 17: return R(60) * T2;
-        default: return R(0);
+// fT = d x+/dT = (F' (x) I) x + (G' (x) I) u, ddp.cpp:930-935 and :1332.
+template <class R> DDP_DEVICE void ft_vector(const R *tp, const R *z, R *fT) {
+    const R fp[18] = {R(0), R(1), tp[1], R(3) * tp[2], R(4) * tp[3], R(5) * tp[4],
+                      R(0), R(0), R(1), R(6) * tp[1], R(12) * tp[2], R(20) * tp[3],
+                      R(0), R(0), R(0), R(6), R(24) * tp[1], R(60) * tp[2]};
+    DDP_UNROLL
+    for (int o = 0; o < 3; o++) {
+        DDP_UNROLL
+        for (int a = 0; a < 3; a++) {
+            R s1 = R(0), s2 = R(0);
+            DDP_UNROLL
+            for (int b = 0; b < 3; b++) {
+                if (b > o) s1 += fp[o * 6 + b] * z[10 + 3 * b + a];
+                s2 += fp[o * 6 + 3 + b] * z[3 * b + a];
+            }
+            fT[3 * o + a] = s1 + s2;
+        }
     }
 }
 // Jerk-cost matrices R, R', R'' (3x3, index 3*i+j), ddp.cpp:991-999.
-template <class R> DDP_DEVICE R rmat_entry(int which, int i, int j, R T) {
-    R T2 = T * T, T3 = T2 * T, T4 = T3 * T, T5 = T4 * T;
-    const int e = i * 3 + j;
+template <class R> DDP_DEVICE void rmat(int which, const R *tp, R *m) {
     if (which == 0) {
-        switch (e) { case 0: return R(36) * T; case 1: case 3: return R(72) * T2; case 2: case 6: return R(120) * T3;
-                     case 4: return R(192) * T3; case 5: case 7: return R(360) * T4; default: return R(720) * T5; }
+        m[0] = R(36) * tp[1]; m[1] = m[3] = R(72) * tp[2]; m[2] = m[6] = R(120) * tp[3];
+        m[4] = R(192) * tp[3]; m[5] = m[7] = R(360) * tp[4]; m[8] = R(720) * tp[5];
     } else if (which == 1) {
-        switch (e) { case 0: return R(36); case 1: case 3: return R(144) * T; case 2: case 6: return R(360) * T2;
-                     case 4: return R(576) * T2; case 5: case 7: return R(1440) * T3; default: return R(3600) * T4; }
+        m[0] = R(36); m[1] = m[3] = R(144) * tp[1]; m[2] = m[6] = R(360) * tp[2];
+        m[4] = R(576) * tp[2]; m[5] = m[7] = R(1440) * tp[3]; m[8] = R(3600) * tp[4];
+    } else {
+        m[0] = R(0); m[1] = m[3] = R(144); m[2] = m[6] = R(720) * tp[1];
+        m[4] = R(1152) * tp[1]; m[5] = m[7] = R(4320) * tp[2]; m[8] = R(14400) * tp[3];
     }
-    switch (e) { case 0: return R(0); case 1: case 3: return R(144); case 2: case 6: return R(720) * T;
-                 case 4: return R(1152) * T; case 5: case 7: return R(4320) * T2; default: return R(14400) * T3; }
 }
-
-// One lane's share of u^T (M (x) I3) u for lane c < 9 (c = 3*i + axis): u_c * sum_j M[i][j] u[3j+axis].
-template <class R> DDP_DEVICE R quad_share(int which, const R *u, int c, R T) {
-    int i = c / 3, a = c - 3 * i;
-    R t = R(0);
+// (M (x) I3) u for the nine high-order coefficients u[3*i+a].
+template <class R> DDP_DEVICE void rmat_times_u(const R *m, const R *u, R *out) {
     DDP_UNROLL
-    for (int j = 0; j < 3; j++) t += rmat_entry<R>(which, i, j, T) * u[3 * j + a];
-    return u[c] * t;
-}
-
-// Load the planes of knot i into shared memory (P x 4).
-template <class R> DDP_DEVICE void load_planes(const Traj<R> &t, int knot, int P, int lane) {
-    const double *pl = t.planes + (long long)knot * t.PM * 4;
-    for (int e = lane; e < 4 * P; e += 32) t.sm[Lay::PL + e] = (R)pl[e];
-}
-
-// =============================================================================================
-// Backward pass (ddp.cpp:440-644).  Returns with t.bfailed / t.opterr set; gains in t.K.
-// =============================================================================================
-template <class R> DDP_DEVICE_NOINLINE void backward_pass(Traj<R> &t) {
-    const int lane_ = t.lane_;
-    const Lay L(t.PM);
-    R *sm = t.sm;
-    const long long clk0 = ddp_clock();
-    t.n_bwd_sweeps++;
-    // regularisation schedule, ddp.cpp:452-474
-    if (t.failed || t.bfailed) t.reg = t.reg + R(1);
-    else if (t.step == 0) t.reg = t.reg - R(1);
-    else if (t.step <= 3) t.reg = t.reg;
-    else t.reg = t.reg + R(1);
-    if (t.reg < R(0)) t.reg = R(0);
-    else if (t.reg > R(24)) t.reg = R(24);
-    const R regadd = rpow(t.reg_base, t.reg) - R(1);  // ddp.cpp:529
-    const R sgn = t.infeas ? R(1) : R(-1);
-    const R mu = t.mu;
-
-    // terminal value function, ddp.cpp:1318-1323: Vx = P (x_N - x_d), Vxx = P = w_terminal I
-    FOR_LANES(lane) {
-        for (int e = lane; e < 81; e += 32) sm[Lay::VXX + e] = (e / 9 == e % 9) ? t.w_terminal : R(0);
-        if (lane < 9) sm[Lay::VX + lane] = t.w_terminal * (t.xu[(long long)t.N * 20 + 10 + lane] - sm[Lay::XD + lane]);
+    for (int i = 0; i < 3; i++) {
+        DDP_UNROLL
+        for (int a = 0; a < 3; a++) {
+            R acc = R(0);
+            DDP_UNROLL
+            for (int j = 0; j < 3; j++) acc += m[i * 3 + j] * u[3 * j + a];
+            out[3 * i + a] = acc;
+        }
     }
-    WARP_SYNC();
+}
+template <class R> DDP_DEVICE R dot9(const R *a, const R *b) {
+    R acc = R(0);
+    DDP_UNROLL
+    for (int c = 0; c < 9; c++) acc += a[c] * b[c];
+    return acc;
+}
+// Stage cost q(x,u), ddp.cpp:1294-1305.
+template <class R> DDP_DEVICE R stage_cost(const Traj<R> &t, const R *tp, const R *u) {
+    R m[9], mu9[9];
+    rmat<R>(0, tp, m);
+    rmat_times_u(m, u, mu9);
+    const R T = tp[1];
+    const R tterm = t.time_power == 2 ? R(0.5) * T * t.w_time * T : R(0.5) * t.w_time * T;
+    return R(0.5) * t.w_snap * dot9(u, mu9) + tterm;
+}
 
-    Reg<R, 3> errs;  // per-lane running maxima: |Qu|, |r|, |c+y|
-    FOR_LANES(lane) { errs(lane, 0) = R(0); errs(lane, 1) = R(0); errs(lane, 2) = R(0); }
+// Plane k of knot `pl` (pointer to that knot's P_max x 4 block).
+template <class R> DDP_DEVICE void load_plane(const double *pl, int k, R *n) {
+    n[0] = (R)pl[4 * k]; n[1] = (R)pl[4 * k + 1]; n[2] = (R)pl[4 * k + 2]; n[3] = (R)pl[4 * k + 3];
+}
 
-    for (int i = t.N - 1; i >= 0; i--) {
-        t.n_bwd_knots++;
-        const int P = t.nplanes[i];
-        Reg<R, 8> s, y;
-        load_rows(t.s + (long long)i * t.MCS, P, s, lane_);
-        if (t.infeas) load_rows(t.y + (long long)i * t.MCS, P, y, lane_);
-        Reg<R, 4> sums;  // per-lane partials: tt (H_TT from constraints), gt (grad_T), u'R'u, u'R''u
-        // ---- phase A: knot state, scaled tables, dynamics/cost pieces ------------------------------
-        FOR_LANES(lane) {
-            if (lane < 20) sm[Lay::ZO + lane] = t.xu[(long long)i * 20 + lane];
-            load_planes(t, i, P, lane);
-            sums(lane, 0) = R(0); sums(lane, 1) = R(0); sums(lane, 2) = R(0); sums(lane, 3) = R(0);
+// Visit every constraint row of knot i at the point z (constraint VALUES only; computecminvo,
+// ddp.cpp:1132-1285): f(row slot, c).
+template <class R, class F> DDP_DEVICE void visit_rows(const Traj<R> &t, int i, const R *z, F &&f) {
+    R tp[6];
+    time_powers(z[9], tp);
+    const int P = t.nplanes[i];
+    const double *pl = t.planes + (long long)i * t.PM * 4;
+    for (int g = 0; g < 6; g++) {
+        R b[6], cp[3];
+        basis_row<R, 0, 0>(t.tab, g, tp, b);
+        DDP_UNROLL
+        for (int a = 0; a < 3; a++) cp[a] = dot_axis<R, 0>(b, z, a);
+        for (int k = 0; k < P; k++) {
+            R n[4];
+            load_plane(pl, k, n);
+            f(g * t.PM + k, ((n[0] * cp[0] + n[1] * cp[1]) + n[2] * cp[2]) + n[3] - t.margin);
         }
-        WARP_SYNC();
-        const R T = sm[Lay::ZO + 9];
-        FOR_LANES(lane) {
-            scale_tables(t.tab, T, sm + Lay::BS, sm + Lay::BDT, lane);
-            if (lane < 18) sm[L.FG() + lane] = fg_entry<R>(lane / 6, lane % 6, T);
-            if (lane < 18) sm[L.RR() + lane] = rmat_entry<R>(lane / 9, (lane % 9) / 3, lane % 3, T);
-            if (lane < 9) {  // fT = d x+/dT = (F' (x) I) x + (G' (x) I) u, ddp.cpp:1332
-                int o = lane / 3, a = lane - 3 * o;
-                R s1 = R(0), s2 = R(0);
-                DDP_UNROLL
-                for (int b = 0; b < 3; b++) {
-                    if (b > o) s1 += fgp_entry<R>(o, b, T) * sm[Lay::ZO + 10 + 3 * b + a];
-                    s2 += fgp_entry<R>(o, 3 + b, T) * sm[Lay::ZO + 3 * b + a];
-                }
-                sm[L.FT() + lane] = s1 + s2;
-                sums(lane, 2) = quad_share<R>(1, sm + Lay::ZO, lane, T);
-                sums(lane, 3) = quad_share<R>(2, sm + Lay::ZO, lane, T);
-            }
+    }
+    const int FB = 6 * t.PM;
+    for (int g = 6; g < 11; g++) {
+        R b[6];
+        basis_row<R, 1, 0>(t.tab, g, tp, b);
+        DDP_UNROLL
+        for (int a = 0; a < 3; a++) {
+            const R v = dot_axis<R, 1>(b, z, a);
+            f(FB + 3 * (g - 6) + a, v - t.max_vel - t.margin);
+            f(FB + 15 + 3 * (g - 6) + a, -v - t.max_vel - t.margin);
         }
-        WARP_SYNC();
-        // ---- phase B: control points and their d/dT ------------------------------------------------
-        FOR_LANES(lane) {
-            transform45(sm + Lay::BS, sm + Lay::ZO, sm + L.TRB(), lane);
-            transform45(sm + Lay::BDT, sm + Lay::ZO, sm + L.TRB() + 45, lane);
-            if (lane < 9) {  // tT = Vxx fT
-                R acc = R(0);
-                DDP_UNROLL
-                for (int q = 0; q < 9; q++) acc += sm[Lay::VXX + lane * 9 + q] * sm[L.FT() + q];
-                sm[L.TT9() + lane] = acc;
-            }
+    }
+    for (int g = 11; g < 15; g++) {
+        R b[6];
+        basis_row<R, 2, 0>(t.tab, g, tp, b);
+        DDP_UNROLL
+        for (int a = 0; a < 3; a++) {
+            const R v = dot_axis<R, 2>(b, z, a);
+            f(FB + 30 + 3 * (g - 11) + a, v - t.max_acc - t.margin);
+            f(FB + 42 + 3 * (g - 11) + a, -v - t.max_acc - t.margin);
         }
-        WARP_SYNC();
-        // ---- phase C: constraint rows -> weights --------------------------------------------------
-        // per row: c, tcol = dc/dT, then (ddp.cpp:535-541 / :583-590)
-        //   infeasible: D = s/y, r = s y - mu, tv2 = (s (c+y) - r)/y ;  feasible: D = s/c, r = s c + mu, tv2 = r/c
-        //   H += sgn J^T D J,   grad += J^T (s + sgn tv2)
-        FOR_LANES(lane) {
-            R emu = errs(lane, 1), ecy = errs(lane, 2);
-            if (lane < P) {
-                const R n0 = sm[Lay::PL + 4 * lane], n1 = sm[Lay::PL + 4 * lane + 1], n2 = sm[Lay::PL + 4 * lane + 2],
-                        n3 = sm[Lay::PL + 4 * lane + 3];
-                R *bv = sm + L.BV() + 10 * lane;
-                bv[0] = n0 * n0; bv[1] = n0 * n1; bv[2] = n0 * n2; bv[3] = n1 * n1; bv[4] = n1 * n2; bv[5] = n2 * n2;
-                bv[6] = n0; bv[7] = n1; bv[8] = n2; bv[9] = R(1);
-                DDP_UNROLL
-                for (int j = 0; j < 6; j++) {
-                    const R *cp = sm + L.TRB() + 3 * j, *cd = sm + L.TRB() + 45 + 3 * j;
-                    R c = ((n0 * cp[0] + n1 * cp[1]) + n2 * cp[2]) + n3 - t.margin;
-                    R tc = (n0 * cd[0] + n1 * cd[1]) + n2 * cd[2];
-                    R sv = s(lane, j), D, r, tv2;
-                    if (t.infeas) {
-                        R yv = y(lane, j), yinv = R(1) / yv;
-                        r = sv * yv - mu; D = sv * yinv; tv2 = yinv * (sv * (c + yv) - r);
-                        ecy = amax(ecy, rabs(c + yv));
-                    } else {
-                        R cinv = R(1) / c;
-                        r = sv * c + mu; D = sv * cinv; tv2 = cinv * r;
-                    }
-                    emu = amax(emu, rabs(r));
-                    R Ds = sgn * D, gw = sv + sgn * tv2;
-                    R *w = sm + L.W() + (j * t.PM + lane);
-                    const int st = 6 * t.PM;
-                    w[0] = Ds; w[st] = Ds * tc; w[2 * st] = (Ds * tc) * tc; w[3 * st] = gw; w[4 * st] = gw * tc;
-                }
-            }
-            if (lane < 28) {
-                R cplus, cminus = R(-1), tc;
-                if (lane < 27) {
-                    R val = sm[L.TRB() + 18 + lane], lim = lane < 15 ? t.max_vel : t.max_acc;
-                    tc = sm[L.TRB() + 45 + 18 + lane];
-                    cplus = val - lim - t.margin; cminus = -val - lim - t.margin;
-                } else {
-                    cplus = -T + R(0.3) - t.margin; tc = R(-1);
-                }
-                R Dsum = R(0), gdiff = R(0);
-                DDP_UNROLL
-                for (int pm = 0; pm < 2; pm++) {
-                    if (pm == 1 && lane == 27) break;
-                    R c = pm ? cminus : cplus, sv = s(lane, 6 + pm), D, r, tv2;
-                    if (t.infeas) {
-                        R yv = y(lane, 6 + pm), yinv = R(1) / yv;
-                        r = sv * yv - mu; D = sv * yinv; tv2 = yinv * (sv * (c + yv) - r);
-                        ecy = amax(ecy, rabs(c + yv));
-                    } else {
-                        R cinv = R(1) / c;
-                        r = sv * c + mu; D = sv * cinv; tv2 = cinv * r;
-                    }
-                    emu = amax(emu, rabs(r));
-                    Dsum += sgn * D;
-                    gdiff += pm ? -(sv + sgn * tv2) : (sv + sgn * tv2);
-                }
-                // the "-" row has Jacobian -J+, so D adds and the gradient weight subtracts
-                if (lane < 27) {
-                    int g = lane < 15 ? lane / 3 : 5 + (lane - 15) / 3, a = lane < 15 ? lane % 3 : (lane - 15) % 3;
-                    R *G = sm + L.G() + 90 + 9 * g;  // fixed groups 0..8 = row groups 6..14
-                    G[a] = Dsum; G[3 + a] = Dsum * tc; G[6 + a] = gdiff;
-                }
-                sums(lane, 0) += (Dsum * tc) * tc;
-                sums(lane, 1) += gdiff * tc;
-            }
-            errs(lane, 1) = emu; errs(lane, 2) = ecy;
+    }
+    f(FB + 54, -z[9] + R(0.3) - t.margin);
+}
+
+// Interior-point weights of one row (ddp.cpp:535-541 infeasible / :583-590 feasible):
+//   infeasible: D = s/y, r = s y - mu, tv2 = (s (c+y) - r)/y ;  feasible: D = s/c, r = s c + mu, tv2 = r/c
+//   the row adds  sgn D a a^T  to the Hessian and  (s + sgn tv2) a  to the gradient (sgn = +1 / -1).
+template <class R>
+DDP_DEVICE void row_weights(int infeas, R mu, R sgn, R c, R sv, R yv, R &Ds, R &gw, R &emu, R &ecy) {
+    R D, r, tv2;
+    if (infeas) {
+        const R yinv = R(1) / yv;
+        r = sv * yv - mu; D = sv * yinv; tv2 = yinv * (sv * (c + yv) - r);
+        ecy = amax(ecy, rabs(c + yv));
+    } else {
+        const R cinv = R(1) / c;
+        r = sv * c + mu; D = sv * cinv; tv2 = cinv * r;
+    }
+    emu = amax(emu, rabs(r));
+    Ds = sgn * D; gw = sv + sgn * tv2;
+}
+
+// One velocity / acceleration group of the linearisation: six rows +-(beta_g . coefficients of axis a) - limit.
+template <class R, int SHIFT>
+DDP_DEVICE void lin_fixed_group(const Traj<R> &t, int g, int i, int plus0, int minus0, R lim, const R *tp, const R *z,
+                                R sgn, R *accT, R *accG, R &tt, R &gt, R &emu, R &ecy, R *msc) {
+    R b[6], bd[6];
+    basis_row<R, SHIFT, 0>(t.tab, g, tp, b);
+    basis_row<R, SHIFT, 1>(t.tab, g, tp, bd);
+    R wv[3], gv[3];
+    DDP_UNROLL
+    for (int a = 0; a < 3; a++) {
+        const R val = dot_axis<R, SHIFT>(b, z, a), tc = dot_axis<R, SHIFT>(bd, z, a);
+        const R sp = t.s[(long long)(plus0 + a) * t.NP + i], sn = t.s[(long long)(minus0 + a) * t.NP + i];
+        R yp = R(1), yn = R(1);
+        if (t.infeas) { yp = t.y[(long long)(plus0 + a) * t.NP + i]; yn = t.y[(long long)(minus0 + a) * t.NP + i]; }
+        R D1, g1, D2, g2;
+        row_weights(t.infeas, t.mu, sgn, val - lim - t.margin, sp, yp, D1, g1, emu, ecy);
+        row_weights(t.infeas, t.mu, sgn, -val - lim - t.margin, sn, yn, D2, g2, emu, ecy);
+        // the "-" row has Jacobian -J+, so D adds and the gradient weight subtracts
+        const R Dsum = D1 + D2, gdiff = g1 - g2;
+        msc[a * 32] = Dsum;
+        wv[a] = Dsum * tc; gv[a] = gdiff;
+        tt += (Dsum * tc) * tc; gt += gdiff * tc;
+    }
+    DDP_UNROLL
+    for (int l = SHIFT; l < 6; l++) {
+        DDP_UNROLL
+        for (int a = 0; a < 3; a++) { accT[l * 3 + a] += b[l] * wv[a]; accG[l * 3 + a] += b[l] * gv[a]; }
+    }
+}
+
+// Second pass of the linearisation, one group: h_a[(l,l')] += beta[l] beta[l'] M_g[a][a] for the three axes.
+template <class R, int SHIFT>
+DDP_DEVICE void lin_diag_group(const R *tab, int g, const R *tp, R m0, R m1, R m2, R *h0, R *h1, R *h2) {
+    R b[6];
+    basis_row<R, SHIFT, 0>(tab, g, tp, b);
+    DDP_UNROLL
+    for (int lb = SHIFT; lb < 6; lb++) {
+        const R s0 = b[lb] * m0, s1 = b[lb] * m1, s2 = b[lb] * m2;
+        DDP_UNROLL
+        for (int la = SHIFT; la <= lb; la++) {
+            h0[pidx(la, lb)] += b[la] * s0; h1[pidx(la, lb)] += b[la] * s1; h2[pidx(la, lb)] += b[la] * s2;
         }
-        WARP_SYNC();
-        // ---- phase D: reduce the corridor rows over planes, per control point ----------------------
-        // outputs per control point j: M (3x3 sym) , w (3), tt, gv (3), gt
+    }
+}
+
+// =============================================================================================
+// Backward pass, knot-parallel part (lane <-> knot): everything of ddp.cpp:476-590 that does not depend
+// on the value function.  Per knot it writes the constraint + stage-cost part of the augmented Hessian
+//   Hc = [ H  g ; g^T . ]  (20 x 20, z order [u(9), T, x(9), gradient])  to t.H and  fT = dx+/dT  to t.aux.
+// Returns per-lane maxima of |r| and |c+y| in errs (ddp.cpp:636-637).
+// =============================================================================================
+template <class R> DDP_DEVICE_NOINLINE void linearize(Traj<R> &t, Reg<R, 2> &errs) {
+    const int lane_ = t.lane_;
+    const R sgn = t.infeas ? R(1) : R(-1);
+    FOR_LANES(lane) { errs(lane, 0) = R(0); errs(lane, 1) = R(0); }
+    for (int base = 0; base < t.N; base += 32) {
         FOR_LANES(lane) {
-            DDP_UNROLL
-            for (int q = 0; q < 3; q++) {
-                int o = lane + 32 * q;
-                if (o < 84) {
-                    int j = o / 14, e = o - 14 * j;
-                    // weight selector / plane-vector selector
-                    int ws = e < 6 ? 0 : (e < 9 ? 1 : (e == 9 ? 2 : (e < 13 ? 3 : 4)));
-                    int bs = e < 6 ? e : (e < 9 ? e : (e == 9 ? 9 : (e < 13 ? e - 4 : 9)));
-                    const R *w = sm + L.W() + ws * 6 * t.PM + j * t.PM;
-                    const R *bv = sm + L.BV() + bs;
-                    R acc = R(0);
-                    for (int k = 0; k < P; k++) acc += w[k] * bv[10 * k];
-                    R *G = sm + L.G() + 15 * j;
-                    if (e < 6) {
-                        const int a = e < 3 ? 0 : (e < 5 ? 1 : 2), b = e < 3 ? e : (e < 5 ? e - 2 : 2);
-                        G[a * 3 + b] = acc; G[b * 3 + a] = acc;
-                    } else if (e < 9) G[9 + (e - 6)] = acc;
-                    else if (e == 9) sums(lane, 0) += acc;
-                    else if (e < 13) G[12 + (e - 10)] = acc;
-                    else sums(lane, 1) += acc;
-                }
-            }
-        }
-        WARP_SYNC();
-        const R ttot = warp_sum(sums, 0, lane_), gtot = warp_sum(sums, 1, lane_);
-        const R uRpu = warp_sum(sums, 2, lane_), uRppu = warp_sum(sums, 3, lane_);
-        // ---- phase E: assemble column `lane` of the augmented Hessian ------------------------------
-        // rows/cols 0..8 u-coefficients, 9 T, 10..18 x, 19 gradient.
-        Reg<R, 20> col;
-        FOR_LANES(lane) {
-            DDP_UNROLL
-            for (int r = 0; r < 20; r++) col(lane, r) = R(0);
-            if (lane < 19 && lane != 9) {
-                const int lp = lane < 9 ? 3 + lane / 3 : (lane - 10) / 3, ap = lane < 9 ? lane % 3 : (lane - 10) % 3;
-                // constraints: sum over the 15 row groups of (beta beta^T) (x) M
+            const int i = base + lane;
+            if (i < t.N) {
+                R emu = errs(lane, 0), ecy = errs(lane, 1);
+                R z[19], tp[6];
                 DDP_UNROLL
-                for (int g = 0; g < 15; g++) {
-                    const int lmin = g < 6 ? 0 : (g < 11 ? 1 : 2);
-                    const R sc = sm[Lay::BS + g * 6 + lp];
-                    R m0, m1, m2, wv, gv;
-                    if (g < 6) {
-                        const R *G = sm + L.G() + 15 * g;
-                        m0 = sc * G[ap]; m1 = sc * G[3 + ap]; m2 = sc * G[6 + ap]; wv = G[9 + ap]; gv = G[12 + ap];
-                    } else {
-                        const R *G = sm + L.G() + 90 + 9 * (g - 6);
-                        R d = sc * G[ap];
-                        m0 = ap == 0 ? d : R(0); m1 = ap == 1 ? d : R(0); m2 = ap == 2 ? d : R(0);
-                        wv = G[3 + ap]; gv = G[6 + ap];
+                for (int e = 0; e < 19; e++) z[e] = t.xu[(long long)i * 20 + e];
+                time_powers(z[9], tp);
+                const int P = t.nplanes[i];
+                const double *pl = t.planes + (long long)i * t.PM * 4;
+                R *msc = t.sm + Lay::MSC + lane;
+                R accT[18], accG[18], tt = R(0), gt = R(0);
+                DDP_UNROLL
+                for (int e = 0; e < 18; e++) { accT[e] = R(0); accG[e] = R(0); }
+                // ---- pass 1: rows -> weights -> per-group blocks ------------------------------------------
+                for (int g = 0; g < 6; g++) {   // position control points: one row per plane of the polytope
+                    R b[6], bd[6], cp[3], cd[3];
+                    basis_row<R, 0, 0>(t.tab, g, tp, b);
+                    basis_row<R, 0, 1>(t.tab, g, tp, bd);
+                    DDP_UNROLL
+                    for (int a = 0; a < 3; a++) { cp[a] = dot_axis<R, 0>(b, z, a); cd[a] = dot_axis<R, 0>(bd, z, a); }
+                    R M[6] = {R(0), R(0), R(0), R(0), R(0), R(0)}, wv[3] = {R(0), R(0), R(0)}, gv[3] = {R(0), R(0), R(0)};
+                    for (int k = 0; k < P; k++) {
+                        R n[4];
+                        load_plane(pl, k, n);
+                        const R c = ((n[0] * cp[0] + n[1] * cp[1]) + n[2] * cp[2]) + n[3] - t.margin;
+                        const R tc = (n[0] * cd[0] + n[1] * cd[1]) + n[2] * cd[2];
+                        const long long ro = (long long)(g * t.PM + k) * t.NP + i;
+                        R Ds, gw;
+                        row_weights(t.infeas, t.mu, sgn, c, t.s[ro], t.infeas ? t.y[ro] : R(1), Ds, gw, emu, ecy);
+                        M[0] += Ds * (n[0] * n[0]); M[1] += Ds * (n[0] * n[1]); M[2] += Ds * (n[0] * n[2]);
+                        M[3] += Ds * (n[1] * n[1]); M[4] += Ds * (n[1] * n[2]); M[5] += Ds * (n[2] * n[2]);
+                        const R dt = Ds * tc, gtc = gw * tc;
+                        wv[0] += dt * n[0]; wv[1] += dt * n[1]; wv[2] += dt * n[2];
+                        gv[0] += gw * n[0]; gv[1] += gw * n[1]; gv[2] += gw * n[2];
+                        tt += dt * tc; gt += gtc;
                     }
                     DDP_UNROLL
-                    for (int l = lmin; l < 6; l++) {
-                        const R bl = sm[Lay::BS + g * 6 + l];
-                        col(lane, zidx(l, 0)) += bl * m0;
-                        col(lane, zidx(l, 1)) += bl * m1;
-                        col(lane, zidx(l, 2)) += bl * m2;
+                    for (int e = 0; e < 6; e++) msc[(g * 6 + e) * 32] = M[e];
+                    DDP_UNROLL
+                    for (int l = 0; l < 6; l++) {
+                        DDP_UNROLL
+                        for (int a = 0; a < 3; a++) { accT[l * 3 + a] += b[l] * wv[a]; accG[l * 3 + a] += b[l] * gv[a]; }
                     }
-                    col(lane, 9) += sc * wv;
-                    col(lane, 19) += sc * gv;
                 }
-                // dynamics: A^T Vxx A and A^T Vx with A = [G (x) I | fT | F (x) I] (ddp.cpp:508-520)
-                R fg0 = sm[L.FG() + lp], fg1 = sm[L.FG() + 6 + lp], fg2 = sm[L.FG() + 12 + lp];
-                R tt[9];
-                DDP_UNROLL
-                for (int p = 0; p < 9; p++)
-                    tt[p] = (sm[Lay::VXX + p * 9 + ap] * fg0 + sm[Lay::VXX + p * 9 + 3 + ap] * fg1) +
-                            sm[Lay::VXX + p * 9 + 6 + ap] * fg2;
+                const int FB = 6 * t.PM;
+                for (int g = 6; g < 11; g++)
+                    lin_fixed_group<R, 1>(t, g, i, FB + 3 * (g - 6), FB + 15 + 3 * (g - 6), t.max_vel, tp, z, sgn, accT, accG,
+                                          tt, gt, emu, ecy, msc + (36 + 3 * (g - 6)) * 32);
+                for (int g = 11; g < 15; g++)
+                    lin_fixed_group<R, 2>(t, g, i, FB + 30 + 3 * (g - 11), FB + 42 + 3 * (g - 11), t.max_acc, tp, z, sgn, accT,
+                                          accG, tt, gt, emu, ecy, msc + (36 + 3 * (g - 6)) * 32);
+                {   // the time row -T + 0.3 <= 0 (ddp.cpp:1279): Jacobian -1 in the T entry only
+                    const long long ro = (long long)(FB + 54) * t.NP + i;
+                    R Ds, gw;
+                    row_weights(t.infeas, t.mu, sgn, -z[9] + R(0.3) - t.margin, t.s[ro], t.infeas ? t.y[ro] : R(1), Ds, gw, emu, ecy);
+                    tt += Ds; gt -= gw;
+                }
+                errs(lane, 0) = emu; errs(lane, 1) = ecy;
+                // ---- stage cost (ddp.cpp:1338-1368): quu = w [R (x) I, R'u; (R'u)^T, .], qu = w [R u; .] --------
+                R rm[9], Ru[9], Rpu[9], Rppu[9];
+                rmat<R>(0, tp, rm);
+                rmat_times_u(rm, z, Ru);
+                {
+                    R r1[9], r2[9];
+                    rmat<R>(1, tp, r1); rmat_times_u(r1, z, Rpu);
+                    rmat<R>(2, tp, r2); rmat_times_u(r2, z, Rppu);
+                }
+                const R uRpu = dot9(z, Rpu), uRppu = dot9(z, Rppu);
+                R quT, quuTT;
+                if (t.time_power == 2) { quT = t.w_time * z[9] + R(0.5) * t.w_snap * uRpu; quuTT = t.w_time + R(0.5) * t.w_snap * uRppu; }
+                else { quT = R(0.5) * t.w_time + R(0.5) * t.w_snap * uRpu; quuTT = R(0.5) * t.w_snap * uRppu; }
+                // ---- write row/column T and the gradient -------------------------------------------------------
+                R *Hi = t.H + (long long)i * 400;
                 DDP_UNROLL
                 for (int l = 0; l < 6; l++) {
-                    const R f0 = sm[L.FG() + l], f1 = sm[L.FG() + 6 + l], f2 = sm[L.FG() + 12 + l];
                     DDP_UNROLL
-                    for (int a = 0; a < 3; a++) col(lane, zidx(l, a)) += (f0 * tt[a] + f1 * tt[3 + a]) + f2 * tt[6 + a];
+                    for (int a = 0; a < 3; a++) {
+                        const int r = zidx(l, a);
+                        R hT = accT[l * 3 + a], gr = accG[l * 3 + a];
+                        if (l >= 3) { hT += t.w_snap * Rpu[r]; gr += t.w_snap * Ru[r]; }
+                        Hi[r * 20 + 9] = hT; Hi[9 * 20 + r] = hT;
+                        Hi[r * 20 + 19] = gr; Hi[19 * 20 + r] = gr;
+                    }
+                }
+                Hi[9 * 20 + 9] = quuTT + tt;
+                Hi[9 * 20 + 19] = quT + gt; Hi[19 * 20 + 9] = quT + gt;
+                Hi[19 * 20 + 19] = R(0);
+                R fT[9];
+                ft_vector(tp, z, fT);
+                DDP_UNROLL
+                for (int q = 0; q < 9; q++) t.aux[(long long)i * 12 + q] = fT[q];
+                // ---- pass 2: H[(l,a),(l',a')] = sum_g beta_g[l] beta_g[l'] M_g[a][a'] ------------------------------
+                {   // same-axis blocks: all 15 groups, plus the stage cost w R (x) I on the u coefficients
+                    R h0[21], h1[21], h2[21];
+                    DDP_UNROLL
+                    for (int e = 0; e < 21; e++) { h0[e] = R(0); h1[e] = R(0); h2[e] = R(0); }
+                    for (int g = 0; g < 6; g++)
+                        lin_diag_group<R, 0>(t.tab, g, tp, msc[(g * 6 + 0) * 32], msc[(g * 6 + 3) * 32], msc[(g * 6 + 5) * 32], h0, h1, h2);
+                    for (int g = 6; g < 11; g++)
+                        lin_diag_group<R, 1>(t.tab, g, tp, msc[(36 + 3 * (g - 6)) * 32], msc[(37 + 3 * (g - 6)) * 32],
+                                             msc[(38 + 3 * (g - 6)) * 32], h0, h1, h2);
+                    for (int g = 11; g < 15; g++)
+                        lin_diag_group<R, 2>(t.tab, g, tp, msc[(36 + 3 * (g - 6)) * 32], msc[(37 + 3 * (g - 6)) * 32],
+                                             msc[(38 + 3 * (g - 6)) * 32], h0, h1, h2);
+                    DDP_UNROLL
+                    for (int lb = 0; lb < 6; lb++) {
+                        DDP_UNROLL
+                        for (int la = 0; la <= lb; la++) {
+                            const int e = pidx(la, lb);
+                            R v0 = h0[e], v1 = h1[e], v2 = h2[e];
+                            if (la >= 3) { const R q = t.w_snap * rm[(la - 3) * 3 + (lb - 3)]; v0 += q; v1 += q; v2 += q; }
+                            const int r = zidx(la, 0), c = zidx(lb, 0);
+                            Hi[r * 20 + c] = v0; Hi[c * 20 + r] = v0;
+                            Hi[(r + 1) * 20 + c + 1] = v1; Hi[(c + 1) * 20 + r + 1] = v1;
+                            Hi[(r + 2) * 20 + c + 2] = v2; Hi[(c + 2) * 20 + r + 2] = v2;
+                        }
+                    }
+                }
+                {   // cross-axis blocks (0,1), (0,2), (1,2): only the position groups have off-diagonal M_g
+                    R h0[21], h1[21], h2[21];
+                    DDP_UNROLL
+                    for (int e = 0; e < 21; e++) { h0[e] = R(0); h1[e] = R(0); h2[e] = R(0); }
+                    for (int g = 0; g < 6; g++)
+                        lin_diag_group<R, 0>(t.tab, g, tp, msc[(g * 6 + 1) * 32], msc[(g * 6 + 2) * 32], msc[(g * 6 + 4) * 32], h0, h1, h2);
+                    DDP_UNROLL
+                    for (int lb = 0; lb < 6; lb++) {
+                        DDP_UNROLL
+                        for (int la = 0; la <= lb; la++) {
+                            const int e = pidx(la, lb);
+                            const int ra = zidx(la, 0), rb = zidx(lb, 0);
+                            // axes (0,1): entries ((la,0),(lb,1)) and ((lb,0),(la,1)) and their transposes; likewise (0,2), (1,2)
+                            Hi[ra * 20 + rb + 1] = h0[e]; Hi[(rb + 1) * 20 + ra] = h0[e];
+                            Hi[rb * 20 + ra + 1] = h0[e]; Hi[(ra + 1) * 20 + rb] = h0[e];
+                            Hi[ra * 20 + rb + 2] = h1[e]; Hi[(rb + 2) * 20 + ra] = h1[e];
+                            Hi[rb * 20 + ra + 2] = h1[e]; Hi[(ra + 2) * 20 + rb] = h1[e];
+                            Hi[(ra + 1) * 20 + rb + 2] = h2[e]; Hi[(rb + 2) * 20 + ra + 1] = h2[e];
+                            Hi[(rb + 1) * 20 + ra + 2] = h2[e]; Hi[(ra + 2) * 20 + rb + 1] = h2[e];
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
+// =============================================================================================
+// Backward pass, sequential part (ddp.cpp:507-638): lane j < 20 owns column j of the augmented matrix
+//   [ Quu Qux Qu ; Qxu Qxx Qx ; Qu^T Qx^T . ]   (z order [u(9), T, x(9), gradient]).
+// Per knot: add the dynamics term A^T Vxx A, A^T Vx (A = [G (x) I | fT | F (x) I], ddp.cpp:508-520) to the
+// linearised part, eliminate the ten u/T columns (Eigen::LLT, ddp.cpp:543/:592), back-substitute the gains
+// [ku | Ku] (ddp.cpp:561-564 / :607-609) and keep the trailing block as Vxx, Vx (ddp.cpp:620-628).
+// Returns false when a pivot is not positive (ddp.cpp:546-551 / :595-600).
+// =============================================================================================
+template <class R> DDP_DEVICE_NOINLINE bool riccati(Traj<R> &t, R regadd, Reg<R, 1> &errq) {
+    const int lane_ = t.lane_;
+    R *sm = t.sm;
+    const int N = t.N;
+    // terminal value function, ddp.cpp:1318-1323: Vx = P (x_N - x_d), Vxx = P = w_terminal I
+    FOR_LANES(lane) {
+        errq(lane, 0) = R(0);
+        for (int e = lane; e < 90; e += 32) {
+            const R v = (e / 10 == e % 10 && e % 10 < 9) ? t.w_terminal : R(0);
+            sm[Lay::S1 + e] = v; sm[Lay::S2 + e] = v;
+        }
+        if (lane < 9) sm[Lay::VX + lane] = t.w_terminal * (t.xu[(long long)N * 20 + 10 + lane] - sm[Lay::XD + lane]);
+    }
+    WARP_SYNC();
+    Reg<R, 20> col, nxt;
+    FOR_LANES(lane) {
+        DDP_UNROLL
+        for (int r = 0; r < 20; r++) nxt(lane, r) = lane < 20 ? t.H[(long long)(N - 1) * 400 + lane * 20 + r] : R(0);
+    }
+    for (int i = N - 1; i >= 0; i--) {
+        t.n_bwd_knots++;
+        // uniform per-knot data: segment time, F/G, fT
+        R tp[6], fg[18], fT[9];
+        time_powers(t.xu[(long long)i * 20 + 9], tp);
+        fg_matrix(tp, fg);
+        DDP_UNROLL
+        for (int q = 0; q < 9; q++) fT[q] = t.aux[(long long)i * 12 + q];
+        FOR_LANES(lane) {
+            DDP_UNROLL
+            for (int r = 0; r < 20; r++) col(lane, r) = nxt(lane, r);
+            if (i > 0 && lane < 20) {   // prefetch the next knot's column while this one is eliminated
+                DDP_UNROLL
+                for (int r = 0; r < 20; r++) nxt(lane, r) = t.H[(long long)(i - 1) * 400 + lane * 20 + r];
+            }
+            if (lane < 20 && lane != 9) {
+                R tj[9];
+                if (lane == 19) {
+                    DDP_UNROLL
+                    for (int p = 0; p < 9; p++) tj[p] = sm[Lay::VX + p];
+                } else {
+                    const int lj = lane < 9 ? 3 + lane / 3 : (lane - 10) / 3, aj = lane < 9 ? lane % 3 : (lane - 10) % 3;
+                    const R f0 = fg[lj], f1 = fg[6 + lj], f2 = fg[12 + lj];
+                    const R *a1 = sm + Lay::S1, *a2 = sm + Lay::S2;
+                    DDP_UNROLL
+                    for (int p = 0; p < 9; p++) {   // V = (S + S^T)/2 (ddp.cpp:628) formed on the fly
+                        const R v0 = R(0.5) * (a1[aj * 10 + p] + a2[aj * 10 + p]);
+                        const R v1 = R(0.5) * (a1[(3 + aj) * 10 + p] + a2[(3 + aj) * 10 + p]);
+                        const R v2 = R(0.5) * (a1[(6 + aj) * 10 + p] + a2[(6 + aj) * 10 + p]);
+                        tj[p] = (v0 * f0 + v1 * f1) + v2 * f2;
+                    }
+                    // gradient row of this column: (A e_j)^T Vx
+                    col(lane, 19) += (f0 * sm[Lay::VX + aj] + f1 * sm[Lay::VX + 3 + aj]) + f2 * sm[Lay::VX + 6 + aj];
+                }
+                DDP_UNROLL
+                for (int l = 0; l < 6; l++) {
+                    DDP_UNROLL
+                    for (int a = 0; a < 3; a++)
+                        col(lane, zidx(l, a)) += (fg[l] * tj[a] + fg[6 + l] * tj[3 + a]) + fg[12 + l] * tj[6 + a];
                 }
                 R hT = R(0);
                 DDP_UNROLL
-                for (int p = 0; p < 9; p++) hT += sm[L.FT() + p] * tt[p];
+                for (int p = 0; p < 9; p++) hT += fT[p] * tj[p];
                 col(lane, 9) += hT;
-                col(lane, 19) += (fg0 * sm[Lay::VX + ap] + fg1 * sm[Lay::VX + 3 + ap]) + fg2 * sm[Lay::VX + 6 + ap];
-                // stage cost (ddp.cpp:1350-1355): quu = w [R (x) I, R'u; (R'u)^T, .], qu = w R u
-                if (lane < 9) {
-                    const int ip = lane / 3;
-                    R Ru = R(0), Rpu = R(0);
-                    DDP_UNROLL
-                    for (int b = 0; b < 3; b++) {
-                        const R rv = sm[L.RR() + ip * 3 + b];
-                        Ru += rv * sm[Lay::ZO + 3 * b + ap];
-                        Rpu += sm[L.RR() + 9 + ip * 3 + b] * sm[Lay::ZO + 3 * b + ap];
-                        const R qv = t.w_snap * rv;
-                        col(lane, 3 * b + 0) += ap == 0 ? qv : R(0);
-                        col(lane, 3 * b + 1) += ap == 1 ? qv : R(0);
-                        col(lane, 3 * b + 2) += ap == 2 ? qv : R(0);
-                    }
-                    col(lane, 9) += t.w_snap * Rpu;
-                    col(lane, 19) += t.w_snap * Ru;
-                }
-                sm[L.XT() + lane] = col(lane, 9);
-                sm[L.X() + lane] = col(lane, 19);
+                sm[Lay::XT + lane] = col(lane, 9);
             }
-            if (lane == 9) {
-                R hTT = R(0), gT = R(0);
+            if (lane >= 10 && lane < 19) {   // (V fT)[p] for the T-T entry
+                const int p = lane - 10;
+                R acc = R(0);
                 DDP_UNROLL
-                for (int p = 0; p < 9; p++) { hTT += sm[L.FT() + p] * sm[L.TT9() + p]; gT += sm[L.FT() + p] * sm[Lay::VX + p]; }
-                R quT, quuTT;
-                if (t.time_power == 2) { quT = t.w_time * T + R(0.5) * t.w_snap * uRpu; quuTT = t.w_time + R(0.5) * t.w_snap * uRppu; }
-                else { quT = R(0.5) * t.w_time + R(0.5) * t.w_snap * uRpu; quuTT = R(0.5) * t.w_snap * uRppu; }
-                col(lane, 9) = (quuTT + hTT) + ttot;
-                col(lane, 19) = (quT + gT) + gtot;
-                sm[L.X() + 9] = col(lane, 19);
+                for (int q = 0; q < 9; q++) acc += (R(0.5) * (sm[Lay::S1 + p * 10 + q] + sm[Lay::S2 + p * 10 + q])) * fT[q];
+                sm[Lay::XH + p] = fT[p] * acc;
             }
         }
         WARP_SYNC();
         FOR_LANES(lane) {
-            if (lane == 9) {
+            if (lane == 9) {   // the T column is the T row of the others (the matrix is symmetric)
                 DDP_UNROLL
-                for (int r = 0; r < 19; r++) if (r != 9) col(lane, r) = sm[L.XT() + r];
-            }
-            if (lane == 19) {
+                for (int r = 0; r < 20; r++) if (r != 9) col(lane, r) = sm[Lay::XT + r];
+                R hTT = R(0);
                 DDP_UNROLL
-                for (int r = 0; r < 19; r++) col(lane, r) = sm[L.X() + r];
+                for (int p = 0; p < 9; p++) hTT += sm[Lay::XH + p];
+                col(lane, 9) += hTT;
             }
-            if (lane < 10) errs(lane, 0) = amax(errs(lane, 0), rabs(col(lane, 19)));  // |Qu|, ddp.cpp:633
+            if (lane == 19) {   // |Qu|_inf, ddp.cpp:633
+                R e = errq(lane, 0);
+                DDP_UNROLL
+                for (int r = 0; r < 10; r++) e = amax(e, rabs(col(lane, r)));
+                errq(lane, 0) = e;
+            }
         }
-        // ---- phase F: ten Cholesky pivots over the u block (Eigen::LLT, ddp.cpp:543/:592) -----------
+        // ---- ten Cholesky pivots over the u block -----------------------------------------------------------
         Reg<R, 10> mult;  // lane c keeps row p of L^-1 [H_u: | g_u] restricted to its column
+        R rinv[10];
+        R d = warp_bcast(col, 0, 0, lane_) + regadd;
         bool fail = false;
         DDP_UNROLL
         for (int p = 0; p < 10; p++) {
-            const R d = warp_bcast(col, p, p, lane_) + regadd;
             if (d <= R(0)) { fail = true; break; }
-            const R piv = rsqrt_(d), inv = R(1) / piv;
+            const R ri = rrsqrt(d);
+            rinv[p] = ri;
+            Reg<R, 1> ahead;
             FOR_LANES(lane) {
-                R m = (lane == p) ? piv : col(lane, p) * inv;
+                const R m = (lane == p) ? d * ri : col(lane, p) * ri;
                 mult(lane, p) = m;
-                if (lane < 20) sm[L.LF() + p * 20 + lane] = m;
+                if (lane < 20) sm[Lay::MB + p * 20 + lane] = m;
+                ahead(lane, 0) = p < 9 ? col(lane, p + 1) - m * m : R(0);   // next pivot's diagonal, sent ahead of the update
             }
-            FOR_LANES(lane) { if (lane == 0) sm[L.XI() + p] = inv; }
+            const R dn = p < 9 ? warp_bcast(ahead, 0, p + 1, lane_) + regadd : R(0);
             WARP_SYNC();
             FOR_LANES(lane) {
                 if (lane > p && lane < 20) {
                     const R m = mult(lane, p);
                     DDP_UNROLL
-                    for (int r = p + 1; r < 20; r++) col(lane, r) -= sm[L.LF() + p * 20 + r] * m;
+                    for (int r = p + 1; r < 20; r++) col(lane, r) -= sm[Lay::MB + p * 20 + r] * m;
                 }
             }
+            d = dn;
         }
-        if (fail) {  // ddp.cpp:546-551 / :595-600
-            t.bfailed = 1;
-            t.opterr = R(INFINITY);
-            t.cyc_bwd += ddp_clock() - clk0;
-            return;
-        }
-        // ---- phase G: gains [ku | Ku] = -(L L^T)^-1 [Qu | Qux] (ddp.cpp:561-564 / :607-609) -----------
+        if (fail) return false;
+        // ---- gains [ku | Ku] = -(L L^T)^-1 [Qu | Qux] ----------------------------------------------------------
         Reg<R, 10> kx;
         FOR_LANES(lane) {
             if (lane >= 10 && lane < 20) {
@@ -613,19 +702,22 @@ template <class R> DDP_DEVICE_NOINLINE void backward_pass(Traj<R> &t) {
                 for (int p = 9; p >= 0; p--) {
                     R v = mult(lane, p);
                     DDP_UNROLL
-                    for (int q = p + 1; q < 10; q++) v -= sm[L.LF() + p * 20 + q] * (-kx(lane, q));
-                    kx(lane, p) = -(v * sm[L.XI() + p]);
+                    for (int q = p + 1; q < 10; q++) v += sm[Lay::MB + p * 20 + q] * kx(lane, q);
+                    kx(lane, p) = -(v * rinv[p]);
                 }
                 const int qc = lane == 19 ? 0 : lane - 9;
                 DDP_UNROLL
-                for (int p = 0; p < 10; p++) sm[Lay::KC + p * 10 + qc] = kx(lane, p);
+                for (int p = 0; p < 10; p++) {
+                    sm[Lay::KC + p * 10 + qc] = kx(lane, p);
+                    t.K[(long long)i * 100 + p * 10 + qc] = kx(lane, p);
+                }
             }
         }
-        WARP_SYNC();
         // The reference backs up with the UNREGULARISED Quu (ddp.cpp:574/:615, :620-627).  With
         // K = -(Quu+rho I)^-1 Qux that equals the Schur complement above minus rho K^T K (and
         // minus rho K^T k for Vx).
         if (regadd != R(0)) {
+            WARP_SYNC();
             FOR_LANES(lane) {
                 if (lane >= 10 && lane < 19) {
                     DDP_UNROLL
@@ -644,304 +736,338 @@ template <class R> DDP_DEVICE_NOINLINE void backward_pass(Traj<R> &t) {
         }
         FOR_LANES(lane) {
             if (lane >= 10 && lane < 19) {
+                const int b = lane - 10;
                 DDP_UNROLL
-                for (int a = 0; a < 9; a++) sm[Lay::VXX + (lane - 10) * 9 + a] = col(lane, 10 + a);
-                sm[Lay::VX + (lane - 10)] = col(lane, 19);
+                for (int a = 0; a < 9; a++) { sm[Lay::S1 + a * 10 + b] = col(lane, 10 + a); sm[Lay::S2 + b * 10 + a] = col(lane, 10 + a); }
+                sm[Lay::VX + b] = col(lane, 19);
             }
-            for (int e = lane; e < 100; e += 32) t.K[(long long)i * 100 + e] = sm[Lay::KC + e];
-        }
-        WARP_SYNC();
-        Reg<R, 3> symv;  // Vxx = (Vxx + Vxx^T)/2, ddp.cpp:628
-        FOR_LANES(lane) {
-            DDP_UNROLL
-            for (int q = 0; q < 3; q++) {
-                int e = lane + 32 * q;
-                if (e < 81) { int a = e / 9, b = e - 9 * a; symv(lane, q) = R(0.5) * (sm[Lay::VXX + e] + sm[Lay::VXX + b * 9 + a]); }
-            }
-        }
-        WARP_SYNC();
-        FOR_LANES(lane) {
-            DDP_UNROLL
-            for (int q = 0; q < 3; q++) { int e = lane + 32 * q; if (e < 81) sm[Lay::VXX + e] = symv(lane, q); }
         }
         WARP_SYNC();
     }
-    t.bfailed = 0;
-    const R e0 = warp_max(errs, 0, lane_), e1 = warp_max(errs, 1, lane_), e2 = warp_max(errs, 2, lane_);
-    t.opterr = rmax(rmax(e0, t.infeas ? e2 : R(0)), e1);  // ddp.cpp:641
+    return true;
+}
+
+// ddp.cpp:440-644.
+template <class R> DDP_DEVICE_NOINLINE void backward_pass(Traj<R> &t) {
+    const int lane_ = t.lane_;
+    const long long clk0 = ddp_clock();
+    t.n_bwd_sweeps++;
+    // regularisation schedule, ddp.cpp:452-474
+    if (t.failed || t.bfailed) t.reg = t.reg + R(1);
+    else if (t.step == 0) t.reg = t.reg - R(1);
+    else if (t.step <= 3) t.reg = t.reg;
+    else t.reg = t.reg + R(1);
+    if (t.reg < R(0)) t.reg = R(0);
+    else if (t.reg > R(24)) t.reg = R(24);
+    const R regadd = rpow(t.reg_base, t.reg) - R(1);  // ddp.cpp:529
+    Reg<R, 2> errs;
+    Reg<R, 1> errq;
+    linearize(t, errs);
+    WARP_SYNC();
+    if (!riccati(t, regadd, errq)) {
+        t.bfailed = 1;
+        t.opterr = R(INFINITY);
+    } else {
+        t.bfailed = 0;
+        const R e0 = warp_max(errq, 0, lane_), e1 = warp_max(errs, 0, lane_), e2 = warp_max(errs, 1, lane_);
+        t.opterr = rmax(rmax(e0, t.infeas ? e2 : R(0)), e1);  // ddp.cpp:641
+    }
     t.cyc_bwd += ddp_clock() - clk0;
 }
 
 // =============================================================================================
-// One rollout: initial roll (mode 0, ddp.cpp:1608-1620) or a line-search trial (mode 1,
-// ddp.cpp:674-734) with step size alpha.  Writes the candidate into xun/sn/yn and returns false when
-// the fraction-to-boundary test fails (ddp.cpp:683-687 / :699-703).
+// Forward pass.
 // =============================================================================================
 template <class R> struct RollOut { R cost, costq, logcost, err; };
 
-template <class R> DDP_DEVICE_NOINLINE bool rollout(Traj<R> &t, int mode, R alpha, R tau, RollOut<R> &out) {
+// Running product of barrier arguments with an occasional log, so that sum(log(.)) costs one log per ~dozens of rows.
+template <class R> struct LogProd {
+    R lp, lsum;
+    DDP_DEVICE void mul(R v) {
+        lp *= v;
+        const R lo = sizeof(R) == 8 ? R(1e-200) : R(1e-25), hi = sizeof(R) == 8 ? R(1e200) : R(1e25);
+        if (!(lp > lo && lp < hi)) { lsum += rlog(lp); lp = R(1); }
+    }
+    DDP_DEVICE R total() const { return lsum + rlog(lp); }
+};
+
+template <class R> struct TrialAcc {
+    LogProd<R> lg;
+    R e1;
+    int bad;
+};
+
+// One constraint row of a line-search trial (ddp.cpp:680-703): slack/dual step from the gains that are
+// recomputed here (ks, Ks dx, ky, Ky dx; ddp.cpp:568-572 / :611-612), fraction-to-boundary test, barrier terms.
+template <class R>
+DDP_DEVICE void trial_row(const Traj<R> &t, long long ro, R cold, R cnew, R jv1, R jv2, R alpha, R tau, TrialAcc<R> &A) {
+    const R sv = t.s[ro];
+    if (t.infeas) {
+        const R yv = t.y[ro], yinv = R(1) / yv;
+        const R r = sv * yv - t.mu, rhat = sv * (cold + yv) - r, D = sv * yinv;
+        const R ks = yinv * (rhat + sv * jv1), ky = -(cold + yv) - jv1;
+        const R ynew = (yv + alpha * ky) + (-jv2), snew = (sv + alpha * ks) + D * jv2;
+        if (ynew < (R(1) - tau) * yv || snew < (R(1) - tau) * sv) A.bad = 1;
+        t.sn[ro] = snew; t.yn[ro] = ynew;
+        A.lg.mul(ynew); A.e1 += rabs(cnew + ynew);
+    } else {
+        const R cinv = R(1) / cold;
+        const R r = sv * cold + t.mu, D = sv * cinv;
+        const R ks = -(cinv * (r + sv * jv1));
+        const R snew = (sv + alpha * ks) + (-(D * jv2));
+        if (cnew > (R(1) - tau) * cold || snew < (R(1) - tau) * sv) A.bad = 1;
+        t.sn[ro] = snew;
+        A.lg.mul(-cnew);
+    }
+}
+
+template <class R, int SHIFT>
+DDP_DEVICE void trial_fixed_group(const Traj<R> &t, int g, int i, int plus0, int minus0, R lim, const R *tpo, const R *tpn,
+                                  const R *zo, const R *zn, const R *v1, const R *v2, R alpha, R tau, TrialAcc<R> &A) {
+    R b[6], bd[6], bn[6];
+    basis_row<R, SHIFT, 0>(t.tab, g, tpo, b);
+    basis_row<R, SHIFT, 1>(t.tab, g, tpo, bd);
+    basis_row<R, SHIFT, 0>(t.tab, g, tpn, bn);
+    DDP_UNROLL
+    for (int a = 0; a < 3; a++) {
+        const R vo = dot_axis<R, SHIFT>(b, zo, a), tc = dot_axis<R, SHIFT>(bd, zo, a), vn = dot_axis<R, SHIFT>(bn, zn, a);
+        const R j1 = dot_axis<R, 3>(b, v1, a) + tc * v1[9], j2 = dot_axis<R, SHIFT>(b, v2, a) + tc * v2[9];
+        trial_row(t, (long long)(plus0 + a) * t.NP + i, vo - lim - t.margin, vn - lim - t.margin, j1, j2, alpha, tau, A);
+        trial_row(t, (long long)(minus0 + a) * t.NP + i, -vo - lim - t.margin, -vn - lim - t.margin, -j1, -j2, alpha, tau, A);
+    }
+}
+
+// One line-search trial with step size alpha (ddp.cpp:674-734).  The closed-loop state/control recursion
+// runs sequentially (lane <-> element) for 32 knots at a time; the constraint rows of those 32 knots are then
+// evaluated lane <-> knot.  Writes the candidate into xun/sn/yn and returns false when the
+// fraction-to-boundary test fails at some knot (ddp.cpp:683-687 / :699-703).
+template <class R> DDP_DEVICE_NOINLINE bool forward_trial(Traj<R> &t, R alpha, R tau, RollOut<R> &out) {
     const int lane_ = t.lane_;
-    const Lay L(t.PM);
     R *sm = t.sm;
-    const R mu = t.mu;
+    const int N = t.N;
+    Reg<R, 1> xcur, xn;
     Reg<R, 3> acc;  // per-lane partials: stage cost, log barrier, |c+y|_1
     FOR_LANES(lane) {
         acc(lane, 0) = R(0); acc(lane, 1) = R(0); acc(lane, 2) = R(0);
-        if (lane < 9) sm[Lay::ZN + 10 + lane] = t.xu[10 + lane];  // xnew[0] = xold[0]
+        xcur(lane, 0) = (lane >= 10 && lane < 19) ? t.xu[lane] : R(0);  // xnew[0] = xold[0]
+        xn(lane, 0) = R(0);
     }
-    WARP_SYNC();
-    for (int i = 0; i < t.N; i++) {
-        if (mode == 1) t.n_fwd_knots++;
-        const int P = t.nplanes[i];
-        Reg<R, 8> s, y;
-        if (mode == 1) {
-            load_rows(t.s + (long long)i * t.MCS, P, s, lane_);
-            if (t.infeas) load_rows(t.y + (long long)i * t.MCS, P, y, lane_);
-        }
-        // ---- phase A ---------------------------------------------------------------------------------
-        FOR_LANES(lane) {
-            if (lane < 20) sm[Lay::ZO + lane] = t.xu[(long long)i * 20 + lane];
-            load_planes(t, i, P, lane);
-            if (mode == 1) for (int e = lane; e < 100; e += 32) sm[Lay::KC + e] = t.K[(long long)i * 100 + e];
-        }
-        WARP_SYNC();
-        const R Told = sm[Lay::ZO + 9];
-        FOR_LANES(lane) {
-            if (mode == 1) {
-                scale_tables(t.tab, Told, sm + Lay::BS, sm + Lay::BDT, lane);
-                if (lane < 9) sm[L.DX() + lane] = sm[Lay::ZN + 10 + lane] - sm[Lay::ZO + 10 + lane];
-            } else if (lane < 10) sm[Lay::ZN + lane] = sm[Lay::ZO + lane];  // initial roll keeps u
-        }
-        WARP_SYNC();
-        // ---- phase B: unew = (uold + alpha ku) + Ku dx (ddp.cpp:689/:695); v1 = [ku;0], v2 = [Ku dx; dx] --
-        if (mode == 1) {
+    for (int base = 0; base < N; base += 32) {
+        const int nk = N - base < 32 ? N - base : 32;
+        for (int i = base; i < base + nk; i++) {
             FOR_LANES(lane) {
+                if (lane >= 10 && lane < 19) {
+                    const R x = xcur(lane, 0);
+                    sm[Lay::DX + lane - 10] = x - t.xu[(long long)i * 20 + lane];
+                    sm[Lay::ZN + lane] = x;
+                    t.xun[(long long)i * 20 + lane] = x;
+                }
+            }
+            WARP_SYNC();
+            FOR_LANES(lane) {   // unew = (uold + alpha ku) + Ku dx (ddp.cpp:689/:695)
                 if (lane < 10) {
+                    const R *Kr = t.K + (long long)i * 100 + lane * 10;
                     R kdx = R(0);
                     DDP_UNROLL
-                    for (int b = 0; b < 9; b++) kdx += sm[Lay::KC + lane * 10 + 1 + b] * sm[L.DX() + b];
-                    const R ku = sm[Lay::KC + lane * 10];
-                    sm[Lay::ZN + lane] = (sm[Lay::ZO + lane] + alpha * ku) + kdx;
-                    sm[L.V1() + lane] = ku; sm[L.V2() + lane] = kdx;
-                } else if (lane < 19) {
-                    sm[L.V1() + lane] = R(0); sm[L.V2() + lane] = sm[L.DX() + lane - 10];
+                    for (int b = 0; b < 9; b++) kdx += Kr[1 + b] * sm[Lay::DX + b];
+                    const R un = (t.xu[(long long)i * 20 + lane] + alpha * Kr[0]) + kdx;
+                    sm[Lay::ZN + lane] = un;
+                    t.xun[(long long)i * 20 + lane] = un;
+                    t.kdx[(long long)i * 10 + lane] = kdx;
                 }
             }
             WARP_SYNC();
-        }
-        const R Tn = sm[Lay::ZN + 9];
-        FOR_LANES(lane) {
-            if (lane < 18) sm[L.FGN() + lane] = fg_entry<R>(lane / 6, lane % 6, Tn);
-            if (mode == 1) {
-                scale_tables<R>(t.tab, Tn, sm + L.BSN(), nullptr, lane);
-                transform45(sm + Lay::BS, sm + Lay::ZO, sm + L.TRF(), lane);
-                transform45(sm + Lay::BDT, sm + Lay::ZO, sm + L.TRF() + 45, lane);
-                transform45(sm + Lay::BS, sm + L.V1(), sm + L.TRF() + 90, lane);
-                transform45(sm + Lay::BS, sm + L.V2(), sm + L.TRF() + 135, lane);
+            R tp[6], fg[18];
+            time_powers(sm[Lay::ZN + 9], tp);
+            fg_matrix(tp, fg);
+            FOR_LANES(lane) {   // x+ = (F (x) I) x + (G (x) I) u (ddp.cpp:1062-1067)
+                if (lane >= 10 && lane < 19) {
+                    const int o = (lane - 10) / 3, a = (lane - 10) % 3;
+                    R s1 = R(0), s2 = R(0);
+                    DDP_UNROLL
+                    for (int b = 0; b < 3; b++) {
+                        if (b >= o) s1 += fg[o * 6 + b] * sm[Lay::ZN + 10 + 3 * b + a];
+                        s2 += fg[o * 6 + 3 + b] * sm[Lay::ZN + 3 * b + a];
+                    }
+                    xn(lane, 0) = s1 + s2;
+                }
             }
-        }
-        WARP_SYNC();
-        if (mode == 1) {
-            FOR_LANES(lane) { transform45(sm + L.BSN(), sm + Lay::ZN, sm + L.TRF() + 180, lane); }
             WARP_SYNC();
+            FOR_LANES(lane) { xcur(lane, 0) = xn(lane, 0); }
         }
-        // ---- phase C: rows ---------------------------------------------------------------------------
-        Reg<int, 1> bad;
-        Reg<R, 8> sn, yn;
-        const R v1T = mode == 1 ? sm[L.V1() + 9] : R(0), v2T = mode == 1 ? sm[L.V2() + 9] : R(0);
-        if (mode == 1) FOR_LANES(lane) {
-            int isbad = 0;
-            R lp = R(1), e1 = R(0);
-            DDP_UNROLL
-            for (int q = 0; q < 8; q++) {
-                if (!row_valid(q, lane, P)) { sn(lane, q) = R(1); yn(lane, q) = R(1); continue; }
-                R cold = R(0), cnew, jv1 = R(0), jv2 = R(0);
-                if (q < 6) {
-                    const R n0 = sm[Lay::PL + 4 * lane], n1 = sm[Lay::PL + 4 * lane + 1], n2 = sm[Lay::PL + 4 * lane + 2],
-                            n3 = sm[Lay::PL + 4 * lane + 3];
-                    const R *f = sm + L.TRF() + 3 * q;
-                    cnew = ((n0 * f[180] + n1 * f[181]) + n2 * f[182]) + n3 - t.margin;
-                    if (mode == 1) {
-                        cold = ((n0 * f[0] + n1 * f[1]) + n2 * f[2]) + n3 - t.margin;
-                        const R tc = (n0 * f[45] + n1 * f[46]) + n2 * f[47];
-                        jv1 = ((n0 * f[90] + n1 * f[91]) + n2 * f[92]) + tc * v1T;
-                        jv2 = ((n0 * f[135] + n1 * f[136]) + n2 * f[137]) + tc * v2T;
-                    }
-                } else if (lane < 27) {
-                    const R sg = q == 6 ? R(1) : R(-1), lim = lane < 15 ? t.max_vel : t.max_acc;
-                    const R *f = sm + L.TRF() + 18 + lane;
-                    cnew = sg * f[180] - lim - t.margin;
-                    if (mode == 1) {
-                        cold = sg * f[0] - lim - t.margin;
-                        jv1 = sg * (f[90] + f[45] * v1T);
-                        jv2 = sg * (f[135] + f[45] * v2T);
-                    }
-                } else {
-                    cnew = -Tn + R(0.3) - t.margin;
-                    if (mode == 1) { cold = -Told + R(0.3) - t.margin; jv1 = -v1T; jv2 = -v2T; }
-                }
-                if (mode == 1) {
-                    const R sv = s(lane, q);
-                    if (t.infeas) {  // ddp.cpp:535-536, :568-572, :680-684
-                        const R yv = y(lane, q), yinv = R(1) / yv;
-                        const R r = sv * yv - mu, rhat = sv * (cold + yv) - r, D = sv * yinv;
-                        const R ks = yinv * (rhat + sv * jv1), ky = -(cold + yv) - jv1;
-                        const R ynew = (yv + alpha * ky) + (-jv2), snew = (sv + alpha * ks) + D * jv2;
-                        if (ynew < (R(1) - tau) * yv || snew < (R(1) - tau) * sv) isbad = 1;
-                        sn(lane, q) = snew; yn(lane, q) = ynew;
-                        lp *= ynew; e1 += rabs(cnew + ynew);
-                    } else {  // ddp.cpp:583-586, :611-612, :694-700
-                        const R cinv = R(1) / cold;
-                        const R r = sv * cold + mu, D = sv * cinv;
-                        const R ks = -(cinv * (r + sv * jv1));
-                        const R snew = (sv + alpha * ks) + (-(D * jv2));
-                        if (cnew > (R(1) - tau) * cold || snew < (R(1) - tau) * sv) isbad = 1;
-                        sn(lane, q) = snew;
-                        lp *= -cnew;
-                    }
-                }
-            }
-            bad(lane, 0) = isbad;
-            if (mode == 1) { acc(lane, 1) += rlog(lp); acc(lane, 2) += e1; }
-        }
-        if (mode == 1) {
-            if (warp_any(bad, 0, lane_)) return false;
-            store_rows(t.sn + (long long)i * t.MCS, P, sn, lane_);
-            if (t.infeas) store_rows(t.yn + (long long)i * t.MCS, P, yn, lane_);
-        }
-        // ---- phase D: stage cost (ddp.cpp:1294-1305), next state (ddp.cpp:1062-1067), store ---------------
-        Reg<R, 1> xn;
+        // ---- rows of knots base .. base+nk-1, lane <-> knot ---------------------------------------------
+        Reg<int, 1> badk;
         FOR_LANES(lane) {
-            if (lane < 9) {
-                acc(lane, 0) += R(0.5) * t.w_snap * quad_share<R>(0, sm + Lay::ZN, lane, Tn);
-                const int o = lane / 3, a = lane - 3 * o;
-                R s1 = R(0), s2 = R(0);
+            const int i = base + lane;
+            badk(lane, 0) = 0x7fffffff;
+            if (i < N) {
+                R zo[19], zn[19], v1[10], v2[19], tpo[6], tpn[6];
                 DDP_UNROLL
-                for (int b = 0; b < 3; b++) {
-                    if (b >= o) s1 += sm[L.FGN() + o * 6 + b] * sm[Lay::ZN + 10 + 3 * b + a];
-                    s2 += sm[L.FGN() + o * 6 + 3 + b] * sm[Lay::ZN + 3 * b + a];
+                for (int e = 0; e < 19; e++) { zo[e] = t.xu[(long long)i * 20 + e]; zn[e] = t.xun[(long long)i * 20 + e]; }
+                DDP_UNROLL
+                for (int e = 0; e < 10; e++) { v1[e] = t.K[(long long)i * 100 + e * 10]; v2[e] = t.kdx[(long long)i * 10 + e]; }
+                DDP_UNROLL
+                for (int e = 10; e < 19; e++) v2[e] = zn[e] - zo[e];
+                time_powers(zo[9], tpo);
+                time_powers(zn[9], tpn);
+                TrialAcc<R> A;
+                A.lg.lp = R(1); A.lg.lsum = R(0); A.e1 = R(0); A.bad = 0;
+                const int P = t.nplanes[i];
+                const double *pl = t.planes + (long long)i * t.PM * 4;
+                for (int g = 0; g < 6; g++) {
+                    R b[6], bd[6], bn[6], co[3], cd[3], cn[3], j1[3], j2[3];
+                    basis_row<R, 0, 0>(t.tab, g, tpo, b);
+                    basis_row<R, 0, 1>(t.tab, g, tpo, bd);
+                    basis_row<R, 0, 0>(t.tab, g, tpn, bn);
+                    DDP_UNROLL
+                    for (int a = 0; a < 3; a++) {
+                        co[a] = dot_axis<R, 0>(b, zo, a); cd[a] = dot_axis<R, 0>(bd, zo, a); cn[a] = dot_axis<R, 0>(bn, zn, a);
+                        j1[a] = dot_axis<R, 3>(b, v1, a); j2[a] = dot_axis<R, 0>(b, v2, a);
+                    }
+                    for (int k = 0; k < P; k++) {
+                        R n[4];
+                        load_plane(pl, k, n);
+                        const R cold = ((n[0] * co[0] + n[1] * co[1]) + n[2] * co[2]) + n[3] - t.margin;
+                        const R cnew = ((n[0] * cn[0] + n[1] * cn[1]) + n[2] * cn[2]) + n[3] - t.margin;
+                        const R tc = (n[0] * cd[0] + n[1] * cd[1]) + n[2] * cd[2];
+                        const R jv1 = ((n[0] * j1[0] + n[1] * j1[1]) + n[2] * j1[2]) + tc * v1[9];
+                        const R jv2 = ((n[0] * j2[0] + n[1] * j2[1]) + n[2] * j2[2]) + tc * v2[9];
+                        trial_row(t, (long long)(g * t.PM + k) * t.NP + i, cold, cnew, jv1, jv2, alpha, tau, A);
+                    }
                 }
-                xn(lane, 0) = s1 + s2;
+                const int FB = 6 * t.PM;
+                for (int g = 6; g < 11; g++)
+                    trial_fixed_group<R, 1>(t, g, i, FB + 3 * (g - 6), FB + 15 + 3 * (g - 6), t.max_vel, tpo, tpn, zo, zn, v1, v2, alpha, tau, A);
+                for (int g = 11; g < 15; g++)
+                    trial_fixed_group<R, 2>(t, g, i, FB + 30 + 3 * (g - 11), FB + 42 + 3 * (g - 11), t.max_acc, tpo, tpn, zo, zn, v1, v2, alpha, tau, A);
+                trial_row(t, (long long)(FB + 54) * t.NP + i, -zo[9] + R(0.3) - t.margin, -zn[9] + R(0.3) - t.margin, -v1[9], -v2[9],
+                          alpha, tau, A);
+                if (A.bad) badk(lane, 0) = i;
+                acc(lane, 0) += stage_cost(t, tpn, zn);
+                acc(lane, 1) += A.lg.total();
+                acc(lane, 2) += A.e1;
             }
-            if (lane == 9) acc(lane, 0) += t.time_power == 2 ? R(0.5) * Tn * t.w_time * Tn : R(0.5) * t.w_time * Tn;
-            R *dst = mode == 1 ? t.xun : t.xu;
-            if (lane < 19) dst[(long long)i * 20 + lane] = sm[Lay::ZN + lane];
         }
-        WARP_SYNC();
-        FOR_LANES(lane) { if (lane < 9) sm[Lay::ZN + 10 + lane] = xn(lane, 0); }
-        WARP_SYNC();
+        const int first = warp_min_int(badk, 0, lane_);
+        if (first != 0x7fffffff) { t.n_fwd_knots += first - base + 1; return false; }
+        t.n_fwd_knots += nk;
     }
     // terminal cost (ddp.cpp:1289-1292) and totals
     Reg<R, 1> pt;
     FOR_LANES(lane) {
         pt(lane, 0) = R(0);
-        if (lane < 9) {
-            const R d = sm[Lay::ZN + 10 + lane] - sm[Lay::XD + lane];
+        if (lane >= 10 && lane < 19) {
+            const R d = xcur(lane, 0) - sm[Lay::XD + lane - 10];
             pt(lane, 0) = d * (t.w_terminal * d);
-            R *dst = mode == 1 ? t.xun : t.xu;
-            dst[(long long)t.N * 20 + 10 + lane] = sm[Lay::ZN + 10 + lane];
+            t.xun[(long long)N * 20 + lane] = xcur(lane, 0);
         }
     }
-    WARP_SYNC();
     const R qs = warp_sum(acc, 0, lane_), p = R(0.5) * warp_sum(pt, 0, lane_);
     out.costq = qs;
     out.cost = qs + p;
-    if (mode == 1) {
-        const R ls = warp_sum(acc, 1, lane_);
-        out.logcost = out.cost - mu * ls;
-        out.err = t.infeas ? rmax(t.tol, warp_sum(acc, 2, lane_)) : R(0);
-    }
+    out.logcost = out.cost - t.mu * warp_sum(acc, 1, lane_);
+    out.err = t.infeas ? rmax(t.tol, warp_sum(acc, 2, lane_)) : R(0);
+    WARP_SYNC();
     return true;
 }
 
-// Barrier cost and infeasibility at the current iterate + filter reset (ddp.cpp:1636-1662).
-template <class R> DDP_DEVICE_NOINLINE void reset_filter(Traj<R> &t) {
+// Open-loop rollout of the initial controls (initialroll, ddp.cpp:1608-1620) and its cost.
+template <class R> DDP_DEVICE_NOINLINE void initial_roll(Traj<R> &t) {
     const int lane_ = t.lane_;
-    const Lay L(t.PM);
     R *sm = t.sm;
-    Reg<R, 2> acc;
-    FOR_LANES(lane) { acc(lane, 0) = R(0); acc(lane, 1) = R(0); }
-    for (int i = 0; i < t.N; i++) {
-        const int P = t.nplanes[i];
-        Reg<R, 8> y;
-        if (t.infeas) load_rows(t.y + (long long)i * t.MCS, P, y, lane_);
+    const int N = t.N;
+    Reg<R, 1> xcur, xn;
+    FOR_LANES(lane) { xcur(lane, 0) = (lane >= 10 && lane < 19) ? t.xu[lane] : R(0); xn(lane, 0) = R(0); }
+    for (int i = 0; i < N; i++) {
         FOR_LANES(lane) {
-            if (lane < 20) sm[Lay::ZO + lane] = t.xu[(long long)i * 20 + lane];
-            load_planes(t, i, P, lane);
+            if (lane >= 10 && lane < 19) { sm[Lay::ZN + lane] = xcur(lane, 0); t.xu[(long long)i * 20 + lane] = xcur(lane, 0); }
+            if (lane < 10) sm[Lay::ZN + lane] = t.xu[(long long)i * 20 + lane];
         }
         WARP_SYNC();
-        const R T = sm[Lay::ZO + 9];
-        FOR_LANES(lane) { scale_tables<R>(t.tab, T, sm + Lay::BS, nullptr, lane); }
-        WARP_SYNC();
-        FOR_LANES(lane) { transform45(sm + Lay::BS, sm + Lay::ZO, sm + L.TRF(), lane); }
-        WARP_SYNC();
+        R tp[6], fg[18];
+        time_powers(sm[Lay::ZN + 9], tp);
+        fg_matrix(tp, fg);
         FOR_LANES(lane) {
-            R lp = R(1), e1 = R(0);
-            DDP_UNROLL
-            for (int q = 0; q < 8; q++) {
-                if (!row_valid(q, lane, P)) continue;
-                R c;
-                if (q < 6) {
-                    const R *f = sm + L.TRF() + 3 * q;
-                    c = ((sm[Lay::PL + 4 * lane] * f[0] + sm[Lay::PL + 4 * lane + 1] * f[1]) + sm[Lay::PL + 4 * lane + 2] * f[2]) +
-                        sm[Lay::PL + 4 * lane + 3] - t.margin;
-                } else if (lane < 27) {
-                    c = (q == 6 ? R(1) : R(-1)) * sm[L.TRF() + 18 + lane] - (lane < 15 ? t.max_vel : t.max_acc) - t.margin;
-                } else c = -T + R(0.3) - t.margin;
-                if (t.infeas) { lp *= y(lane, q); e1 += rabs(c + y(lane, q)); }
-                else lp *= -c;
+            if (lane >= 10 && lane < 19) {
+                const int o = (lane - 10) / 3, a = (lane - 10) % 3;
+                R s1 = R(0), s2 = R(0);
+                DDP_UNROLL
+                for (int b = 0; b < 3; b++) {
+                    if (b >= o) s1 += fg[o * 6 + b] * sm[Lay::ZN + 10 + 3 * b + a];
+                    s2 += fg[o * 6 + 3 + b] * sm[Lay::ZN + 3 * b + a];
+                }
+                xn(lane, 0) = s1 + s2;
             }
-            acc(lane, 0) += rlog(lp); acc(lane, 1) += e1;
         }
         WARP_SYNC();
+        FOR_LANES(lane) { xcur(lane, 0) = xn(lane, 0); }
     }
-    t.logcost = t.cost - t.mu * warp_sum(acc, 0, lane_);
+    Reg<R, 2> acc;
+    FOR_LANES(lane) {
+        acc(lane, 0) = R(0); acc(lane, 1) = R(0);
+        if (lane >= 10 && lane < 19) {
+            t.xu[(long long)N * 20 + lane] = xcur(lane, 0);
+            const R d = xcur(lane, 0) - sm[Lay::XD + lane - 10];
+            acc(lane, 1) = d * (t.w_terminal * d);
+        }
+        for (int i = lane; i < N; i += 32) {
+            R u[10], tp[6];
+            DDP_UNROLL
+            for (int e = 0; e < 10; e++) u[e] = t.xu[(long long)i * 20 + e];
+            time_powers(u[9], tp);
+            acc(lane, 0) += stage_cost(t, tp, u);
+        }
+    }
+    t.costq = warp_sum(acc, 0, lane_);
+    t.cost = t.costq + R(0.5) * warp_sum(acc, 1, lane_);
+    WARP_SYNC();
+}
+
+// Constraint scan at the current iterate, lane <-> knot.
+//   mode 0: barrier sum and infeasibility (resetfilter, ddp.cpp:1636-1662) -> lsum, e1; returns false
+//   mode 1: any c >= thresh (ddp.cpp:346-355);  mode 2: any c > thresh (ddp.cpp:255-269)
+template <class R> DDP_DEVICE_NOINLINE bool scan_constraints(Traj<R> &t, int mode, R thresh, R &lsum, R &e1sum) {
+    const int lane_ = t.lane_;
+    Reg<R, 2> acc;
+    Reg<int, 1> viol;
+    FOR_LANES(lane) {
+        acc(lane, 0) = R(0); acc(lane, 1) = R(0); viol(lane, 0) = 0;
+        for (int i = lane; i < t.N; i += 32) {
+            R z[19];
+            DDP_UNROLL
+            for (int e = 0; e < 19; e++) z[e] = t.xu[(long long)i * 20 + e];
+            LogProd<R> lg;
+            lg.lp = R(1); lg.lsum = R(0);
+            R e1 = R(0);
+            int v = 0;
+            visit_rows(t, i, z, [&](int slot, R c) {
+                if (mode == 0) {
+                    if (t.infeas) { const R yv = t.y[(long long)slot * t.NP + i]; lg.mul(yv); e1 += rabs(c + yv); }
+                    else lg.mul(-c);
+                } else if (mode == 1) { if (c >= thresh) v = 1; }
+                else { if (c > thresh) v = 1; }
+            });
+            if (mode == 0) { acc(lane, 0) += lg.total(); acc(lane, 1) += e1; }
+            if (v) viol(lane, 0) = 1;
+        }
+    }
+    if (mode == 0) { lsum = warp_sum(acc, 0, lane_); e1sum = warp_sum(acc, 1, lane_); return false; }
+    return warp_any(viol, 0, lane_);
+}
+
+// Barrier cost and infeasibility at the current iterate + filter reset (ddp.cpp:1636-1662).
+template <class R> DDP_DEVICE void reset_filter(Traj<R> &t) {
+    const int lane_ = t.lane_;
+    R lsum = R(0), e1 = R(0);
+    scan_constraints(t, 0, R(0), lsum, e1);
+    t.logcost = t.cost - t.mu * lsum;
     t.err = R(0);
-    if (t.infeas) { t.err = warp_sum(acc, 1, lane_); if (t.err < t.tol) t.err = R(0); }
+    if (t.infeas) { t.err = e1; if (t.err < t.tol) t.err = R(0); }
     FOR_LANES(lane) { if (lane == 0) { t.filt[0] = t.logcost; t.filt[1] = t.err; } }
     WARP_SYNC();
     t.nfilter = 1;
     t.step = 0;
     t.failed = 0;
-}
-
-// Number of constraint rows with c >= 2e-4 at the current iterate (ddp.cpp:346-355).
-template <class R> DDP_DEVICE_NOINLINE bool any_violation(Traj<R> &t, R thresh, bool strict) {
-    const int lane_ = t.lane_;
-    const Lay L(t.PM);
-    R *sm = t.sm;
-    Reg<int, 1> viol;
-    FOR_LANES(lane) { viol(lane, 0) = 0; }
-    for (int i = 0; i < t.N; i++) {
-        const int P = t.nplanes[i];
-        FOR_LANES(lane) {
-            if (lane < 20) sm[Lay::ZO + lane] = t.xu[(long long)i * 20 + lane];
-            load_planes(t, i, P, lane);
-        }
-        WARP_SYNC();
-        const R T = sm[Lay::ZO + 9];
-        FOR_LANES(lane) { scale_tables<R>(t.tab, T, sm + Lay::BS, nullptr, lane); }
-        WARP_SYNC();
-        FOR_LANES(lane) { transform45(sm + Lay::BS, sm + Lay::ZO, sm + L.TRF(), lane); }
-        WARP_SYNC();
-        FOR_LANES(lane) {
-            DDP_UNROLL
-            for (int q = 0; q < 8; q++) {
-                if (!row_valid(q, lane, P)) continue;
-                R c;
-                if (q < 6) {
-                    const R *f = sm + L.TRF() + 3 * q;
-                    c = ((sm[Lay::PL + 4 * lane] * f[0] + sm[Lay::PL + 4 * lane + 1] * f[1]) + sm[Lay::PL + 4 * lane + 2] * f[2]) +
-                        sm[Lay::PL + 4 * lane + 3] - t.margin;
-                } else if (lane < 27) {
-                    c = (q == 6 ? R(1) : R(-1)) * sm[L.TRF() + 18 + lane] - (lane < 15 ? t.max_vel : t.max_acc) - t.margin;
-                } else c = -T + R(0.3) - t.margin;
-                if (strict ? (c > thresh) : (c >= thresh)) viol(lane, 0) = 1;
-            }
-        }
-        WARP_SYNC();
-    }
-    return warp_any(viol, 0, lane_);
 }
 
 // Line search with the filter (ddp.cpp:647-778).
@@ -957,7 +1083,7 @@ template <class R> DDP_DEVICE_NOINLINE void forward_pass(Traj<R> &t) {
         stepsize = R(1);
         for (int k = 0; k < step; k++) stepsize = stepsize * R(0.5);  // 2^-step exactly (ddp.cpp:670)
         t.n_fwd_trials++;
-        if (!rollout(t, 1, stepsize, tau, ro)) continue;
+        if (!forward_trial(t, stepsize, tau, ro)) continue;
         // filter acceptance, ddp.cpp:741-757: rejected if some entry is <= the candidate in both
         // coordinates; an accepted candidate evicts the entries it dominates.  Lane 0 owns the filter.
         FOR_LANES(lane) {
@@ -974,13 +1100,13 @@ template <class R> DDP_DEVICE_NOINLINE void forward_pass(Traj<R> &t) {
                     if (nk >= t.fcap) nk = t.fcap - 1;
                     t.filt[2 * nk] = ro.logcost; t.filt[2 * nk + 1] = ro.err;
                 }
-                t.sm[Lay::ZO + 19] = rej ? R(1) : R(0);
-                t.sm[Lay::ZN + 19] = R(nk);
+                t.sm[Lay::FL] = rej ? R(1) : R(0);
+                t.sm[Lay::FL + 1] = R(nk);
             }
         }
         WARP_SYNC();
-        const bool rej = t.sm[Lay::ZO + 19] != R(0);
-        const int nkeep = (int)t.sm[Lay::ZN + 19];
+        const bool rej = t.sm[Lay::FL] != R(0);
+        const int nkeep = (int)t.sm[Lay::FL + 1];
         WARP_SYNC();
         if (rej) continue;
         t.nfilter = nkeep + 1;
@@ -1010,13 +1136,14 @@ template <class R> DDP_DEVICE_NOINLINE void solve_one(const SolveArgs &A, int st
     const int N = A.N;
     const WsLay wl = ws_layout(N, A.PM, A.fcap);
     Traj<R> t;
-    t.N = N; t.PM = A.PM; t.MCS = wl.MCS; t.lane_ = lane_;
+    t.N = N; t.PM = A.PM; t.NP = wl.NP; t.MCS = wl.MCS; t.lane_ = lane_;
     t.planes = A.planes + (long long)b * N * A.PM * 4;
     t.nplanes = A.nplanes + (long long)b * N;
     t.sm = sm;
     t.tab = tabs + (cfg.minvo ? 180 : 0);
-    t.xu = ws + wl.xu; t.xun = ws + wl.xun; t.s = ws + wl.s; t.sn = ws + wl.sn; t.y = ws + wl.y; t.yn = ws + wl.yn;
-    t.K = ws + wl.K; t.filt = ws + wl.filt; t.fcap = A.fcap;
+    t.xu = ws + wl.xu; t.xun = ws + wl.xun; t.K = ws + wl.K; t.kdx = ws + wl.kdx; t.aux = ws + wl.aux; t.H = ws + wl.H;
+    t.s = ws + wl.s; t.sn = ws + wl.sn; t.y = ws + wl.y; t.yn = ws + wl.yn;
+    t.filt = ws + wl.filt; t.fcap = A.fcap;
     t.max_vel = (R)A.max_vel; t.max_acc = (R)A.max_acc;
     t.w_snap = (R)cfg.w_snap; t.w_terminal = (R)cfg.w_terminal; t.w_time = (R)cfg.w_time;
     t.margin = cfg.minvo ? R(0) : R(2.0e-4);  // ddp.cpp:1281-1283
@@ -1025,6 +1152,7 @@ template <class R> DDP_DEVICE_NOINLINE void solve_one(const SolveArgs &A, int st
     t.reg_base = cfg.zero_init ? R(1.6) : R(4.0);      // ddp.cpp:60-61
     t.n_bwd_sweeps = t.n_bwd_knots = t.n_fwd_trials = t.n_fwd_knots = 0;
     t.cyc_bwd = t.cyc_fwd = 0; t.cyc_t0 = ddp_clock();
+    t.mu = R(0); t.step = 0; t.failed = 0; t.bfailed = 0;
     const bool from_stage0 = (A.two_stage && st == 1);
     int infeas_in;
     if (from_stage0) infeas_in = A.out[0].infeas_out ? A.out[0].infeas_out[b] : 1;
@@ -1036,54 +1164,90 @@ template <class R> DDP_DEVICE_NOINLINE void solve_one(const SolveArgs &A, int st
         ibez = A.bez_tmp + (long long)b * N * 18;
         if (A.out[0].rtn[b] == 2) dur = A.time_tmp + (long long)b * N;  // UpdateTime, teach_repeat_planner.cpp:911-912
     }
-    const Lay L(t.PM);
 
-    // ---- setup (ddp.cpp:104-193) ---------------------------------------------------------------------
+    // ---- setup (ddp.cpp:104-250), lane <-> knot --------------------------------------------------------
     FOR_LANES(lane) {
         if (lane < 9) {
             sm[Lay::XD + lane] = (R)A.xd[(long long)b * 9 + lane];
             t.xu[10 + lane] = (R)A.x0[(long long)b * 9 + lane];
         }
-    }
-    for (int i = 0; i < N; i++) {
-        const int P = t.nplanes[i];
-        const double T = dur[i];
-        FOR_LANES(lane) {
-            // warm start: Bezier [x*6,y*6,z*6] scaled by T -> monomial coefficients 3..5 (ddp.cpp:167-193,:782-796)
-            if (lane < 9) {
-                R uv = R(0);
-                if (!cfg.zero_init && !cfg.line_init && ibez) {
-                    const int cidx = 3 + lane / 3, a = lane % 3;
-                    // (poly2bez * t2tauMat)(j, c) = BERN[c][j] / T^c
-                    const double Tk = 1.0 / T;
+        for (int i = lane; i < N; i += 32) {
+            const double T = dur[i];
+            R u[10];
+            DDP_UNROLL
+            for (int e = 0; e < 9; e++) u[e] = R(0);
+            u[9] = (R)T;
+            if (!cfg.zero_init && !cfg.line_init && ibez) {
+                // warm start: Bezier [x*6,y*6,z*6] scaled by T -> monomial coefficients 3..5 (ddp.cpp:167-193, :782-796);
+                // (poly2bez * t2tauMat)(j, c) = BERN[c][j] / T^c
+                const double bern[3][6] = {{-10, 30, -30, 10, 0, 0}, {5, -20, 30, -20, 5, 0}, {-1, 5, -10, 10, -5, 1}};
+                const double Tk = 1.0 / T;
+                DDP_UNROLL
+                for (int ci = 0; ci < 3; ci++) {
                     double pw = 1.0;
-                    for (int k = 0; k < cidx; k++) pw = (k == 0) ? Tk : pw * Tk;
-                    const int bern[3][6] = {{-10, 30, -30, 10, 0, 0}, {5, -20, 30, -20, 5, 0}, {-1, 5, -10, 10, -5, 1}};
-                    double accv = 0.0;
-                    for (int j = 0; j < 6; j++) accv += (T * ibez[(long long)i * 18 + a * 6 + j]) * (bern[cidx - 3][j] * pw);
-                    uv = (R)accv;
+                    for (int k = 0; k < ci + 3; k++) pw = (k == 0) ? Tk : pw * Tk;
+                    DDP_UNROLL
+                    for (int a = 0; a < 3; a++) {
+                        double accv = 0.0;
+                        DDP_UNROLL
+                        for (int j = 0; j < 6; j++) accv += (T * ibez[(long long)i * 18 + a * 6 + j]) * (bern[ci][j] * pw);
+                        u[ci * 3 + a] = (R)accv;
+                    }
                 }
-                t.xu[(long long)i * 20 + lane] = uv;
             }
-            if (lane == 9) t.xu[(long long)i * 20 + 9] = (R)T;
-            const int mc = 6 * P + 55;
-            for (int e = lane; e < mc; e += 32) {
-                t.s[(long long)i * t.MCS + e] = R(0.1);   // ddp.cpp:150-151
-                t.y[(long long)i * t.MCS + e] = R(0.01);
+            if (cfg.line_init) {
+                // straight-line initialisation (ddp.cpp:195-247): rest-to-rest quintic between consecutive seeds,
+                // segment time doubled (at most 5 times) until every constraint of the knot is negative
+                R z[19];
+                DDP_UNROLL
+                for (int e = 0; e < 19; e++) z[e] = R(0);
+                R p1[3];
+                DDP_UNROLL
+                for (int a = 0; a < 3; a++) {
+                    z[10 + a] = (i == 0) ? (R)A.x0[(long long)b * 9 + a] : (R)A.seeds[((long long)b * N + i) * 3 + a];
+                    p1[a] = (i == N - 1) ? (R)A.xd[(long long)b * 9 + a] : (R)A.seeds[((long long)b * N + i + 1) * 3 + a];
+                }
+                z[9] = u[9];
+                int vio = 1, cnt = 0;
+                while (vio && cnt <= 4) {
+                    const R Tk = z[9], Tk2 = Tk * Tk, Tk3 = Tk2 * Tk, Tk4 = Tk3 * Tk, Tk5 = Tk4 * Tk;
+                    const R Gi[3] = {R(10.0) / Tk3, R(-15.0) / Tk4, R(6.0) / Tk5};   // first column of G^-1
+                    DDP_UNROLL
+                    for (int a = 0; a < 3; a++) {
+                        const R rhs = p1[a] - z[10 + a];   // only the position rows of xnext - F xcur are nonzero
+                        DDP_UNROLL
+                        for (int c = 0; c < 3; c++) z[c * 3 + a] = Gi[c] * rhs;
+                    }
+                    int all_neg = 1;
+                    visit_rows(t, i, z, [&](int, R c) { if (!(c < R(0))) all_neg = 0; });
+                    if (all_neg) vio = 0;
+                    else { z[9] = R(2) * Tk; cnt++; }
+                }
+                DDP_UNROLL
+                for (int e = 0; e < 10; e++) u[e] = z[e];
+            }
+            DDP_UNROLL
+            for (int e = 0; e < 10; e++) t.xu[(long long)i * 20 + e] = u[e];
+            for (int r = 0; r < t.MCS; r++) {
+                t.s[(long long)r * t.NP + i] = R(0.1);   // ddp.cpp:150-151
+                t.y[(long long)r * t.NP + i] = R(0.01);
             }
         }
     }
     WARP_SYNC();
-    RollOut<R> ro;
-    rollout(t, 0, R(0), R(0), ro);  // initialroll, ddp.cpp:252
-    t.cost = ro.cost; t.costq = ro.costq;
+    initial_roll(t);  // ddp.cpp:252
+    R dummy0 = R(0), dummy1 = R(0);
+    if (cfg.line_init) {  // ddp.cpp:255-269
+        if (!scan_constraints(t, 2, R(0), dummy0, dummy1)) t.infeas = 0;
+    }
     t.mu = t.cost / R(N) / R(6 * t.nplanes[0] + 55);  // ddp.cpp:281 (hazard H3)
     reset_filter(t);
     t.reg = R(0); t.bfailed = 0;  // resetreg
+    if (cfg.line_init) t.reg = R(10);
 
     int rtn = 0, infeas_out = infeas_in, line_failed_out = 1;
     R cost_prev = t.cost;
-    int iter = 0, bp_no_upd_count = 0;
+    int iter = 0, bp_no_upd_count = 0, no_upd_count = 0;
     const int bp_no_upd_count_max = 20;
     int trace_n = 0;
     for (iter = 0; iter < cfg.iter_max; iter++) {
@@ -1123,7 +1287,7 @@ template <class R> DDP_DEVICE_NOINLINE void solve_one(const SolveArgs &A, int st
             reset_filter(t);
             t.reg = R(0); t.bfailed = 0;
         }
-        if (!any_violation(t, R(2.0e-4), false)) {  // ddp.cpp:346-390 (hazard H8)
+        if (!scan_constraints(t, 1, R(2.0e-4), dummy0, dummy1)) {  // ddp.cpp:346-390 (hazard H8)
             if (cfg.zero_init) { infeas_out = 0; rtn = 2; break; }
             if (!cfg.zero_init && !cfg.line_init) {
                 const R dc = t.cost - cost_m2;
@@ -1135,12 +1299,17 @@ template <class R> DDP_DEVICE_NOINLINE void solve_one(const SolveArgs &A, int st
             }
         }
         if (bp_no_upd_count > bp_no_upd_count_max) { rtn = -4; break; }  // ddp.cpp:392-396
+        if (cfg.line_init) {   // ddp.cpp:398-409
+            if (t.stepsize < R(1.0e-6)) no_upd_count++;
+            else no_upd_count = 0;
+            if (no_upd_count > 100) break;
+        }
     }
     if (A.trace && b == 0 && (st == 1 || !A.two_stage) && A.trace_len) {
         FOR_LANES(lane) { if (lane == 0) *A.trace_len = trace_n; }
     }
 
-    // ---- outputs (ddp.cpp:418-437) -----------------------------------------------------------------------
+    // ---- outputs (ddp.cpp:418-437), lane <-> knot ---------------------------------------------------------
     const OutPtrs &O = A.out[A.two_stage ? st : 1];
     const bool carry = (A.two_stage && st == 0);
     FOR_LANES(lane) {
@@ -1157,43 +1326,47 @@ template <class R> DDP_DEVICE_NOINLINE void solve_one(const SolveArgs &A, int st
             }
         }
         if (lane < 9 && O.x_final) O.x_final[(long long)b * 9 + lane] = (double)t.xu[(long long)N * 20 + 10 + lane];
-    }
-    for (int i = 0; i < N; i++) {
-        FOR_LANES(lane) { if (lane < 20) sm[Lay::ZO + lane] = t.xu[(long long)i * 20 + lane]; }
-        WARP_SYNC();
-        const R T = sm[Lay::ZO + 9];
-        Reg<R, 1> jk;
-        FOR_LANES(lane) {
-            jk(lane, 0) = lane < 9 ? quad_share<R>(0, sm + Lay::ZO, lane, T) : R(0);  // finalroll, ddp.cpp:1624-1634
-            if (lane < 18) {
-                // PolyCoeff row = [Ek_inv * x, u[0:9]] (ddp.cpp:814-823); index l*3+a
-                const int l = lane / 3, a = lane % 3;
-                R pc = sm[Lay::ZO + zidx(l, a)];
-                if (l == 2) pc = pc * R(0.5);
-                if (O.poly_coeff) O.poly_coeff[((long long)b * N + i) * 18 + lane] = (double)pc;
-                // BezCoeff = (1/T) * Bezier control points (poly2bezFunc, ddp.cpp:799-812: the inverse of
-                // poly2bez*t2tauMat is the Bezier table with column k scaled by T^k), re-laid [x*6,y*6,z*6]
-                const int j = lane / 3;
-                R accv = R(0), pw = R(1);
+        for (int i = lane; i < N; i += 32) {
+            R z[19], tp[6], m[9], mu9[9];
+            DDP_UNROLL
+            for (int e = 0; e < 19; e++) z[e] = t.xu[(long long)i * 20 + e];
+            const R T = z[9];
+            time_powers(T, tp);
+            rmat<R>(0, tp, m);
+            rmat_times_u(m, z, mu9);
+            if (O.jerk) O.jerk[(long long)b * N + i] = (double)dot9(z, mu9);  // finalroll, ddp.cpp:1624-1634
+            if (O.poly_time) O.poly_time[(long long)b * N + i] = (double)T;
+            if (carry) A.time_tmp[(long long)b * N + i] = (double)T;
+            DDP_UNROLL
+            for (int l = 0; l < 6; l++) {
                 DDP_UNROLL
-                for (int k = 0; k < 6; k++) {
-                    R ck = sm[Lay::ZO + zidx(k, a)];
-                    if (k == 2) ck = ck * R(0.5);
-                    accv += (tabs[j * 6 + k] * pw) * ((R(1) / T) * ck);
-                    pw = pw * T;
+                for (int a = 0; a < 3; a++) {
+                    // PolyCoeff row = [Ek_inv * x, u[0:9]] (ddp.cpp:814-823); index l*3+a
+                    R pc = z[zidx(l, a)];
+                    if (l == 2) pc = pc * R(0.5);
+                    if (O.poly_coeff) O.poly_coeff[((long long)b * N + i) * 18 + l * 3 + a] = (double)pc;
                 }
-                const double bzv = (double)accv;
-                if (O.bez_coeff) O.bez_coeff[((long long)b * N + i) * 18 + a * 6 + j] = bzv;
-                if (carry) A.bez_tmp[((long long)b * N + i) * 18 + a * 6 + j] = bzv;
             }
-            if (lane == 9) {
-                if (O.poly_time) O.poly_time[(long long)b * N + i] = (double)T;
-                if (carry) A.time_tmp[(long long)b * N + i] = (double)T;
+            // BezCoeff = (1/T) * Bezier control points (poly2bezFunc, ddp.cpp:799-812: the inverse of
+            // poly2bez*t2tauMat is the Bezier table with column k scaled by T^k), re-laid [x*6,y*6,z*6]
+            DDP_UNROLL
+            for (int j = 0; j < 6; j++) {
+                DDP_UNROLL
+                for (int a = 0; a < 3; a++) {
+                    R accv = R(0), pw = R(1);
+                    DDP_UNROLL
+                    for (int k = 0; k < 6; k++) {
+                        R ck = z[zidx(k, a)];
+                        if (k == 2) ck = ck * R(0.5);
+                        accv += (tabs[j * 6 + k] * pw) * ((R(1) / T) * ck);
+                        pw = pw * T;
+                    }
+                    const double bzv = (double)accv;
+                    if (O.bez_coeff) O.bez_coeff[((long long)b * N + i) * 18 + a * 6 + j] = bzv;
+                    if (carry) A.bez_tmp[((long long)b * N + i) * 18 + a * 6 + j] = bzv;
+                }
             }
         }
-        const R jsum = warp_sum(jk, 0, lane_);
-        FOR_LANES(lane) { if (lane == 0 && O.jerk) O.jerk[(long long)b * N + i] = (double)jsum; }
-        WARP_SYNC();
     }
     WARP_SYNC();  // stage-0 outputs (bez_tmp/time_tmp/rtn) are read by other lanes of this warp in stage 1
 }

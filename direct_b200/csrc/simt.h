@@ -98,6 +98,18 @@ template <class T, int N> DDP_DEVICE T warp_bcast(const Reg<T, N> &r, int i, int
     return r.v[src][i];
 #endif
 }
+// Minimum over the warp of element i (int).
+template <int N> DDP_DEVICE int warp_min_int(const Reg<int, N> &r, int i, int lane_) {
+#if DDP_GPU
+    (void)lane_;
+    return __reduce_min_sync(0xffffffffu, r.v[i]);
+#else
+    (void)lane_;
+    int x = r.v[0][i];
+    for (int l = 1; l < 32; l++) if (r.v[l][i] < x) x = r.v[l][i];
+    return x;
+#endif
+}
 template <int N> DDP_DEVICE bool warp_any(const Reg<int, N> &r, int i, int lane_) {
 #if DDP_GPU
     (void)lane_;
@@ -113,6 +125,15 @@ DDP_DEVICE double rlog(double x) { return log(x); }
 DDP_DEVICE float rlog(float x) { return logf(x); }
 DDP_DEVICE double rsqrt_(double x) { return sqrt(x); }
 DDP_DEVICE float rsqrt_(float x) { return sqrtf(x); }
+// 1/sqrt(x): the Cholesky pivot scale.  GPU: rsqrt() (MUFU.RSQ64H + Newton, ~1 ulp), shorter dependent chain than
+// sqrt followed by a division.
+#if DDP_GPU
+DDP_DEVICE double rrsqrt(double x) { return rsqrt(x); }
+DDP_DEVICE float rrsqrt(float x) { return rsqrtf(x); }
+#else
+DDP_DEVICE double rrsqrt(double x) { return 1.0 / sqrt(x); }
+DDP_DEVICE float rrsqrt(float x) { return 1.0f / sqrtf(x); }
+#endif
 DDP_DEVICE double rabs(double x) { return fabs(x); }
 DDP_DEVICE float rabs(float x) { return fabsf(x); }
 DDP_DEVICE double rpow(double x, double y) { return pow(x, y); }

@@ -35,6 +35,16 @@ def test_emulated_kernel_matches_reference_fixtures(emu, name):
     assert rel_err(r1.jerk.sum(1), d["s1_jerk_sum"]) < TOL64
 
 
+def test_emulated_kernel_line_init_fixture(emu):
+    """line_init_flag = true (ddp_optimizer.cpp:195-247, :255-269, :381-388) against the reference's own output."""
+    pb, d = load_golden("box_n6_lineinit")
+    r = emu.solve_batch(pb, infeas=1, zero_init=0, line_init=1, w_snap=1.0, w_terminal=100.0, w_time=50.0, iter_max=60)
+    assert (r.rtn == d["s1_rtn"]).all() and (r.iters == d["s1_iters"]).all()
+    assert (r.line_failed_out == d["s1_line_failed_out"]).all()
+    for f in OUT_FIELDS:
+        assert rel_err(getattr(r, f), d["s1_" + f]) < TOL64, f
+
+
 def test_emulated_two_stage_matches_oracle_ragged_planes(emu, oracle):
     pb = make_batch(6, 17, "poly", first=321)
     a0, a1 = oracle.two_stage_batch(pb, nthreads=2)
