@@ -69,11 +69,14 @@ def load_library(build_if_missing: bool = True):
     """dlopen libdirect_ddp_b200.so (building it with nvcc when absent or stale and nvcc is available)."""
     global _lib
     if _lib is None:
-        if build_if_missing and _build.is_stale():
-            _build.build()
-        if not os.path.exists(_build.LIB):
-            raise RuntimeError("libdirect_ddp_b200.so is missing: run `python -m direct_b200.build` (needs nvcc)")
-        lib = C.CDLL(_build.LIB)
+        path = os.environ.get("DIRECT_DDP_LIB")   # tuning experiments: another build of the same sources
+        if not path:
+            path = _build.LIB
+            if build_if_missing and _build.is_stale():
+                _build.build()
+        if not os.path.exists(path):
+            raise RuntimeError(f"{path} is missing: run `python -m direct_b200.build` (needs nvcc)")
+        lib = C.CDLL(path)
         lib.direct_ddp_last_error.restype = C.c_char_p
         lib.direct_ddp_last_error.argtypes = [C.c_void_p]
         lib.direct_ddp_create.argtypes = [C.POINTER(Opts), C.POINTER(C.c_void_p)]

@@ -80,7 +80,7 @@ def test_gpu_full_size_properties(solver):
     _, g2 = solver.solve_two_stage(pb, want_stage0=False)
     assert np.array_equal(g.poly_coeff, g2.poly_coeff) and np.array_equal(g.rtn, g2.rtn)  # run-to-run identical
     assert np.isin(g.rtn, (0, 1)).all() and (g.rtn == 1).mean() > 0.95
-    assert (g.poly_time > 0.3).all()
+    assert (g.poly_time > 0.3 - 2.0e-4).all()                          # time row -T + 0.3 - 2e-4 < 0 (ddp_optimizer.cpp:1279-1283)
     cp = g.bez_coeff.reshape(B, N, 3, 6) * g.poly_time[:, :, None, None]
     val = np.einsum("bnpa,bnaj->bnpj", pb.planes[..., :3], cp) + pb.planes[..., 3:4]
     assert (val < 1e-9).all()                                         # every control point inside its polytope
