@@ -142,8 +142,10 @@ struct Lay {
         ZN = 530,   // rollout broadcast: new [u(10); x(9)] (20)
         DX = 550,   // rollout broadcast: xnew - xold (9)
         FL = 560,   // filter decision (2)
-        MSC = 564,  // per-lane 3x3 blocks M_g of the linearisation: MSC[e*32+lane], e < 63
-        TOTAL = 564 + 63 * 32
+        FTN = 564,  // riccati: fT (9) and segment time (1) of the knot about to be processed, staged one knot ahead
+        RI = 574,   // riccati: 1/sqrt(pivot) of the ten Cholesky pivots
+        MSC = 584,  // per-lane 3x3 blocks M_g of the linearisation: MSC[e*32+lane], e < 63
+        TOTAL = 584 + 63 * 32
     };
 };
 DDP_HD int smem_elems_per_warp(int /*pm*/) { return Lay::TOTAL; }
@@ -300,6 +302,28 @@ template <class R> DDP_DEVICE R stage_cost(const Traj<R> &t, const R *tp, const 
     return R(0.5) * t.w_snap * dot9(u, mu9) + tterm;
 }
 
+// Hot-loop view of the trajectory: plain by-value locals.  Traj<> is passed by reference to the out-of-line
+// phases, so every t.field read inside a loop is a local-memory load that has to be repeated after each
+// store (profiles/r1b); the phases copy what they need into a RowCtx once.
+template <class R> struct RowCtx {
+    const R *DDP_RESTRICT s;
+    const R *DDP_RESTRICT y;
+    R *DDP_RESTRICT sn;
+    R *DDP_RESTRICT yn;
+    const R *tab;
+    const double *planes;
+    const int32_t *nplanes;
+    long long NP;
+    int PM, infeas;
+    R mu, margin, max_vel, max_acc;
+};
+template <class R> DDP_DEVICE RowCtx<R> row_ctx(const Traj<R> &t) {
+    RowCtx<R> c;
+    c.s = t.s; c.y = t.y; c.sn = t.sn; c.yn = t.yn; c.tab = t.tab; c.planes = t.planes; c.nplanes = t.nplanes;
+    c.NP = t.NP; c.PM = t.PM; c.infeas = t.infeas; c.mu = t.mu; c.margin = t.margin; c.max_vel = t.max_vel; c.max_acc = t.max_acc;
+    return c;
+}
+
 // Plane k of knot `pl` (pointer to that knot's P_max x 4 block).
 template <class R> DDP_DEVICE void load_plane(const double *pl, int k, R *n) {
     n[0] = (R)pl[4 * k]; n[1] = (R)pl[4 * k + 1]; n[2] = (R)pl[4 * k + 2]; n[3] = (R)pl[4 * k + 3];
@@ -307,11 +331,12 @@ template <class R> DDP_DEVICE void load_plane(const double *pl, int k, R *n) {
 
 // Visit every constraint row of knot i at the point z (constraint VALUES only; computecminvo,
 // ddp.cpp:1132-1285): f(row slot, c).
-template <class R, class F> DDP_DEVICE void visit_rows(const Traj<R> &t, int i, const R *z, F &&f) {
+template <class R, class F> DDP_DEVICE void visit_rows(const RowCtx<R> &t, int i, const R *z, F &&f) {
     R tp[6];
     time_powers(z[9], tp);
     const int P = t.nplanes[i];
     const double *pl = t.planes + (long long)i * t.PM * 4;
+    DDP_NOUNROLL
     for (int g = 0; g < 6; g++) {
         R b[6], cp[3];
         basis_row<R, 0, 0>(t.tab, g, tp, b);
@@ -324,6 +349,7 @@ template <class R, class F> DDP_DEVICE void visit_rows(const Traj<R> &t, int i, 
         }
     }
     const int FB = 6 * t.PM;
+    DDP_NOUNROLL
     for (int g = 6; g < 11; g++) {
         R b[6];
         basis_row<R, 1, 0>(t.tab, g, tp, b);
@@ -334,6 +360,7 @@ template <class R, class F> DDP_DEVICE void visit_rows(const Traj<R> &t, int i, 
             f(FB + 15 + 3 * (g - 6) + a, -v - t.max_vel - t.margin);
         }
     }
+    DDP_NOUNROLL
     for (int g = 11; g < 15; g++) {
         R b[6];
         basis_row<R, 2, 0>(t.tab, g, tp, b);
@@ -354,11 +381,11 @@ template <class R>
 DDP_DEVICE void row_weights(int infeas, R mu, R sgn, R c, R sv, R yv, R &Ds, R &gw, R &emu, R &ecy) {
     R D, r, tv2;
     if (infeas) {
-        const R yinv = R(1) / yv;
+        const R yinv = rrcp(yv);
         r = sv * yv - mu; D = sv * yinv; tv2 = yinv * (sv * (c + yv) - r);
         ecy = amax(ecy, rabs(c + yv));
     } else {
-        const R cinv = R(1) / c;
+        const R cinv = rrcp(c);
         r = sv * c + mu; D = sv * cinv; tv2 = cinv * r;
     }
     emu = amax(emu, rabs(r));
@@ -366,22 +393,26 @@ DDP_DEVICE void row_weights(int infeas, R mu, R sgn, R c, R sv, R yv, R &Ds, R &
 }
 
 // One velocity / acceleration group of the linearisation: six rows +-(beta_g . coefficients of axis a) - limit.
+// The six slack (and dual-slack) values are loaded before any of them is used.
 template <class R, int SHIFT>
-DDP_DEVICE void lin_fixed_group(const Traj<R> &t, int g, int i, int plus0, int minus0, R lim, const R *tp, const R *z,
+DDP_DEVICE void lin_fixed_group(const RowCtx<R> &t, int g, int i, int plus0, int minus0, R lim, const R *tp, const R *z,
                                 R sgn, R *accT, R *accG, R &tt, R &gt, R &emu, R &ecy, R *msc) {
     R b[6], bd[6];
     basis_row<R, SHIFT, 0>(t.tab, g, tp, b);
     basis_row<R, SHIFT, 1>(t.tab, g, tp, bd);
-    R wv[3], gv[3];
+    R wv[3], gv[3], sp[3], sm_[3], yp[3], ym[3];
+    DDP_UNROLL
+    for (int a = 0; a < 3; a++) {
+        sp[a] = t.s[(long long)(plus0 + a) * t.NP + i]; sm_[a] = t.s[(long long)(minus0 + a) * t.NP + i];
+        yp[a] = R(1); ym[a] = R(1);
+        if (t.infeas) { yp[a] = t.y[(long long)(plus0 + a) * t.NP + i]; ym[a] = t.y[(long long)(minus0 + a) * t.NP + i]; }
+    }
     DDP_UNROLL
     for (int a = 0; a < 3; a++) {
         const R val = dot_axis<R, SHIFT>(b, z, a), tc = dot_axis<R, SHIFT>(bd, z, a);
-        const R sp = t.s[(long long)(plus0 + a) * t.NP + i], sn = t.s[(long long)(minus0 + a) * t.NP + i];
-        R yp = R(1), yn = R(1);
-        if (t.infeas) { yp = t.y[(long long)(plus0 + a) * t.NP + i]; yn = t.y[(long long)(minus0 + a) * t.NP + i]; }
         R D1, g1, D2, g2;
-        row_weights(t.infeas, t.mu, sgn, val - lim - t.margin, sp, yp, D1, g1, emu, ecy);
-        row_weights(t.infeas, t.mu, sgn, -val - lim - t.margin, sn, yn, D2, g2, emu, ecy);
+        row_weights(t.infeas, t.mu, sgn, val - lim - t.margin, sp[a], yp[a], D1, g1, emu, ecy);
+        row_weights(t.infeas, t.mu, sgn, -val - lim - t.margin, sm_[a], ym[a], D2, g2, emu, ecy);
         // the "-" row has Jacobian -J+, so D adds and the gradient weight subtracts
         const R Dsum = D1 + D2, gdiff = g1 - g2;
         msc[a * 32] = Dsum;
@@ -416,26 +447,34 @@ DDP_DEVICE void lin_diag_group(const R *tab, int g, const R *tp, R m0, R m1, R m
 //   Hc = [ H  g ; g^T . ]  (20 x 20, z order [u(9), T, x(9), gradient])  to t.H and  fT = dx+/dT  to t.aux.
 // Returns per-lane maxima of |r| and |c+y| in errs (ddp.cpp:636-637).
 // =============================================================================================
-template <class R> DDP_DEVICE_NOINLINE void linearize(Traj<R> &t, Reg<R, 2> &errs) {
-    const int lane_ = t.lane_;
+template <class R> DDP_DEVICE_NOINLINE void linearize(Traj<R> &tt_, Reg<R, 2> &errs) {
+    const int lane_ = tt_.lane_;
+    const RowCtx<R> t = row_ctx(tt_);
+    const int N = tt_.N, time_power = tt_.time_power;
+    const R w_snap = tt_.w_snap, w_time = tt_.w_time;
+    const R *DDP_RESTRICT xu = tt_.xu;
+    R *DDP_RESTRICT Hout = tt_.H;
+    R *DDP_RESTRICT auxout = tt_.aux;
+    R *smw = tt_.sm;
     const R sgn = t.infeas ? R(1) : R(-1);
     FOR_LANES(lane) { errs(lane, 0) = R(0); errs(lane, 1) = R(0); }
-    for (int base = 0; base < t.N; base += 32) {
+    for (int base = 0; base < N; base += 32) {
         FOR_LANES(lane) {
             const int i = base + lane;
-            if (i < t.N) {
+            if (i < N) {
                 R emu = errs(lane, 0), ecy = errs(lane, 1);
                 R z[19], tp[6];
                 DDP_UNROLL
-                for (int e = 0; e < 19; e++) z[e] = t.xu[(long long)i * 20 + e];
+                for (int e = 0; e < 19; e++) z[e] = xu[(long long)i * 20 + e];
                 time_powers(z[9], tp);
                 const int P = t.nplanes[i];
                 const double *pl = t.planes + (long long)i * t.PM * 4;
-                R *msc = t.sm + Lay::MSC + lane;
+                R *msc = smw + Lay::MSC + lane;
                 R accT[18], accG[18], tt = R(0), gt = R(0);
                 DDP_UNROLL
                 for (int e = 0; e < 18; e++) { accT[e] = R(0); accG[e] = R(0); }
                 // ---- pass 1: rows -> weights -> per-group blocks ------------------------------------------
+                DDP_NOUNROLL
                 for (int g = 0; g < 6; g++) {   // position control points: one row per plane of the polytope
                     R b[6], bd[6], cp[3], cd[3];
                     basis_row<R, 0, 0>(t.tab, g, tp, b);
@@ -443,20 +482,33 @@ template <class R> DDP_DEVICE_NOINLINE void linearize(Traj<R> &t, Reg<R, 2> &err
                     DDP_UNROLL
                     for (int a = 0; a < 3; a++) { cp[a] = dot_axis<R, 0>(b, z, a); cd[a] = dot_axis<R, 0>(bd, z, a); }
                     R M[6] = {R(0), R(0), R(0), R(0), R(0), R(0)}, wv[3] = {R(0), R(0), R(0)}, gv[3] = {R(0), R(0), R(0)};
-                    for (int k = 0; k < P; k++) {
-                        R n[4];
-                        load_plane(pl, k, n);
-                        const R c = ((n[0] * cp[0] + n[1] * cp[1]) + n[2] * cp[2]) + n[3] - t.margin;
-                        const R tc = (n[0] * cd[0] + n[1] * cd[1]) + n[2] * cd[2];
-                        const long long ro = (long long)(g * t.PM + k) * t.NP + i;
-                        R Ds, gw;
-                        row_weights(t.infeas, t.mu, sgn, c, t.s[ro], t.infeas ? t.y[ro] : R(1), Ds, gw, emu, ecy);
-                        M[0] += Ds * (n[0] * n[0]); M[1] += Ds * (n[0] * n[1]); M[2] += Ds * (n[0] * n[2]);
-                        M[3] += Ds * (n[1] * n[1]); M[4] += Ds * (n[1] * n[2]); M[5] += Ds * (n[2] * n[2]);
-                        const R dt = Ds * tc, gtc = gw * tc;
-                        wv[0] += dt * n[0]; wv[1] += dt * n[1]; wv[2] += dt * n[2];
-                        gv[0] += gw * n[0]; gv[1] += gw * n[1]; gv[2] += gw * n[2];
-                        tt += dt * tc; gt += gtc;
+                    DDP_NOUNROLL
+                    for (int k0 = 0; k0 < P; k0 += 3) {   // three rows at a time: their loads are issued together
+                        R sv[3], yv[3], nn[3][4];
+                        DDP_UNROLL
+                        for (int j = 0; j < 3; j++) {
+                            const int k = k0 + j < P ? k0 + j : P - 1;
+                            const long long ro = (long long)(g * t.PM + k) * t.NP + i;
+                            sv[j] = t.s[ro];
+                            yv[j] = t.infeas ? t.y[ro] : R(1);
+                            load_plane(pl, k, nn[j]);
+                        }
+                        DDP_UNROLL
+                        for (int j = 0; j < 3; j++) {
+                            if (k0 + j < P) {
+                                const R *n = nn[j];
+                                const R c = ((n[0] * cp[0] + n[1] * cp[1]) + n[2] * cp[2]) + n[3] - t.margin;
+                                const R tc = (n[0] * cd[0] + n[1] * cd[1]) + n[2] * cd[2];
+                                R Ds, gw;
+                                row_weights(t.infeas, t.mu, sgn, c, sv[j], yv[j], Ds, gw, emu, ecy);
+                                M[0] += Ds * (n[0] * n[0]); M[1] += Ds * (n[0] * n[1]); M[2] += Ds * (n[0] * n[2]);
+                                M[3] += Ds * (n[1] * n[1]); M[4] += Ds * (n[1] * n[2]); M[5] += Ds * (n[2] * n[2]);
+                                const R dt = Ds * tc, gtc = gw * tc;
+                                wv[0] += dt * n[0]; wv[1] += dt * n[1]; wv[2] += dt * n[2];
+                                gv[0] += gw * n[0]; gv[1] += gw * n[1]; gv[2] += gw * n[2];
+                                tt += dt * tc; gt += gtc;
+                            }
+                        }
                     }
                     DDP_UNROLL
                     for (int e = 0; e < 6; e++) msc[(g * 6 + e) * 32] = M[e];
@@ -467,9 +519,11 @@ template <class R> DDP_DEVICE_NOINLINE void linearize(Traj<R> &t, Reg<R, 2> &err
                     }
                 }
                 const int FB = 6 * t.PM;
+                DDP_NOUNROLL
                 for (int g = 6; g < 11; g++)
                     lin_fixed_group<R, 1>(t, g, i, FB + 3 * (g - 6), FB + 15 + 3 * (g - 6), t.max_vel, tp, z, sgn, accT, accG,
                                           tt, gt, emu, ecy, msc + (36 + 3 * (g - 6)) * 32);
+                DDP_NOUNROLL
                 for (int g = 11; g < 15; g++)
                     lin_fixed_group<R, 2>(t, g, i, FB + 30 + 3 * (g - 11), FB + 42 + 3 * (g - 11), t.max_acc, tp, z, sgn, accT,
                                           accG, tt, gt, emu, ecy, msc + (36 + 3 * (g - 6)) * 32);
@@ -491,17 +545,17 @@ template <class R> DDP_DEVICE_NOINLINE void linearize(Traj<R> &t, Reg<R, 2> &err
                 }
                 const R uRpu = dot9(z, Rpu), uRppu = dot9(z, Rppu);
                 R quT, quuTT;
-                if (t.time_power == 2) { quT = t.w_time * z[9] + R(0.5) * t.w_snap * uRpu; quuTT = t.w_time + R(0.5) * t.w_snap * uRppu; }
-                else { quT = R(0.5) * t.w_time + R(0.5) * t.w_snap * uRpu; quuTT = R(0.5) * t.w_snap * uRppu; }
+                if (time_power == 2) { quT = w_time * z[9] + R(0.5) * w_snap * uRpu; quuTT = w_time + R(0.5) * w_snap * uRppu; }
+                else { quT = R(0.5) * w_time + R(0.5) * w_snap * uRpu; quuTT = R(0.5) * w_snap * uRppu; }
                 // ---- write row/column T and the gradient -------------------------------------------------------
-                R *Hi = t.H + (long long)i * 400;
+                R *Hi = Hout + (long long)i * 400;
                 DDP_UNROLL
                 for (int l = 0; l < 6; l++) {
                     DDP_UNROLL
                     for (int a = 0; a < 3; a++) {
                         const int r = zidx(l, a);
                         R hT = accT[l * 3 + a], gr = accG[l * 3 + a];
-                        if (l >= 3) { hT += t.w_snap * Rpu[r]; gr += t.w_snap * Ru[r]; }
+                        if (l >= 3) { hT += w_snap * Rpu[r]; gr += w_snap * Ru[r]; }
                         Hi[r * 20 + 9] = hT; Hi[9 * 20 + r] = hT;
                         Hi[r * 20 + 19] = gr; Hi[19 * 20 + r] = gr;
                     }
@@ -512,17 +566,20 @@ template <class R> DDP_DEVICE_NOINLINE void linearize(Traj<R> &t, Reg<R, 2> &err
                 R fT[9];
                 ft_vector(tp, z, fT);
                 DDP_UNROLL
-                for (int q = 0; q < 9; q++) t.aux[(long long)i * 12 + q] = fT[q];
+                for (int q = 0; q < 9; q++) auxout[(long long)i * 12 + q] = fT[q];
                 // ---- pass 2: H[(l,a),(l',a')] = sum_g beta_g[l] beta_g[l'] M_g[a][a'] ------------------------------
                 {   // same-axis blocks: all 15 groups, plus the stage cost w R (x) I on the u coefficients
                     R h0[21], h1[21], h2[21];
                     DDP_UNROLL
                     for (int e = 0; e < 21; e++) { h0[e] = R(0); h1[e] = R(0); h2[e] = R(0); }
+                    DDP_NOUNROLL
                     for (int g = 0; g < 6; g++)
                         lin_diag_group<R, 0>(t.tab, g, tp, msc[(g * 6 + 0) * 32], msc[(g * 6 + 3) * 32], msc[(g * 6 + 5) * 32], h0, h1, h2);
+                    DDP_NOUNROLL
                     for (int g = 6; g < 11; g++)
                         lin_diag_group<R, 1>(t.tab, g, tp, msc[(36 + 3 * (g - 6)) * 32], msc[(37 + 3 * (g - 6)) * 32],
                                              msc[(38 + 3 * (g - 6)) * 32], h0, h1, h2);
+                    DDP_NOUNROLL
                     for (int g = 11; g < 15; g++)
                         lin_diag_group<R, 2>(t.tab, g, tp, msc[(36 + 3 * (g - 6)) * 32], msc[(37 + 3 * (g - 6)) * 32],
                                              msc[(38 + 3 * (g - 6)) * 32], h0, h1, h2);
@@ -532,7 +589,7 @@ template <class R> DDP_DEVICE_NOINLINE void linearize(Traj<R> &t, Reg<R, 2> &err
                         for (int la = 0; la <= lb; la++) {
                             const int e = pidx(la, lb);
                             R v0 = h0[e], v1 = h1[e], v2 = h2[e];
-                            if (la >= 3) { const R q = t.w_snap * rm[(la - 3) * 3 + (lb - 3)]; v0 += q; v1 += q; v2 += q; }
+                            if (la >= 3) { const R q = w_snap * rm[(la - 3) * 3 + (lb - 3)]; v0 += q; v1 += q; v2 += q; }
                             const int r = zidx(la, 0), c = zidx(lb, 0);
                             Hi[r * 20 + c] = v0; Hi[c * 20 + r] = v0;
                             Hi[(r + 1) * 20 + c + 1] = v1; Hi[(c + 1) * 20 + r + 1] = v1;
@@ -544,6 +601,7 @@ template <class R> DDP_DEVICE_NOINLINE void linearize(Traj<R> &t, Reg<R, 2> &err
                     R h0[21], h1[21], h2[21];
                     DDP_UNROLL
                     for (int e = 0; e < 21; e++) { h0[e] = R(0); h1[e] = R(0); h2[e] = R(0); }
+                    DDP_NOUNROLL
                     for (int g = 0; g < 6; g++)
                         lin_diag_group<R, 0>(t.tab, g, tp, msc[(g * 6 + 1) * 32], msc[(g * 6 + 2) * 32], msc[(g * 6 + 4) * 32], h0, h1, h2);
                     DDP_UNROLL
@@ -579,35 +637,52 @@ template <class R> DDP_DEVICE_NOINLINE bool riccati(Traj<R> &t, R regadd, Reg<R,
     const int lane_ = t.lane_;
     R *sm = t.sm;
     const int N = t.N;
+    const R *DDP_RESTRICT Hin = t.H;
+    const R *DDP_RESTRICT xu = t.xu;
+    const R *DDP_RESTRICT aux = t.aux;
+    R *DDP_RESTRICT Kout = t.K;
+    const R w_terminal = t.w_terminal;
     // terminal value function, ddp.cpp:1318-1323: Vx = P (x_N - x_d), Vxx = P = w_terminal I
     FOR_LANES(lane) {
         errq(lane, 0) = R(0);
         for (int e = lane; e < 90; e += 32) {
-            const R v = (e / 10 == e % 10 && e % 10 < 9) ? t.w_terminal : R(0);
+            const R v = (e / 10 == e % 10 && e % 10 < 9) ? w_terminal : R(0);
             sm[Lay::S1 + e] = v; sm[Lay::S2 + e] = v;
         }
-        if (lane < 9) sm[Lay::VX + lane] = t.w_terminal * (t.xu[(long long)N * 20 + 10 + lane] - sm[Lay::XD + lane]);
+        if (lane < 9) {
+            sm[Lay::VX + lane] = w_terminal * (xu[(long long)N * 20 + 10 + lane] - sm[Lay::XD + lane]);
+            sm[Lay::FTN + lane] = aux[(long long)(N - 1) * 12 + lane];
+        }
+        if (lane == 9) sm[Lay::FTN + 9] = xu[(long long)(N - 1) * 20 + 9];
     }
     WARP_SYNC();
     Reg<R, 20> col, nxt;
+    Reg<R, 1> pre;   // next knot's fT (lanes 0-8) / segment time (lane 9), loaded one knot ahead
     FOR_LANES(lane) {
         DDP_UNROLL
-        for (int r = 0; r < 20; r++) nxt(lane, r) = lane < 20 ? t.H[(long long)(N - 1) * 400 + lane * 20 + r] : R(0);
+        for (int r = 0; r < 20; r++) nxt(lane, r) = lane < 20 ? Hin[(long long)(N - 1) * 400 + lane * 20 + r] : R(0);
     }
+    long long knots = 0;
+    bool ok = true;
     for (int i = N - 1; i >= 0; i--) {
-        t.n_bwd_knots++;
-        // uniform per-knot data: segment time, F/G, fT
+        knots++;
+        // uniform per-knot data: segment time, F/G, fT (staged in shared memory by the previous iteration)
         R tp[6], fg[18], fT[9];
-        time_powers(t.xu[(long long)i * 20 + 9], tp);
+        time_powers(sm[Lay::FTN + 9], tp);
         fg_matrix(tp, fg);
         DDP_UNROLL
-        for (int q = 0; q < 9; q++) fT[q] = t.aux[(long long)i * 12 + q];
+        for (int q = 0; q < 9; q++) fT[q] = sm[Lay::FTN + q];
         FOR_LANES(lane) {
             DDP_UNROLL
             for (int r = 0; r < 20; r++) col(lane, r) = nxt(lane, r);
-            if (i > 0 && lane < 20) {   // prefetch the next knot's column while this one is eliminated
-                DDP_UNROLL
-                for (int r = 0; r < 20; r++) nxt(lane, r) = t.H[(long long)(i - 1) * 400 + lane * 20 + r];
+            pre(lane, 0) = R(0);
+            if (i > 0) {   // prefetch the next knot's column, fT and time while this one is eliminated
+                if (lane < 20) {
+                    DDP_UNROLL
+                    for (int r = 0; r < 20; r++) nxt(lane, r) = Hin[(long long)(i - 1) * 400 + lane * 20 + r];
+                }
+                if (lane < 9) pre(lane, 0) = aux[(long long)(i - 1) * 12 + lane];
+                else if (lane == 9) pre(lane, 0) = xu[(long long)(i - 1) * 20 + 9];
             }
             if (lane < 20 && lane != 9) {
                 R tj[9];
@@ -666,50 +741,51 @@ template <class R> DDP_DEVICE_NOINLINE bool riccati(Traj<R> &t, R regadd, Reg<R,
             }
         }
         // ---- ten Cholesky pivots over the u block -----------------------------------------------------------
-        Reg<R, 10> mult;  // lane c keeps row p of L^-1 [H_u: | g_u] restricted to its column
-        R rinv[10];
+        // One rolled loop: after every pivot each lane shifts its column up by one row, so the pivot row is
+        // always element 0 and the loop body has static register indices (ten unrolled copies were 600 SASS
+        // instructions of the v2 kernel's instruction-cache footprint).  Row p + r of the matrix sits in
+        // element r; elements that would belong to rows >= 20 hold don't-care values that are never read.
         R d = warp_bcast(col, 0, 0, lane_) + regadd;
-        bool fail = false;
-        DDP_UNROLL
+        DDP_NOUNROLL
         for (int p = 0; p < 10; p++) {
-            if (d <= R(0)) { fail = true; break; }
+            if (d <= R(0)) { ok = false; break; }
             const R ri = rrsqrt(d);
-            rinv[p] = ri;
-            Reg<R, 1> ahead;
+            Reg<R, 1> ahead, mreg;
             FOR_LANES(lane) {
-                const R m = (lane == p) ? d * ri : col(lane, p) * ri;
-                mult(lane, p) = m;
-                if (lane < 20) sm[Lay::MB + p * 20 + lane] = m;
-                ahead(lane, 0) = p < 9 ? col(lane, p + 1) - m * m : R(0);   // next pivot's diagonal, sent ahead of the update
+                const R m = (lane == p) ? d * ri : col(lane, 0) * ri;
+                mreg(lane, 0) = m;
+                if (lane < 20) sm[Lay::MB + p * 20 + lane] = m;   // MB[p*20+r] = L[r][p]
+                if (lane == 0) sm[Lay::RI + p] = ri;
+                ahead(lane, 0) = col(lane, 1) - m * m;   // next pivot's diagonal, sent ahead of the update
             }
-            const R dn = p < 9 ? warp_bcast(ahead, 0, p + 1, lane_) + regadd : R(0);
+            const R dn = warp_bcast(ahead, 0, p + 1, lane_) + regadd;
             WARP_SYNC();
             FOR_LANES(lane) {
-                if (lane > p && lane < 20) {
-                    const R m = mult(lane, p);
-                    DDP_UNROLL
-                    for (int r = p + 1; r < 20; r++) col(lane, r) -= sm[Lay::MB + p * 20 + r] * m;
-                }
+                const R m = mreg(lane, 0);
+                const R *Lp = sm + Lay::MB + p * 20 + p;
+                DDP_UNROLL
+                for (int r = 1; r < 20; r++) col(lane, r - 1) = col(lane, r) - Lp[r] * m;
             }
             d = dn;
         }
-        if (fail) return false;
+        if (!ok) break;
+        // rows 10..19 of the matrix (V_xx block and gradient) now sit in elements 0..9 of lanes 10..19
         // ---- gains [ku | Ku] = -(L L^T)^-1 [Qu | Qux] ----------------------------------------------------------
         Reg<R, 10> kx;
         FOR_LANES(lane) {
             if (lane >= 10 && lane < 20) {
                 DDP_UNROLL
                 for (int p = 9; p >= 0; p--) {
-                    R v = mult(lane, p);
+                    R v = sm[Lay::MB + p * 20 + lane];
                     DDP_UNROLL
                     for (int q = p + 1; q < 10; q++) v += sm[Lay::MB + p * 20 + q] * kx(lane, q);
-                    kx(lane, p) = -(v * rinv[p]);
+                    kx(lane, p) = -(v * sm[Lay::RI + p]);
                 }
                 const int qc = lane == 19 ? 0 : lane - 9;
                 DDP_UNROLL
                 for (int p = 0; p < 10; p++) {
                     sm[Lay::KC + p * 10 + qc] = kx(lane, p);
-                    t.K[(long long)i * 100 + p * 10 + qc] = kx(lane, p);
+                    Kout[(long long)i * 100 + p * 10 + qc] = kx(lane, p);
                 }
             }
         }
@@ -721,16 +797,16 @@ template <class R> DDP_DEVICE_NOINLINE bool riccati(Traj<R> &t, R regadd, Reg<R,
             FOR_LANES(lane) {
                 if (lane >= 10 && lane < 19) {
                     DDP_UNROLL
-                    for (int r = 10; r < 19; r++) {
+                    for (int r = 0; r < 9; r++) {
                         R acc = R(0);
                         DDP_UNROLL
-                        for (int p = 0; p < 10; p++) acc += sm[Lay::KC + p * 10 + (r - 9)] * kx(lane, p);
+                        for (int p = 0; p < 10; p++) acc += sm[Lay::KC + p * 10 + (r + 1)] * kx(lane, p);
                         col(lane, r) -= regadd * acc;
                     }
                     R acc = R(0);
                     DDP_UNROLL
                     for (int p = 0; p < 10; p++) acc += sm[Lay::KC + p * 10] * kx(lane, p);
-                    col(lane, 19) -= regadd * acc;
+                    col(lane, 9) -= regadd * acc;
                 }
             }
         }
@@ -738,13 +814,15 @@ template <class R> DDP_DEVICE_NOINLINE bool riccati(Traj<R> &t, R regadd, Reg<R,
             if (lane >= 10 && lane < 19) {
                 const int b = lane - 10;
                 DDP_UNROLL
-                for (int a = 0; a < 9; a++) { sm[Lay::S1 + a * 10 + b] = col(lane, 10 + a); sm[Lay::S2 + b * 10 + a] = col(lane, 10 + a); }
-                sm[Lay::VX + b] = col(lane, 19);
+                for (int a = 0; a < 9; a++) { sm[Lay::S1 + a * 10 + b] = col(lane, a); sm[Lay::S2 + b * 10 + a] = col(lane, a); }
+                sm[Lay::VX + b] = col(lane, 9);
             }
+            if (lane < 10) sm[Lay::FTN + lane] = pre(lane, 0);
         }
         WARP_SYNC();
     }
-    return true;
+    t.n_bwd_knots += knots;
+    return ok;
 }
 
 // ddp.cpp:440-644.
@@ -799,11 +877,12 @@ template <class R> struct TrialAcc {
 
 // One constraint row of a line-search trial (ddp.cpp:680-703): slack/dual step from the gains that are
 // recomputed here (ks, Ks dx, ky, Ky dx; ddp.cpp:568-572 / :611-612), fraction-to-boundary test, barrier terms.
+// sv, yv are the row's slack / dual slack, loaded by the caller ahead of use.
 template <class R>
-DDP_DEVICE void trial_row(const Traj<R> &t, long long ro, R cold, R cnew, R jv1, R jv2, R alpha, R tau, TrialAcc<R> &A) {
-    const R sv = t.s[ro];
+DDP_DEVICE void trial_row(const RowCtx<R> &t, long long ro, R sv, R yv, R cold, R cnew, R jv1, R jv2, R alpha, R tau,
+                          TrialAcc<R> &A) {
     if (t.infeas) {
-        const R yv = t.y[ro], yinv = R(1) / yv;
+        const R yinv = rrcp(yv);
         const R r = sv * yv - t.mu, rhat = sv * (cold + yv) - r, D = sv * yinv;
         const R ks = yinv * (rhat + sv * jv1), ky = -(cold + yv) - jv1;
         const R ynew = (yv + alpha * ky) + (-jv2), snew = (sv + alpha * ks) + D * jv2;
@@ -811,7 +890,7 @@ DDP_DEVICE void trial_row(const Traj<R> &t, long long ro, R cold, R cnew, R jv1,
         t.sn[ro] = snew; t.yn[ro] = ynew;
         A.lg.mul(ynew); A.e1 += rabs(cnew + ynew);
     } else {
-        const R cinv = R(1) / cold;
+        const R cinv = rrcp(cold);
         const R r = sv * cold + t.mu, D = sv * cinv;
         const R ks = -(cinv * (r + sv * jv1));
         const R snew = (sv + alpha * ks) + (-(D * jv2));
@@ -822,18 +901,25 @@ DDP_DEVICE void trial_row(const Traj<R> &t, long long ro, R cold, R cnew, R jv1,
 }
 
 template <class R, int SHIFT>
-DDP_DEVICE void trial_fixed_group(const Traj<R> &t, int g, int i, int plus0, int minus0, R lim, const R *tpo, const R *tpn,
+DDP_DEVICE void trial_fixed_group(const RowCtx<R> &t, int g, int i, int plus0, int minus0, R lim, const R *tpo, const R *tpn,
                                   const R *zo, const R *zn, const R *v1, const R *v2, R alpha, R tau, TrialAcc<R> &A) {
     R b[6], bd[6], bn[6];
     basis_row<R, SHIFT, 0>(t.tab, g, tpo, b);
     basis_row<R, SHIFT, 1>(t.tab, g, tpo, bd);
     basis_row<R, SHIFT, 0>(t.tab, g, tpn, bn);
+    R sp[3], sm_[3], yp[3], ym[3];   // the six rows' slacks first, then the arithmetic
+    DDP_UNROLL
+    for (int a = 0; a < 3; a++) {
+        sp[a] = t.s[(long long)(plus0 + a) * t.NP + i]; sm_[a] = t.s[(long long)(minus0 + a) * t.NP + i];
+        yp[a] = R(1); ym[a] = R(1);
+        if (t.infeas) { yp[a] = t.y[(long long)(plus0 + a) * t.NP + i]; ym[a] = t.y[(long long)(minus0 + a) * t.NP + i]; }
+    }
     DDP_UNROLL
     for (int a = 0; a < 3; a++) {
         const R vo = dot_axis<R, SHIFT>(b, zo, a), tc = dot_axis<R, SHIFT>(bd, zo, a), vn = dot_axis<R, SHIFT>(bn, zn, a);
         const R j1 = dot_axis<R, 3>(b, v1, a) + tc * v1[9], j2 = dot_axis<R, SHIFT>(b, v2, a) + tc * v2[9];
-        trial_row(t, (long long)(plus0 + a) * t.NP + i, vo - lim - t.margin, vn - lim - t.margin, j1, j2, alpha, tau, A);
-        trial_row(t, (long long)(minus0 + a) * t.NP + i, -vo - lim - t.margin, -vn - lim - t.margin, -j1, -j2, alpha, tau, A);
+        trial_row(t, (long long)(plus0 + a) * t.NP + i, sp[a], yp[a], vo - lim - t.margin, vn - lim - t.margin, j1, j2, alpha, tau, A);
+        trial_row(t, (long long)(minus0 + a) * t.NP + i, sm_[a], ym[a], -vo - lim - t.margin, -vn - lim - t.margin, -j1, -j2, alpha, tau, A);
     }
 }
 
@@ -841,39 +927,61 @@ DDP_DEVICE void trial_fixed_group(const Traj<R> &t, int g, int i, int plus0, int
 // runs sequentially (lane <-> element) for 32 knots at a time; the constraint rows of those 32 knots are then
 // evaluated lane <-> knot.  Writes the candidate into xun/sn/yn and returns false when the
 // fraction-to-boundary test fails at some knot (ddp.cpp:683-687 / :699-703).
-template <class R> DDP_DEVICE_NOINLINE bool forward_trial(Traj<R> &t, R alpha, R tau, RollOut<R> &out) {
-    const int lane_ = t.lane_;
-    R *sm = t.sm;
-    const int N = t.N;
-    Reg<R, 1> xcur, xn;
+template <class R> DDP_DEVICE_NOINLINE bool forward_trial(Traj<R> &tt_, R alpha, R tau, RollOut<R> &out) {
+    const int lane_ = tt_.lane_;
+    const RowCtx<R> t = row_ctx(tt_);
+    R *sm = tt_.sm;
+    const int N = tt_.N;
+    const R *DDP_RESTRICT xu = tt_.xu;
+    R *DDP_RESTRICT xun = tt_.xun;
+    const R *DDP_RESTRICT Kin = tt_.K;
+    R *DDP_RESTRICT kdxo = tt_.kdx;
+    const R w_terminal = tt_.w_terminal, w_snap = tt_.w_snap, w_time = tt_.w_time, tol = tt_.tol;
+    const int time_power = tt_.time_power;
+    long long fwd_knots = 0;
+    Reg<R, 1> xcur, xn, zo_c, zo_n;   // zo_*: old [u; x] entry of this lane at the current / next knot
+    Reg<R, 10> Kc, Kn;                // lanes 0-9: row `lane` of [ku | Ku] at the current / next knot
     Reg<R, 3> acc;  // per-lane partials: stage cost, log barrier, |c+y|_1
     FOR_LANES(lane) {
         acc(lane, 0) = R(0); acc(lane, 1) = R(0); acc(lane, 2) = R(0);
-        xcur(lane, 0) = (lane >= 10 && lane < 19) ? t.xu[lane] : R(0);  // xnew[0] = xold[0]
+        xcur(lane, 0) = (lane >= 10 && lane < 19) ? xu[lane] : R(0);  // xnew[0] = xold[0]
         xn(lane, 0) = R(0);
+        zo_n(lane, 0) = lane < 19 ? xu[lane] : R(0);
+        DDP_UNROLL
+        for (int e = 0; e < 10; e++) Kn(lane, e) = lane < 10 ? Kin[lane * 10 + e] : R(0);
     }
-    for (int base = 0; base < N; base += 32) {
+    bool ok = true;
+    for (int base = 0; base < N && ok; base += 32) {
         const int nk = N - base < 32 ? N - base : 32;
         for (int i = base; i < base + nk; i++) {
             FOR_LANES(lane) {
+                zo_c(lane, 0) = zo_n(lane, 0);
+                DDP_UNROLL
+                for (int e = 0; e < 10; e++) Kc(lane, e) = Kn(lane, e);
+                if (i + 1 < N) {   // next knot's old point and gains, in flight during this knot's recursion
+                    if (lane < 19) zo_n(lane, 0) = xu[(long long)(i + 1) * 20 + lane];
+                    if (lane < 10) {
+                        DDP_UNROLL
+                        for (int e = 0; e < 10; e++) Kn(lane, e) = Kin[(long long)(i + 1) * 100 + lane * 10 + e];
+                    }
+                }
                 if (lane >= 10 && lane < 19) {
                     const R x = xcur(lane, 0);
-                    sm[Lay::DX + lane - 10] = x - t.xu[(long long)i * 20 + lane];
+                    sm[Lay::DX + lane - 10] = x - zo_c(lane, 0);
                     sm[Lay::ZN + lane] = x;
-                    t.xun[(long long)i * 20 + lane] = x;
+                    xun[(long long)i * 20 + lane] = x;
                 }
             }
             WARP_SYNC();
             FOR_LANES(lane) {   // unew = (uold + alpha ku) + Ku dx (ddp.cpp:689/:695)
                 if (lane < 10) {
-                    const R *Kr = t.K + (long long)i * 100 + lane * 10;
                     R kdx = R(0);
                     DDP_UNROLL
-                    for (int b = 0; b < 9; b++) kdx += Kr[1 + b] * sm[Lay::DX + b];
-                    const R un = (t.xu[(long long)i * 20 + lane] + alpha * Kr[0]) + kdx;
+                    for (int b = 0; b < 9; b++) kdx += Kc(lane, 1 + b) * sm[Lay::DX + b];
+                    const R un = (zo_c(lane, 0) + alpha * Kc(lane, 0)) + kdx;
                     sm[Lay::ZN + lane] = un;
-                    t.xun[(long long)i * 20 + lane] = un;
-                    t.kdx[(long long)i * 10 + lane] = kdx;
+                    xun[(long long)i * 20 + lane] = un;
+                    kdxo[(long long)i * 10 + lane] = kdx;
                 }
             }
             WARP_SYNC();
@@ -903,9 +1011,9 @@ template <class R> DDP_DEVICE_NOINLINE bool forward_trial(Traj<R> &t, R alpha, R
             if (i < N) {
                 R zo[19], zn[19], v1[10], v2[19], tpo[6], tpn[6];
                 DDP_UNROLL
-                for (int e = 0; e < 19; e++) { zo[e] = t.xu[(long long)i * 20 + e]; zn[e] = t.xun[(long long)i * 20 + e]; }
+                for (int e = 0; e < 19; e++) { zo[e] = xu[(long long)i * 20 + e]; zn[e] = xun[(long long)i * 20 + e]; }
                 DDP_UNROLL
-                for (int e = 0; e < 10; e++) { v1[e] = t.K[(long long)i * 100 + e * 10]; v2[e] = t.kdx[(long long)i * 10 + e]; }
+                for (int e = 0; e < 10; e++) { v1[e] = Kin[(long long)i * 100 + e * 10]; v2[e] = kdxo[(long long)i * 10 + e]; }
                 DDP_UNROLL
                 for (int e = 10; e < 19; e++) v2[e] = zn[e] - zo[e];
                 time_powers(zo[9], tpo);
@@ -914,6 +1022,7 @@ template <class R> DDP_DEVICE_NOINLINE bool forward_trial(Traj<R> &t, R alpha, R
                 A.lg.lp = R(1); A.lg.lsum = R(0); A.e1 = R(0); A.bad = 0;
                 const int P = t.nplanes[i];
                 const double *pl = t.planes + (long long)i * t.PM * 4;
+                DDP_NOUNROLL
                 for (int g = 0; g < 6; g++) {
                     R b[6], bd[6], bn[6], co[3], cd[3], cn[3], j1[3], j2[3];
                     basis_row<R, 0, 0>(t.tab, g, tpo, b);
@@ -924,49 +1033,77 @@ template <class R> DDP_DEVICE_NOINLINE bool forward_trial(Traj<R> &t, R alpha, R
                         co[a] = dot_axis<R, 0>(b, zo, a); cd[a] = dot_axis<R, 0>(bd, zo, a); cn[a] = dot_axis<R, 0>(bn, zn, a);
                         j1[a] = dot_axis<R, 3>(b, v1, a); j2[a] = dot_axis<R, 0>(b, v2, a);
                     }
-                    for (int k = 0; k < P; k++) {
-                        R n[4];
-                        load_plane(pl, k, n);
-                        const R cold = ((n[0] * co[0] + n[1] * co[1]) + n[2] * co[2]) + n[3] - t.margin;
-                        const R cnew = ((n[0] * cn[0] + n[1] * cn[1]) + n[2] * cn[2]) + n[3] - t.margin;
-                        const R tc = (n[0] * cd[0] + n[1] * cd[1]) + n[2] * cd[2];
-                        const R jv1 = ((n[0] * j1[0] + n[1] * j1[1]) + n[2] * j1[2]) + tc * v1[9];
-                        const R jv2 = ((n[0] * j2[0] + n[1] * j2[1]) + n[2] * j2[2]) + tc * v2[9];
-                        trial_row(t, (long long)(g * t.PM + k) * t.NP + i, cold, cnew, jv1, jv2, alpha, tau, A);
+                    DDP_NOUNROLL
+                    for (int k0 = 0; k0 < P; k0 += 3) {   // three rows at a time: their loads are issued together
+                        R sv[3], yv[3], nn[3][4];
+                        DDP_UNROLL
+                        for (int j = 0; j < 3; j++) {
+                            const int k = k0 + j < P ? k0 + j : P - 1;
+                            const long long ro = (long long)(g * t.PM + k) * t.NP + i;
+                            sv[j] = t.s[ro];
+                            yv[j] = t.infeas ? t.y[ro] : R(1);
+                            load_plane(pl, k, nn[j]);
+                        }
+                        DDP_UNROLL
+                        for (int j = 0; j < 3; j++) {
+                            if (k0 + j < P) {
+                                const R *n = nn[j];
+                                const R cold = ((n[0] * co[0] + n[1] * co[1]) + n[2] * co[2]) + n[3] - t.margin;
+                                const R cnew = ((n[0] * cn[0] + n[1] * cn[1]) + n[2] * cn[2]) + n[3] - t.margin;
+                                const R tc = (n[0] * cd[0] + n[1] * cd[1]) + n[2] * cd[2];
+                                const R jv1 = ((n[0] * j1[0] + n[1] * j1[1]) + n[2] * j1[2]) + tc * v1[9];
+                                const R jv2 = ((n[0] * j2[0] + n[1] * j2[1]) + n[2] * j2[2]) + tc * v2[9];
+                                trial_row(t, (long long)(g * t.PM + k0 + j) * t.NP + i, sv[j], yv[j], cold, cnew, jv1, jv2, alpha, tau, A);
+                            }
+                        }
                     }
                 }
                 const int FB = 6 * t.PM;
+                DDP_NOUNROLL
                 for (int g = 6; g < 11; g++)
                     trial_fixed_group<R, 1>(t, g, i, FB + 3 * (g - 6), FB + 15 + 3 * (g - 6), t.max_vel, tpo, tpn, zo, zn, v1, v2, alpha, tau, A);
+                DDP_NOUNROLL
                 for (int g = 11; g < 15; g++)
                     trial_fixed_group<R, 2>(t, g, i, FB + 30 + 3 * (g - 11), FB + 42 + 3 * (g - 11), t.max_acc, tpo, tpn, zo, zn, v1, v2, alpha, tau, A);
-                trial_row(t, (long long)(FB + 54) * t.NP + i, -zo[9] + R(0.3) - t.margin, -zn[9] + R(0.3) - t.margin, -v1[9], -v2[9],
-                          alpha, tau, A);
+                {
+                    const long long ro = (long long)(FB + 54) * t.NP + i;
+                    trial_row(t, ro, t.s[ro], t.infeas ? t.y[ro] : R(1), -zo[9] + R(0.3) - t.margin, -zn[9] + R(0.3) - t.margin, -v1[9], -v2[9],
+                              alpha, tau, A);
+                }
                 if (A.bad) badk(lane, 0) = i;
-                acc(lane, 0) += stage_cost(t, tpn, zn);
+                {   // stage cost q(x,u), ddp.cpp:1294-1305
+                    R m[9], mu9[9];
+                    rmat<R>(0, tpn, m);
+                    rmat_times_u(m, zn, mu9);
+                    const R T = tpn[1];
+                    const R tterm = time_power == 2 ? R(0.5) * T * w_time * T : R(0.5) * w_time * T;
+                    acc(lane, 0) += R(0.5) * w_snap * dot9(zn, mu9) + tterm;
+                }
                 acc(lane, 1) += A.lg.total();
                 acc(lane, 2) += A.e1;
             }
         }
         const int first = warp_min_int(badk, 0, lane_);
-        if (first != 0x7fffffff) { t.n_fwd_knots += first - base + 1; return false; }
-        t.n_fwd_knots += nk;
+        if (first != 0x7fffffff) { fwd_knots += first - base + 1; ok = false; }
+        else fwd_knots += nk;
     }
+    tt_.n_fwd_knots += fwd_knots;
+    if (!ok) return false;
     // terminal cost (ddp.cpp:1289-1292) and totals
     Reg<R, 1> pt;
     FOR_LANES(lane) {
         pt(lane, 0) = R(0);
         if (lane >= 10 && lane < 19) {
             const R d = xcur(lane, 0) - sm[Lay::XD + lane - 10];
-            pt(lane, 0) = d * (t.w_terminal * d);
-            t.xun[(long long)N * 20 + lane] = xcur(lane, 0);
+            pt(lane, 0) = d * (w_terminal * d);
+            xun[(long long)N * 20 + lane] = xcur(lane, 0);
         }
     }
     const R qs = warp_sum(acc, 0, lane_), p = R(0.5) * warp_sum(pt, 0, lane_);
     out.costq = qs;
     out.cost = qs + p;
     out.logcost = out.cost - t.mu * warp_sum(acc, 1, lane_);
-    out.err = t.infeas ? rmax(t.tol, warp_sum(acc, 2, lane_)) : R(0);
+    out.err = t.infeas ? rmax(tol, warp_sum(acc, 2, lane_)) : R(0);
     WARP_SYNC();
     return true;
 }
@@ -1028,21 +1165,24 @@ template <class R> DDP_DEVICE_NOINLINE void initial_roll(Traj<R> &t) {
 //   mode 1: any c >= thresh (ddp.cpp:346-355);  mode 2: any c > thresh (ddp.cpp:255-269)
 template <class R> DDP_DEVICE_NOINLINE bool scan_constraints(Traj<R> &t, int mode, R thresh, R &lsum, R &e1sum) {
     const int lane_ = t.lane_;
+    const RowCtx<R> c_ = row_ctx(t);
+    const R *DDP_RESTRICT xu = t.xu;
+    const int N = t.N;
     Reg<R, 2> acc;
     Reg<int, 1> viol;
     FOR_LANES(lane) {
         acc(lane, 0) = R(0); acc(lane, 1) = R(0); viol(lane, 0) = 0;
-        for (int i = lane; i < t.N; i += 32) {
+        for (int i = lane; i < N; i += 32) {
             R z[19];
             DDP_UNROLL
-            for (int e = 0; e < 19; e++) z[e] = t.xu[(long long)i * 20 + e];
+            for (int e = 0; e < 19; e++) z[e] = xu[(long long)i * 20 + e];
             LogProd<R> lg;
             lg.lp = R(1); lg.lsum = R(0);
             R e1 = R(0);
             int v = 0;
-            visit_rows(t, i, z, [&](int slot, R c) {
+            visit_rows(c_, i, z, [&](int slot, R c) {
                 if (mode == 0) {
-                    if (t.infeas) { const R yv = t.y[(long long)slot * t.NP + i]; lg.mul(yv); e1 += rabs(c + yv); }
+                    if (c_.infeas) { const R yv = c_.y[(long long)slot * c_.NP + i]; lg.mul(yv); e1 += rabs(c + yv); }
                     else lg.mul(-c);
                 } else if (mode == 1) { if (c >= thresh) v = 1; }
                 else { if (c > thresh) v = 1; }
@@ -1219,7 +1359,7 @@ template <class R> DDP_DEVICE_NOINLINE void solve_one(const SolveArgs &A, int st
                         for (int c = 0; c < 3; c++) z[c * 3 + a] = Gi[c] * rhs;
                     }
                     int all_neg = 1;
-                    visit_rows(t, i, z, [&](int, R c) { if (!(c < R(0))) all_neg = 0; });
+                    visit_rows(row_ctx(t), i, z, [&](int, R c) { if (!(c < R(0))) all_neg = 0; });
                     if (all_neg) vio = 0;
                     else { z[9] = R(2) * Tk; cnt++; }
                 }

@@ -20,6 +20,8 @@
 #define FOR_LANES(lane) for (int lane = lane_, once_ = 1; once_; once_ = 0)
 #define WARP_SYNC() __syncwarp()
 #define DDP_UNROLL _Pragma("unroll")
+#define DDP_NOUNROLL _Pragma("unroll 1")
+#define DDP_RESTRICT __restrict__
 #else
 #define DDP_GPU 0
 #define DDP_DEVICE inline
@@ -28,6 +30,8 @@
 #define FOR_LANES(lane) for (int lane = 0; lane < 32; ++lane)
 #define WARP_SYNC() ((void)0)
 #define DDP_UNROLL
+#define DDP_NOUNROLL
+#define DDP_RESTRICT __restrict__
 #endif
 
 namespace ddp {
@@ -121,14 +125,43 @@ template <int N> DDP_DEVICE bool warp_any(const Reg<int, N> &r, int i, int lane_
 #endif
 }
 
+// log(): called rarely (LogProd) but ~100 SASS instructions per inlined fp64 copy; kept out of line so the hot
+// row loops stay small (the v2 profile showed 35 % instruction-fetch stalls, profiles/r1b).
+#if DDP_GPU
+static __device__ __noinline__ double rlog(double x) { return log(x); }
+#else
 DDP_DEVICE double rlog(double x) { return log(x); }
+#endif
 DDP_DEVICE float rlog(float x) { return logf(x); }
+// 1/x for the interior-point weights.  GPU fp64: MUFU.RCP64H seed + two Newton steps (~1 ulp, no slow-path
+// call); arguments are slack/constraint values kept away from 0 by the fraction-to-boundary rule.
+#if DDP_GPU
+DDP_DEVICE double rrcp(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    return fma(r, e, r);
+}
+DDP_DEVICE float rrcp(float x) { return 1.0f / x; }
+#else
+DDP_DEVICE double rrcp(double x) { return 1.0 / x; }
+DDP_DEVICE float rrcp(float x) { return 1.0f / x; }
+#endif
 DDP_DEVICE double rsqrt_(double x) { return sqrt(x); }
 DDP_DEVICE float rsqrt_(float x) { return sqrtf(x); }
 // 1/sqrt(x): the Cholesky pivot scale.  GPU: rsqrt() (MUFU.RSQ64H + Newton, ~1 ulp), shorter dependent chain than
 // sqrt followed by a division.
 #if DDP_GPU
-DDP_DEVICE double rrsqrt(double x) { return rsqrt(x); }
+DDP_DEVICE double rrsqrt(double x) {   // x > 0 checked by the caller; seed ~2^-20, two Newton steps
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double h = 0.5 * x * y, e = fma(-h, y, 0.5);
+    y = fma(y, e, y);
+    h = 0.5 * x * y; e = fma(-h, y, 0.5);
+    return fma(y, e, y);
+}
 DDP_DEVICE float rrsqrt(float x) { return rsqrtf(x); }
 #else
 DDP_DEVICE double rrsqrt(double x) { return 1.0 / sqrt(x); }
@@ -136,7 +169,11 @@ DDP_DEVICE float rrsqrt(float x) { return 1.0f / sqrtf(x); }
 #endif
 DDP_DEVICE double rabs(double x) { return fabs(x); }
 DDP_DEVICE float rabs(float x) { return fabsf(x); }
+#if DDP_GPU
+static __device__ __noinline__ double rpow(double x, double y) { return pow(x, y); }
+#else
 DDP_DEVICE double rpow(double x, double y) { return pow(x, y); }
+#endif
 DDP_DEVICE float rpow(float x, float y) { return powf(x, y); }
 template <class T> DDP_DEVICE T rmax(T a, T b) { return (a < b) ? b : a; }   // std::max(a, b)
 template <class T> DDP_DEVICE T rmin(T a, T b) { return (b < a) ? b : a; }   // std::min(a, b)

@@ -50,6 +50,8 @@ def build(ref: bool = True) -> None:
     if ref and os.path.exists("/root/reference/global_planner/src/ddp_optimizer.cpp") \
             and os.path.exists(os.path.join(_HERE, "ref_driver.cpp")):
         subprocess.check_call(["make", "-s", "-C", _HERE, "ref"])
+        if os.path.exists(os.path.join(_HERE, "..", "direct_b200", "libdirect_ddp_b200.so")):
+            subprocess.check_call(["make", "-s", "-C", _HERE, "dropin"])
 
 
 _lib = None
@@ -83,6 +85,23 @@ def ref_lib():
         _ref = C.CDLL(os.path.join(_HERE, "_ref", "libddp_ref.so"))
         _ref.ddp_ref_solve_batch.argtypes = [C.POINTER(_Batch), C.POINTER(_Out), C.c_int]
     return _ref
+
+
+_dropin = None
+
+
+def dropin_available() -> bool:
+    return os.path.exists(os.path.join(_HERE, "_ref", "libddp_dropin.so"))
+
+
+def dropin_lib():
+    """ref_driver.cpp linked with direct_b200/host/ddp_optimizer_b200.cpp (the B200 drop-in TU) instead of the
+    reference's ddp_optimizer.cpp: exercises the product through the reference's C++ class API."""
+    global _dropin
+    if _dropin is None:
+        _dropin = C.CDLL(os.path.join(_HERE, "_ref", "libddp_dropin.so"))
+        _dropin.ddp_ref_solve_batch.argtypes = [C.POINTER(_Batch), C.POINTER(_Out), C.c_int]
+    return _dropin
 
 
 def _p(a, t=_dp):
@@ -127,13 +146,16 @@ def _batch_struct(pb, keep, *, init_bez=None, durations=None, infeas=1, zero_ini
                   int(zero_init), int(line_init), int(minvo), _p(inf_arr, _ip), inf_all)
 
 
-def solve_batch(pb, nthreads=1, use_ref=False, **kw) -> Result:
+def solve_batch(pb, nthreads=1, use_ref=False, use_dropin=False, **kw) -> Result:
     """One polyCurveGeneration call per trajectory of ProblemBatch ``pb``."""
     keep = []
     b = _batch_struct(pb, keep, **kw)
     out = Result(pb.B, pb.N)
     o = out.c_struct()
-    fn = ref_lib().ddp_ref_solve_batch if use_ref else lib().ipddp_oracle_solve_batch
+    if use_dropin:
+        fn = dropin_lib().ddp_ref_solve_batch
+    else:
+        fn = ref_lib().ddp_ref_solve_batch if use_ref else lib().ipddp_oracle_solve_batch
     st = fn(C.byref(b), C.byref(o), int(nthreads))
     if st:
         raise RuntimeError(f"oracle solve failed with status {st}")

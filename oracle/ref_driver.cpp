@@ -63,6 +63,7 @@ static void solve_one(const oracle_batch *b, const oracle_out *o, int i) {
                                        initbez, b->w_snap, b->w_terminal, b->w_time, b->iter_max, infeas,
                                        b->zero_init != 0, b->line_init != 0, line_failed, b->time_power, b->minvo != 0);
     if (o->rtn) o->rtn[i] = rtn;
+    if (rtn <= -100) { delete opt; return; }   // the B200 drop-in TU could not reach its device: nothing to read back
     if (o->infeas_out) o->infeas_out[i] = infeas;
     if (o->line_failed_out) o->line_failed_out[i] = line_failed;
     if (o->iters) o->iters[i] = opt->getIterUsed();

@@ -57,3 +57,15 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".h", ".cpp", ".cuh")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "oracle_py" not in txt and "ipddp_oracle" not in txt and "libemu" not in txt, f
+
+
+@pytest.mark.skipif(has_gpu(), reason="checks the loud failure on a GPU-less host")
+def test_dropin_translation_unit_fails_loudly_without_gpu(oracle):
+    """The replacement for the reference's ddp_optimizer.cpp compiles against the reference's unchanged header
+    (where /root/reference is mounted) and, with no B200 visible, returns -100 instead of computing on the CPU."""
+    oracle.build(ref=True)
+    if not oracle.dropin_available():
+        pytest.skip("the reference's headers are not mounted here")
+    from direct_b200.problems import make_batch
+    r = oracle.solve_batch(make_batch(2, 4, "box"), use_dropin=True, infeas=1, zero_init=1)
+    assert (r.rtn == -100).all() and not r.poly_coeff.any()
