@@ -203,6 +203,8 @@ template <class R> struct Traj {
     int time_power, infeas, zero_init, line_init;
     R mu, tol, reg, reg_base, opterr, cost, costq, logcost, err, stepsize;
     int step, failed, bfailed, nfilter;
+    int lin_valid;          // t.H / t.aux hold the linearisation of the current iterate at the current mu
+    R lin_emu, lin_ecy;     // its max |r| and max |c + y| (ddp.cpp:636-637)
     long long n_bwd_sweeps, n_bwd_knots, n_fwd_trials, n_fwd_knots;
     long long cyc_bwd, cyc_fwd, cyc_t0;  // clock64 accounting (0 in the emulation)
 };
@@ -838,17 +840,24 @@ template <class R> DDP_DEVICE_NOINLINE void backward_pass(Traj<R> &t) {
     if (t.reg < R(0)) t.reg = R(0);
     else if (t.reg > R(24)) t.reg = R(24);
     const R regadd = rpow(t.reg_base, t.reg) - R(1);  // ddp.cpp:529
-    Reg<R, 2> errs;
     Reg<R, 1> errq;
-    linearize(t, errs);
+    // The linearisation depends on the iterate and on mu only: a retry after a failed factorisation or after a
+    // failed line search (the reference does not relinearise either, ddp.cpp:476) reuses it.
+    if (!t.lin_valid) {
+        Reg<R, 2> errs;
+        linearize(t, errs);
+        t.lin_emu = warp_max(errs, 0, lane_);
+        t.lin_ecy = warp_max(errs, 1, lane_);
+        t.lin_valid = 1;
+    }
     WARP_SYNC();
     if (!riccati(t, regadd, errq)) {
         t.bfailed = 1;
         t.opterr = R(INFINITY);
     } else {
         t.bfailed = 0;
-        const R e0 = warp_max(errq, 0, lane_), e1 = warp_max(errs, 0, lane_), e2 = warp_max(errs, 1, lane_);
-        t.opterr = rmax(rmax(e0, t.infeas ? e2 : R(0)), e1);  // ddp.cpp:641
+        const R e0 = warp_max(errq, 0, lane_);
+        t.opterr = rmax(rmax(e0, t.infeas ? t.lin_ecy : R(0)), t.lin_emu);  // ddp.cpp:641
     }
     t.cyc_bwd += ddp_clock() - clk0;
 }
@@ -1263,6 +1272,7 @@ template <class R> DDP_DEVICE_NOINLINE void forward_pass(Traj<R> &t) {
         tmp = t.s; t.s = t.sn; t.sn = tmp;
         if (t.infeas) { tmp = t.y; t.y = t.yn; t.yn = tmp; }
         t.stepsize = stepsize; t.step = step; t.failed = 0;
+        t.lin_valid = 0;
     }
     t.cyc_fwd += ddp_clock() - clk0;
 }
@@ -1292,7 +1302,7 @@ template <class R> DDP_DEVICE_NOINLINE void solve_one(const SolveArgs &A, int st
     t.reg_base = cfg.zero_init ? R(1.6) : R(4.0);      // ddp.cpp:60-61
     t.n_bwd_sweeps = t.n_bwd_knots = t.n_fwd_trials = t.n_fwd_knots = 0;
     t.cyc_bwd = t.cyc_fwd = 0; t.cyc_t0 = ddp_clock();
-    t.mu = R(0); t.step = 0; t.failed = 0; t.bfailed = 0;
+    t.mu = R(0); t.step = 0; t.failed = 0; t.bfailed = 0; t.lin_valid = 0;
     const bool from_stage0 = (A.two_stage && st == 1);
     int infeas_in;
     if (from_stage0) infeas_in = A.out[0].infeas_out ? A.out[0].infeas_out[b] : 1;
@@ -1426,6 +1436,7 @@ template <class R> DDP_DEVICE_NOINLINE void solve_one(const SolveArgs &A, int st
             t.mu = rmax(t.tol / R(10), rmin(R(0.2) * t.mu, rpow(t.mu, R(1.2))));
             reset_filter(t);
             t.reg = R(0); t.bfailed = 0;
+            t.lin_valid = 0;
         }
         if (!scan_constraints(t, 1, R(2.0e-4), dummy0, dummy1)) {  // ddp.cpp:346-390 (hazard H8)
             if (cfg.zero_init) { infeas_out = 0; rtn = 2; break; }

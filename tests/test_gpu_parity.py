@@ -83,9 +83,10 @@ def test_gpu_full_size_properties(solver):
     assert (g.poly_time > 0.3 - 2.0e-4).all()                          # time row -T + 0.3 - 2e-4 < 0 (ddp_optimizer.cpp:1279-1283)
     cp = g.bez_coeff.reshape(B, N, 3, 6) * g.poly_time[:, :, None, None]
     val = np.einsum("bnpa,bnaj->bnpj", pb.planes[..., :3], cp) + pb.planes[..., 3:4]
-    # every control point of a converged solve (rtn 1) is inside its polytope; the few solves that run into
-    # iter_max (rtn 0) carry no such guarantee in the reference either (ddp_optimizer.cpp:346-378)
-    assert (val[g.rtn == 1] < 1e-9).all()
+    # every control point of a converged solve (rtn 1) is inside its polytope relaxed by the reference's own
+    # 2e-4 margin (c = n.p + d - 2e-4 < 0, ddp_optimizer.cpp:1281-1283); solves that run into iter_max (rtn 0)
+    # carry no such guarantee in the reference either (ddp_optimizer.cpp:346-378)
+    assert (val[g.rtn == 1] < 2.0e-4).all()
     pc = g.poly_coeff.reshape(B, N, 6, 3)
     T = g.poly_time
     for k, fac in ((0, [1, 1, 1, 1, 1, 1]), (1, [0, 1, 2, 3, 4, 5]), (2, [0, 0, 1, 3, 6, 10])):
