@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -171,6 +172,8 @@ template <class R> int launch(H *h, SolveArgs &A, cudaStream_t s) {
     const size_t smem = (size_t)(360 + wpb * ddp::smem_elems_per_warp(A.PM)) * sizeof(R);
     auto kern = ipddp_solve_kernel<R>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (const char *e = getenv("DIRECT_DDP_CARVEOUT"))   // tuning knob: shared-memory share of the unified L1 (percent)
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e)));
     int per_sm = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
     if (per_sm < 1) { h->err = "kernel does not fit on an SM (shared memory)"; return DIRECT_DDP_ERR_CUDA; }

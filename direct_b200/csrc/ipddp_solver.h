@@ -144,7 +144,8 @@ struct Lay {
         FL = 560,   // filter decision (2)
         FTN = 564,  // riccati: fT (9) and segment time (1) of the knot about to be processed, staged one knot ahead
         RI = 574,   // riccati: 1/sqrt(pivot) of the ten Cholesky pivots
-        MSC = 584,  // per-lane 3x3 blocks M_g of the linearisation: MSC[e*32+lane], e < 63
+        MSC = 584,  // per-lane 3x3 blocks M_g of the linearisation: MSC[e*32+lane], e < 63.  During the line search
+                    // (no linearisation in flight) the same area holds forward_trial's knot ring [0, 480).
         TOTAL = 584 + 63 * 32
     };
 };
@@ -207,6 +208,7 @@ template <class R> struct Traj {
     R lin_emu, lin_ecy;     // its max |r| and max |c + y| (ddp.cpp:636-637)
     long long n_bwd_sweeps, n_bwd_knots, n_fwd_trials, n_fwd_knots;
     long long cyc_bwd, cyc_fwd, cyc_t0;  // clock64 accounting (0 in the emulation)
+    long long cyc_ric, cyc_seq;          // of which: Riccati recursion, sequential state rollout
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -236,6 +238,78 @@ template <class R, int LMIN> DDP_DEVICE R dot_axis(const R *b, const R *v, int a
     for (int l = LMIN; l < 6; l++) acc += b[l] * v[zidx(l, 0) + a];
     return acc;
 }
+
+// basis_row with the shift chosen at run time (sd = SHIFT + DER in 0..3), so that ONE copy of the row code serves the
+// position, velocity and acceleration groups: multiplying by 1 where the template version does not multiply is exact.
+template <class R> DDP_DEVICE void basis_row_rt(const R *tabrow, int sd, const R *tp, R *b) {
+    DDP_UNROLL
+    for (int l = 0; l < 6; l++) {
+        R pw = l >= 1 ? tp[l] : R(1);
+        if (sd == 1) pw = l >= 2 ? tp[l - 1] : R(1);
+        else if (sd == 2) pw = l >= 3 ? tp[l - 2] : R(1);
+        else if (sd == 3) pw = l >= 4 ? tp[l - 3] : R(1);
+        R v = tabrow[l] * pw;
+        if (l == 2) v = v * R(0.5);
+        b[l] = v;
+    }
+}
+// Row groups: g < 6 position control points (one row per plane), 6..10 velocity, 11..14 acceleration control points
+// (six rows each, visited +x,-x,+y,-y,+z,-z like ddp.cpp:1228-1272).
+DDP_DEVICE int group_shift(int g) { return g < 6 ? 0 : (g < 11 ? 1 : 2); }
+// Row slot of row r of group g: corridor rows g*PM + k, then +v (15), -v (15), +a (12), -a (12), time.
+DDP_DEVICE int row_slot(int g, int r, int PM) {
+    if (g < 6) return g * PM + r;
+    const int FB = 6 * PM, a = r >> 1, neg = r & 1;
+    if (g < 11) return FB + (neg ? 15 : 0) + 3 * (g - 6) + a;
+    return FB + 30 + (neg ? 12 : 0) + 3 * (g - 11) + a;
+}
+// Direction and offset of a velocity / acceleration row: n = +-e_a, d = -limit (ddp.cpp:1238, :1276).
+template <class R> DDP_DEVICE void fixed_row(int r, R lim, R *n) {
+    const int a = r >> 1;
+    const R sg = (r & 1) ? R(-1) : R(1);
+    n[0] = a == 0 ? sg : R(0); n[1] = a == 1 ? sg : R(0); n[2] = a == 2 ? sg : R(0); n[3] = -lim;
+}
+
+// Plane k of knot `pl` (pointer to that knot's P_max x 4 block).
+template <class R> DDP_DEVICE void load_plane(const double *pl, int k, R *n) {
+    n[0] = (R)pl[4 * k]; n[1] = (R)pl[4 * k + 1]; n[2] = (R)pl[4 * k + 2]; n[3] = (R)pl[4 * k + 3];
+}
+
+// Two-deep software pipeline over the rows of one group: slack, dual slack and plane of rows r+1 and r+2 are in
+// flight while row r is processed (the rolled row loops would otherwise wait one full memory latency per row).
+template <class R> struct RowPipe {
+    R s[2], y[2], n[2][4];
+    const R *sp, *yp;          // row arrays offset by the knot
+    const double *pl;
+    long long NP;
+    int g, PM, nr, infeas;
+    DDP_DEVICE void fetch(int slot, int r) {
+        if (r < nr) {
+            const long long ro = (long long)row_slot(g, r, PM) * NP;
+            s[slot] = sp[ro];
+            if (infeas) y[slot] = yp[ro];
+            if (g < 6) load_plane(pl, r, n[slot]);
+        }
+    }
+    DDP_DEVICE void start(int g_, int nr_) {
+        g = g_; nr = nr_;
+        s[0] = s[1] = R(0); y[0] = y[1] = R(1);
+        DDP_UNROLL
+        for (int e = 0; e < 4; e++) { n[0][e] = R(0); n[1][e] = R(0); }
+        fetch(0, 0);
+        fetch(1, 1);
+    }
+    // Row r: returns its data and starts loading row r+2 into the slot just freed.
+    DDP_DEVICE void next(int r, R lim, R &sv, R &yv, R *nn) {
+        sv = s[0]; yv = y[0];
+        if (g < 6) { nn[0] = n[0][0]; nn[1] = n[0][1]; nn[2] = n[0][2]; nn[3] = n[0][3]; }
+        else fixed_row(r, lim, nn);
+        s[0] = s[1]; y[0] = y[1];
+        DDP_UNROLL
+        for (int e = 0; e < 4; e++) n[0][e] = n[1][e];
+        fetch(1, r + 2);
+    }
+};
 
 // F, G of the segment dynamics x+ = (F (x) I3) x + (G (x) I3) u[0:9], ddp.cpp:862-871.  fg[o*6+l].
 template <class R> DDP_DEVICE void fg_matrix(const R *tp, R *fg) {
@@ -326,11 +400,6 @@ template <class R> DDP_DEVICE RowCtx<R> row_ctx(const Traj<R> &t) {
     return c;
 }
 
-// Plane k of knot `pl` (pointer to that knot's P_max x 4 block).
-template <class R> DDP_DEVICE void load_plane(const double *pl, int k, R *n) {
-    n[0] = (R)pl[4 * k]; n[1] = (R)pl[4 * k + 1]; n[2] = (R)pl[4 * k + 2]; n[3] = (R)pl[4 * k + 3];
-}
-
 // Visit every constraint row of knot i at the point z (constraint VALUES only; computecminvo,
 // ddp.cpp:1132-1285): f(row slot, c).
 template <class R, class F> DDP_DEVICE void visit_rows(const RowCtx<R> &t, int i, const R *z, F &&f) {
@@ -339,41 +408,22 @@ template <class R, class F> DDP_DEVICE void visit_rows(const RowCtx<R> &t, int i
     const int P = t.nplanes[i];
     const double *pl = t.planes + (long long)i * t.PM * 4;
     DDP_NOUNROLL
-    for (int g = 0; g < 6; g++) {
+    for (int g = 0; g < 15; g++) {
         R b[6], cp[3];
-        basis_row<R, 0, 0>(t.tab, g, tp, b);
+        basis_row_rt(t.tab + g * 6, group_shift(g), tp, b);
         DDP_UNROLL
         for (int a = 0; a < 3; a++) cp[a] = dot_axis<R, 0>(b, z, a);
-        for (int k = 0; k < P; k++) {
+        const int nr = g < 6 ? P : 6;
+        const R lim = g < 11 ? t.max_vel : t.max_acc;
+        DDP_NOUNROLL
+        for (int r = 0; r < nr; r++) {
             R n[4];
-            load_plane(pl, k, n);
-            f(g * t.PM + k, ((n[0] * cp[0] + n[1] * cp[1]) + n[2] * cp[2]) + n[3] - t.margin);
+            if (g < 6) load_plane(pl, r, n);
+            else fixed_row(r, lim, n);
+            f(row_slot(g, r, t.PM), ((n[0] * cp[0] + n[1] * cp[1]) + n[2] * cp[2]) + n[3] - t.margin);
         }
     }
-    const int FB = 6 * t.PM;
-    DDP_NOUNROLL
-    for (int g = 6; g < 11; g++) {
-        R b[6];
-        basis_row<R, 1, 0>(t.tab, g, tp, b);
-        DDP_UNROLL
-        for (int a = 0; a < 3; a++) {
-            const R v = dot_axis<R, 1>(b, z, a);
-            f(FB + 3 * (g - 6) + a, v - t.max_vel - t.margin);
-            f(FB + 15 + 3 * (g - 6) + a, -v - t.max_vel - t.margin);
-        }
-    }
-    DDP_NOUNROLL
-    for (int g = 11; g < 15; g++) {
-        R b[6];
-        basis_row<R, 2, 0>(t.tab, g, tp, b);
-        DDP_UNROLL
-        for (int a = 0; a < 3; a++) {
-            const R v = dot_axis<R, 2>(b, z, a);
-            f(FB + 30 + 3 * (g - 11) + a, v - t.max_acc - t.margin);
-            f(FB + 42 + 3 * (g - 11) + a, -v - t.max_acc - t.margin);
-        }
-    }
-    f(FB + 54, -z[9] + R(0.3) - t.margin);
+    f(6 * t.PM + 54, -z[9] + R(0.3) - t.margin);
 }
 
 // Interior-point weights of one row (ddp.cpp:535-541 infeasible / :583-590 feasible):
@@ -392,40 +442,6 @@ DDP_DEVICE void row_weights(int infeas, R mu, R sgn, R c, R sv, R yv, R &Ds, R &
     }
     emu = amax(emu, rabs(r));
     Ds = sgn * D; gw = sv + sgn * tv2;
-}
-
-// One velocity / acceleration group of the linearisation: six rows +-(beta_g . coefficients of axis a) - limit.
-// The six slack (and dual-slack) values are loaded before any of them is used.
-template <class R, int SHIFT>
-DDP_DEVICE void lin_fixed_group(const RowCtx<R> &t, int g, int i, int plus0, int minus0, R lim, const R *tp, const R *z,
-                                R sgn, R *accT, R *accG, R &tt, R &gt, R &emu, R &ecy, R *msc) {
-    R b[6], bd[6];
-    basis_row<R, SHIFT, 0>(t.tab, g, tp, b);
-    basis_row<R, SHIFT, 1>(t.tab, g, tp, bd);
-    R wv[3], gv[3], sp[3], sm_[3], yp[3], ym[3];
-    DDP_UNROLL
-    for (int a = 0; a < 3; a++) {
-        sp[a] = t.s[(long long)(plus0 + a) * t.NP + i]; sm_[a] = t.s[(long long)(minus0 + a) * t.NP + i];
-        yp[a] = R(1); ym[a] = R(1);
-        if (t.infeas) { yp[a] = t.y[(long long)(plus0 + a) * t.NP + i]; ym[a] = t.y[(long long)(minus0 + a) * t.NP + i]; }
-    }
-    DDP_UNROLL
-    for (int a = 0; a < 3; a++) {
-        const R val = dot_axis<R, SHIFT>(b, z, a), tc = dot_axis<R, SHIFT>(bd, z, a);
-        R D1, g1, D2, g2;
-        row_weights(t.infeas, t.mu, sgn, val - lim - t.margin, sp[a], yp[a], D1, g1, emu, ecy);
-        row_weights(t.infeas, t.mu, sgn, -val - lim - t.margin, sm_[a], ym[a], D2, g2, emu, ecy);
-        // the "-" row has Jacobian -J+, so D adds and the gradient weight subtracts
-        const R Dsum = D1 + D2, gdiff = g1 - g2;
-        msc[a * 32] = Dsum;
-        wv[a] = Dsum * tc; gv[a] = gdiff;
-        tt += (Dsum * tc) * tc; gt += gdiff * tc;
-    }
-    DDP_UNROLL
-    for (int l = SHIFT; l < 6; l++) {
-        DDP_UNROLL
-        for (int a = 0; a < 3; a++) { accT[l * 3 + a] += b[l] * wv[a]; accG[l * 3 + a] += b[l] * gv[a]; }
-    }
 }
 
 // Second pass of the linearisation, one group: h_a[(l,l')] += beta[l] beta[l'] M_g[a][a] for the three axes.
@@ -475,62 +491,51 @@ template <class R> DDP_DEVICE_NOINLINE void linearize(Traj<R> &tt_, Reg<R, 2> &e
                 R accT[18], accG[18], tt = R(0), gt = R(0);
                 DDP_UNROLL
                 for (int e = 0; e < 18; e++) { accT[e] = R(0); accG[e] = R(0); }
-                // ---- pass 1: rows -> weights -> per-group blocks ------------------------------------------
+                // ---- pass 1: rows -> weights -> per-group blocks.  One rolled loop over the 15 row groups and one over
+                // the rows of a group (a single copy of the row code: the kernel is instruction-fetch bound,
+                // profiles/r1c); the slack of row r+1 is loaded while row r is processed. ------------------------
+                RowPipe<R> pipe;
+                pipe.sp = t.s + i; pipe.yp = t.y + i; pipe.pl = pl; pipe.NP = t.NP; pipe.PM = t.PM; pipe.infeas = t.infeas;
                 DDP_NOUNROLL
-                for (int g = 0; g < 6; g++) {   // position control points: one row per plane of the polytope
+                for (int g = 0; g < 15; g++) {
+                    const int shift = group_shift(g), nr = g < 6 ? P : 6;
+                    const R lim = g < 11 ? t.max_vel : t.max_acc;
                     R b[6], bd[6], cp[3], cd[3];
-                    basis_row<R, 0, 0>(t.tab, g, tp, b);
-                    basis_row<R, 0, 1>(t.tab, g, tp, bd);
+                    basis_row_rt(t.tab + g * 6, shift, tp, b);
+                    basis_row_rt(t.tab + 90 + g * 6, shift + 1, tp, bd);
                     DDP_UNROLL
                     for (int a = 0; a < 3; a++) { cp[a] = dot_axis<R, 0>(b, z, a); cd[a] = dot_axis<R, 0>(bd, z, a); }
                     R M[6] = {R(0), R(0), R(0), R(0), R(0), R(0)}, wv[3] = {R(0), R(0), R(0)}, gv[3] = {R(0), R(0), R(0)};
+                    pipe.start(g, nr);
                     DDP_NOUNROLL
-                    for (int k0 = 0; k0 < P; k0 += 3) {   // three rows at a time: their loads are issued together
-                        R sv[3], yv[3], nn[3][4];
-                        DDP_UNROLL
-                        for (int j = 0; j < 3; j++) {
-                            const int k = k0 + j < P ? k0 + j : P - 1;
-                            const long long ro = (long long)(g * t.PM + k) * t.NP + i;
-                            sv[j] = t.s[ro];
-                            yv[j] = t.infeas ? t.y[ro] : R(1);
-                            load_plane(pl, k, nn[j]);
-                        }
-                        DDP_UNROLL
-                        for (int j = 0; j < 3; j++) {
-                            if (k0 + j < P) {
-                                const R *n = nn[j];
-                                const R c = ((n[0] * cp[0] + n[1] * cp[1]) + n[2] * cp[2]) + n[3] - t.margin;
-                                const R tc = (n[0] * cd[0] + n[1] * cd[1]) + n[2] * cd[2];
-                                R Ds, gw;
-                                row_weights(t.infeas, t.mu, sgn, c, sv[j], yv[j], Ds, gw, emu, ecy);
-                                M[0] += Ds * (n[0] * n[0]); M[1] += Ds * (n[0] * n[1]); M[2] += Ds * (n[0] * n[2]);
-                                M[3] += Ds * (n[1] * n[1]); M[4] += Ds * (n[1] * n[2]); M[5] += Ds * (n[2] * n[2]);
-                                const R dt = Ds * tc, gtc = gw * tc;
-                                wv[0] += dt * n[0]; wv[1] += dt * n[1]; wv[2] += dt * n[2];
-                                gv[0] += gw * n[0]; gv[1] += gw * n[1]; gv[2] += gw * n[2];
-                                tt += dt * tc; gt += gtc;
-                            }
-                        }
+                    for (int r = 0; r < nr; r++) {
+                        R sv, yv, n[4];
+                        pipe.next(r, lim, sv, yv, n);
+                        const R c = ((n[0] * cp[0] + n[1] * cp[1]) + n[2] * cp[2]) + n[3] - t.margin;
+                        const R tc = (n[0] * cd[0] + n[1] * cd[1]) + n[2] * cd[2];
+                        R Ds, gw;
+                        row_weights(t.infeas, t.mu, sgn, c, sv, yv, Ds, gw, emu, ecy);
+                        M[0] += Ds * (n[0] * n[0]); M[1] += Ds * (n[0] * n[1]); M[2] += Ds * (n[0] * n[2]);
+                        M[3] += Ds * (n[1] * n[1]); M[4] += Ds * (n[1] * n[2]); M[5] += Ds * (n[2] * n[2]);
+                        const R dt = Ds * tc, gtc = gw * tc;
+                        wv[0] += dt * n[0]; wv[1] += dt * n[1]; wv[2] += dt * n[2];
+                        gv[0] += gw * n[0]; gv[1] += gw * n[1]; gv[2] += gw * n[2];
+                        tt += dt * tc; gt += gtc;
                     }
-                    DDP_UNROLL
-                    for (int e = 0; e < 6; e++) msc[(g * 6 + e) * 32] = M[e];
+                    if (g < 6) {
+                        DDP_UNROLL
+                        for (int e = 0; e < 6; e++) msc[(g * 6 + e) * 32] = M[e];
+                    } else {   // +-e_a rows: M is diagonal
+                        msc[(36 + 3 * (g - 6)) * 32] = M[0]; msc[(37 + 3 * (g - 6)) * 32] = M[3]; msc[(38 + 3 * (g - 6)) * 32] = M[5];
+                    }
                     DDP_UNROLL
                     for (int l = 0; l < 6; l++) {
                         DDP_UNROLL
                         for (int a = 0; a < 3; a++) { accT[l * 3 + a] += b[l] * wv[a]; accG[l * 3 + a] += b[l] * gv[a]; }
                     }
                 }
-                const int FB = 6 * t.PM;
-                DDP_NOUNROLL
-                for (int g = 6; g < 11; g++)
-                    lin_fixed_group<R, 1>(t, g, i, FB + 3 * (g - 6), FB + 15 + 3 * (g - 6), t.max_vel, tp, z, sgn, accT, accG,
-                                          tt, gt, emu, ecy, msc + (36 + 3 * (g - 6)) * 32);
-                DDP_NOUNROLL
-                for (int g = 11; g < 15; g++)
-                    lin_fixed_group<R, 2>(t, g, i, FB + 30 + 3 * (g - 11), FB + 42 + 3 * (g - 11), t.max_acc, tp, z, sgn, accT,
-                                          accG, tt, gt, emu, ecy, msc + (36 + 3 * (g - 6)) * 32);
                 {   // the time row -T + 0.3 <= 0 (ddp.cpp:1279): Jacobian -1 in the T entry only
-                    const long long ro = (long long)(FB + 54) * t.NP + i;
+                    const long long ro = (long long)(6 * t.PM + 54) * t.NP + i;
                     R Ds, gw;
                     row_weights(t.infeas, t.mu, sgn, -z[9] + R(0.3) - t.margin, t.s[ro], t.infeas ? t.y[ro] : R(1), Ds, gw, emu, ecy);
                     tt += Ds; gt -= gw;
@@ -851,7 +856,10 @@ template <class R> DDP_DEVICE_NOINLINE void backward_pass(Traj<R> &t) {
         t.lin_valid = 1;
     }
     WARP_SYNC();
-    if (!riccati(t, regadd, errq)) {
+    const long long clk_r = ddp_clock();
+    const bool ric_ok = riccati(t, regadd, errq);
+    t.cyc_ric += ddp_clock() - clk_r;
+    if (!ric_ok) {
         t.bfailed = 1;
         t.opterr = R(INFINITY);
     } else {
@@ -909,27 +917,15 @@ DDP_DEVICE void trial_row(const RowCtx<R> &t, long long ro, R sv, R yv, R cold, 
     }
 }
 
-template <class R, int SHIFT>
-DDP_DEVICE void trial_fixed_group(const RowCtx<R> &t, int g, int i, int plus0, int minus0, R lim, const R *tpo, const R *tpn,
-                                  const R *zo, const R *zn, const R *v1, const R *v2, R alpha, R tau, TrialAcc<R> &A) {
-    R b[6], bd[6], bn[6];
-    basis_row<R, SHIFT, 0>(t.tab, g, tpo, b);
-    basis_row<R, SHIFT, 1>(t.tab, g, tpo, bd);
-    basis_row<R, SHIFT, 0>(t.tab, g, tpn, bn);
-    R sp[3], sm_[3], yp[3], ym[3];   // the six rows' slacks first, then the arithmetic
-    DDP_UNROLL
-    for (int a = 0; a < 3; a++) {
-        sp[a] = t.s[(long long)(plus0 + a) * t.NP + i]; sm_[a] = t.s[(long long)(minus0 + a) * t.NP + i];
-        yp[a] = R(1); ym[a] = R(1);
-        if (t.infeas) { yp[a] = t.y[(long long)(plus0 + a) * t.NP + i]; ym[a] = t.y[(long long)(minus0 + a) * t.NP + i]; }
-    }
-    DDP_UNROLL
-    for (int a = 0; a < 3; a++) {
-        const R vo = dot_axis<R, SHIFT>(b, zo, a), tc = dot_axis<R, SHIFT>(bd, zo, a), vn = dot_axis<R, SHIFT>(bn, zn, a);
-        const R j1 = dot_axis<R, 3>(b, v1, a) + tc * v1[9], j2 = dot_axis<R, SHIFT>(b, v2, a) + tc * v2[9];
-        trial_row(t, (long long)(plus0 + a) * t.NP + i, sp[a], yp[a], vo - lim - t.margin, vn - lim - t.margin, j1, j2, alpha, tau, A);
-        trial_row(t, (long long)(minus0 + a) * t.NP + i, sm_[a], ym[a], -vo - lim - t.margin, -vn - lim - t.margin, -j1, -j2, alpha, tau, A);
-    }
+// cp.async of `n` elements (a multiple of 16 bytes, 16-byte aligned on both sides) by the whole warp.
+template <class R> DDP_DEVICE void warp_copy_async(R *dst, const R *src, int n, int lane) {
+    const int chunks = n * (int)sizeof(R) / 16;
+    for (int c = lane; c < chunks; c += 32) cp_async<16>((char *)dst + 16 * c, (const char *)src + 16 * c);
+}
+// Stage knot i of the line search: gains [ku | Ku] (100) and the old point [u; x] (20).
+template <class R> DDP_DEVICE void stage_knot(R *slot, const R *K, const R *xu, int i, int lane) {
+    warp_copy_async(slot, K + (long long)i * 100, 100, lane);
+    warp_copy_async(slot + 100, xu + (long long)i * 20, 20, lane);
 }
 
 // One line-search trial with step size alpha (ddp.cpp:674-734).  The closed-loop state/control recursion
@@ -947,36 +943,38 @@ template <class R> DDP_DEVICE_NOINLINE bool forward_trial(Traj<R> &tt_, R alpha,
     R *DDP_RESTRICT kdxo = tt_.kdx;
     const R w_terminal = tt_.w_terminal, w_snap = tt_.w_snap, w_time = tt_.w_time, tol = tt_.tol;
     const int time_power = tt_.time_power;
-    long long fwd_knots = 0;
-    Reg<R, 1> xcur, xn, zo_c, zo_n;   // zo_*: old [u; x] entry of this lane at the current / next knot
-    Reg<R, 10> Kc, Kn;                // lanes 0-9: row `lane` of [ku | Ku] at the current / next knot
+    long long fwd_knots = 0, cyc_seq = 0;
+    Reg<R, 1> xcur, xn;
     Reg<R, 3> acc;  // per-lane partials: stage cost, log barrier, |c+y|_1
+    // Old point and gains of the next knots stream into a 4-deep shared-memory ring by cp.async, three knots ahead of
+    // the recursion (the MSC scratch of the linearisation is free during the line search): slot = [K_i (100) | xu_i (20)].
+    R *ring = sm + Lay::MSC;
     FOR_LANES(lane) {
         acc(lane, 0) = R(0); acc(lane, 1) = R(0); acc(lane, 2) = R(0);
         xcur(lane, 0) = (lane >= 10 && lane < 19) ? xu[lane] : R(0);  // xnew[0] = xold[0]
         xn(lane, 0) = R(0);
-        zo_n(lane, 0) = lane < 19 ? xu[lane] : R(0);
         DDP_UNROLL
-        for (int e = 0; e < 10; e++) Kn(lane, e) = lane < 10 ? Kin[lane * 10 + e] : R(0);
+        for (int d = 0; d < 3; d++) {
+            if (d < N) stage_knot(ring + (d & 3) * 120, Kin, xu, d, lane);
+            cp_commit();
+        }
     }
     bool ok = true;
     for (int base = 0; base < N && ok; base += 32) {
         const int nk = N - base < 32 ? N - base : 32;
+        const long long clk_s = ddp_clock();
         for (int i = base; i < base + nk; i++) {
+            const R *slot = ring + (i & 3) * 120;
             FOR_LANES(lane) {
-                zo_c(lane, 0) = zo_n(lane, 0);
-                DDP_UNROLL
-                for (int e = 0; e < 10; e++) Kc(lane, e) = Kn(lane, e);
-                if (i + 1 < N) {   // next knot's old point and gains, in flight during this knot's recursion
-                    if (lane < 19) zo_n(lane, 0) = xu[(long long)(i + 1) * 20 + lane];
-                    if (lane < 10) {
-                        DDP_UNROLL
-                        for (int e = 0; e < 10; e++) Kn(lane, e) = Kin[(long long)(i + 1) * 100 + lane * 10 + e];
-                    }
-                }
+                if (i + 3 < N) stage_knot(ring + ((i + 3) & 3) * 120, Kin, xu, i + 3, lane);
+                cp_commit();
+                cp_wait<3>();
+            }
+            WARP_SYNC();
+            FOR_LANES(lane) {
                 if (lane >= 10 && lane < 19) {
                     const R x = xcur(lane, 0);
-                    sm[Lay::DX + lane - 10] = x - zo_c(lane, 0);
+                    sm[Lay::DX + lane - 10] = x - slot[100 + lane];
                     sm[Lay::ZN + lane] = x;
                     xun[(long long)i * 20 + lane] = x;
                 }
@@ -984,10 +982,11 @@ template <class R> DDP_DEVICE_NOINLINE bool forward_trial(Traj<R> &tt_, R alpha,
             WARP_SYNC();
             FOR_LANES(lane) {   // unew = (uold + alpha ku) + Ku dx (ddp.cpp:689/:695)
                 if (lane < 10) {
+                    const R *Kr = slot + lane * 10;
                     R kdx = R(0);
                     DDP_UNROLL
-                    for (int b = 0; b < 9; b++) kdx += Kc(lane, 1 + b) * sm[Lay::DX + b];
-                    const R un = (zo_c(lane, 0) + alpha * Kc(lane, 0)) + kdx;
+                    for (int b = 0; b < 9; b++) kdx += Kr[1 + b] * sm[Lay::DX + b];
+                    const R un = (slot[100 + lane] + alpha * Kr[0]) + kdx;
                     sm[Lay::ZN + lane] = un;
                     xun[(long long)i * 20 + lane] = un;
                     kdxo[(long long)i * 10 + lane] = kdx;
@@ -1012,6 +1011,7 @@ template <class R> DDP_DEVICE_NOINLINE bool forward_trial(Traj<R> &tt_, R alpha,
             WARP_SYNC();
             FOR_LANES(lane) { xcur(lane, 0) = xn(lane, 0); }
         }
+        cyc_seq += ddp_clock() - clk_s;
         // ---- rows of knots base .. base+nk-1, lane <-> knot ---------------------------------------------
         Reg<int, 1> badk;
         FOR_LANES(lane) {
@@ -1031,53 +1031,39 @@ template <class R> DDP_DEVICE_NOINLINE bool forward_trial(Traj<R> &tt_, R alpha,
                 A.lg.lp = R(1); A.lg.lsum = R(0); A.e1 = R(0); A.bad = 0;
                 const int P = t.nplanes[i];
                 const double *pl = t.planes + (long long)i * t.PM * 4;
+                RowPipe<R> pipe;
+                pipe.sp = t.s + i; pipe.yp = t.y + i; pipe.pl = pl; pipe.NP = t.NP; pipe.PM = t.PM; pipe.infeas = t.infeas;
                 DDP_NOUNROLL
-                for (int g = 0; g < 6; g++) {
+                for (int g = 0; g < 15; g++) {   // one copy of the row code for all groups (see linearize)
+                    const int shift = group_shift(g), nr = g < 6 ? P : 6;
+                    const R lim = g < 11 ? t.max_vel : t.max_acc;
                     R b[6], bd[6], bn[6], co[3], cd[3], cn[3], j1[3], j2[3];
-                    basis_row<R, 0, 0>(t.tab, g, tpo, b);
-                    basis_row<R, 0, 1>(t.tab, g, tpo, bd);
-                    basis_row<R, 0, 0>(t.tab, g, tpn, bn);
+                    basis_row_rt(t.tab + g * 6, shift, tpo, b);
+                    basis_row_rt(t.tab + 90 + g * 6, shift + 1, tpo, bd);
+                    basis_row_rt(t.tab + g * 6, shift, tpn, bn);
                     DDP_UNROLL
                     for (int a = 0; a < 3; a++) {
                         co[a] = dot_axis<R, 0>(b, zo, a); cd[a] = dot_axis<R, 0>(bd, zo, a); cn[a] = dot_axis<R, 0>(bn, zn, a);
                         j1[a] = dot_axis<R, 3>(b, v1, a); j2[a] = dot_axis<R, 0>(b, v2, a);
                     }
+                    pipe.start(g, nr);
                     DDP_NOUNROLL
-                    for (int k0 = 0; k0 < P; k0 += 3) {   // three rows at a time: their loads are issued together
-                        R sv[3], yv[3], nn[3][4];
-                        DDP_UNROLL
-                        for (int j = 0; j < 3; j++) {
-                            const int k = k0 + j < P ? k0 + j : P - 1;
-                            const long long ro = (long long)(g * t.PM + k) * t.NP + i;
-                            sv[j] = t.s[ro];
-                            yv[j] = t.infeas ? t.y[ro] : R(1);
-                            load_plane(pl, k, nn[j]);
-                        }
-                        DDP_UNROLL
-                        for (int j = 0; j < 3; j++) {
-                            if (k0 + j < P) {
-                                const R *n = nn[j];
-                                const R cold = ((n[0] * co[0] + n[1] * co[1]) + n[2] * co[2]) + n[3] - t.margin;
-                                const R cnew = ((n[0] * cn[0] + n[1] * cn[1]) + n[2] * cn[2]) + n[3] - t.margin;
-                                const R tc = (n[0] * cd[0] + n[1] * cd[1]) + n[2] * cd[2];
-                                const R jv1 = ((n[0] * j1[0] + n[1] * j1[1]) + n[2] * j1[2]) + tc * v1[9];
-                                const R jv2 = ((n[0] * j2[0] + n[1] * j2[1]) + n[2] * j2[2]) + tc * v2[9];
-                                trial_row(t, (long long)(g * t.PM + k0 + j) * t.NP + i, sv[j], yv[j], cold, cnew, jv1, jv2, alpha, tau, A);
-                            }
-                        }
+                    for (int r = 0; r < nr; r++) {
+                        R sv, yv, n[4];
+                        const long long ro_cur = (long long)row_slot(g, r, t.PM) * t.NP + i;
+                        pipe.next(r, lim, sv, yv, n);
+                        const R cold = ((n[0] * co[0] + n[1] * co[1]) + n[2] * co[2]) + n[3] - t.margin;
+                        const R cnew = ((n[0] * cn[0] + n[1] * cn[1]) + n[2] * cn[2]) + n[3] - t.margin;
+                        const R tc = (n[0] * cd[0] + n[1] * cd[1]) + n[2] * cd[2];
+                        const R jv1 = ((n[0] * j1[0] + n[1] * j1[1]) + n[2] * j1[2]) + tc * v1[9];
+                        const R jv2 = ((n[0] * j2[0] + n[1] * j2[1]) + n[2] * j2[2]) + tc * v2[9];
+                        trial_row(t, ro_cur, sv, yv, cold, cnew, jv1, jv2, alpha, tau, A);
                     }
                 }
-                const int FB = 6 * t.PM;
-                DDP_NOUNROLL
-                for (int g = 6; g < 11; g++)
-                    trial_fixed_group<R, 1>(t, g, i, FB + 3 * (g - 6), FB + 15 + 3 * (g - 6), t.max_vel, tpo, tpn, zo, zn, v1, v2, alpha, tau, A);
-                DDP_NOUNROLL
-                for (int g = 11; g < 15; g++)
-                    trial_fixed_group<R, 2>(t, g, i, FB + 30 + 3 * (g - 11), FB + 42 + 3 * (g - 11), t.max_acc, tpo, tpn, zo, zn, v1, v2, alpha, tau, A);
                 {
-                    const long long ro = (long long)(FB + 54) * t.NP + i;
-                    trial_row(t, ro, t.s[ro], t.infeas ? t.y[ro] : R(1), -zo[9] + R(0.3) - t.margin, -zn[9] + R(0.3) - t.margin, -v1[9], -v2[9],
-                              alpha, tau, A);
+                    const long long ro = (long long)(6 * t.PM + 54) * t.NP + i;
+                    trial_row(t, ro, t.s[ro], t.infeas ? t.y[ro] : R(1), -zo[9] + R(0.3) - t.margin, -zn[9] + R(0.3) - t.margin, -v1[9],
+                              -v2[9], alpha, tau, A);
                 }
                 if (A.bad) badk(lane, 0) = i;
                 {   // stage cost q(x,u), ddp.cpp:1294-1305
@@ -1096,7 +1082,10 @@ template <class R> DDP_DEVICE_NOINLINE bool forward_trial(Traj<R> &tt_, R alpha,
         if (first != 0x7fffffff) { fwd_knots += first - base + 1; ok = false; }
         else fwd_knots += nk;
     }
+    FOR_LANES(lane) { cp_wait<0>(); }   // nothing of the ring / staging may land after this trial
+    WARP_SYNC();
     tt_.n_fwd_knots += fwd_knots;
+    tt_.cyc_seq += cyc_seq;
     if (!ok) return false;
     // terminal cost (ddp.cpp:1289-1292) and totals
     Reg<R, 1> pt;
@@ -1301,7 +1290,7 @@ template <class R> DDP_DEVICE_NOINLINE void solve_one(const SolveArgs &A, int st
     t.tol = R(1.0e-7);                                 // ddp.cpp:43
     t.reg_base = cfg.zero_init ? R(1.6) : R(4.0);      // ddp.cpp:60-61
     t.n_bwd_sweeps = t.n_bwd_knots = t.n_fwd_trials = t.n_fwd_knots = 0;
-    t.cyc_bwd = t.cyc_fwd = 0; t.cyc_t0 = ddp_clock();
+    t.cyc_bwd = t.cyc_fwd = 0; t.cyc_ric = t.cyc_seq = 0; t.cyc_t0 = ddp_clock();
     t.mu = R(0); t.step = 0; t.failed = 0; t.bfailed = 0; t.lin_valid = 0;
     const bool from_stage0 = (A.two_stage && st == 1);
     int infeas_in;
@@ -1473,7 +1462,8 @@ template <class R> DDP_DEVICE_NOINLINE void solve_one(const SolveArgs &A, int st
             if (O.stats) {
                 long long *S = O.stats + (long long)b * 8;
                 S[0] = t.n_bwd_sweeps; S[1] = t.n_bwd_knots; S[2] = t.n_fwd_trials; S[3] = t.n_fwd_knots;
-                S[4] = t.cyc_bwd; S[5] = t.cyc_fwd; S[6] = ddp_clock() - t.cyc_t0; S[7] = 0;
+                S[4] = t.cyc_bwd; S[5] = t.cyc_fwd; S[6] = ddp_clock() - t.cyc_t0;
+                S[7] = (t.cyc_ric >> 10) | ((t.cyc_seq >> 10) << 32);   // kilo-cycles: Riccati | sequential rollout
             }
         }
         if (lane < 9 && O.x_final) O.x_final[(long long)b * 9 + lane] = (double)t.xu[(long long)N * 20 + 10 + lane];

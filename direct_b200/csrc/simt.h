@@ -11,6 +11,7 @@
 
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 #if defined(__CUDACC__) && !defined(DDP_EMULATE)
 #define DDP_GPU 1
@@ -124,6 +125,23 @@ template <int N> DDP_DEVICE bool warp_any(const Reg<int, N> &r, int i, int lane_
     return false;
 #endif
 }
+
+// Asynchronous global -> shared copies (LDGSTS): the data never occupies registers, so a phase can keep several
+// knots / row chunks in flight ahead of their use.  Per-thread semantics: cp_wait<N>() makes this thread's own
+// copies (all but the N most recent groups) visible to itself; other lanes need a WARP_SYNC() after it.
+#if DDP_GPU
+template <int BYTES> DDP_DEVICE void cp_async(void *smem_dst, const void *gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    if (BYTES == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+    else asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(d), "l"(gsrc), "n"(BYTES) : "memory");
+}
+DDP_DEVICE void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> DDP_DEVICE void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+#else
+template <int BYTES> DDP_DEVICE void cp_async(void *smem_dst, const void *gsrc) { memcpy(smem_dst, gsrc, BYTES); }
+DDP_DEVICE void cp_commit() {}
+template <int N> DDP_DEVICE void cp_wait() {}
+#endif
 
 // log(): called rarely (LogProd) but ~100 SASS instructions per inlined fp64 copy; kept out of line so the hot
 // row loops stay small (the v2 profile showed 35 % instruction-fetch stalls, profiles/r1b).

@@ -88,7 +88,8 @@ typedef struct direct_ddp_batch {
  *   jerk           per-segment jerk cost; getJerkCost() is its sum
  *   x_final        fp.x.back(); getTerminalNorm() = |x_final - xd|^2
  *   stats          [B][8] backward sweeps, backward knots, line-search rollouts, rollout knots,
- *                  SM cycles in backward passes, in line searches, in the whole solve, reserved
+ *                  SM cycles in backward passes, in line searches, in the whole solve; [7] = kilo-cycles of the
+ *                  Riccati recursion (low 32 bits) and of the sequential state rollout (high 32 bits)
  */
 typedef struct direct_ddp_result {
     int32_t *rtn, *infeas_out, *line_failed_out, *iters;

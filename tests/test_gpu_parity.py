@@ -130,8 +130,9 @@ def test_gpu_rejects_bad_arguments(solver):
     pb = make_batch(2, 3, "box")
     with pytest.raises(DirectDdpError, match="time_power"):
         solver.solve_batch(pb, infeas=1, zero_init=1, **dict(STAGE0, time_power=3))
-    with pytest.raises(DirectDdpError, match="line_init"):
-        solver.solve_batch(pb, infeas=1, zero_init=0, line_init=1, **STAGE1)
+    import dataclasses
+    with pytest.raises(DirectDdpError, match="line_init"):   # line_init reads the seeds (ddp_optimizer.cpp:195-247)
+        solver.solve_batch(dataclasses.replace(pb, seeds=None), infeas=1, zero_init=0, line_init=1, **STAGE1)
 
 
 @pytest.mark.parametrize("name", ["box_n5", "poly_n12", "box_n50_single"])

@@ -43,4 +43,9 @@ print(f"   slot busy fraction {tot.sum() / (slots * kcyc):.3f}; longest solve {t
       f"p50/p90/p99/max Mcycles {np.percentile(tot, 50) / 1e6:.2f}/{np.percentile(tot, 90) / 1e6:.2f}/{np.percentile(tot, 99) / 1e6:.2f}/{tot.max() / 1e6:.2f}")
 print(f"   cycles per backward knot {cyc[:, 0].sum() / bk:.0f} ({bk} knots); per rollout knot {cyc[:, 1].sum() / fk:.0f} ({fk} knots); "
       f"share bwd {cyc[:, 0].sum() / tot.sum():.3f} fwd {cyc[:, 1].sum() / tot.sum():.3f}")
+s7 = s0[:, 7] + s1[:, 7]   # packed kilo-cycles: Riccati | sequential rollout (both stages summed field-wise)
+ric = ((s0[:, 7] & 0xffffffff) + (s1[:, 7] & 0xffffffff)).sum() * 1024.0
+seq = ((s0[:, 7] >> 32) + (s1[:, 7] >> 32)).sum() * 1024.0
+print(f"   Riccati {ric / bk:.0f} cycles/backward knot, linearisation + rest {(cyc[:, 0].sum() - ric) / bk:.0f}; sequential rollout {seq / fk:.0f} cycles/rollout knot, "
+      f"rows + rest {(cyc[:, 1].sum() - seq) / fk:.0f}")
 s.close()
