@@ -275,42 +275,6 @@ template <class R> DDP_DEVICE void load_plane(const double *pl, int k, R *n) {
     n[0] = (R)pl[4 * k]; n[1] = (R)pl[4 * k + 1]; n[2] = (R)pl[4 * k + 2]; n[3] = (R)pl[4 * k + 3];
 }
 
-// Two-deep software pipeline over the rows of one group: slack, dual slack and plane of rows r+1 and r+2 are in
-// flight while row r is processed (the rolled row loops would otherwise wait one full memory latency per row).
-template <class R> struct RowPipe {
-    R s[2], y[2], n[2][4];
-    const R *sp, *yp;          // row arrays offset by the knot
-    const double *pl;
-    long long NP;
-    int g, PM, nr, infeas;
-    DDP_DEVICE void fetch(int slot, int r) {
-        if (r < nr) {
-            const long long ro = (long long)row_slot(g, r, PM) * NP;
-            s[slot] = sp[ro];
-            if (infeas) y[slot] = yp[ro];
-            if (g < 6) load_plane(pl, r, n[slot]);
-        }
-    }
-    DDP_DEVICE void start(int g_, int nr_) {
-        g = g_; nr = nr_;
-        s[0] = s[1] = R(0); y[0] = y[1] = R(1);
-        DDP_UNROLL
-        for (int e = 0; e < 4; e++) { n[0][e] = R(0); n[1][e] = R(0); }
-        fetch(0, 0);
-        fetch(1, 1);
-    }
-    // Row r: returns its data and starts loading row r+2 into the slot just freed.
-    DDP_DEVICE void next(int r, R lim, R &sv, R &yv, R *nn) {
-        sv = s[0]; yv = y[0];
-        if (g < 6) { nn[0] = n[0][0]; nn[1] = n[0][1]; nn[2] = n[0][2]; nn[3] = n[0][3]; }
-        else fixed_row(r, lim, nn);
-        s[0] = s[1]; y[0] = y[1];
-        DDP_UNROLL
-        for (int e = 0; e < 4; e++) n[0][e] = n[1][e];
-        fetch(1, r + 2);
-    }
-};
-
 // F, G of the segment dynamics x+ = (F (x) I3) x + (G (x) I3) u[0:9], ddp.cpp:862-871.  fg[o*6+l].
 template <class R> DDP_DEVICE void fg_matrix(const R *tp, R *fg) {
     fg[0] = R(1); fg[1] = tp[1]; fg[2] = tp[2] / R(2); fg[3] = tp[3]; fg[4] = tp[4]; fg[5] = tp[5];
@@ -494,8 +458,6 @@ template <class R> DDP_DEVICE_NOINLINE void linearize(Traj<R> &tt_, Reg<R, 2> &e
                 // ---- pass 1: rows -> weights -> per-group blocks.  One rolled loop over the 15 row groups and one over
                 // the rows of a group (a single copy of the row code: the kernel is instruction-fetch bound,
                 // profiles/r1c); the slack of row r+1 is loaded while row r is processed. ------------------------
-                RowPipe<R> pipe;
-                pipe.sp = t.s + i; pipe.yp = t.y + i; pipe.pl = pl; pipe.NP = t.NP; pipe.PM = t.PM; pipe.infeas = t.infeas;
                 DDP_NOUNROLL
                 for (int g = 0; g < 15; g++) {
                     const int shift = group_shift(g), nr = g < 6 ? P : 6;
@@ -506,11 +468,28 @@ template <class R> DDP_DEVICE_NOINLINE void linearize(Traj<R> &tt_, Reg<R, 2> &e
                     DDP_UNROLL
                     for (int a = 0; a < 3; a++) { cp[a] = dot_axis<R, 0>(b, z, a); cd[a] = dot_axis<R, 0>(bd, z, a); }
                     R M[6] = {R(0), R(0), R(0), R(0), R(0), R(0)}, wv[3] = {R(0), R(0), R(0)}, gv[3] = {R(0), R(0), R(0)};
-                    pipe.start(g, nr);
+                    // one-deep software pipeline: slack (and plane) of row r+1 are loaded while row r is processed.  Deeper
+                    // pipelines / two-row unrolling were measured slower at full occupancy: the kernel is bound by
+                    // instruction fetch and every extra copy of the row body costs more than the latency it hides.
+                    R s_n = R(0), y_n = R(1), n_n[4] = {R(0), R(0), R(0), R(0)};
+                    if (nr > 0) {
+                        const long long ro = (long long)row_slot(g, 0, t.PM) * t.NP + i;
+                        s_n = t.s[ro];
+                        if (t.infeas) y_n = t.y[ro];
+                        if (g < 6) load_plane(pl, 0, n_n);
+                    }
                     DDP_NOUNROLL
                     for (int r = 0; r < nr; r++) {
-                        R sv, yv, n[4];
-                        pipe.next(r, lim, sv, yv, n);
+                        const R sv = s_n, yv = y_n;
+                        R n[4];
+                        if (g < 6) { n[0] = n_n[0]; n[1] = n_n[1]; n[2] = n_n[2]; n[3] = n_n[3]; }
+                        else fixed_row(r, lim, n);
+                        if (r + 1 < nr) {
+                            const long long ro = (long long)row_slot(g, r + 1, t.PM) * t.NP + i;
+                            s_n = t.s[ro];
+                            if (t.infeas) y_n = t.y[ro];
+                            if (g < 6) load_plane(pl, r + 1, n_n);
+                        }
                         const R c = ((n[0] * cp[0] + n[1] * cp[1]) + n[2] * cp[2]) + n[3] - t.margin;
                         const R tc = (n[0] * cd[0] + n[1] * cd[1]) + n[2] * cd[2];
                         R Ds, gw;
@@ -1031,8 +1010,6 @@ template <class R> DDP_DEVICE_NOINLINE bool forward_trial(Traj<R> &tt_, R alpha,
                 A.lg.lp = R(1); A.lg.lsum = R(0); A.e1 = R(0); A.bad = 0;
                 const int P = t.nplanes[i];
                 const double *pl = t.planes + (long long)i * t.PM * 4;
-                RowPipe<R> pipe;
-                pipe.sp = t.s + i; pipe.yp = t.y + i; pipe.pl = pl; pipe.NP = t.NP; pipe.PM = t.PM; pipe.infeas = t.infeas;
                 DDP_NOUNROLL
                 for (int g = 0; g < 15; g++) {   // one copy of the row code for all groups (see linearize)
                     const int shift = group_shift(g), nr = g < 6 ? P : 6;
@@ -1046,12 +1023,26 @@ template <class R> DDP_DEVICE_NOINLINE bool forward_trial(Traj<R> &tt_, R alpha,
                         co[a] = dot_axis<R, 0>(b, zo, a); cd[a] = dot_axis<R, 0>(bd, zo, a); cn[a] = dot_axis<R, 0>(bn, zn, a);
                         j1[a] = dot_axis<R, 3>(b, v1, a); j2[a] = dot_axis<R, 0>(b, v2, a);
                     }
-                    pipe.start(g, nr);
+                    R s_n = R(0), y_n = R(1), n_n[4] = {R(0), R(0), R(0), R(0)};   // one-deep pipeline, see linearize
+                    if (nr > 0) {
+                        const long long ro = (long long)row_slot(g, 0, t.PM) * t.NP + i;
+                        s_n = t.s[ro];
+                        if (t.infeas) y_n = t.y[ro];
+                        if (g < 6) load_plane(pl, 0, n_n);
+                    }
                     DDP_NOUNROLL
                     for (int r = 0; r < nr; r++) {
-                        R sv, yv, n[4];
+                        const R sv = s_n, yv = y_n;
                         const long long ro_cur = (long long)row_slot(g, r, t.PM) * t.NP + i;
-                        pipe.next(r, lim, sv, yv, n);
+                        R n[4];
+                        if (g < 6) { n[0] = n_n[0]; n[1] = n_n[1]; n[2] = n_n[2]; n[3] = n_n[3]; }
+                        else fixed_row(r, lim, n);
+                        if (r + 1 < nr) {
+                            const long long ro = (long long)row_slot(g, r + 1, t.PM) * t.NP + i;
+                            s_n = t.s[ro];
+                            if (t.infeas) y_n = t.y[ro];
+                            if (g < 6) load_plane(pl, r + 1, n_n);
+                        }
                         const R cold = ((n[0] * co[0] + n[1] * co[1]) + n[2] * co[2]) + n[3] - t.margin;
                         const R cnew = ((n[0] * cn[0] + n[1] * cn[1]) + n[2] * cn[2]) + n[3] - t.margin;
                         const R tc = (n[0] * cd[0] + n[1] * cd[1]) + n[2] * cd[2];
