@@ -16,10 +16,10 @@
 #include "ipddp_solver.h"
 
 #ifndef DDP_MAX_THREADS
-#define DDP_MAX_THREADS 64   // two trajectories (warps) per CTA
+#define DDP_MAX_THREADS 128  // four trajectories (warps) per CTA: up to three helpers for the last solve of a CTA
 #endif
 #ifndef DDP_MIN_BLOCKS
-#define DDP_MIN_BLOCKS 4     // => <= 255 registers/thread available, >= 8 resident trajectories per SM
+#define DDP_MIN_BLOCKS 2     // => <= 255 registers/thread available, 8 resident trajectories per SM
 #endif
 
 namespace {
@@ -33,19 +33,30 @@ __global__ void __launch_bounds__(DDP_MAX_THREADS, DDP_MIN_BLOCKS) ipddp_solve_k
     R *tabs = sm_all;  // 360 table entries shared by the block
     for (int i = threadIdx.x; i < 360; i += blockDim.x) tabs[i] = tabs_g[i];
     __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
     const int per_warp = ddp::smem_elems_per_warp(A.PM);
     R *sm = sm_all + 360 + warp * per_warp;
-    const long long slot = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+    // job boards (one per warp) + CTA control block behind the per-warp scratch areas, 16-byte aligned
+    ddp::JobBoard<R> *boards = reinterpret_cast<ddp::JobBoard<R> *>(
+        smraw + (((size_t)(360 + wpb * per_warp) * sizeof(R) + 15) & ~(size_t)15));
+    ddp::BlockCtl *ctl = reinterpret_cast<ddp::BlockCtl *>(boards + wpb);
+    if (lane == 0) { boards[warp].word = 0ull; boards[warp].done = 0; boards[warp].owner_seq = 0; }
+    if (threadIdx.x == 0) { ctl->active_owners = wpb; ctl->jobs_ctr = A.counter + 1; }
+    __syncthreads();
+    const long long slot = (long long)blockIdx.x * wpb + warp;
     R *ws = reinterpret_cast<R *>(A.ws) + slot * A.ws_stride;
     while (true) {
         unsigned int b = 0;
         if (lane == 0) b = atomicAdd(A.counter, 1u);
         b = __shfl_sync(0xffffffffu, b, 0);
         if (b >= (unsigned int)A.B) break;
-        if (A.two_stage) ddp::solve_one<R>(A, 0, (int)b, sm, tabs, ws, lane);
-        ddp::solve_one<R>(A, A.two_stage ? 1 : 0, (int)b, sm, tabs, ws, lane);
+        if (A.two_stage) ddp::solve_one<R>(A, 0, (int)b, sm, tabs, ws, lane, boards + warp, A.coop ? ctl : nullptr, wpb);
+        ddp::solve_one<R>(A, A.two_stage ? 1 : 0, (int)b, sm, tabs, ws, lane, boards + warp, A.coop ? ctl : nullptr, wpb);
     }
+    // queue empty: help the warps of this CTA that still own a trajectory (ipddp_solver.h "Intra-CTA cooperation")
+    if (lane == 0) atomicSub(&ctl->active_owners, 1);
+    __syncwarp();
+    if (wpb > 1 && A.coop) ddp::helper_loop<R>(boards, ctl, wpb, warp, sm, lane, A.counter + 2);
 }
 
 // initTimeAllocation, teach_repeat_planner.cpp:583-639 (v0 = 0): one thread per segment.
@@ -169,7 +180,8 @@ template <class R> int launch(H *h, SolveArgs &A, cudaStream_t s) {
     const int wpb = h->opts.warps_per_block > 0 ? h->opts.warps_per_block : DDP_MAX_THREADS / 32;
     const int threads = wpb * 32;
     if (threads > DDP_MAX_THREADS) { h->err = "warps_per_block exceeds the kernel's launch bound"; return DIRECT_DDP_ERR_ARG; }
-    const size_t smem = (size_t)(360 + wpb * ddp::smem_elems_per_warp(A.PM)) * sizeof(R);
+    const size_t smem = (((size_t)(360 + wpb * ddp::smem_elems_per_warp(A.PM)) * sizeof(R) + 15) & ~(size_t)15) +
+                        (size_t)ddp::coop_smem_bytes<R>(wpb);
     auto kern = ipddp_solve_kernel<R>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (const char *e = getenv("DIRECT_DDP_CARVEOUT"))   // tuning knob: shared-memory share of the unified L1 (percent)
@@ -197,6 +209,10 @@ template <class R> int launch(H *h, SolveArgs &A, cudaStream_t s) {
     if (st) return st;
     CK(cudaMemsetAsync(h->counter.p, 0, 16, s));
     A.counter = (unsigned int *)h->counter.p;
+    {
+        const char *e = getenv("DIRECT_DDP_COOP");   // tuning knob: 0 disables the tail balancing
+        A.coop = (e && atoi(e) == 0) ? 0 : 1;
+    }
     if (h->opts.trace) {
         if ((st = ensure(h, h->trace, 512 * 12 * sizeof(double)))) return st;
         if ((st = ensure(h, h->trace_len, 16))) return st;
@@ -500,6 +516,9 @@ int direct_ddp_last_stats(direct_ddp_handle h, direct_ddp_stats *out) {
             for (int i = 0; i < h->last_B; i++) for (int k = 0; k < 4; k++) tot[k] += tmp[(size_t)i * 8 + k];
         }
         h->stats.bwd_sweeps = tot[0]; h->stats.bwd_knots = tot[1]; h->stats.fwd_trials = tot[2]; h->stats.fwd_knots = tot[3];
+        unsigned int cnt[4] = {0, 0, 0, 0};
+        CK(cudaMemcpy(cnt, h->counter.p, sizeof cnt, cudaMemcpyDeviceToHost));
+        h->stats.coop_jobs = cnt[1]; h->stats.helper_units = cnt[2];
         h->stats_valid = true;
     }
     *out = h->stats;

@@ -113,6 +113,7 @@ struct SolveArgs {
     const int32_t *infeas;
     double max_vel, max_acc;
     StageCfg cfg[2];
+    int coop;          // 1: idle warps of a CTA help its remaining solves (tail balancing)
     int two_stage;     // 0: cfg[0] only, outputs -> out[1]; 1: stage 0 (out[0] optional) then stage 1
     OutPtrs out[2];
     double *bez_tmp, *time_tmp;  // [B][N][18], [B][N] scratch carrying stage 0 -> stage 1
@@ -209,6 +210,8 @@ template <class R> struct Traj {
     long long n_bwd_sweeps, n_bwd_knots, n_fwd_trials, n_fwd_knots;
     long long cyc_bwd, cyc_fwd, cyc_t0;  // clock64 accounting (0 in the emulation)
     long long cyc_ric, cyc_seq;          // of which: Riccati recursion, sequential state rollout
+    void *board, *ctl;                   // JobBoard<R> of this warp / BlockCtl of the CTA (null: no cooperation)
+    int wpb;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -424,12 +427,381 @@ DDP_DEVICE void lin_diag_group(const R *tab, int g, const R *tp, R m0, R m1, R m
 }
 
 // =============================================================================================
+// Intra-CTA cooperation.  A batch is heavy-tailed: a few solves run stage 1 to iter_max with ~5 full rollouts per
+// iteration and take 10-15x the mean, so once the work queue is empty the kernel time is the latency of the last
+// few solves, each on ONE warp (tools/cycle_report.py: 0.87 of the kernel at B = 4096).  A warp that finds the
+// queue empty therefore stays as a HELPER of the warps of its CTA that still own a trajectory: the owner posts the
+// knot-parallel phases as jobs of independent units on a board in shared memory (linearisation: one unit per 32
+// knots; line-search rows of a 32-knot block: four units of row groups), owner and helpers claim units with a CAS
+// on one packed word and the owner reduces the per-unit results in unit order, so the arithmetic - and the result,
+// bit for bit - is the same with or without helpers.
+// =============================================================================================
+enum { JOB_LIN = 1, JOB_ROWS = 2, JOB_MAX_UNITS = 16 };
+template <class R> struct JobCtx {   // everything a unit needs; copied to registers by whoever runs the unit
+    RowCtx<R> row;
+    const R *xu, *xun, *K, *kdx;
+    R *H, *aux;
+    int N, base, time_power, type;
+    R w_snap, w_time, alpha, tau;
+};
+template <class R> struct JobBoard {
+    unsigned long long word;   // (job sequence number << 32) | (units << 16) | next unclaimed unit
+    int done;                  // units completed
+    int owner_seq;             // owner only: last sequence number used
+    JobCtx<R> ctx;
+    R res[JOB_MAX_UNITS][2];   // JOB_LIN: per-unit max |r|, max |c + y|
+    R *part;                   // JOB_ROWS: [4][3][32] per-unit, per-lane {stage cost, sum log, |c + y|_1} and
+    int *badl;                 //           [4][32] per-lane first failing knot, both in the OWNER's MSC scratch
+};
+struct BlockCtl {
+    int active_owners;         // warps of the CTA that still pull trajectories from the queue
+    int pad;
+    unsigned int *jobs_ctr;    // global counter of posted jobs (statistics)
+};
+template <class R> DDP_HD int coop_smem_bytes(int warps_per_block) {
+    return (int)(sizeof(JobBoard<R>) * warps_per_block + sizeof(BlockCtl));
+}
+
+// =============================================================================================
 // Backward pass, knot-parallel part (lane <-> knot): everything of ddp.cpp:476-590 that does not depend
 // on the value function.  Per knot it writes the constraint + stage-cost part of the augmented Hessian
 //   Hc = [ H  g ; g^T . ]  (20 x 20, z order [u(9), T, x(9), gradient])  to t.H and  fT = dx+/dT  to t.aux.
 // Returns per-lane maxima of |r| and |c+y| in errs (ddp.cpp:636-637).
 // =============================================================================================
-template <class R> DDP_DEVICE_NOINLINE void linearize(Traj<R> &tt_, Reg<R, 2> &errs) {
+template <class R> DDP_DEVICE_NOINLINE void lin_unit(const JobCtx<R> *cp_, int u, R *smw, int lane_, Reg<R, 2> &errs) {
+    const JobCtx<R> c = *cp_;
+    const RowCtx<R> t = c.row;
+    const int N = c.N, time_power = c.time_power;
+    const R w_snap = c.w_snap, w_time = c.w_time;
+    const R *DDP_RESTRICT xu = c.xu;
+    R *DDP_RESTRICT Hout = c.H;
+    R *DDP_RESTRICT auxout = c.aux;
+    const R sgn = t.infeas ? R(1) : R(-1);
+    {
+        const int base = 32 * (c.base + u);
+        FOR_LANES(lane) {
+            const int i = base + lane;
+            if (i < N) {
+                R emu = errs(lane, 0), ecy = errs(lane, 1);
+                R z[19], tp[6];
+                DDP_UNROLL
+                for (int e = 0; e < 19; e++) z[e] = xu[(long long)i * 20 + e];
+                time_powers(z[9], tp);
+                const int P = t.nplanes[i];
+                const double *pl = t.planes + (long long)i * t.PM * 4;
+                R *msc = smw + Lay::MSC + lane;
+                R accT[18], accG[18], tt = R(0), gt = R(0);
+                DDP_UNROLL
+                for (int e = 0; e < 18; e++) { accT[e] = R(0); accG[e] = R(0); }
+                // ---- pass 1: rows -> weights -> per-group blocks.  One rolled loop over the 15 row groups and one over
+                // the rows of a group (a single copy of the row code: the kernel is instruction-fetch bound,
+                // profiles/r1c); the slack of row r+1 is loaded while row r is processed. ------------------------
+                DDP_NOUNROLL
+                for (int g = 0; g < 15; g++) {
+                    const int shift = group_shift(g), nr = g < 6 ? P : 6;
+                    const R lim = g < 11 ? t.max_vel : t.max_acc;
+                    R b[6], bd[6], cp[3], cd[3];
+                    basis_row_rt(t.tab + g * 6, shift, tp, b);
+                    basis_row_rt(t.tab + 90 + g * 6, shift + 1, tp, bd);
+                    DDP_UNROLL
+                    for (int a = 0; a < 3; a++) { cp[a] = dot_axis<R, 0>(b, z, a); cd[a] = dot_axis<R, 0>(bd, z, a); }
+                    R M[6] = {R(0), R(0), R(0), R(0), R(0), R(0)}, wv[3] = {R(0), R(0), R(0)}, gv[3] = {R(0), R(0), R(0)};
+                    // one-deep software pipeline: slack (and plane) of row r+1 are loaded while row r is processed.  Deeper
+                    // pipelines / two-row unrolling were measured slower at full occupancy: the kernel is bound by
+                    // instruction fetch and every extra copy of the row body costs more than the latency it hides.
+                    R s_n = R(0), y_n = R(1), n_n[4] = {R(0), R(0), R(0), R(0)};
+                    if (nr > 0) {
+                        const long long ro = (long long)row_slot(g, 0, t.PM) * t.NP + i;
+                        s_n = t.s[ro];
+                        if (t.infeas) y_n = t.y[ro];
+                        if (g < 6) load_plane(pl, 0, n_n);
+                    }
+                    DDP_NOUNROLL
+                    for (int r = 0; r < nr; r++) {
+                        const R sv = s_n, yv = y_n;
+                        R n[4];
+                        if (g < 6) { n[0] = n_n[0]; n[1] = n_n[1]; n[2] = n_n[2]; n[3] = n_n[3]; }
+                        else fixed_row(r, lim, n);
+                        if (r + 1 < nr) {
+                            const long long ro = (long long)row_slot(g, r + 1, t.PM) * t.NP + i;
+                            s_n = t.s[ro];
+                            if (t.infeas) y_n = t.y[ro];
+                            if (g < 6) load_plane(pl, r + 1, n_n);
+                        }
+                        const R c = ((n[0] * cp[0] + n[1] * cp[1]) + n[2] * cp[2]) + n[3] - t.margin;
+                        const R tc = (n[0] * cd[0] + n[1] * cd[1]) + n[2] * cd[2];
+                        R Ds, gw;
+                        row_weights(t.infeas, t.mu, sgn, c, sv, yv, Ds, gw, emu, ecy);
+                        M[0] += Ds * (n[0] * n[0]); M[1] += Ds * (n[0] * n[1]); M[2] += Ds * (n[0] * n[2]);
+                        M[3] += Ds * (n[1] * n[1]); M[4] += Ds * (n[1] * n[2]); M[5] += Ds * (n[2] * n[2]);
+                        const R dt = Ds * tc, gtc = gw * tc;
+                        wv[0] += dt * n[0]; wv[1] += dt * n[1]; wv[2] += dt * n[2];
+                        gv[0] += gw * n[0]; gv[1] += gw * n[1]; gv[2] += gw * n[2];
+                        tt += dt * tc; gt += gtc;
+                    }
+                    if (g < 6) {
+                        DDP_UNROLL
+                        for (int e = 0; e < 6; e++) msc[(g * 6 + e) * 32] = M[e];
+                    } else {   // +-e_a rows: M is diagonal
+                        msc[(36 + 3 * (g - 6)) * 32] = M[0]; msc[(37 + 3 * (g - 6)) * 32] = M[3]; msc[(38 + 3 * (g - 6)) * 32] = M[5];
+                    }
+                    DDP_UNROLL
+                    for (int l = 0; l < 6; l++) {
+                        DDP_UNROLL
+                        for (int a = 0; a < 3; a++) { accT[l * 3 + a] += b[l] * wv[a]; accG[l * 3 + a] += b[l] * gv[a]; }
+                    }
+                }
+                {   // the time row -T + 0.3 <= 0 (ddp.cpp:1279): Jacobian -1 in the T entry only
+                    const long long ro = (long long)(6 * t.PM + 54) * t.NP + i;
+                    R Ds, gw;
+                    row_weights(t.infeas, t.mu, sgn, -z[9] + R(0.3) - t.margin, t.s[ro], t.infeas ? t.y[ro] : R(1), Ds, gw, emu, ecy);
+                    tt += Ds; gt -= gw;
+                }
+                errs(lane, 0) = emu; errs(lane, 1) = ecy;
+                // ---- stage cost (ddp.cpp:1338-1368): quu = w [R (x) I, R'u; (R'u)^T, .], qu = w [R u; .] --------
+                R rm[9], Ru[9], Rpu[9], Rppu[9];
+                rmat<R>(0, tp, rm);
+                rmat_times_u(rm, z, Ru);
+                {
+                    R r1[9], r2[9];
+                    rmat<R>(1, tp, r1); rmat_times_u(r1, z, Rpu);
+                    rmat<R>(2, tp, r2); rmat_times_u(r2, z, Rppu);
+                }
+                const R uRpu = dot9(z, Rpu), uRppu = dot9(z, Rppu);
+                R quT, quuTT;
+                if (time_power == 2) { quT = w_time * z[9] + R(0.5) * w_snap * uRpu; quuTT = w_time + R(0.5) * w_snap * uRppu; }
+                else { quT = R(0.5) * w_time + R(0.5) * w_snap * uRpu; quuTT = R(0.5) * w_snap * uRppu; }
+                // ---- write row/column T and the gradient -------------------------------------------------------
+                R *Hi = Hout + (long long)i * 400;
+                DDP_UNROLL
+                for (int l = 0; l < 6; l++) {
+                    DDP_UNROLL
+                    for (int a = 0; a < 3; a++) {
+                        const int r = zidx(l, a);
+                        R hT = accT[l * 3 + a], gr = accG[l * 3 + a];
+                        if (l >= 3) { hT += w_snap * Rpu[r]; gr += w_snap * Ru[r]; }
+                        Hi[r * 20 + 9] = hT; Hi[9 * 20 + r] = hT;
+                        Hi[r * 20 + 19] = gr; Hi[19 * 20 + r] = gr;
+                    }
+                }
+                Hi[9 * 20 + 9] = quuTT + tt;
+                Hi[9 * 20 + 19] = quT + gt; Hi[19 * 20 + 9] = quT + gt;
+                Hi[19 * 20 + 19] = R(0);
+                R fT[9];
+                ft_vector(tp, z, fT);
+                DDP_UNROLL
+                for (int q = 0; q < 9; q++) auxout[(long long)i * 12 + q] = fT[q];
+                // ---- pass 2: H[(l,a),(l',a')] = sum_g beta_g[l] beta_g[l'] M_g[a][a'] ------------------------------
+                {   // same-axis blocks: all 15 groups, plus the stage cost w R (x) I on the u coefficients
+                    R h0[21], h1[21], h2[21];
+                    DDP_UNROLL
+                    for (int e = 0; e < 21; e++) { h0[e] = R(0); h1[e] = R(0); h2[e] = R(0); }
+                    DDP_NOUNROLL
+                    for (int g = 0; g < 6; g++)
+                        lin_diag_group<R, 0>(t.tab, g, tp, msc[(g * 6 + 0) * 32], msc[(g * 6 + 3) * 32], msc[(g * 6 + 5) * 32], h0, h1, h2);
+                    DDP_NOUNROLL
+                    for (int g = 6; g < 11; g++)
+                        lin_diag_group<R, 1>(t.tab, g, tp, msc[(36 + 3 * (g - 6)) * 32], msc[(37 + 3 * (g - 6)) * 32],
+                                             msc[(38 + 3 * (g - 6)) * 32], h0, h1, h2);
+                    DDP_NOUNROLL
+                    for (int g = 11; g < 15; g++)
+                        lin_diag_group<R, 2>(t.tab, g, tp, msc[(36 + 3 * (g - 6)) * 32], msc[(37 + 3 * (g - 6)) * 32],
+                                             msc[(38 + 3 * (g - 6)) * 32], h0, h1, h2);
+                    DDP_UNROLL
+                    for (int lb = 0; lb < 6; lb++) {
+                        DDP_UNROLL
+                        for (int la = 0; la <= lb; la++) {
+                            const int e = pidx(la, lb);
+                            R v0 = h0[e], v1 = h1[e], v2 = h2[e];
+                            if (la >= 3) { const R q = w_snap * rm[(la - 3) * 3 + (lb - 3)]; v0 += q; v1 += q; v2 += q; }
+                            const int r = zidx(la, 0), c = zidx(lb, 0);
+                            Hi[r * 20 + c] = v0; Hi[c * 20 + r] = v0;
+                            Hi[(r + 1) * 20 + c + 1] = v1; Hi[(c + 1) * 20 + r + 1] = v1;
+                            Hi[(r + 2) * 20 + c + 2] = v2; Hi[(c + 2) * 20 + r + 2] = v2;
+                        }
+                    }
+                }
+                {   // cross-axis blocks (0,1), (0,2), (1,2): only the position groups have off-diagonal M_g
+                    R h0[21], h1[21], h2[21];
+                    DDP_UNROLL
+                    for (int e = 0; e < 21; e++) { h0[e] = R(0); h1[e] = R(0); h2[e] = R(0); }
+                    DDP_NOUNROLL
+                    for (int g = 0; g < 6; g++)
+                        lin_diag_group<R, 0>(t.tab, g, tp, msc[(g * 6 + 1) * 32], msc[(g * 6 + 2) * 32], msc[(g * 6 + 4) * 32], h0, h1, h2);
+                    DDP_UNROLL
+                    for (int lb = 0; lb < 6; lb++) {
+                        DDP_UNROLL
+                        for (int la = 0; la <= lb; la++) {
+                            const int e = pidx(la, lb);
+                            const int ra = zidx(la, 0), rb = zidx(lb, 0);
+                            // axes (0,1): entries ((la,0),(lb,1)) and ((lb,0),(la,1)) and their transposes; likewise (0,2), (1,2)
+                            Hi[ra * 20 + rb + 1] = h0[e]; Hi[(rb + 1) * 20 + ra] = h0[e];
+                            Hi[rb * 20 + ra + 1] = h0[e]; Hi[(ra + 1) * 20 + rb] = h0[e];
+                            Hi[ra * 20 + rb + 2] = h1[e]; Hi[(rb + 2) * 20 + ra] = h1[e];
+                            Hi[rb * 20 + ra + 2] = h1[e]; Hi[(ra + 2) * 20 + rb] = h1[e];
+                            Hi[(ra + 1) * 20 + rb + 2] = h2[e]; Hi[(rb + 2) * 20 + ra + 1] = h2[e];
+                            Hi[(rb + 1) * 20 + ra + 2] = h2[e]; Hi[(ra + 2) * 20 + rb + 1] = h2[e];
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
+// ---- job board protocol (GPU only; the CPU emulation runs every unit in the owner) --------------------------------
+// One unit of the line-search rows (defined below): per-lane partials of units u0 .. u1-1 into part / badk.
+template <class R>
+DDP_DEVICE_NOINLINE void rows_unit(const JobCtx<R> *cp_, int u0, int u1, int lane_, Reg<R, 12> &part, Reg<int, 4> &badk);
+
+#if DDP_GPU
+// Claim the next unit of the job currently posted on `b` (any job when want_seq == 0): returns the unit or -1.
+template <class R> DDP_DEVICE int job_claim(JobBoard<R> *b, unsigned want_seq) {
+    int u = -1;
+    if ((threadIdx.x & 31) == 0) {
+        unsigned long long w = *(volatile unsigned long long *)&b->word;
+        while (true) {
+            const unsigned sq = (unsigned)(w >> 32);
+            const int n = (int)((w >> 16) & 0xffff), nx = (int)(w & 0xffff);
+            if (sq == 0 || (want_seq != 0 && sq != want_seq) || nx >= n) { u = -1; break; }
+            const unsigned long long old = atomicCAS(&b->word, w, w + 1);
+            if (old == w) { u = nx; break; }
+            w = old;
+        }
+    }
+    return __shfl_sync(0xffffffffu, u, 0);
+}
+// Run unit u of the job on `b` with this warp's scratch and leave its result on the board.
+template <class R> DDP_DEVICE_NOINLINE void job_run_unit(JobBoard<R> *b, int u, R *smw, int lane_) {
+    if (*(volatile int *)&b->ctx.type == JOB_LIN) {
+        Reg<R, 2> errs;
+        errs(lane_, 0) = R(0); errs(lane_, 1) = R(0);
+        lin_unit(&b->ctx, u, smw, lane_, errs);
+        const R e0 = warp_max(errs, 0, lane_), e1 = warp_max(errs, 1, lane_);
+        if (lane_ == 0) { b->res[u][0] = e0; b->res[u][1] = e1; }
+    } else {
+        Reg<R, 12> part;
+        Reg<int, 4> badk;
+        rows_unit(&b->ctx, u, u + 1, lane_, part, badk);
+        DDP_UNROLL
+        for (int e = 0; e < 4; e++) {
+            if (e == u) {
+                R *pp = b->part + e * 96 + lane_;
+                pp[0] = part(lane_, 3 * e); pp[32] = part(lane_, 3 * e + 1); pp[64] = part(lane_, 3 * e + 2);
+                b->badl[e * 32 + lane_] = badk(lane_, e);
+            }
+        }
+    }
+    __threadfence_block();   // the unit's global and shared writes are visible to the CTA before it counts as done
+    __syncwarp();
+    if (lane_ == 0) atomicAdd(&b->done, 1);
+}
+// Owner: post a job of n units, work on it together with the helpers, return when every unit is done.
+template <class R> DDP_DEVICE_NOINLINE void job_run(Traj<R> &t, const JobCtx<R> &ctx, int n) {
+    const int lane_ = t.lane_;
+    JobBoard<R> *b = (JobBoard<R> *)t.board;
+    __threadfence_block();   // this warp's global writes (candidate point, gains) before the job becomes visible
+    __syncwarp();
+    unsigned seq = 0;
+    if (lane_ == 0) {
+        atomicAdd(((BlockCtl *)t.ctl)->jobs_ctr, 1u);
+        seq = (unsigned)(++b->owner_seq);
+        b->ctx = ctx;
+        b->part = t.sm + Lay::MSC + 512;                 // behind forward_trial's knot ring [0, 480)
+        b->badl = (int *)(t.sm + Lay::MSC + 896);
+        b->done = 0;
+        __threadfence_block();
+        *(volatile unsigned long long *)&b->word = ((unsigned long long)seq << 32) | ((unsigned long long)n << 16);
+    }
+    seq = __shfl_sync(0xffffffffu, seq, 0);
+    while (true) {
+        const int u = job_claim(b, seq);
+        if (u < 0) break;
+        job_run_unit(b, u, t.sm, lane_);
+    }
+    if (lane_ == 0) {
+        while (*(volatile int *)&b->done < n) __nanosleep(100);
+    }
+    __syncwarp();
+    __threadfence_block();
+}
+// A warp without a trajectory serves the boards of its CTA until no warp of the CTA owns one any more.
+template <class R>
+DDP_DEVICE_NOINLINE void helper_loop(JobBoard<R> *boards, BlockCtl *ctl, int wpb, int me, R *sm, int lane_, unsigned int *units_ctr) {
+    while (*(volatile int *)&ctl->active_owners > 0) {
+        bool found = false;
+        for (int w = 0; w < wpb; w++) {
+            if (w == me) continue;
+            const int u = job_claim(boards + w, 0u);
+            if (u < 0) continue;
+            found = true;
+            job_run_unit(boards + w, u, sm, lane_);
+            if (lane_ == 0) atomicAdd(units_ctr, 1u);
+        }
+        if (!found) __nanosleep(400);
+    }
+}
+#endif
+
+template <class R> DDP_DEVICE bool coop_has_helpers(const Traj<R> &t) {
+#if DDP_GPU
+    return t.ctl != nullptr && *(volatile int *)&((BlockCtl *)t.ctl)->active_owners < t.wpb;
+#else
+    (void)t;
+    return false;
+#endif
+}
+
+// Line-search rows of one 32-knot block: per-lane partials of the four units.  Alone (one call, the knot's data
+// loaded once) or, when a warp of the CTA is idle, as a job of four units; the partials are the same either way.
+template <class R> DDP_DEVICE void run_rows(Traj<R> &t, const JobCtx<R> &ctx, Reg<R, 12> &part, Reg<int, 4> &badk) {
+    const int lane_ = t.lane_;
+#if DDP_GPU
+    if (coop_has_helpers(t)) {
+        job_run(t, ctx, 4);
+        JobBoard<R> *b = (JobBoard<R> *)t.board;
+        DDP_UNROLL
+        for (int e = 0; e < 4; e++) {
+            const R *pp = b->part + e * 96 + lane_;
+            part(lane_, 3 * e) = pp[0]; part(lane_, 3 * e + 1) = pp[32]; part(lane_, 3 * e + 2) = pp[64];
+            badk(lane_, e) = b->badl[e * 32 + lane_];
+        }
+        __syncwarp();
+        return;
+    }
+#endif
+    rows_unit(&ctx, 0, 4, lane_, part, badk);
+}
+
+// Linearisation of the whole trajectory as a job of one unit per 32 knots (idle warps of the CTA available).
+template <class R> DDP_DEVICE_NOINLINE void linearize_coop(Traj<R> &t, R &emu_max, R &ecy_max) {
+    const int lane_ = t.lane_;
+    JobCtx<R> c;
+    c.row = row_ctx(t);
+    c.xu = t.xu; c.xun = t.xun; c.K = t.K; c.kdx = t.kdx; c.H = t.H; c.aux = t.aux;
+    c.N = t.N; c.base = 0; c.time_power = t.time_power; c.type = JOB_LIN;
+    c.w_snap = t.w_snap; c.w_time = t.w_time; c.alpha = R(0); c.tau = R(0);
+    const int n = (t.N + 31) / 32;
+    emu_max = R(0); ecy_max = R(0);
+#if DDP_GPU
+    if (n > 1 && n <= JOB_MAX_UNITS && coop_has_helpers(t)) {
+        job_run(t, c, n);
+        JobBoard<R> *b = (JobBoard<R> *)t.board;
+        for (int u = 0; u < n; u++) { emu_max = amax(emu_max, b->res[u][0]); ecy_max = amax(ecy_max, b->res[u][1]); }
+        __syncwarp();
+        return;
+    }
+#endif
+    Reg<R, 2> errs;
+    FOR_LANES(lane) { errs(lane, 0) = R(0); errs(lane, 1) = R(0); }
+    for (int u = 0; u < n; u++) lin_unit(&c, u, t.sm, lane_, errs);
+    emu_max = warp_max(errs, 0, lane_);
+    ecy_max = warp_max(errs, 1, lane_);
+}
+
+// The same linearisation for a warp working alone (the common case): lin_unit's arithmetic over all 32-knot chunks in
+// one function, so that the bulk of a batch runs the small code it ran before cooperation existed.
+template <class R> DDP_DEVICE_NOINLINE void linearize_solo(Traj<R> &tt_, Reg<R, 2> &errs) {
     const int lane_ = tt_.lane_;
     const RowCtx<R> t = row_ctx(tt_);
     const int N = tt_.N, time_power = tt_.time_power;
@@ -828,10 +1200,14 @@ template <class R> DDP_DEVICE_NOINLINE void backward_pass(Traj<R> &t) {
     // The linearisation depends on the iterate and on mu only: a retry after a failed factorisation or after a
     // failed line search (the reference does not relinearise either, ddp.cpp:476) reuses it.
     if (!t.lin_valid) {
-        Reg<R, 2> errs;
-        linearize(t, errs);
-        t.lin_emu = warp_max(errs, 0, lane_);
-        t.lin_ecy = warp_max(errs, 1, lane_);
+        if (coop_has_helpers(t)) {
+            linearize_coop(t, t.lin_emu, t.lin_ecy);
+        } else {
+            Reg<R, 2> errs;
+            linearize_solo(t, errs);
+            t.lin_emu = warp_max(errs, 0, lane_);
+            t.lin_ecy = warp_max(errs, 1, lane_);
+        }
         t.lin_valid = 1;
     }
     WARP_SYNC();
@@ -902,16 +1278,266 @@ template <class R> DDP_DEVICE void warp_copy_async(R *dst, const R *src, int n, 
     for (int c = lane; c < chunks; c += 32) cp_async<16>((char *)dst + 16 * c, (const char *)src + 16 * c);
 }
 // Stage knot i of the line search: gains [ku | Ku] (100) and the old point [u; x] (20).
-template <class R> DDP_DEVICE void stage_knot(R *slot, const R *K, const R *xu, int i, int lane) {
+template <class R> DDP_DEVICE_NOINLINE void stage_knot(R *slot, const R *K, const R *xu, int i, int lane) {
     warp_copy_async(slot, K + (long long)i * 100, 100, lane);
     warp_copy_async(slot + 100, xu + (long long)i * 20, 20, lane);
+}
+
+// Units u0 .. u1-1 of the line-search rows of the 32-knot block c.base (lane <-> knot).  Unit u covers the row
+// groups 4u .. 4u+3; the last one (groups 12-14) also takes the time row and the stage cost.  Per unit and lane:
+// part(3u..3u+2) = {stage cost, sum log(barrier argument), |c + y|_1}, badk(u) = this lane's knot if it fails the
+// fraction-to-boundary rule (ddp.cpp:683-687 / :699-703), else 0x7fffffff.
+template <class R>
+DDP_DEVICE_NOINLINE void rows_unit(const JobCtx<R> *cp_, int u0, int u1, int lane_, Reg<R, 12> &part, Reg<int, 4> &badk) {
+    (void)lane_;
+    const JobCtx<R> c = *cp_;
+    const RowCtx<R> t = c.row;
+    const int N = c.N, time_power = c.time_power;
+    const R w_snap = c.w_snap, w_time = c.w_time, alpha = c.alpha, tau = c.tau;
+    const R *DDP_RESTRICT xu = c.xu;
+    const R *DDP_RESTRICT xun = c.xun;
+    const R *DDP_RESTRICT Kin = c.K;
+    const R *DDP_RESTRICT kdxo = c.kdx;
+    // the knot's old/new point and gains are loaded once for all units of the call
+    FOR_LANES(lane) {
+        const int i = c.base + lane;
+        DDP_UNROLL
+        for (int e = 0; e < 12; e++) part(lane, e) = R(0);
+        DDP_UNROLL
+        for (int e = 0; e < 4; e++) badk(lane, e) = 0x7fffffff;
+        if (i < N) {
+            R zo[19], zn[19], v1[10], v2[19], tpo[6], tpn[6];
+            DDP_UNROLL
+            for (int e = 0; e < 19; e++) { zo[e] = xu[(long long)i * 20 + e]; zn[e] = xun[(long long)i * 20 + e]; }
+            DDP_UNROLL
+            for (int e = 0; e < 10; e++) { v1[e] = Kin[(long long)i * 100 + e * 10]; v2[e] = kdxo[(long long)i * 10 + e]; }
+            DDP_UNROLL
+            for (int e = 10; e < 19; e++) v2[e] = zn[e] - zo[e];
+            time_powers(zo[9], tpo);
+            time_powers(zn[9], tpn);
+            const int P = t.nplanes[i];
+            const double *pl = t.planes + (long long)i * t.PM * 4;
+            TrialAcc<R> A;
+            A.lg.lp = R(1); A.lg.lsum = R(0); A.e1 = R(0); A.bad = 0;
+            R q_cost = R(0);
+            DDP_NOUNROLL
+            for (int g = 4 * u0; g < 16 && g < 4 * u1; g++) {   // g = 15: the time row and the stage cost
+                if (g < 15) {   // one copy of the row code for all groups (see lin_unit)
+                    const int shift = group_shift(g), nr = g < 6 ? P : 6;
+                    const R lim = g < 11 ? t.max_vel : t.max_acc;
+                    R b[6], bd[6], bn[6], co[3], cd[3], cn[3], j1[3], j2[3];
+                    basis_row_rt(t.tab + g * 6, shift, tpo, b);
+                    basis_row_rt(t.tab + 90 + g * 6, shift + 1, tpo, bd);
+                    basis_row_rt(t.tab + g * 6, shift, tpn, bn);
+                    DDP_UNROLL
+                    for (int a = 0; a < 3; a++) {
+                        co[a] = dot_axis<R, 0>(b, zo, a); cd[a] = dot_axis<R, 0>(bd, zo, a); cn[a] = dot_axis<R, 0>(bn, zn, a);
+                        j1[a] = dot_axis<R, 3>(b, v1, a); j2[a] = dot_axis<R, 0>(b, v2, a);
+                    }
+                    R s_n = R(0), y_n = R(1), n_n[4] = {R(0), R(0), R(0), R(0)};   // one-deep pipeline, see lin_unit
+                    if (nr > 0) {
+                        const long long ro = (long long)row_slot(g, 0, t.PM) * t.NP + i;
+                        s_n = t.s[ro];
+                        if (t.infeas) y_n = t.y[ro];
+                        if (g < 6) load_plane(pl, 0, n_n);
+                    }
+                    DDP_NOUNROLL
+                    for (int r = 0; r < nr; r++) {
+                        const R sv = s_n, yv = y_n;
+                        const long long ro_cur = (long long)row_slot(g, r, t.PM) * t.NP + i;
+                        R n[4];
+                        if (g < 6) { n[0] = n_n[0]; n[1] = n_n[1]; n[2] = n_n[2]; n[3] = n_n[3]; }
+                        else fixed_row(r, lim, n);
+                        if (r + 1 < nr) {
+                            const long long ro = (long long)row_slot(g, r + 1, t.PM) * t.NP + i;
+                            s_n = t.s[ro];
+                            if (t.infeas) y_n = t.y[ro];
+                            if (g < 6) load_plane(pl, r + 1, n_n);
+                        }
+                        const R cold = ((n[0] * co[0] + n[1] * co[1]) + n[2] * co[2]) + n[3] - t.margin;
+                        const R cnew = ((n[0] * cn[0] + n[1] * cn[1]) + n[2] * cn[2]) + n[3] - t.margin;
+                        const R tc = (n[0] * cd[0] + n[1] * cd[1]) + n[2] * cd[2];
+                        const R jv1 = ((n[0] * j1[0] + n[1] * j1[1]) + n[2] * j1[2]) + tc * v1[9];
+                        const R jv2 = ((n[0] * j2[0] + n[1] * j2[1]) + n[2] * j2[2]) + tc * v2[9];
+                        trial_row(t, ro_cur, sv, yv, cold, cnew, jv1, jv2, alpha, tau, A);
+                    }
+                } else {
+                    const long long ro = (long long)(6 * t.PM + 54) * t.NP + i;
+                    trial_row(t, ro, t.s[ro], t.infeas ? t.y[ro] : R(1), -zo[9] + R(0.3) - t.margin, -zn[9] + R(0.3) - t.margin, -v1[9],
+                              -v2[9], alpha, tau, A);
+                    // stage cost q(x,u), ddp.cpp:1294-1305
+                    R m[9], mu9[9];
+                    rmat<R>(0, tpn, m);
+                    rmat_times_u(m, zn, mu9);
+                    const R T = tpn[1];
+                    const R tterm = time_power == 2 ? R(0.5) * T * w_time * T : R(0.5) * w_time * T;
+                    q_cost = R(0.5) * w_snap * dot9(zn, mu9) + tterm;
+                }
+                if ((g & 3) == 3) {   // end of unit g / 4: bank its partials and start the next unit's accumulators
+                    const int uu = g >> 2;
+                    DDP_UNROLL
+                    for (int e = 0; e < 4; e++) {
+                        if (e == uu) {
+                            part(lane, 3 * e) = q_cost; part(lane, 3 * e + 1) = A.lg.total(); part(lane, 3 * e + 2) = A.e1;
+                            if (A.bad) badk(lane, e) = i;
+                        }
+                    }
+                    A.lg.lp = R(1); A.lg.lsum = R(0); A.e1 = R(0); A.bad = 0;
+                }
+            }
+        }
+    }
+}
+
+// Closed-loop state / control recursion over knots base .. base+nk-1 of a line-search trial (ddp.cpp:689-697, :1062-1067):
+// lanes 0-9 own u, lanes 10-18 own x.  Out of line on purpose: inside forward_trial the register allocator spilled this
+// loop's state around the calls of the row phase.  xcur carries the state across blocks.
+template <class R>
+DDP_DEVICE_NOINLINE void rollout_block(R *sm, const R *DDP_RESTRICT xu, R *DDP_RESTRICT xun, const R *DDP_RESTRICT Kin,
+                                       R *DDP_RESTRICT kdxo, int N, int base, int nk, R alpha, int lane_, Reg<R, 1> &xcur_io) {
+    R *ring = sm + Lay::MSC;
+    Reg<R, 1> xn, xcur;   // local copy: a by-reference Reg lives in local memory and would be re-read after every store
+    FOR_LANES(lane) { xn(lane, 0) = R(0); xcur(lane, 0) = xcur_io(lane, 0); }
+        for (int i = base; i < base + nk; i++) {
+            const R *slot = ring + (i & 3) * 120;
+            FOR_LANES(lane) {
+                if (i + 3 < N) stage_knot(ring + ((i + 3) & 3) * 120, Kin, xu, i + 3, lane);
+                cp_commit();
+                cp_wait<3>();
+            }
+            WARP_SYNC();
+            FOR_LANES(lane) {
+                if (lane >= 10 && lane < 19) {
+                    const R x = xcur(lane, 0);
+                    sm[Lay::DX + lane - 10] = x - slot[100 + lane];
+                    sm[Lay::ZN + lane] = x;
+                    xun[(long long)i * 20 + lane] = x;
+                }
+            }
+            WARP_SYNC();
+            FOR_LANES(lane) {   // unew = (uold + alpha ku) + Ku dx (ddp.cpp:689/:695)
+                if (lane < 10) {
+                    const R *Kr = slot + lane * 10;
+                    R kdx = R(0);
+                    DDP_UNROLL
+                    for (int b = 0; b < 9; b++) kdx += Kr[1 + b] * sm[Lay::DX + b];
+                    const R un = (slot[100 + lane] + alpha * Kr[0]) + kdx;
+                    sm[Lay::ZN + lane] = un;
+                    xun[(long long)i * 20 + lane] = un;
+                    kdxo[(long long)i * 10 + lane] = kdx;
+                }
+            }
+            WARP_SYNC();
+            R tp[6], fg[18];
+            time_powers(sm[Lay::ZN + 9], tp);
+            fg_matrix(tp, fg);
+            FOR_LANES(lane) {   // x+ = (F (x) I) x + (G (x) I) u (ddp.cpp:1062-1067)
+                if (lane >= 10 && lane < 19) {
+                    const int o = (lane - 10) / 3, a = (lane - 10) % 3;
+                    R s1 = R(0), s2 = R(0);
+                    DDP_UNROLL
+                    for (int b = 0; b < 3; b++) {
+                        if (b >= o) s1 += fg[o * 6 + b] * sm[Lay::ZN + 10 + 3 * b + a];
+                        s2 += fg[o * 6 + 3 + b] * sm[Lay::ZN + 3 * b + a];
+                    }
+                    xn(lane, 0) = s1 + s2;
+                }
+            }
+            WARP_SYNC();
+            FOR_LANES(lane) { xcur(lane, 0) = xn(lane, 0); }
+        }
+    FOR_LANES(lane) { xcur_io(lane, 0) = xcur(lane, 0); }
 }
 
 // One line-search trial with step size alpha (ddp.cpp:674-734).  The closed-loop state/control recursion
 // runs sequentially (lane <-> element) for 32 knots at a time; the constraint rows of those 32 knots are then
 // evaluated lane <-> knot.  Writes the candidate into xun/sn/yn and returns false when the
 // fraction-to-boundary test fails at some knot (ddp.cpp:683-687 / :699-703).
-template <class R> DDP_DEVICE_NOINLINE bool forward_trial(Traj<R> &tt_, R alpha, R tau, RollOut<R> &out) {
+template <class R> DDP_DEVICE_NOINLINE bool forward_trial_coop(Traj<R> &tt_, R alpha, R tau, RollOut<R> &out) {
+    const int lane_ = tt_.lane_;
+    const RowCtx<R> t = row_ctx(tt_);
+    R *sm = tt_.sm;
+    const int N = tt_.N;
+    const R *DDP_RESTRICT xu = tt_.xu;
+    R *DDP_RESTRICT xun = tt_.xun;
+    const R *DDP_RESTRICT Kin = tt_.K;
+    R *DDP_RESTRICT kdxo = tt_.kdx;
+    const R w_terminal = tt_.w_terminal, w_snap = tt_.w_snap, w_time = tt_.w_time, tol = tt_.tol;
+    const int time_power = tt_.time_power;
+    long long fwd_knots = 0, cyc_seq = 0;
+    Reg<R, 1> xcur;
+    Reg<R, 3> acc;  // per-lane partials: stage cost, log barrier, |c+y|_1
+    // Old point and gains of the next knots stream into a 4-deep shared-memory ring by cp.async, three knots ahead of
+    // the recursion (the MSC scratch of the linearisation is free during the line search): slot = [K_i (100) | xu_i (20)].
+    R *ring = sm + Lay::MSC;
+    FOR_LANES(lane) {
+        acc(lane, 0) = R(0); acc(lane, 1) = R(0); acc(lane, 2) = R(0);
+        xcur(lane, 0) = (lane >= 10 && lane < 19) ? xu[lane] : R(0);  // xnew[0] = xold[0]
+        DDP_UNROLL
+        for (int d = 0; d < 3; d++) {
+            if (d < N) stage_knot(ring + (d & 3) * 120, Kin, xu, d, lane);
+            cp_commit();
+        }
+    }
+    bool ok = true;
+    for (int base = 0; base < N && ok; base += 32) {
+        const int nk = N - base < 32 ? N - base : 32;
+        const long long clk_s = ddp_clock();
+        rollout_block(sm, xu, xun, Kin, kdxo, N, base, nk, alpha, lane_, xcur);
+        cyc_seq += ddp_clock() - clk_s;
+        // ---- rows of knots base .. base+nk-1, lane <-> knot: four units of row groups (run_job) --------------
+        {
+            JobCtx<R> c;
+            c.row = t;
+            c.xu = xu; c.xun = xun; c.K = Kin; c.kdx = kdxo; c.H = nullptr; c.aux = nullptr;
+            c.N = N; c.base = base; c.time_power = time_power; c.type = JOB_ROWS;
+            c.w_snap = w_snap; c.w_time = w_time; c.alpha = alpha; c.tau = tau;
+            Reg<R, 12> part;
+            Reg<int, 4> badk;
+            run_rows(tt_, c, part, badk);
+            Reg<int, 1> bmin;
+            FOR_LANES(lane) {   // units in fixed order per lane: the same sums whoever ran the units
+                int m = 0x7fffffff;
+                DDP_UNROLL
+                for (int u = 0; u < 4; u++) {
+                    acc(lane, 0) += part(lane, 3 * u); acc(lane, 1) += part(lane, 3 * u + 1); acc(lane, 2) += part(lane, 3 * u + 2);
+                    if (badk(lane, u) < m) m = badk(lane, u);
+                }
+                bmin(lane, 0) = m;
+            }
+            const int first = warp_min_int(bmin, 0, lane_);
+            if (first != 0x7fffffff) { fwd_knots += first - base + 1; ok = false; }
+            else fwd_knots += nk;
+        }
+    }
+    FOR_LANES(lane) { cp_wait<0>(); }   // nothing of the ring / staging may land after this trial
+    WARP_SYNC();
+    tt_.n_fwd_knots += fwd_knots;
+    tt_.cyc_seq += cyc_seq;
+    if (!ok) return false;
+    // terminal cost (ddp.cpp:1289-1292) and totals
+    Reg<R, 1> pt;
+    FOR_LANES(lane) {
+        pt(lane, 0) = R(0);
+        if (lane >= 10 && lane < 19) {
+            const R d = xcur(lane, 0) - sm[Lay::XD + lane - 10];
+            pt(lane, 0) = d * (w_terminal * d);
+            xun[(long long)N * 20 + lane] = xcur(lane, 0);
+        }
+    }
+    const R qs = warp_sum(acc, 0, lane_), p = R(0.5) * warp_sum(pt, 0, lane_);
+    out.costq = qs;
+    out.cost = qs + p;
+    out.logcost = out.cost - t.mu * warp_sum(acc, 1, lane_);
+    out.err = t.infeas ? rmax(tol, warp_sum(acc, 2, lane_)) : R(0);
+    WARP_SYNC();
+    return true;
+}
+
+// The same trial for a warp working alone (the common case): recursion and rows of each 32-knot block in one function.
+// The row partials are banked per unit (row groups 4u .. 4u+3) exactly like rows_unit does, so a trial gives the same
+// bits whether it ran here or as jobs.
+template <class R> DDP_DEVICE_NOINLINE bool forward_trial_solo(Traj<R> &tt_, R alpha, R tau, RollOut<R> &out) {
     const int lane_ = tt_.lane_;
     const RowCtx<R> t = row_ctx(tt_);
     R *sm = tt_.sm;
@@ -1049,6 +1675,12 @@ template <class R> DDP_DEVICE_NOINLINE bool forward_trial(Traj<R> &tt_, R alpha,
                         const R jv1 = ((n[0] * j1[0] + n[1] * j1[1]) + n[2] * j1[2]) + tc * v1[9];
                         const R jv2 = ((n[0] * j2[0] + n[1] * j2[1]) + n[2] * j2[2]) + tc * v2[9];
                         trial_row(t, ro_cur, sv, yv, cold, cnew, jv1, jv2, alpha, tau, A);
+                    }
+                    if ((g & 3) == 3) {   // end of unit g / 4 (see rows_unit): bank its partials, restart the accumulators
+                        acc(lane, 1) += A.lg.total();
+                        acc(lane, 2) += A.e1;
+                        if (A.bad) badk(lane, 0) = i;
+                        A.lg.lp = R(1); A.lg.lsum = R(0); A.e1 = R(0); A.bad = 0;
                     }
                 }
                 {
@@ -1212,7 +1844,7 @@ template <class R> DDP_DEVICE_NOINLINE void forward_pass(Traj<R> &t) {
         stepsize = R(1);
         for (int k = 0; k < step; k++) stepsize = stepsize * R(0.5);  // 2^-step exactly (ddp.cpp:670)
         t.n_fwd_trials++;
-        if (!forward_trial(t, stepsize, tau, ro)) continue;
+        if (!(coop_has_helpers(t) ? forward_trial_coop(t, stepsize, tau, ro) : forward_trial_solo(t, stepsize, tau, ro))) continue;
         // filter acceptance, ddp.cpp:741-757: rejected if some entry is <= the candidate in both
         // coordinates; an accepted candidate evicts the entries it dominates.  Lane 0 owns the filter.
         FOR_LANES(lane) {
@@ -1261,12 +1893,13 @@ template <class R> DDP_DEVICE_NOINLINE void forward_pass(Traj<R> &t) {
 // One polyCurveGeneration (ddp.cpp:5-438) for trajectory `b`, stage `st` of the call.
 // =============================================================================================
 template <class R> DDP_DEVICE_NOINLINE void solve_one(const SolveArgs &A, int st, int b, R *sm, const R *tabs, R *ws,
-                                                      int lane_) {
+                                                      int lane_, void *board = nullptr, void *ctl = nullptr, int wpb = 1) {
     const StageCfg &cfg = A.cfg[st];
     const int N = A.N;
     const WsLay wl = ws_layout(N, A.PM, A.fcap);
     Traj<R> t;
     t.N = N; t.PM = A.PM; t.NP = wl.NP; t.MCS = wl.MCS; t.lane_ = lane_;
+    t.board = board; t.ctl = ctl; t.wpb = wpb;
     t.planes = A.planes + (long long)b * N * A.PM * 4;
     t.nplanes = A.nplanes + (long long)b * N;
     t.sm = sm;

@@ -118,6 +118,7 @@ typedef struct direct_ddp_stats {
     int64_t kernel_launches;
     int grid_blocks, block_threads, smem_bytes_per_block, workspace_slots;
     int64_t h2d_bytes, d2h_bytes;
+    int64_t coop_jobs, helper_units; /* jobs posted to idle warps of the CTA / units those warps ran (tail balancing) */
 } direct_ddp_stats;
 
 typedef struct direct_ddp_trace_row {
