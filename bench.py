@@ -124,7 +124,7 @@ def reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, per_gpu=sample),
+        "config": dict(workload_config(args, per_gpu=args.batch), reference_sample_per_step=sample),
         "cpu_baseline": {"value": value, "unit": "solves/s", "cores": cores, "kind": kind,
                          "sample": f"first {sample} trajectories of the workload per step, {cores} OpenMP threads, "
                                    + ("reference ddp_optimizer.cpp compiled unmodified against oracle/shim (eager Eigen stand-in)"
@@ -140,7 +140,7 @@ def workload_config(args, per_gpu):
                         f"{args.knots} knots, 9-state/10-input flat quadrotor model, {args.kind} corridor "
                         f"(P={'6' if args.kind == 'box' else '6..14'} planes/cell), weights of global_planner.launch",
             "batch_per_gpu": per_gpu, "knots": args.knots, "corridor": args.kind, "precision": args.precision,
-            "l2": "256 MiB L2 flush written between timed steps; per-warp workspace (>1 GB) exceeds L2 anyway"}
+            "l2": "256 MiB buffer written between timed steps (L2 flush); the per-warp workspaces (1 GB) exceed L2 anyway"}
 
 
 def main():
@@ -153,7 +153,7 @@ def main():
     ap.add_argument("--knots", type=int, default=100)
     ap.add_argument("--kind", default="box", choices=["box", "poly"])
     ap.add_argument("--precision", default="fp64", choices=["fp64", "fp32"])
-    ap.add_argument("--cpu-sample", type=int, default=128)
+    ap.add_argument("--cpu-sample", type=int, default=4096)
     ap.add_argument("--ref-sample", type=int, default=48)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -294,8 +294,16 @@ def main():
     # algorithmic bytes per knot visit: backward reads x,u,s(,y) and writes the gains; a rollout reads x,u,s(,y),gains
     # and writes x,u,s(,y)   (SURVEY.md 8(d) "algorithmic bytes"; y only in stage 0)
     alg_bytes = elem * (bwd_knots * (19 + 1.5 * m_c + 100) + fwd_knots * (2 * 19 + 3.0 * m_c + 100))
+    traffic, traffic_src = None, None
+    try:   # dram__bytes_read.sum + dram__bytes_write.sum of the solve kernel, one ncu --set full capture (profiles/)
+        prof = json.load(open(os.path.join(ROOT, "profiles", "latest_ncu.json")))
+        if prof.get("workload") == f"{B}x{N} {args.kind} {args.precision}":
+            traffic, traffic_src = prof["dram_bytes_per_launch"], prof["source"]
+    except Exception:
+        pass
     roofline = {"bound": "fp64_fma" if args.precision == "fp64" else "fp32_fma", "achieved": achieved_tf, "peak": peak_tf,
-                "unit": "TFLOP/s", "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": None,
+                "unit": "TFLOP/s", "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": traffic,
+                "traffic_source": traffic_src,
                 "peak_source": "register-resident FMA microbenchmark run on this device by bench.py "
                                "(MEASURED_PEAKS.json has no CUDA-core FMA entry)",
                 "flops_per_bwd_knot": bwd_flops_per_knot(mean_planes), "bwd_knots_per_launch": bwd_knots,
@@ -321,7 +329,8 @@ def main():
                         "mean_stage1_iters": float(iters1.mean()), "bwd_sweeps_per_solve": st.bwd_sweeps / B,
                         "rollouts_per_solve": st.fwd_trials / B, "grid_blocks": st.grid_blocks,
                         "block_threads": st.block_threads, "smem_bytes_per_block": st.smem_bytes_per_block,
-                        "warp_slots": st.workspace_slots, "cycle_share_bwd": float(cyc[0] / max(1, cyc[2])),
+                        "warp_slots": st.workspace_slots, "coop_jobs": int(st.coop_jobs), "helper_units": int(st.helper_units),
+                        "cycle_share_bwd": float(cyc[0] / max(1, cyc[2])),
                         "cycle_share_linesearch": float(cyc[1] / max(1, cyc[2]))},
     }
     if rank == 0 and not args.no_cpu_baseline:

@@ -60,7 +60,7 @@ class TraceRow(C.Structure):
 EXPORTS = ["direct_ddp_version", "direct_ddp_create", "direct_ddp_destroy", "direct_ddp_last_error",
            "direct_ddp_solve_batch", "direct_ddp_solve_batch_device", "direct_ddp_solve_two_stage",
            "direct_ddp_solve_two_stage_device", "direct_ddp_time_allocation_device", "direct_ddp_last_stats",
-           "direct_ddp_last_trace", "direct_ddp_measure_fma_peak"]
+           "direct_ddp_last_trace", "direct_ddp_measure_fma_peak", "direct_ddp_sample", "direct_ddp_sample_device"]
 
 _lib = None
 
@@ -92,6 +92,8 @@ def load_library(build_if_missing: bool = True):
         lib.direct_ddp_last_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
         lib.direct_ddp_last_trace.argtypes = [C.c_void_p, C.POINTER(TraceRow), C.c_int, C.POINTER(C.c_int)]
         lib.direct_ddp_measure_fma_peak.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]
+        lib.direct_ddp_sample.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 5
+        lib.direct_ddp_sample_device.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 6
         _lib = lib
     return _lib
 
@@ -211,6 +213,18 @@ class Solver:
     def time_allocation_device(self, B, N, start, end, seeds, max_vel, max_acc, durations, stream: int = 0):
         self._check(self.lib.direct_ddp_time_allocation_device(self.h, B, N, start, end, seeds, max_vel, max_acc,
                                                                durations, C.c_void_p(stream)))
+
+    def sample(self, bez_coeff: np.ndarray, poly_time: np.ndarray, S: int):
+        """Bernstein::getPos/getVel/getAcc of every segment at s_k = k/(S-1) (host buffers): pos, vel, acc [B][N][S][3]."""
+        bez = np.ascontiguousarray(bez_coeff, dtype=np.float64)
+        tim = np.ascontiguousarray(poly_time, dtype=np.float64)
+        B, N = tim.shape
+        out = [np.zeros((B, N, S, 3)) for _ in range(3)]
+        self._check(self.lib.direct_ddp_sample(self.h, B, N, S, _ptr(bez), _ptr(tim), _ptr(out[0]), _ptr(out[1]), _ptr(out[2])))
+        return tuple(out)
+
+    def sample_device(self, B, N, S, bez, tim, pos, vel, acc, stream: int = 0):
+        self._check(self.lib.direct_ddp_sample_device(self.h, B, N, S, bez, tim, pos, vel, acc, C.c_void_p(stream)))
 
     def stats(self) -> Stats:
         s = Stats()

@@ -90,6 +90,33 @@ __global__ void time_allocation_kernel(int B, int N, const double *start, const 
     durations[idx] = dt;
 }
 
+// Bernstein evaluation of solved trajectories (utils/bezier_base.h:77-115), one thread per (segment, sample).
+// HBM-bound: 19 doubles read per segment (shared by its S threads through L1), 9 doubles written per sample.
+__global__ void bezier_sample_kernel(long long nseg, int S, const double *__restrict__ bez, const double *__restrict__ times,
+                                     double *__restrict__ pos, double *__restrict__ vel, double *__restrict__ acc) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nseg * S) return;
+    const long long seg = idx / S;
+    const int k = (int)(idx % S);
+    const double s = S > 1 ? (double)k / (double)(S - 1) : 0.0, q = 1.0 - s, T = times[seg];
+    double sp[6], qp[6];
+    sp[0] = 1.0; qp[0] = 1.0;
+    for (int j = 1; j < 6; j++) { sp[j] = sp[j - 1] * s; qp[j] = qp[j - 1] * q; }
+    const double c5[6] = {1, 5, 10, 10, 5, 1}, c4[5] = {1, 4, 6, 4, 1}, c3[4] = {1, 3, 3, 1};
+    const double *cp = bez + seg * 18;
+    for (int a = 0; a < 3; a++) {
+        double c[6];
+        for (int j = 0; j < 6; j++) c[j] = cp[a * 6 + j];
+        double p = 0.0, v = 0.0, w = 0.0;
+        for (int j = 0; j < 6; j++) p += c5[j] * c[j] * sp[j] * qp[5 - j];
+        for (int j = 0; j < 5; j++) v += c4[j] * 5.0 * (c[j + 1] - c[j]) * sp[j] * qp[4 - j];
+        for (int j = 0; j < 4; j++) w += c3[j] * 20.0 * (c[j + 2] - 2.0 * c[j + 1] + c[j]) * sp[j] * qp[3 - j];
+        if (pos) pos[idx * 3 + a] = T * p;
+        if (vel) vel[idx * 3 + a] = v;
+        if (acc) acc[idx * 3 + a] = w / T;
+    }
+}
+
 // Register-resident FMA throughput probe: the measured denominator of the FMA roofline (MEASURED_PEAKS.json
 // only carries HBM and bf16 tensor numbers).  8 independent chains per thread, 2 flops per FMA.
 template <class R> __global__ void fma_peak_kernel(R *out, int iters, R a, R b) {
@@ -473,6 +500,39 @@ int direct_ddp_time_allocation_device(direct_ddp_handle h, int B, int N, const d
     const long long n = (long long)B * N;
     time_allocation_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(B, N, start, end, seeds, max_vel, max_acc, durations);
     CK(cudaGetLastError());
+    return 0;
+}
+
+int direct_ddp_sample_device(direct_ddp_handle h, int B, int N, int S, const double *bez_coeff, const double *poly_time,
+                             double *pos, double *vel, double *acc, void *stream) {
+    REQUIRE_DEVICE(h)
+    if (B <= 0 || N <= 0 || S <= 0 || !bez_coeff || !poly_time) { h->err = "bad argument"; return DIRECT_DDP_ERR_ARG; }
+    CK(cudaSetDevice(h->opts.device));
+    const long long n = (long long)B * N * S;
+    bezier_sample_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((long long)B * N, S, bez_coeff, poly_time, pos, vel, acc);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int direct_ddp_sample(direct_ddp_handle h, int B, int N, int S, const double *bez_coeff, const double *poly_time,
+                      double *pos, double *vel, double *acc) {
+    REQUIRE_DEVICE(h)
+    if (B <= 0 || N <= 0 || S <= 0 || !bez_coeff || !poly_time) { h->err = "bad argument"; return DIRECT_DDP_ERR_ARG; }
+    CK(cudaSetDevice(h->opts.device));
+    const size_t nb = (size_t)B * N * 18 * 8, nt = (size_t)B * N * 8, no = (size_t)B * N * S * 3 * 8;
+    int st;
+    if ((st = ensure(h, h->o_bz[0], nb))) return st;
+    if ((st = ensure(h, h->o_pt[0], nt))) return st;
+    if ((st = ensure(h, h->o_pc[0], no * 3))) return st;
+    double *d_bez = (double *)h->o_bz[0].p, *d_t = (double *)h->o_pt[0].p, *d_o = (double *)h->o_pc[0].p;
+    CK(cudaMemcpyAsync(d_bez, bez_coeff, nb, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(d_t, poly_time, nt, cudaMemcpyHostToDevice, h->stream));
+    const size_t ne = (size_t)B * N * S * 3;
+    if ((st = direct_ddp_sample_device(h, B, N, S, d_bez, d_t, pos ? d_o : nullptr, vel ? d_o + ne : nullptr, acc ? d_o + 2 * ne : nullptr, h->stream))) return st;
+    if (pos) CK(cudaMemcpyAsync(pos, d_o, no, cudaMemcpyDeviceToHost, h->stream));
+    if (vel) CK(cudaMemcpyAsync(vel, d_o + ne, no, cudaMemcpyDeviceToHost, h->stream));
+    if (acc) CK(cudaMemcpyAsync(acc, d_o + 2 * ne, no, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
     return 0;
 }
 

@@ -153,6 +153,16 @@ int direct_ddp_time_allocation_device(direct_ddp_handle h, int B, int N, const d
                                       const double *end /*[B][3]*/, const double *seeds /*[B][N][3]*/,
                                       double max_vel, double max_acc, double *durations, void *stream);
 
+/* Batched trajectory sampling: Bernstein::getPos / getVel / getAcc (utils/bezier_base.h:77-115) of every segment at the
+ * S parameters s_k = k / (S - 1), scaled as the node does (teach_repeat_planner.cpp:1557-1560 position = time * getPos,
+ * :681-682 velocity = getVel, acceleration = getAcc / time).  bez_coeff [B][N][18] and poly_time [B][N] as returned by
+ * the solve; pos / vel / acc [B][N][S][3], any of them may be NULL.  Device pointers; asynchronous on `stream`. */
+int direct_ddp_sample_device(direct_ddp_handle h, int B, int N, int S, const double *bez_coeff, const double *poly_time,
+                             double *pos, double *vel, double *acc, void *stream);
+/* The same with host buffers (H2D, kernel, D2H inside the call). */
+int direct_ddp_sample(direct_ddp_handle h, int B, int N, int S, const double *bez_coeff, const double *poly_time,
+                      double *pos, double *vel, double *acc);
+
 int direct_ddp_last_stats(direct_ddp_handle h, direct_ddp_stats *out);
 /* Register-resident FMA throughput of the device (TFLOP/s, 2 flops per FMA) for DIRECT_DDP_FP64 or
  * DIRECT_DDP_FP32: the measured denominator of the FMA roofline bench.py reports. */

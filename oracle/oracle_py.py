@@ -197,3 +197,30 @@ def solve_traced(pb, i=0, cap=512, **kw):
 def max_threads() -> int:
     lib().ipddp_oracle_max_threads.restype = C.c_int
     return int(lib().ipddp_oracle_max_threads())
+
+
+# ---- §8(f) #3: trajectory sampling, restated from the reference's Bernstein evaluators ---------------------------
+def bezier_sample(bez_coeff, poly_time, S):
+    """Bernstein::getPos / getVel / getAcc of global_planner/include/global_planner/utils/bezier_base.h:77-115 at the
+    S parameters s_k = k / (S - 1) of every segment, scaled like the callers do (teach_repeat_planner.cpp:1557-1560:
+    position = time * getPosFromBezier; :681-682: velocity = getVel, acceleration = getAcc / time).
+    bez_coeff [B][N][18] rows [x*6, y*6, z*6] (scaled by 1/T), poly_time [B][N].  Returns pos, vel, acc [B][N][S][3].
+    Plain numpy with pow() exactly as the reference writes it; TEST INFRASTRUCTURE ONLY."""
+    from math import comb
+    bez = np.asarray(bez_coeff, dtype=np.float64)
+    T = np.asarray(poly_time, dtype=np.float64)
+    B, N = T.shape
+    n = 5
+    cp = bez.reshape(B, N, 3, n + 1)
+    s = (np.arange(S, dtype=np.float64) / (S - 1)) if S > 1 else np.zeros(1)
+    pos = np.zeros((B, N, S, 3)); vel = np.zeros_like(pos); acc = np.zeros_like(pos)
+    for j in range(n + 1):
+        w = comb(n, j) * np.power(s, j) * np.power(1 - s, n - j)
+        pos += cp[:, :, None, :, j] * w[None, None, :, None]
+    for j in range(n):
+        w = comb(n - 1, j) * n * np.power(s, j) * np.power(1 - s, n - j - 1)
+        vel += (cp[:, :, None, :, j + 1] - cp[:, :, None, :, j]) * w[None, None, :, None]
+    for j in range(n - 1):
+        w = comb(n - 2, j) * n * (n - 1) * np.power(s, j) * np.power(1 - s, n - j - 2)
+        acc += (cp[:, :, None, :, j + 2] - 2 * cp[:, :, None, :, j + 1] + cp[:, :, None, :, j]) * w[None, None, :, None]
+    return pos * T[:, :, None, None], vel, acc / T[:, :, None, None]

@@ -155,3 +155,20 @@ def test_gpu_dropin_translation_unit_matches_reference_fixtures(oracle, name):
         assert rel_err(getattr(r1, f), d["s1_" + f]) < TOL64, f
     assert rel_err(r1.jerk[:, 0], d["s1_jerk_sum"]) < TOL64               # getJerkCost()
     assert rel_err(r1.x_final[:, 0], d["s1_terminal_norm"]) < TOL64       # getTerminalNorm()
+
+
+def test_gpu_bezier_sampling_matches_reference_formulas(solver, oracle):
+    """batched Bernstein evaluation of solved trajectories against the numpy restatement of
+    bezier_base.h:77-115; plus the properties the node relies on (segment ends = control points 0 / 5, C0-C2 joins)."""
+    pb = make_batch(32, 40, "poly", first=77)
+    _, g = solver.solve_two_stage(pb, want_stage0=False)
+    S = 9
+    pos, vel, acc = solver.sample(g.bez_coeff, g.poly_time, S)
+    rp, rv, ra = oracle.bezier_sample(g.bez_coeff, g.poly_time, S)
+    for a, b in ((pos, rp), (vel, rv), (acc, ra)):
+        assert rel_err(a, b) < 1e-12
+    cp = g.bez_coeff.reshape(32, 40, 3, 6) * g.poly_time[:, :, None, None]
+    assert rel_err(pos[:, :, 0], cp[..., 0]) < 1e-12 and rel_err(pos[:, :, -1], cp[..., 5]) < 1e-12
+    ok = g.rtn == 1
+    for arr in (pos, vel, acc):                       # consecutive segments join in position, velocity, acceleration
+        assert rel_err(arr[ok][:, :-1, -1], arr[ok][:, 1:, 0]) < 1e-6

@@ -132,3 +132,18 @@ def test_edge_cases_single_knot_and_unreachable_goal(oracle):
     r0, r1 = oracle.two_stage_batch(pb)
     assert set(np.unique(r1.rtn)).issubset({0, 1, 2, -3, -4})
     assert (r1.iters <= 100).all()
+
+
+def test_bezier_sampling_oracle_endpoints_and_derivatives(oracle):
+    """The numpy restatement of Bernstein::getPos/getVel/getAcc (bezier_base.h:77-115): end points are control points
+    0 and 5, and velocity / acceleration are the finite-difference derivatives of position in time."""
+    rng = np.random.default_rng(3)
+    bez = rng.normal(size=(2, 3, 18)); T = rng.uniform(0.5, 2.0, size=(2, 3))
+    S = 2001
+    pos, vel, acc = oracle.bezier_sample(bez, T, S)
+    cp = bez.reshape(2, 3, 3, 6) * T[:, :, None, None]
+    assert np.allclose(pos[:, :, 0], cp[..., 0]) and np.allclose(pos[:, :, -1], cp[..., 5])
+    dt = T[:, :, None, None] / (S - 1)
+    inner = slice(1, -1)   # central differences; the one-sided end points are only first-order accurate
+    assert np.allclose((np.gradient(pos, axis=2) / dt)[:, :, inner], vel[:, :, inner], rtol=0, atol=1e-4 * np.abs(vel).max())
+    assert np.allclose((np.gradient(vel, axis=2) / dt)[:, :, inner], acc[:, :, inner], rtol=0, atol=1e-4 * np.abs(acc).max())

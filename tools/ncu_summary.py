@@ -30,6 +30,14 @@ print("== headline metrics")
 for i, h in enumerate(hdr):
     if h in want:
         print(f"  {h:70s} {vals[i]} {units[i]}")
+if "--json" in sys.argv:   # per-launch DRAM traffic for bench.py's roofline.traffic
+    import json
+    v = {h: float(vals[i]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[units[i]] for i, h in enumerate(hdr)
+         if h in ("dram__bytes_read.sum", "dram__bytes_write.sum")}
+    out = {"dram_bytes_per_launch": v["dram__bytes_read.sum"] + v["dram__bytes_write.sum"], "dram_bytes_read": v["dram__bytes_read.sum"],
+           "dram_bytes_write": v["dram__bytes_write.sum"], "source": sys.argv[sys.argv.index("--json") + 1],
+           "workload": sys.argv[sys.argv.index("--json") + 2]}
+    json.dump(out, open("profiles/latest_ncu.json", "w"), indent=1)
 print("== warp stall samples (pc sampling)")
 st = {h: int(vals[i]) for i, h in enumerate(hdr) if h.startswith("smsp__pcsamp_warps_issue_stalled") and "not_issued" not in h and vals[i].isdigit()}
 tot = sum(st.values())
