@@ -87,6 +87,14 @@ class ClockSampler:
                 "reasons": sorted(reasons)}
 
 
+def host_cores() -> int:
+    """Host threads this process may use (torchrun exports OMP_NUM_THREADS=1; the CPU arms pass the count explicitly)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def reference_arm(args):
     """The reference's own CPU implementation of the path on the host cores (rank 0 only)."""
     rank = int(os.environ.get("RANK", "0"))
@@ -96,7 +104,7 @@ def reference_arm(args):
     from oracle import oracle_py as O
     O.build(ref=True)
     use_ref = O.ref_available()
-    cores = O.max_threads()
+    cores = host_cores()
     sample = args.ref_sample
     pb = make_batch(sample, args.knots, args.kind)
 
@@ -333,10 +341,10 @@ def main():
                         "cycle_share_bwd": float(cyc[0] / max(1, cyc[2])),
                         "cycle_share_linesearch": float(cyc[1] / max(1, cyc[2]))},
     }
-    if rank == 0 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:   # reported at N = 1 only
         from oracle import oracle_py as O   # checker / CPU baseline only, never on the product path
         O.build(ref=False)
-        cores = O.max_threads()
+        cores = host_cores()
         smp = min(args.cpu_sample, B)
         sub = pb.slice(0, smp)
         t0 = time.perf_counter()
