@@ -374,10 +374,11 @@ template <class R, class F> DDP_DEVICE void visit_rows(const RowCtx<R> &t, int i
     time_powers(z[9], tp);
     const int P = t.nplanes[i];
     const double *pl = t.planes + (long long)i * t.PM * 4;
+    const R *tab = as_shared(t.tab);
     DDP_NOUNROLL
     for (int g = 0; g < 15; g++) {
         R b[6], cp[3];
-        basis_row_rt(t.tab + g * 6, group_shift(g), tp, b);
+        basis_row_rt(tab + g * 6, group_shift(g), tp, b);
         DDP_UNROLL
         for (int a = 0; a < 3; a++) cp[a] = dot_axis<R, 0>(b, z, a);
         const int nr = g < 6 ? P : 6;
@@ -471,6 +472,8 @@ template <class R> DDP_HD int coop_smem_bytes(int warps_per_block) {
 template <class R> DDP_DEVICE_NOINLINE void lin_unit(const JobCtx<R> *cp_, int u, R *smw, int lane_, Reg<R, 2> &errs) {
     const JobCtx<R> c = *cp_;
     const RowCtx<R> t = c.row;
+    smw = as_shared(smw);
+    const R *tab = as_shared(t.tab);
     const int N = c.N, time_power = c.time_power;
     const R w_snap = c.w_snap, w_time = c.w_time;
     const R *DDP_RESTRICT xu = c.xu;
@@ -501,8 +504,8 @@ template <class R> DDP_DEVICE_NOINLINE void lin_unit(const JobCtx<R> *cp_, int u
                     const int shift = group_shift(g), nr = g < 6 ? P : 6;
                     const R lim = g < 11 ? t.max_vel : t.max_acc;
                     R b[6], bd[6], cp[3], cd[3];
-                    basis_row_rt(t.tab + g * 6, shift, tp, b);
-                    basis_row_rt(t.tab + 90 + g * 6, shift + 1, tp, bd);
+                    basis_row_rt(tab + g * 6, shift, tp, b);
+                    basis_row_rt(tab + 90 + g * 6, shift + 1, tp, bd);
                     DDP_UNROLL
                     for (int a = 0; a < 3; a++) { cp[a] = dot_axis<R, 0>(b, z, a); cd[a] = dot_axis<R, 0>(bd, z, a); }
                     R M[6] = {R(0), R(0), R(0), R(0), R(0), R(0)}, wv[3] = {R(0), R(0), R(0)}, gv[3] = {R(0), R(0), R(0)};
@@ -598,14 +601,14 @@ template <class R> DDP_DEVICE_NOINLINE void lin_unit(const JobCtx<R> *cp_, int u
                     for (int e = 0; e < 21; e++) { h0[e] = R(0); h1[e] = R(0); h2[e] = R(0); }
                     DDP_NOUNROLL
                     for (int g = 0; g < 6; g++)
-                        lin_diag_group<R, 0>(t.tab, g, tp, msc[(g * 6 + 0) * 32], msc[(g * 6 + 3) * 32], msc[(g * 6 + 5) * 32], h0, h1, h2);
+                        lin_diag_group<R, 0>(tab, g, tp, msc[(g * 6 + 0) * 32], msc[(g * 6 + 3) * 32], msc[(g * 6 + 5) * 32], h0, h1, h2);
                     DDP_NOUNROLL
                     for (int g = 6; g < 11; g++)
-                        lin_diag_group<R, 1>(t.tab, g, tp, msc[(36 + 3 * (g - 6)) * 32], msc[(37 + 3 * (g - 6)) * 32],
+                        lin_diag_group<R, 1>(tab, g, tp, msc[(36 + 3 * (g - 6)) * 32], msc[(37 + 3 * (g - 6)) * 32],
                                              msc[(38 + 3 * (g - 6)) * 32], h0, h1, h2);
                     DDP_NOUNROLL
                     for (int g = 11; g < 15; g++)
-                        lin_diag_group<R, 2>(t.tab, g, tp, msc[(36 + 3 * (g - 6)) * 32], msc[(37 + 3 * (g - 6)) * 32],
+                        lin_diag_group<R, 2>(tab, g, tp, msc[(36 + 3 * (g - 6)) * 32], msc[(37 + 3 * (g - 6)) * 32],
                                              msc[(38 + 3 * (g - 6)) * 32], h0, h1, h2);
                     DDP_UNROLL
                     for (int lb = 0; lb < 6; lb++) {
@@ -627,7 +630,7 @@ template <class R> DDP_DEVICE_NOINLINE void lin_unit(const JobCtx<R> *cp_, int u
                     for (int e = 0; e < 21; e++) { h0[e] = R(0); h1[e] = R(0); h2[e] = R(0); }
                     DDP_NOUNROLL
                     for (int g = 0; g < 6; g++)
-                        lin_diag_group<R, 0>(t.tab, g, tp, msc[(g * 6 + 1) * 32], msc[(g * 6 + 2) * 32], msc[(g * 6 + 4) * 32], h0, h1, h2);
+                        lin_diag_group<R, 0>(tab, g, tp, msc[(g * 6 + 1) * 32], msc[(g * 6 + 2) * 32], msc[(g * 6 + 4) * 32], h0, h1, h2);
                     DDP_UNROLL
                     for (int lb = 0; lb < 6; lb++) {
                         DDP_UNROLL
@@ -809,7 +812,8 @@ template <class R> DDP_DEVICE_NOINLINE void linearize_solo(Traj<R> &tt_, Reg<R, 
     const R *DDP_RESTRICT xu = tt_.xu;
     R *DDP_RESTRICT Hout = tt_.H;
     R *DDP_RESTRICT auxout = tt_.aux;
-    R *smw = tt_.sm;
+    R *smw = as_shared(tt_.sm);
+    const R *tab = as_shared(t.tab);
     const R sgn = t.infeas ? R(1) : R(-1);
     FOR_LANES(lane) { errs(lane, 0) = R(0); errs(lane, 1) = R(0); }
     for (int base = 0; base < N; base += 32) {
@@ -835,8 +839,8 @@ template <class R> DDP_DEVICE_NOINLINE void linearize_solo(Traj<R> &tt_, Reg<R, 
                     const int shift = group_shift(g), nr = g < 6 ? P : 6;
                     const R lim = g < 11 ? t.max_vel : t.max_acc;
                     R b[6], bd[6], cp[3], cd[3];
-                    basis_row_rt(t.tab + g * 6, shift, tp, b);
-                    basis_row_rt(t.tab + 90 + g * 6, shift + 1, tp, bd);
+                    basis_row_rt(tab + g * 6, shift, tp, b);
+                    basis_row_rt(tab + 90 + g * 6, shift + 1, tp, bd);
                     DDP_UNROLL
                     for (int a = 0; a < 3; a++) { cp[a] = dot_axis<R, 0>(b, z, a); cd[a] = dot_axis<R, 0>(bd, z, a); }
                     R M[6] = {R(0), R(0), R(0), R(0), R(0), R(0)}, wv[3] = {R(0), R(0), R(0)}, gv[3] = {R(0), R(0), R(0)};
@@ -932,14 +936,14 @@ template <class R> DDP_DEVICE_NOINLINE void linearize_solo(Traj<R> &tt_, Reg<R, 
                     for (int e = 0; e < 21; e++) { h0[e] = R(0); h1[e] = R(0); h2[e] = R(0); }
                     DDP_NOUNROLL
                     for (int g = 0; g < 6; g++)
-                        lin_diag_group<R, 0>(t.tab, g, tp, msc[(g * 6 + 0) * 32], msc[(g * 6 + 3) * 32], msc[(g * 6 + 5) * 32], h0, h1, h2);
+                        lin_diag_group<R, 0>(tab, g, tp, msc[(g * 6 + 0) * 32], msc[(g * 6 + 3) * 32], msc[(g * 6 + 5) * 32], h0, h1, h2);
                     DDP_NOUNROLL
                     for (int g = 6; g < 11; g++)
-                        lin_diag_group<R, 1>(t.tab, g, tp, msc[(36 + 3 * (g - 6)) * 32], msc[(37 + 3 * (g - 6)) * 32],
+                        lin_diag_group<R, 1>(tab, g, tp, msc[(36 + 3 * (g - 6)) * 32], msc[(37 + 3 * (g - 6)) * 32],
                                              msc[(38 + 3 * (g - 6)) * 32], h0, h1, h2);
                     DDP_NOUNROLL
                     for (int g = 11; g < 15; g++)
-                        lin_diag_group<R, 2>(t.tab, g, tp, msc[(36 + 3 * (g - 6)) * 32], msc[(37 + 3 * (g - 6)) * 32],
+                        lin_diag_group<R, 2>(tab, g, tp, msc[(36 + 3 * (g - 6)) * 32], msc[(37 + 3 * (g - 6)) * 32],
                                              msc[(38 + 3 * (g - 6)) * 32], h0, h1, h2);
                     DDP_UNROLL
                     for (int lb = 0; lb < 6; lb++) {
@@ -961,7 +965,7 @@ template <class R> DDP_DEVICE_NOINLINE void linearize_solo(Traj<R> &tt_, Reg<R, 
                     for (int e = 0; e < 21; e++) { h0[e] = R(0); h1[e] = R(0); h2[e] = R(0); }
                     DDP_NOUNROLL
                     for (int g = 0; g < 6; g++)
-                        lin_diag_group<R, 0>(t.tab, g, tp, msc[(g * 6 + 1) * 32], msc[(g * 6 + 2) * 32], msc[(g * 6 + 4) * 32], h0, h1, h2);
+                        lin_diag_group<R, 0>(tab, g, tp, msc[(g * 6 + 1) * 32], msc[(g * 6 + 2) * 32], msc[(g * 6 + 4) * 32], h0, h1, h2);
                     DDP_UNROLL
                     for (int lb = 0; lb < 6; lb++) {
                         DDP_UNROLL
@@ -993,7 +997,7 @@ template <class R> DDP_DEVICE_NOINLINE void linearize_solo(Traj<R> &tt_, Reg<R, 
 // =============================================================================================
 template <class R> DDP_DEVICE_NOINLINE bool riccati(Traj<R> &t, R regadd, Reg<R, 1> &errq) {
     const int lane_ = t.lane_;
-    R *sm = t.sm;
+    R *sm = as_shared(t.sm);
     const int N = t.N;
     const R *DDP_RESTRICT Hin = t.H;
     const R *DDP_RESTRICT xu = t.xu;
@@ -1298,6 +1302,7 @@ DDP_DEVICE_NOINLINE void rows_unit(const JobCtx<R> *cp_, int u0, int u1, int lan
     const R *DDP_RESTRICT xun = c.xun;
     const R *DDP_RESTRICT Kin = c.K;
     const R *DDP_RESTRICT kdxo = c.kdx;
+    const R *tab = as_shared(t.tab);
     // the knot's old/new point and gains are loaded once for all units of the call
     FOR_LANES(lane) {
         const int i = c.base + lane;
@@ -1326,9 +1331,9 @@ DDP_DEVICE_NOINLINE void rows_unit(const JobCtx<R> *cp_, int u0, int u1, int lan
                     const int shift = group_shift(g), nr = g < 6 ? P : 6;
                     const R lim = g < 11 ? t.max_vel : t.max_acc;
                     R b[6], bd[6], bn[6], co[3], cd[3], cn[3], j1[3], j2[3];
-                    basis_row_rt(t.tab + g * 6, shift, tpo, b);
-                    basis_row_rt(t.tab + 90 + g * 6, shift + 1, tpo, bd);
-                    basis_row_rt(t.tab + g * 6, shift, tpn, bn);
+                    basis_row_rt(tab + g * 6, shift, tpo, b);
+                    basis_row_rt(tab + 90 + g * 6, shift + 1, tpo, bd);
+                    basis_row_rt(tab + g * 6, shift, tpn, bn);
                     DDP_UNROLL
                     for (int a = 0; a < 3; a++) {
                         co[a] = dot_axis<R, 0>(b, zo, a); cd[a] = dot_axis<R, 0>(bd, zo, a); cn[a] = dot_axis<R, 0>(bn, zn, a);
@@ -1395,6 +1400,7 @@ DDP_DEVICE_NOINLINE void rows_unit(const JobCtx<R> *cp_, int u0, int u1, int lan
 template <class R>
 DDP_DEVICE_NOINLINE void rollout_block(R *sm, const R *DDP_RESTRICT xu, R *DDP_RESTRICT xun, const R *DDP_RESTRICT Kin,
                                        R *DDP_RESTRICT kdxo, int N, int base, int nk, R alpha, int lane_, Reg<R, 1> &xcur_io) {
+    sm = as_shared(sm);
     R *ring = sm + Lay::MSC;
     Reg<R, 1> xn, xcur;   // local copy: a by-reference Reg lives in local memory and would be re-read after every store
     FOR_LANES(lane) { xn(lane, 0) = R(0); xcur(lane, 0) = xcur_io(lane, 0); }
@@ -1456,7 +1462,9 @@ DDP_DEVICE_NOINLINE void rollout_block(R *sm, const R *DDP_RESTRICT xu, R *DDP_R
 template <class R> DDP_DEVICE_NOINLINE bool forward_trial_coop(Traj<R> &tt_, R alpha, R tau, RollOut<R> &out) {
     const int lane_ = tt_.lane_;
     const RowCtx<R> t = row_ctx(tt_);
-    R *sm = tt_.sm;
+    R *sm = as_shared(tt_.sm);
+    const R *tab = as_shared(t.tab);
+    (void)tab;
     const int N = tt_.N;
     const R *DDP_RESTRICT xu = tt_.xu;
     R *DDP_RESTRICT xun = tt_.xun;
@@ -1540,7 +1548,9 @@ template <class R> DDP_DEVICE_NOINLINE bool forward_trial_coop(Traj<R> &tt_, R a
 template <class R> DDP_DEVICE_NOINLINE bool forward_trial_solo(Traj<R> &tt_, R alpha, R tau, RollOut<R> &out) {
     const int lane_ = tt_.lane_;
     const RowCtx<R> t = row_ctx(tt_);
-    R *sm = tt_.sm;
+    R *sm = as_shared(tt_.sm);
+    const R *tab = as_shared(t.tab);
+    (void)tab;
     const int N = tt_.N;
     const R *DDP_RESTRICT xu = tt_.xu;
     R *DDP_RESTRICT xun = tt_.xun;
@@ -1641,9 +1651,9 @@ template <class R> DDP_DEVICE_NOINLINE bool forward_trial_solo(Traj<R> &tt_, R a
                     const int shift = group_shift(g), nr = g < 6 ? P : 6;
                     const R lim = g < 11 ? t.max_vel : t.max_acc;
                     R b[6], bd[6], bn[6], co[3], cd[3], cn[3], j1[3], j2[3];
-                    basis_row_rt(t.tab + g * 6, shift, tpo, b);
-                    basis_row_rt(t.tab + 90 + g * 6, shift + 1, tpo, bd);
-                    basis_row_rt(t.tab + g * 6, shift, tpn, bn);
+                    basis_row_rt(tab + g * 6, shift, tpo, b);
+                    basis_row_rt(tab + 90 + g * 6, shift + 1, tpo, bd);
+                    basis_row_rt(tab + g * 6, shift, tpn, bn);
                     DDP_UNROLL
                     for (int a = 0; a < 3; a++) {
                         co[a] = dot_axis<R, 0>(b, zo, a); cd[a] = dot_axis<R, 0>(bd, zo, a); cn[a] = dot_axis<R, 0>(bn, zn, a);
@@ -1732,7 +1742,7 @@ template <class R> DDP_DEVICE_NOINLINE bool forward_trial_solo(Traj<R> &tt_, R a
 // Open-loop rollout of the initial controls (initialroll, ddp.cpp:1608-1620) and its cost.
 template <class R> DDP_DEVICE_NOINLINE void initial_roll(Traj<R> &t) {
     const int lane_ = t.lane_;
-    R *sm = t.sm;
+    R *sm = as_shared(t.sm);
     const int N = t.N;
     Reg<R, 1> xcur, xn;
     FOR_LANES(lane) { xcur(lane, 0) = (lane >= 10 && lane < 19) ? t.xu[lane] : R(0); xn(lane, 0) = R(0); }
@@ -1895,6 +1905,8 @@ template <class R> DDP_DEVICE_NOINLINE void forward_pass(Traj<R> &t) {
 template <class R> DDP_DEVICE_NOINLINE void solve_one(const SolveArgs &A, int st, int b, R *sm, const R *tabs, R *ws,
                                                       int lane_, void *board = nullptr, void *ctl = nullptr, int wpb = 1) {
     const StageCfg &cfg = A.cfg[st];
+    sm = as_shared(sm);
+    tabs = as_shared(tabs);
     const int N = A.N;
     const WsLay wl = ws_layout(N, A.PM, A.fcap);
     Traj<R> t;

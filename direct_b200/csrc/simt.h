@@ -57,6 +57,19 @@ DDP_DEVICE double shfl_idx(double x, int s) { return __shfl_sync(0xffffffffu, x,
 DDP_DEVICE float shfl_idx(float x, int s) { return __shfl_sync(0xffffffffu, x, s); }
 #endif
 
+// A per-warp scratch pointer travels through structs and out-of-line calls as a generic pointer, and every access through it
+// became a generic LD/ST plus address arithmetic (profiles/r1g: riccati had 352 LD.E.64 and not one LDS).  as_shared()
+// re-derives the pointer from the dynamic shared-memory symbol, so the compiler knows the address space again.
+#if DDP_GPU
+template <class T> DDP_DEVICE T *as_shared(T *p) {
+    extern __shared__ __align__(16) unsigned char ddp_dyn_smem[];
+    const unsigned off = (unsigned)__cvta_generic_to_shared(p) - (unsigned)__cvta_generic_to_shared(ddp_dyn_smem);
+    return reinterpret_cast<T *>(ddp_dyn_smem + off);
+}
+#else
+template <class T> DDP_DEVICE T *as_shared(T *p) { return p; }
+#endif
+
 // Butterfly all-reduce over the warp, element i of r; every lane ends with the same value, returned.
 // The emulation reproduces the butterfly's association order so both builds round identically.
 template <class T, int N> DDP_DEVICE T warp_sum(Reg<T, N> &r, int i, int lane_) {
