@@ -225,7 +225,7 @@ template <class R> int launch(H *h, SolveArgs &A, cudaStream_t s) {
     A.fcap = max_iter + 2;
     const ddp::WsLay wl = ddp::ws_layout(A.N, A.PM, A.fcap);
     A.ws_stride = wl.total;
-    const size_t ws_bytes = (size_t)grid * wpb * wl.total * sizeof(R);
+    const size_t ws_bytes = (size_t)grid * wpb * wl.total * sizeof(R) + 65536;   // + slack: the row loops prefetch a few rows past the last array
     if (h->ws.cap < ws_bytes) {
         int st = ensure(h, h->ws, ws_bytes);
         if (st) return st;

@@ -154,7 +154,7 @@ DDP_HD int smem_elems_per_warp(int /*pm*/) { return Lay::TOTAL; }
 
 // Workspace slot layout (elements of Real).  Row arrays (s, y and their trial copies) are stored
 // [row slot][knot] with the knot index padded to a multiple of 32, so lane <-> knot accesses coalesce.
-// Row slots: corridor row (control point j, plane k) -> j*PM+k; then +v (15), -v (15), +a (12), -a (12), time.
+// Row slots (row_slot below): corridor row (control point j, plane k) -> j*PM+k; then 6 rows per v / a group; time.
 struct WsLay {
     long long xu, xun, K, kdx, aux, H, s, sn, y, yn, filt, total;
     int MCS, NP;
@@ -259,13 +259,11 @@ template <class R> DDP_DEVICE void basis_row_rt(const R *tabrow, int sd, const R
 // Row groups: g < 6 position control points (one row per plane), 6..10 velocity, 11..14 acceleration control points
 // (six rows each, visited +x,-x,+y,-y,+z,-z like ddp.cpp:1228-1272).
 DDP_DEVICE int group_shift(int g) { return g < 6 ? 0 : (g < 11 ? 1 : 2); }
-// Row slot of row r of group g: corridor rows g*PM + k, then +v (15), -v (15), +a (12), -a (12), time.
-DDP_DEVICE int row_slot(int g, int r, int PM) {
-    if (g < 6) return g * PM + r;
-    const int FB = 6 * PM, a = r >> 1, neg = r & 1;
-    if (g < 11) return FB + (neg ? 15 : 0) + 3 * (g - 6) + a;
-    return FB + 30 + (neg ? 12 : 0) + 3 * (g - 11) + a;
-}
+// Row slot of row r of group g, in VISIT order (the slot order is internal to the workspace): corridor rows g*PM + k,
+// then the six rows of every velocity / acceleration group, then the time row.  The row visited k rows later therefore
+// sits k*NP elements further on (exactly so for g >= 6 or a full polytope), which is what the row loops prefetch.
+DDP_DEVICE int row_slot(int g, int r, int PM) { return g < 6 ? g * PM + r : 6 * PM + 6 * (g - 6) + r; }
+enum { ROW_PREFETCH = 3 };   // rows ahead
 // Direction and offset of a velocity / acceleration row: n = +-e_a, d = -limit (ddp.cpp:1238, :1276).
 template <class R> DDP_DEVICE void fixed_row(int r, R lim, R *n) {
     const int a = r >> 1;
@@ -362,8 +360,16 @@ template <class R> struct RowCtx {
 };
 template <class R> DDP_DEVICE RowCtx<R> row_ctx(const Traj<R> &t) {
     RowCtx<R> c;
-    c.s = t.s; c.y = t.y; c.sn = t.sn; c.yn = t.yn; c.tab = t.tab; c.planes = t.planes; c.nplanes = t.nplanes;
+    c.s = as_global(t.s); c.y = as_global(t.y); c.sn = as_global(t.sn); c.yn = as_global(t.yn); c.tab = t.tab;
+    c.planes = as_global(t.planes); c.nplanes = as_global(t.nplanes);
     c.NP = t.NP; c.PM = t.PM; c.infeas = t.infeas; c.mu = t.mu; c.margin = t.margin; c.max_vel = t.max_vel; c.max_acc = t.max_acc;
+    return c;
+}
+
+// A RowCtx that went through memory (job board) lost what the compiler knew about its pointers.
+template <class R> DDP_DEVICE RowCtx<R> row_global(RowCtx<R> c) {
+    c.s = as_global(c.s); c.y = as_global(c.y); c.sn = as_global(c.sn); c.yn = as_global(c.yn);
+    c.planes = as_global(c.planes); c.nplanes = as_global(c.nplanes);
     return c;
 }
 
@@ -471,14 +477,14 @@ template <class R> DDP_HD int coop_smem_bytes(int warps_per_block) {
 // =============================================================================================
 template <class R> DDP_DEVICE_NOINLINE void lin_unit(const JobCtx<R> *cp_, int u, R *smw, int lane_, Reg<R, 2> &errs) {
     const JobCtx<R> c = *cp_;
-    const RowCtx<R> t = c.row;
+    const RowCtx<R> t = row_global(c.row);
     smw = as_shared(smw);
     const R *tab = as_shared(t.tab);
     const int N = c.N, time_power = c.time_power;
     const R w_snap = c.w_snap, w_time = c.w_time;
-    const R *DDP_RESTRICT xu = c.xu;
-    R *DDP_RESTRICT Hout = c.H;
-    R *DDP_RESTRICT auxout = c.aux;
+    const R *DDP_RESTRICT xu = as_global(c.xu);
+    R *DDP_RESTRICT Hout = as_global(c.H);
+    R *DDP_RESTRICT auxout = as_global(c.aux);
     const R sgn = t.infeas ? R(1) : R(-1);
     {
         const int base = 32 * (c.base + u);
@@ -525,11 +531,15 @@ template <class R> DDP_DEVICE_NOINLINE void lin_unit(const JobCtx<R> *cp_, int u
                         R n[4];
                         if (g < 6) { n[0] = n_n[0]; n[1] = n_n[1]; n[2] = n_n[2]; n[3] = n_n[3]; }
                         else fixed_row(r, lim, n);
-                        if (r + 1 < nr) {
+                        {
                             const long long ro = (long long)row_slot(g, r + 1, t.PM) * t.NP + i;
-                            s_n = t.s[ro];
-                            if (t.infeas) y_n = t.y[ro];
-                            if (g < 6) load_plane(pl, r + 1, n_n);
+                            prefetch_l1(t.s + ro + (ROW_PREFETCH - 1) * t.NP);
+                            if (t.infeas) prefetch_l1(t.y + ro + (ROW_PREFETCH - 1) * t.NP);
+                            if (r + 1 < nr) {
+                                s_n = t.s[ro];
+                                if (t.infeas) y_n = t.y[ro];
+                                if (g < 6) load_plane(pl, r + 1, n_n);
+                            }
                         }
                         const R c = ((n[0] * cp[0] + n[1] * cp[1]) + n[2] * cp[2]) + n[3] - t.margin;
                         const R tc = (n[0] * cd[0] + n[1] * cd[1]) + n[2] * cd[2];
@@ -809,9 +819,9 @@ template <class R> DDP_DEVICE_NOINLINE void linearize_solo(Traj<R> &tt_, Reg<R, 
     const RowCtx<R> t = row_ctx(tt_);
     const int N = tt_.N, time_power = tt_.time_power;
     const R w_snap = tt_.w_snap, w_time = tt_.w_time;
-    const R *DDP_RESTRICT xu = tt_.xu;
-    R *DDP_RESTRICT Hout = tt_.H;
-    R *DDP_RESTRICT auxout = tt_.aux;
+    const R *DDP_RESTRICT xu = as_global(tt_.xu);
+    R *DDP_RESTRICT Hout = as_global(tt_.H);
+    R *DDP_RESTRICT auxout = as_global(tt_.aux);
     R *smw = as_shared(tt_.sm);
     const R *tab = as_shared(t.tab);
     const R sgn = t.infeas ? R(1) : R(-1);
@@ -860,11 +870,15 @@ template <class R> DDP_DEVICE_NOINLINE void linearize_solo(Traj<R> &tt_, Reg<R, 
                         R n[4];
                         if (g < 6) { n[0] = n_n[0]; n[1] = n_n[1]; n[2] = n_n[2]; n[3] = n_n[3]; }
                         else fixed_row(r, lim, n);
-                        if (r + 1 < nr) {
+                        {
                             const long long ro = (long long)row_slot(g, r + 1, t.PM) * t.NP + i;
-                            s_n = t.s[ro];
-                            if (t.infeas) y_n = t.y[ro];
-                            if (g < 6) load_plane(pl, r + 1, n_n);
+                            prefetch_l1(t.s + ro + (ROW_PREFETCH - 1) * t.NP);
+                            if (t.infeas) prefetch_l1(t.y + ro + (ROW_PREFETCH - 1) * t.NP);
+                            if (r + 1 < nr) {
+                                s_n = t.s[ro];
+                                if (t.infeas) y_n = t.y[ro];
+                                if (g < 6) load_plane(pl, r + 1, n_n);
+                            }
                         }
                         const R c = ((n[0] * cp[0] + n[1] * cp[1]) + n[2] * cp[2]) + n[3] - t.margin;
                         const R tc = (n[0] * cd[0] + n[1] * cd[1]) + n[2] * cd[2];
@@ -999,10 +1013,10 @@ template <class R> DDP_DEVICE_NOINLINE bool riccati(Traj<R> &t, R regadd, Reg<R,
     const int lane_ = t.lane_;
     R *sm = as_shared(t.sm);
     const int N = t.N;
-    const R *DDP_RESTRICT Hin = t.H;
-    const R *DDP_RESTRICT xu = t.xu;
-    const R *DDP_RESTRICT aux = t.aux;
-    R *DDP_RESTRICT Kout = t.K;
+    const R *DDP_RESTRICT Hin = as_global(t.H);
+    const R *DDP_RESTRICT xu = as_global(t.xu);
+    const R *DDP_RESTRICT aux = as_global(t.aux);
+    R *DDP_RESTRICT Kout = as_global(t.K);
     const R w_terminal = t.w_terminal;
     // terminal value function, ddp.cpp:1318-1323: Vx = P (x_N - x_d), Vxx = P = w_terminal I
     FOR_LANES(lane) {
@@ -1295,13 +1309,13 @@ template <class R>
 DDP_DEVICE_NOINLINE void rows_unit(const JobCtx<R> *cp_, int u0, int u1, int lane_, Reg<R, 12> &part, Reg<int, 4> &badk) {
     (void)lane_;
     const JobCtx<R> c = *cp_;
-    const RowCtx<R> t = c.row;
+    const RowCtx<R> t = row_global(c.row);
     const int N = c.N, time_power = c.time_power;
     const R w_snap = c.w_snap, w_time = c.w_time, alpha = c.alpha, tau = c.tau;
-    const R *DDP_RESTRICT xu = c.xu;
-    const R *DDP_RESTRICT xun = c.xun;
-    const R *DDP_RESTRICT Kin = c.K;
-    const R *DDP_RESTRICT kdxo = c.kdx;
+    const R *DDP_RESTRICT xu = as_global(c.xu);
+    const R *DDP_RESTRICT xun = as_global(c.xun);
+    const R *DDP_RESTRICT Kin = as_global(c.K);
+    const R *DDP_RESTRICT kdxo = as_global(c.kdx);
     const R *tab = as_shared(t.tab);
     // the knot's old/new point and gains are loaded once for all units of the call
     FOR_LANES(lane) {
@@ -1353,8 +1367,10 @@ DDP_DEVICE_NOINLINE void rows_unit(const JobCtx<R> *cp_, int u0, int u1, int lan
                         R n[4];
                         if (g < 6) { n[0] = n_n[0]; n[1] = n_n[1]; n[2] = n_n[2]; n[3] = n_n[3]; }
                         else fixed_row(r, lim, n);
+                        prefetch_l1(t.s + ro_cur + ROW_PREFETCH * t.NP);
+                        if (t.infeas) prefetch_l1(t.y + ro_cur + ROW_PREFETCH * t.NP);
                         if (r + 1 < nr) {
-                            const long long ro = (long long)row_slot(g, r + 1, t.PM) * t.NP + i;
+                            const long long ro = ro_cur + t.NP;
                             s_n = t.s[ro];
                             if (t.infeas) y_n = t.y[ro];
                             if (g < 6) load_plane(pl, r + 1, n_n);
@@ -1401,6 +1417,7 @@ template <class R>
 DDP_DEVICE_NOINLINE void rollout_block(R *sm, const R *DDP_RESTRICT xu, R *DDP_RESTRICT xun, const R *DDP_RESTRICT Kin,
                                        R *DDP_RESTRICT kdxo, int N, int base, int nk, R alpha, int lane_, Reg<R, 1> &xcur_io) {
     sm = as_shared(sm);
+    xu = as_global(xu); xun = as_global(xun); Kin = as_global(Kin); kdxo = as_global(kdxo);
     R *ring = sm + Lay::MSC;
     Reg<R, 1> xn, xcur;   // local copy: a by-reference Reg lives in local memory and would be re-read after every store
     FOR_LANES(lane) { xn(lane, 0) = R(0); xcur(lane, 0) = xcur_io(lane, 0); }
@@ -1466,10 +1483,10 @@ template <class R> DDP_DEVICE_NOINLINE bool forward_trial_coop(Traj<R> &tt_, R a
     const R *tab = as_shared(t.tab);
     (void)tab;
     const int N = tt_.N;
-    const R *DDP_RESTRICT xu = tt_.xu;
-    R *DDP_RESTRICT xun = tt_.xun;
-    const R *DDP_RESTRICT Kin = tt_.K;
-    R *DDP_RESTRICT kdxo = tt_.kdx;
+    const R *DDP_RESTRICT xu = as_global(tt_.xu);
+    R *DDP_RESTRICT xun = as_global(tt_.xun);
+    const R *DDP_RESTRICT Kin = as_global(tt_.K);
+    R *DDP_RESTRICT kdxo = as_global(tt_.kdx);
     const R w_terminal = tt_.w_terminal, w_snap = tt_.w_snap, w_time = tt_.w_time, tol = tt_.tol;
     const int time_power = tt_.time_power;
     long long fwd_knots = 0, cyc_seq = 0;
@@ -1552,10 +1569,10 @@ template <class R> DDP_DEVICE_NOINLINE bool forward_trial_solo(Traj<R> &tt_, R a
     const R *tab = as_shared(t.tab);
     (void)tab;
     const int N = tt_.N;
-    const R *DDP_RESTRICT xu = tt_.xu;
-    R *DDP_RESTRICT xun = tt_.xun;
-    const R *DDP_RESTRICT Kin = tt_.K;
-    R *DDP_RESTRICT kdxo = tt_.kdx;
+    const R *DDP_RESTRICT xu = as_global(tt_.xu);
+    R *DDP_RESTRICT xun = as_global(tt_.xun);
+    const R *DDP_RESTRICT Kin = as_global(tt_.K);
+    R *DDP_RESTRICT kdxo = as_global(tt_.kdx);
     const R w_terminal = tt_.w_terminal, w_snap = tt_.w_snap, w_time = tt_.w_time, tol = tt_.tol;
     const int time_power = tt_.time_power;
     long long fwd_knots = 0, cyc_seq = 0;
@@ -1673,8 +1690,10 @@ template <class R> DDP_DEVICE_NOINLINE bool forward_trial_solo(Traj<R> &tt_, R a
                         R n[4];
                         if (g < 6) { n[0] = n_n[0]; n[1] = n_n[1]; n[2] = n_n[2]; n[3] = n_n[3]; }
                         else fixed_row(r, lim, n);
+                        prefetch_l1(t.s + ro_cur + ROW_PREFETCH * t.NP);
+                        if (t.infeas) prefetch_l1(t.y + ro_cur + ROW_PREFETCH * t.NP);
                         if (r + 1 < nr) {
-                            const long long ro = (long long)row_slot(g, r + 1, t.PM) * t.NP + i;
+                            const long long ro = ro_cur + t.NP;
                             s_n = t.s[ro];
                             if (t.infeas) y_n = t.y[ro];
                             if (g < 6) load_plane(pl, r + 1, n_n);

@@ -66,8 +66,14 @@ template <class T> DDP_DEVICE T *as_shared(T *p) {
     const unsigned off = (unsigned)__cvta_generic_to_shared(p) - (unsigned)__cvta_generic_to_shared(ddp_dyn_smem);
     return reinterpret_cast<T *>(ddp_dyn_smem + off);
 }
+// The same for pointers into the workspace / the caller's arrays: tell the compiler they are global (LDG/STG).
+template <class T> DDP_DEVICE T *as_global(T *p) {
+    __builtin_assume(__isGlobal(p));
+    return p;
+}
 #else
 template <class T> DDP_DEVICE T *as_shared(T *p) { return p; }
+template <class T> DDP_DEVICE T *as_global(T *p) { return p; }
 #endif
 
 // Butterfly all-reduce over the warp, element i of r; every lane ends with the same value, returned.
@@ -154,6 +160,13 @@ template <int N> DDP_DEVICE void cp_wait() { asm volatile("cp.async.wait_group %
 template <int BYTES> DDP_DEVICE void cp_async(void *smem_dst, const void *gsrc) { memcpy(smem_dst, gsrc, BYTES); }
 DDP_DEVICE void cp_commit() {}
 template <int N> DDP_DEVICE void cp_wait() {}
+#endif
+
+// Software prefetch of a global line that a later iteration of a row loop will load (no register is tied up).
+#if DDP_GPU
+DDP_DEVICE void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(__cvta_generic_to_global(p))); }
+#else
+DDP_DEVICE void prefetch_l1(const void *) {}
 #endif
 
 // log(): called rarely (LogProd) but ~100 SASS instructions per inlined fp64 copy; kept out of line so the hot
