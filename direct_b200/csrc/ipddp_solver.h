@@ -134,7 +134,7 @@ struct Lay {
     enum {
         XD = 0,     // desired terminal state (9)
         S1 = 10,    // value-function Hessian as left by the Schur complement, S1[a*10+b] = S[a][b]
-        S2 = 100,   // the same transposed, S2[b*10+a] = S[a][b]; V = (S + S^T)/2 is formed by the reader
+        S2 = 100,   // V = (S + S^T)/2 (ddp.cpp:628), V[b*10+a], formed by the writer of S1
         VX = 190,   // V_x (9)
         MB = 200,   // Cholesky multiplier rows, MB[p*20+r] = L[r][p]  (10 x 20)
         XT = 400,   // row T of every column, for the T column (20)
@@ -263,7 +263,10 @@ DDP_DEVICE int group_shift(int g) { return g < 6 ? 0 : (g < 11 ? 1 : 2); }
 // then the six rows of every velocity / acceleration group, then the time row.  The row visited k rows later therefore
 // sits k*NP elements further on (exactly so for g >= 6 or a full polytope), which is what the row loops prefetch.
 DDP_DEVICE int row_slot(int g, int r, int PM) { return g < 6 ? g * PM + r : 6 * PM + 6 * (g - 6) + r; }
-enum { ROW_PREFETCH = 3 };   // rows ahead
+#ifndef DDP_ROW_PREFETCH
+#define DDP_ROW_PREFETCH 3
+#endif
+enum { ROW_PREFETCH = DDP_ROW_PREFETCH };   // rows ahead
 // Direction and offset of a velocity / acceleration row: n = +-e_a, d = -limit (ddp.cpp:1238, :1276).
 template <class R> DDP_DEVICE void fixed_row(int r, R lim, R *n) {
     const int a = r >> 1;
@@ -1035,8 +1038,11 @@ template <class R> DDP_DEVICE_NOINLINE bool riccati(Traj<R> &t, R regadd, Reg<R,
     Reg<R, 20> col, nxt;
     Reg<R, 1> pre;   // next knot's fT (lanes 0-8) / segment time (lane 9), loaded one knot ahead
     FOR_LANES(lane) {
-        DDP_UNROLL
-        for (int r = 0; r < 20; r++) nxt(lane, r) = lane < 20 ? Hin[(long long)(N - 1) * 400 + lane * 20 + r] : R(0);
+        if (lane < 20) load20(Hin + (long long)(N - 1) * 400 + lane * 20, &nxt(lane, 0));
+        else {
+            DDP_UNROLL
+            for (int r = 0; r < 20; r++) nxt(lane, r) = R(0);
+        }
     }
     long long knots = 0;
     bool ok = true;
@@ -1053,10 +1059,7 @@ template <class R> DDP_DEVICE_NOINLINE bool riccati(Traj<R> &t, R regadd, Reg<R,
             for (int r = 0; r < 20; r++) col(lane, r) = nxt(lane, r);
             pre(lane, 0) = R(0);
             if (i > 0) {   // prefetch the next knot's column, fT and time while this one is eliminated
-                if (lane < 20) {
-                    DDP_UNROLL
-                    for (int r = 0; r < 20; r++) nxt(lane, r) = Hin[(long long)(i - 1) * 400 + lane * 20 + r];
-                }
+                if (lane < 20) load20(Hin + (long long)(i - 1) * 400 + lane * 20, &nxt(lane, 0));
                 if (lane < 9) pre(lane, 0) = aux[(long long)(i - 1) * 12 + lane];
                 else if (lane == 9) pre(lane, 0) = xu[(long long)(i - 1) * 20 + 9];
             }
@@ -1068,12 +1071,10 @@ template <class R> DDP_DEVICE_NOINLINE bool riccati(Traj<R> &t, R regadd, Reg<R,
                 } else {
                     const int lj = lane < 9 ? 3 + lane / 3 : (lane - 10) / 3, aj = lane < 9 ? lane % 3 : (lane - 10) % 3;
                     const R f0 = fg[lj], f1 = fg[6 + lj], f2 = fg[12 + lj];
-                    const R *a1 = sm + Lay::S1, *a2 = sm + Lay::S2;
+                    const R *V = sm + Lay::S2;   // V = (S + S^T)/2 (ddp.cpp:628), symmetrised by the writer below
                     DDP_UNROLL
-                    for (int p = 0; p < 9; p++) {   // V = (S + S^T)/2 (ddp.cpp:628) formed on the fly
-                        const R v0 = R(0.5) * (a1[aj * 10 + p] + a2[aj * 10 + p]);
-                        const R v1 = R(0.5) * (a1[(3 + aj) * 10 + p] + a2[(3 + aj) * 10 + p]);
-                        const R v2 = R(0.5) * (a1[(6 + aj) * 10 + p] + a2[(6 + aj) * 10 + p]);
+                    for (int p = 0; p < 9; p++) {
+                        const R v0 = V[aj * 10 + p], v1 = V[(3 + aj) * 10 + p], v2 = V[(6 + aj) * 10 + p];
                         tj[p] = (v0 * f0 + v1 * f1) + v2 * f2;
                     }
                     // gradient row of this column: (A e_j)^T Vx
@@ -1095,7 +1096,7 @@ template <class R> DDP_DEVICE_NOINLINE bool riccati(Traj<R> &t, R regadd, Reg<R,
                 const int p = lane - 10;
                 R acc = R(0);
                 DDP_UNROLL
-                for (int q = 0; q < 9; q++) acc += (R(0.5) * (sm[Lay::S1 + p * 10 + q] + sm[Lay::S2 + p * 10 + q])) * fT[q];
+                for (int q = 0; q < 9; q++) acc += sm[Lay::S2 + p * 10 + q] * fT[q];
                 sm[Lay::XH + p] = fT[p] * acc;
             }
         }
@@ -1150,12 +1151,16 @@ template <class R> DDP_DEVICE_NOINLINE bool riccati(Traj<R> &t, R regadd, Reg<R,
         Reg<R, 10> kx;
         FOR_LANES(lane) {
             if (lane >= 10 && lane < 20) {
+                // column-oriented back-substitution: once k_p is known the nine partial sums below it are updated
+                // independently (dependent chain of 10 instead of 45 FMAs)
+                R v[10];
+                DDP_UNROLL
+                for (int p = 0; p < 10; p++) v[p] = sm[Lay::MB + p * 20 + lane];
                 DDP_UNROLL
                 for (int p = 9; p >= 0; p--) {
-                    R v = sm[Lay::MB + p * 20 + lane];
+                    kx(lane, p) = -(v[p] * sm[Lay::RI + p]);
                     DDP_UNROLL
-                    for (int q = p + 1; q < 10; q++) v += sm[Lay::MB + p * 20 + q] * kx(lane, q);
-                    kx(lane, p) = -(v * sm[Lay::RI + p]);
+                    for (int r = 0; r < p; r++) v[r] += sm[Lay::MB + r * 20 + p] * kx(lane, p);
                 }
                 const int qc = lane == 19 ? 0 : lane - 9;
                 DDP_UNROLL
@@ -1190,10 +1195,18 @@ template <class R> DDP_DEVICE_NOINLINE bool riccati(Traj<R> &t, R regadd, Reg<R,
             if (lane >= 10 && lane < 19) {
                 const int b = lane - 10;
                 DDP_UNROLL
-                for (int a = 0; a < 9; a++) { sm[Lay::S1 + a * 10 + b] = col(lane, a); sm[Lay::S2 + b * 10 + a] = col(lane, a); }
+                for (int a = 0; a < 9; a++) sm[Lay::S1 + a * 10 + b] = col(lane, a);   // S[a][b]
                 sm[Lay::VX + b] = col(lane, 9);
             }
             if (lane < 10) sm[Lay::FTN + lane] = pre(lane, 0);
+        }
+        WARP_SYNC();
+        FOR_LANES(lane) {   // V[b][a] = (S[a][b] + S[b][a]) / 2, row b of S1 was written by the other lanes
+            if (lane >= 10 && lane < 19) {
+                const int b = lane - 10;
+                DDP_UNROLL
+                for (int a = 0; a < 9; a++) sm[Lay::S2 + b * 10 + a] = R(0.5) * (sm[Lay::S1 + b * 10 + a] + col(lane, a));
+            }
         }
         WARP_SYNC();
     }

@@ -169,6 +169,19 @@ DDP_DEVICE void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%
 DDP_DEVICE void prefetch_l1(const void *) {}
 #endif
 
+// 20 consecutive elements (16-byte aligned) into registers: ten 128-bit loads in fp64 on the GPU.
+template <class T> DDP_DEVICE void load20(const T *p, T *out) {
+    DDP_UNROLL
+    for (int r = 0; r < 20; r++) out[r] = p[r];
+}
+#if DDP_GPU
+template <> DDP_DEVICE void load20<double>(const double *p, double *out) {
+    const double2 *q = reinterpret_cast<const double2 *>(p);
+    DDP_UNROLL
+    for (int r = 0; r < 10; r++) { const double2 v = q[r]; out[2 * r] = v.x; out[2 * r + 1] = v.y; }
+}
+#endif
+
 // log(): called rarely (LogProd) but ~100 SASS instructions per inlined fp64 copy; kept out of line so the hot
 // row loops stay small (the v2 profile showed 35 % instruction-fetch stalls, profiles/r1b).
 #if DDP_GPU
