@@ -52,11 +52,16 @@ __global__ void __launch_bounds__(DDP_MAX_THREADS, DDP_MIN_BLOCKS) ipddp_solve_k
         if (b >= (unsigned int)A.B) break;
         if (A.two_stage) ddp::solve_one<R>(A, 0, (int)b, sm, tabs, ws, lane, boards + warp, A.coop ? ctl : nullptr, wpb);
         ddp::solve_one<R>(A, A.two_stage ? 1 : 0, (int)b, sm, tabs, ws, lane, boards + warp, A.coop ? ctl : nullptr, wpb);
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) atomicAdd(A.counter + 3, 1u);   // trajectories finished (the warps of idle CTAs leave when all are)
     }
     // queue empty: help the warps of this CTA that still own a trajectory (ipddp_solver.h "Intra-CTA cooperation")
     if (lane == 0) atomicSub(&ctl->active_owners, 1);
     __syncwarp();
     if (wpb > 1 && A.coop) ddp::helper_loop<R>(boards, ctl, wpb, warp, sm, lane, A.counter + 2);
+    // no warp of this CTA owns a trajectory any more: run line-search trials of the remaining solves of other CTAs
+    if (A.gspec) ddp::gspec_helper_loop<R>(A, sm, tabs, ws, (int)slot, lane);
 }
 
 // initTimeAllocation, teach_repeat_planner.cpp:583-639 (v0 = 0): one thread per segment.
@@ -145,7 +150,7 @@ struct direct_ddp_handle_s {
     // grow-only device buffers
     DevBuf planes, nplanes, durations, seeds, x0, xd, init_bez, infeas;
     DevBuf o_int[2], o_cost[2], o_xf[2], o_pc[2], o_bz[2], o_pt[2], o_jk[2], o_st[2];
-    DevBuf ws, counter, tabs, bez_tmp, time_tmp, trace, trace_len, scratch_i;
+    DevBuf ws, counter, tabs, bez_tmp, time_tmp, trace, trace_len, scratch_i, gboards, gwords;
     const long long *last_stats_dev = nullptr;  // device [B][4] of the last solve (stage 1 / single)
     const long long *last_stats_dev0 = nullptr; // stage 0 when two-stage
     int last_B = 0;
@@ -232,13 +237,24 @@ template <class R> int launch(H *h, SolveArgs &A, cudaStream_t s) {
         CK(cudaMemsetAsync(h->ws.p, 0, ws_bytes, s));
     }
     A.ws = h->ws.p;
-    int st = ensure(h, h->counter, 16);
+    int st = ensure(h, h->counter, 64);
     if (st) return st;
-    CK(cudaMemsetAsync(h->counter.p, 0, 16, s));
+    CK(cudaMemsetAsync(h->counter.p, 0, 64, s));
     A.counter = (unsigned int *)h->counter.p;
     {
         const char *e = getenv("DIRECT_DDP_COOP");   // tuning knob: 0 disables the tail balancing
         A.coop = (e && atoi(e) == 0) ? 0 : 1;
+        e = getenv("DIRECT_DDP_GSPEC");              // tuning knob: 0 disables the speculative line search of the tail
+        A.gspec = (e && atoi(e) == 0) ? 0 : A.coop;
+    }
+    A.gboards = nullptr; A.gwords = nullptr;
+    if (A.gspec) {
+        const size_t nb = (size_t)2 * grid * wpb;
+        if ((st = ensure(h, h->gboards, nb * sizeof(ddp::GBoard<R>)))) return st;
+        if ((st = ensure(h, h->gwords, nb * sizeof(unsigned long long)))) return st;
+        CK(cudaMemsetAsync(h->gboards.p, 0, nb * sizeof(ddp::GBoard<R>), s));
+        CK(cudaMemsetAsync(h->gwords.p, 0, nb * sizeof(unsigned long long), s));
+        A.gboards = h->gboards.p; A.gwords = (unsigned long long *)h->gwords.p;
     }
     if (h->opts.trace) {
         if ((st = ensure(h, h->trace, 512 * 12 * sizeof(double)))) return st;
@@ -448,7 +464,8 @@ void direct_ddp_destroy(direct_ddp_handle h) {
     if (h->sm_count > 0) {
         cudaSetDevice(h->opts.device);
         DevBuf *bufs[] = {&h->planes, &h->nplanes, &h->durations, &h->seeds, &h->x0, &h->xd, &h->init_bez, &h->infeas,
-                          &h->ws, &h->counter, &h->tabs, &h->bez_tmp, &h->time_tmp, &h->trace, &h->trace_len, &h->scratch_i};
+                          &h->ws, &h->counter, &h->tabs, &h->bez_tmp, &h->time_tmp, &h->trace, &h->trace_len, &h->scratch_i,
+                          &h->gboards, &h->gwords};
         for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
         for (int k = 0; k < 2; k++) {
             DevBuf *ob[] = {&h->o_int[k], &h->o_cost[k], &h->o_xf[k], &h->o_pc[k], &h->o_bz[k], &h->o_pt[k], &h->o_jk[k], &h->o_st[k]};
@@ -576,9 +593,10 @@ int direct_ddp_last_stats(direct_ddp_handle h, direct_ddp_stats *out) {
             for (int i = 0; i < h->last_B; i++) for (int k = 0; k < 4; k++) tot[k] += tmp[(size_t)i * 8 + k];
         }
         h->stats.bwd_sweeps = tot[0]; h->stats.bwd_knots = tot[1]; h->stats.fwd_trials = tot[2]; h->stats.fwd_knots = tot[3];
-        unsigned int cnt[4] = {0, 0, 0, 0};
+        unsigned int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         CK(cudaMemcpy(cnt, h->counter.p, sizeof cnt, cudaMemcpyDeviceToHost));
         h->stats.coop_jobs = cnt[1]; h->stats.helper_units = cnt[2];
+        h->stats.spec_searches = cnt[5]; h->stats.spec_trials = cnt[6];
         h->stats_valid = true;
     }
     *out = h->stats;

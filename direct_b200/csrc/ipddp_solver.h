@@ -120,7 +120,11 @@ struct SolveArgs {
     void *ws;                    // workspace, ws_stride elements of Real per warp slot
     long long ws_stride;
     int fcap;                    // filter capacity per slot
-    unsigned int *counter;       // work queue
+    unsigned int *counter;       // [0] work queue, [1] jobs posted, [2] units run by CTA helpers, [3] trajectories finished,
+                                 // [4] warps of fully idle CTAs, [5] speculative line searches posted, [6] remote trials run
+    int gspec;                   // 1: warps of idle CTAs run line-search trials of the remaining solves ("Speculative line search")
+    void *gboards;               // GBoard<R>[2 * slots]
+    unsigned long long *gwords;  // their claim words, [2 * slots]
     double *trace;               // optional [cap][12] trace of trajectory 0 (last stage), or NULL
     int trace_cap;
     int *trace_len;
@@ -212,6 +216,13 @@ template <class R> struct Traj {
     long long cyc_ric, cyc_seq;          // of which: Riccati recursion, sequential state rollout
     void *board, *ctl;                   // JobBoard<R> of this warp / BlockCtl of the CTA (null: no cooperation)
     int wpb;
+    // speculative line search over the warps of idle CTAs (null / 0: off)
+    void *gb;                            // this slot's two GBoard<R>
+    unsigned long long *gw;              // and their claim words
+    unsigned int *gctr;                  // SolveArgs::counter
+    R *ws_all;                           // workspace of slot 0
+    long long ws_stride, off_xun, off_sn, off_yn, off_kdx;
+    int gflip, minvo;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -1873,6 +1884,91 @@ template <class R> DDP_DEVICE void reset_filter(Traj<R> &t) {
     t.failed = 0;
 }
 
+// Filter acceptance of a trial that passed the fraction-to-boundary rule, ddp.cpp:741-757: rejected if some entry is <=
+// the candidate in both coordinates; an accepted candidate evicts the entries it dominates.  Lane 0 owns the filter.
+template <class R> DDP_DEVICE bool filter_try(Traj<R> &t, R logcost, R err) {
+    const int lane_ = t.lane_;
+    FOR_LANES(lane) {
+        if (lane == 0) {
+            bool rej = false;
+            for (int k = 0; k < t.nfilter; k++)
+                if (logcost >= t.filt[2 * k] && err >= t.filt[2 * k + 1]) { rej = true; break; }
+            int nk = 0;
+            if (!rej) {
+                for (int k = 0; k < t.nfilter; k++) {
+                    const R f0 = t.filt[2 * k], f1 = t.filt[2 * k + 1];
+                    if (logcost > f0 || err > f1) { t.filt[2 * nk] = f0; t.filt[2 * nk + 1] = f1; nk++; }
+                }
+                if (nk >= t.fcap) nk = t.fcap - 1;
+                t.filt[2 * nk] = logcost; t.filt[2 * nk + 1] = err;
+            }
+            t.sm[Lay::FL] = rej ? R(1) : R(0);
+            t.sm[Lay::FL + 1] = R(nk);
+        }
+    }
+    WARP_SYNC();
+    const bool rej = t.sm[Lay::FL] != R(0);
+    const int nkeep = (int)t.sm[Lay::FL + 1];
+    WARP_SYNC();
+    if (rej) return false;
+    t.nfilter = nkeep + 1;
+    return true;
+}
+
+// =============================================================================================
+// Speculative line search.  The solves that dominate the tail of a batch run stage 1 to iter_max, and ~40 % of
+// their line searches FAIL: eleven full-length trials one after the other, every one rejected (tools/tail_report.py).
+// The trials of one line search are independent of each other (the filter only changes when a trial is accepted), so
+// once whole CTAs are idle their warps run the trials 2^-1 .. 2^-10 of a remaining solve concurrently with the owner's
+// own trial 2^0, each into the candidate buffers of its own (idle) workspace slot.  The owner then walks the results in
+// step order - exactly the decisions of the sequential search - and copies the winning candidate, if any, into its own
+// buffers.  Boards live in global memory (two per slot, used alternately so that a cancelled search never has to be
+// waited for); claimed units always run to completion, and an owner that finds units unclaimed when its own trial is
+// over closes the board and carries on sequentially, so nothing ever waits on a warp that is itself waiting.
+// =============================================================================================
+enum { GSPEC_UNITS = 10, GSPEC_MIN_IDLE = 12 };
+template <class R> struct GBoard {
+    Traj<R> t;          // the owner's view of the trajectory when it posted the search
+    R xd[9];            // desired terminal state (lives in the owner's shared memory)
+    R tau;
+    int seq_ctr;        // generations posted by this slot so far (kept in the first board of the pair; never reset in a launch)
+    int done;           // units finished
+    int retired;        // last generation whose candidates the owner no longer needs
+    int claimed_final;  // units that had been claimed when the last search on this board was closed
+    struct Res { int ok, slot; long long knots; R cost, costq, logcost, err; } res[GSPEC_UNITS];
+};
+
+#if DDP_GPU
+template <class R> DDP_DEVICE bool gspec_ready(const Traj<R> &t) {
+    return t.gb != nullptr && *(volatile unsigned int *)(t.gctr + 4) >= (unsigned)GSPEC_MIN_IDLE;
+}
+// Close a board: no further claims.  Returns how many units were claimed.
+DDP_DEVICE int gspec_close(unsigned long long *w) {
+    unsigned long long cur = *(volatile unsigned long long *)w;
+    while (true) {
+        const int n = (int)((cur >> 16) & 0xffff), nx = (int)(cur & 0xffff);
+        const int claimed = nx < n ? nx : n;
+        const unsigned long long closed = (cur & ~0xffffull) | (unsigned long long)n;
+        const unsigned long long old = atomicCAS(w, cur, closed);
+        if (old == cur) return claimed;
+        cur = old;
+    }
+}
+template <class R> DDP_DEVICE void warp_copy_global(R *DDP_RESTRICT dst, const R *DDP_RESTRICT src, long long n, int lane) {
+    dst = as_global(dst); src = as_global(src);
+    long long e = lane;
+    for (; e + 96 < n; e += 128) {
+        const R a = src[e], b = src[e + 32], c = src[e + 64], d = src[e + 96];
+        dst[e] = a; dst[e + 32] = b; dst[e + 64] = c; dst[e + 96] = d;
+    }
+    for (; e < n; e += 32) dst[e] = src[e];
+}
+#endif
+
+template <class R> DDP_DEVICE bool run_trial(Traj<R> &t, R alpha, R tau, RollOut<R> &ro) {
+    return coop_has_helpers(t) ? forward_trial_coop(t, alpha, tau, ro) : forward_trial_solo(t, alpha, tau, ro);
+}
+
 // Line search with the filter (ddp.cpp:647-778).
 template <class R> DDP_DEVICE_NOINLINE void forward_pass(Traj<R> &t) {
     const int lane_ = t.lane_;
@@ -1881,38 +1977,86 @@ template <class R> DDP_DEVICE_NOINLINE void forward_pass(Traj<R> &t) {
     bool failed = true;
     RollOut<R> ro;
     R stepsize = R(0);
-    int step;
-    for (step = 0; step < 11; step++) {
+    int step = 0;
+#if DDP_GPU
+    if (gspec_ready(t)) {
+        GBoard<R> *b = (GBoard<R> *)t.gb + t.gflip;
+        unsigned long long *w = t.gw + t.gflip;
+        t.gflip ^= 1;
+        int seq = 0;
+        __threadfence();   // every lane's part of the iterate and the gains before the board is posted
+        __syncwarp();
+        if (lane_ == 0) {
+            // the previous search on this board may have been closed with units in flight: they are long done
+            while (*(volatile int *)&b->done < *(volatile int *)&b->claimed_final) __nanosleep(200);
+            __threadfence();
+            GBoard<R> *b0 = (GBoard<R> *)t.gb;
+            seq = b0->seq_ctr + 1;
+            b0->seq_ctr = seq;
+            b->t = t;
+            for (int e = 0; e < 9; e++) b->xd[e] = t.sm[Lay::XD + e];
+            b->tau = tau; b->done = 0; b->claimed_final = GSPEC_UNITS;
+            __threadfence();   // the board before the claim word
+            *(volatile unsigned long long *)w = ((unsigned long long)(unsigned)seq << 32) | ((unsigned long long)GSPEC_UNITS << 16);
+            atomicAdd(t.gctr + 5, 1u);
+        }
+        seq = __shfl_sync(0xffffffffu, seq, 0);
+        // the owner's own trial: step 2^0
+        t.n_fwd_trials++;
+        stepsize = R(1);
+        bool acc0 = run_trial(t, stepsize, tau, ro);
+        if (acc0) acc0 = filter_try(t, ro.logcost, ro.err);
+        int claimed = 0;
+        if (lane_ == 0) { claimed = gspec_close(w); *(volatile int *)&b->claimed_final = claimed; }
+        claimed = __shfl_sync(0xffffffffu, claimed, 0);
+        if (acc0) {
+            if (lane_ == 0) { __threadfence(); *(volatile int *)&b->retired = seq; }   // nobody's candidate is needed
+            failed = false;
+            step = 0;
+        } else {
+            if (lane_ == 0) {
+                while (*(volatile int *)&b->done < claimed) __nanosleep(200);
+            }
+            __syncwarp();
+            __threadfence();   // acquire: results and candidate buffers of the finished units
+            int win = -1;
+            for (int u = 0; u < claimed; u++) {
+                const typename GBoard<R>::Res *rs = &b->res[u];
+                t.n_fwd_trials++;
+                t.n_fwd_knots += *(volatile long long *)&rs->knots;
+                if (*(volatile int *)&rs->ok) {
+                    const R lc = *(volatile R *)&rs->logcost, er = *(volatile R *)&rs->err;
+                    if (filter_try(t, lc, er)) { win = u; break; }
+                }
+            }
+            if (win >= 0) {
+                const typename GBoard<R>::Res *rs = &b->res[win];
+                ro.cost = *(volatile R *)&rs->cost; ro.costq = *(volatile R *)&rs->costq;
+                ro.logcost = *(volatile R *)&rs->logcost; ro.err = *(volatile R *)&rs->err;
+                const R *src = t.ws_all + (long long)(*(volatile int *)&rs->slot) * t.ws_stride;
+                warp_copy_global(t.xun, src + t.off_xun, (long long)(t.N + 1) * 20, lane_);
+                warp_copy_global(t.sn, src + t.off_sn, (long long)t.MCS * t.NP, lane_);
+                if (t.infeas) warp_copy_global(t.yn, src + t.off_yn, (long long)t.MCS * t.NP, lane_);
+                __syncwarp();
+                failed = false;
+                step = win + 1;
+                stepsize = R(1);
+                for (int k = 0; k < step; k++) stepsize = stepsize * R(0.5);
+            } else {
+                step = claimed + 1;   // carry on sequentially below
+            }
+            if (lane_ == 0) { __threadfence(); *(volatile int *)&b->retired = seq; }
+        }
+        __syncwarp();
+    }
+    if (failed)
+#endif
+    for (; step < 11; step++) {
         stepsize = R(1);
         for (int k = 0; k < step; k++) stepsize = stepsize * R(0.5);  // 2^-step exactly (ddp.cpp:670)
         t.n_fwd_trials++;
-        if (!(coop_has_helpers(t) ? forward_trial_coop(t, stepsize, tau, ro) : forward_trial_solo(t, stepsize, tau, ro))) continue;
-        // filter acceptance, ddp.cpp:741-757: rejected if some entry is <= the candidate in both
-        // coordinates; an accepted candidate evicts the entries it dominates.  Lane 0 owns the filter.
-        FOR_LANES(lane) {
-            if (lane == 0) {
-                bool rej = false;
-                for (int k = 0; k < t.nfilter; k++)
-                    if (ro.logcost >= t.filt[2 * k] && ro.err >= t.filt[2 * k + 1]) { rej = true; break; }
-                int nk = 0;
-                if (!rej) {
-                    for (int k = 0; k < t.nfilter; k++) {
-                        const R f0 = t.filt[2 * k], f1 = t.filt[2 * k + 1];
-                        if (ro.logcost > f0 || ro.err > f1) { t.filt[2 * nk] = f0; t.filt[2 * nk + 1] = f1; nk++; }
-                    }
-                    if (nk >= t.fcap) nk = t.fcap - 1;
-                    t.filt[2 * nk] = ro.logcost; t.filt[2 * nk + 1] = ro.err;
-                }
-                t.sm[Lay::FL] = rej ? R(1) : R(0);
-                t.sm[Lay::FL + 1] = R(nk);
-            }
-        }
-        WARP_SYNC();
-        const bool rej = t.sm[Lay::FL] != R(0);
-        const int nkeep = (int)t.sm[Lay::FL + 1];
-        WARP_SYNC();
-        if (rej) continue;
-        t.nfilter = nkeep + 1;
+        if (!run_trial(t, stepsize, tau, ro)) continue;
+        if (!filter_try(t, ro.logcost, ro.err)) continue;
         failed = false;
         break;
     }
@@ -1931,6 +2075,80 @@ template <class R> DDP_DEVICE_NOINLINE void forward_pass(Traj<R> &t) {
     t.cyc_fwd += ddp_clock() - clk0;
 }
 
+#if DDP_GPU
+// A warp of a fully idle CTA: run line-search trials posted by the remaining solves until every trajectory is finished.
+template <class R>
+DDP_DEVICE_NOINLINE void gspec_helper_loop(const SolveArgs &A, R *sm, const R *tabs, R *ws, int slot, int lane_) {
+    GBoard<R> *boards = (GBoard<R> *)A.gboards;
+    const int nboards = 2 * (int)(gridDim.x * (blockDim.x >> 5));
+    const WsLay wl = ws_layout(A.N, A.PM, A.fcap);
+    sm = as_shared(sm);
+    if (lane_ == 0) atomicAdd(A.counter + 4, 1u);
+    while (*(volatile unsigned int *)(A.counter + 3) < (unsigned)A.B) {
+        // scan the claim words, 32 per step
+        int bi = -1, unit = -1;
+        unsigned seq = 0;
+        for (int base = 0; base < nboards && bi < 0; base += 32) {
+            const int k = base + lane_;
+            unsigned long long wv = 0;
+            if (k < nboards) wv = *(volatile unsigned long long *)(A.gwords + k);
+            const bool open = (wv >> 32) != 0 && (int)(wv & 0xffff) < (int)((wv >> 16) & 0xffff);
+            unsigned m = __ballot_sync(0xffffffffu, open);
+            while (m && bi < 0) {
+                const int l = __ffs(m) - 1;
+                m &= m - 1;
+                const int cand = base + l;
+                int u = -1;
+                unsigned sq = 0;
+                if (lane_ == 0) {
+                    unsigned long long cur = *(volatile unsigned long long *)(A.gwords + cand);
+                    while (true) {
+                        const int n = (int)((cur >> 16) & 0xffff), nx = (int)(cur & 0xffff);
+                        if ((cur >> 32) == 0 || nx >= n) break;
+                        const unsigned long long old = atomicCAS(A.gwords + cand, cur, cur + 1);
+                        if (old == cur) { u = nx; sq = (unsigned)(cur >> 32); break; }
+                        cur = old;
+                    }
+                }
+                u = __shfl_sync(0xffffffffu, u, 0);
+                sq = __shfl_sync(0xffffffffu, sq, 0);
+                if (u >= 0) { bi = cand; unit = u; seq = sq; }
+            }
+        }
+        if (bi < 0) { __nanosleep(2000); continue; }
+        __threadfence();   // acquire: the board and the owner's arrays as of the posting
+        GBoard<R> *b = boards + bi;
+        Traj<R> t = b->t;
+        t.lane_ = lane_; t.sm = sm; t.tab = tabs + (t.minvo ? 180 : 0);
+        t.board = nullptr; t.ctl = nullptr; t.gb = nullptr;
+        t.xun = ws + wl.xun; t.sn = ws + wl.sn; t.yn = ws + wl.yn; t.kdx = ws + wl.kdx;
+        t.n_fwd_knots = 0; t.cyc_seq = 0;
+        if (lane_ < 9) sm[Lay::XD + lane_] = b->xd[lane_];
+        __syncwarp();
+        const int step = unit + 1;
+        R alpha = R(1);
+        for (int k = 0; k < step; k++) alpha = alpha * R(0.5);
+        RollOut<R> ro;
+        ro.cost = ro.costq = ro.logcost = ro.err = R(0);
+        const bool ok = forward_trial_solo(t, alpha, b->tau, ro);
+        if (lane_ == 0) {
+            typename GBoard<R>::Res *rs = &b->res[unit];
+            rs->ok = ok ? 1 : 0; rs->slot = slot; rs->knots = t.n_fwd_knots;
+            rs->cost = ro.cost; rs->costq = ro.costq; rs->logcost = ro.logcost; rs->err = ro.err;
+            atomicAdd(A.counter + 6, 1u);
+        }
+        __threadfence();   // the candidate buffers and the result before the unit counts as done
+        __syncwarp();
+        if (lane_ == 0) {
+            atomicAdd(&b->done, 1);
+            // the candidate stays untouched until the owner has taken it or discarded the search
+            if (ok) while (*(volatile int *)&b->retired < (int)seq && *(volatile unsigned int *)(A.counter + 3) < (unsigned)A.B) __nanosleep(500);
+        }
+        __syncwarp();
+    }
+}
+#endif
+
 // =============================================================================================
 // One polyCurveGeneration (ddp.cpp:5-438) for trajectory `b`, stage `st` of the call.
 // =============================================================================================
@@ -1944,6 +2162,16 @@ template <class R> DDP_DEVICE_NOINLINE void solve_one(const SolveArgs &A, int st
     Traj<R> t;
     t.N = N; t.PM = A.PM; t.NP = wl.NP; t.MCS = wl.MCS; t.lane_ = lane_;
     t.board = board; t.ctl = ctl; t.wpb = wpb;
+    t.gb = nullptr; t.gw = nullptr; t.gctr = A.counter; t.gflip = 0; t.minvo = cfg.minvo;
+#if DDP_GPU
+    if (A.gspec && A.gboards) {
+        const long long slot = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+        t.gb = (GBoard<R> *)A.gboards + 2 * slot;
+        t.gw = A.gwords + 2 * slot;
+        t.ws_all = (R *)A.ws; t.ws_stride = A.ws_stride;
+        t.off_xun = wl.xun; t.off_sn = wl.sn; t.off_yn = wl.yn; t.off_kdx = wl.kdx;
+    }
+#endif
     t.planes = A.planes + (long long)b * N * A.PM * 4;
     t.nplanes = A.nplanes + (long long)b * N;
     t.sm = sm;

@@ -119,6 +119,7 @@ typedef struct direct_ddp_stats {
     int grid_blocks, block_threads, smem_bytes_per_block, workspace_slots;
     int64_t h2d_bytes, d2h_bytes;
     int64_t coop_jobs, helper_units; /* jobs posted to idle warps of the CTA / units those warps ran (tail balancing) */
+    int64_t spec_searches, spec_trials; /* line searches posted to the warps of idle CTAs / trials those warps ran */
 } direct_ddp_stats;
 
 typedef struct direct_ddp_trace_row {
