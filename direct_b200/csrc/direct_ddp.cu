@@ -60,8 +60,10 @@ __global__ void __launch_bounds__(DDP_MAX_THREADS, DDP_MIN_BLOCKS) ipddp_solve_k
     if (lane == 0) atomicSub(&ctl->active_owners, 1);
     __syncwarp();
     if (wpb > 1 && A.coop) ddp::helper_loop<R>(boards, ctl, wpb, warp, sm, lane, A.counter + 2);
-    // no warp of this CTA owns a trajectory any more: run line-search trials of the remaining solves of other CTAs
-    if (A.gspec) ddp::gspec_helper_loop<R>(A, sm, tabs, ws, (int)slot, lane);
+    // no warp of this CTA owns a trajectory any more: run whole line-search trials of the remaining solves of other CTAs
+    // ("Speculative line search").  Measured: letting idle warps of CTAs that still own a trajectory take remote trials as
+    // well is slower (204 vs 196 ms at B = 4096): their owner loses its row helpers while the SM is still contended.
+    if (A.gspec) ddp::gspec_helper_loop<R>(A, sm, tabs, ws, (int)slot, lane, boards, (wpb > 1 && A.coop) ? ctl : nullptr, wpb, warp);
 }
 
 // initTimeAllocation, teach_repeat_planner.cpp:583-639 (v0 = 0): one thread per segment.

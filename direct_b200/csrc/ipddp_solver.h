@@ -209,6 +209,8 @@ template <class R> struct Traj {
     int time_power, infeas, zero_init, line_init;
     R mu, tol, reg, reg_base, opterr, cost, costq, logcost, err, stepsize;
     int step, failed, bfailed, nfilter;
+    int cmax_valid;         // cmax is the largest constraint value at the current iterate (from the accepted trial)
+    R cmax;
     int lin_valid;          // t.H / t.aux hold the linearisation of the current iterate at the current mu
     R lin_emu, lin_ecy;     // its max |r| and max |c + y| (ddp.cpp:636-637)
     long long n_bwd_sweeps, n_bwd_knots, n_fwd_trials, n_fwd_knots;
@@ -471,7 +473,7 @@ template <class R> struct JobBoard {
     int owner_seq;             // owner only: last sequence number used
     JobCtx<R> ctx;
     R res[JOB_MAX_UNITS][2];   // JOB_LIN: per-unit max |r|, max |c + y|
-    R *part;                   // JOB_ROWS: [4][3][32] per-unit, per-lane {stage cost, sum log, |c + y|_1} and
+    R *part;                   // JOB_ROWS: [4][4][32] per-unit, per-lane {stage cost, sum log, |c + y|_1, max c} and
     int *badl;                 //           [4][32] per-lane first failing knot, both in the OWNER's MSC scratch
 };
 struct BlockCtl {
@@ -679,7 +681,7 @@ template <class R> DDP_DEVICE_NOINLINE void lin_unit(const JobCtx<R> *cp_, int u
 // ---- job board protocol (GPU only; the CPU emulation runs every unit in the owner) --------------------------------
 // One unit of the line-search rows (defined below): per-lane partials of units u0 .. u1-1 into part / badk.
 template <class R>
-DDP_DEVICE_NOINLINE void rows_unit(const JobCtx<R> *cp_, int u0, int u1, int lane_, Reg<R, 12> &part, Reg<int, 4> &badk);
+DDP_DEVICE_NOINLINE void rows_unit(const JobCtx<R> *cp_, int u0, int u1, int lane_, Reg<R, 16> &part, Reg<int, 4> &badk);
 
 #if DDP_GPU
 // Claim the next unit of the job currently posted on `b` (any job when want_seq == 0): returns the unit or -1.
@@ -707,14 +709,14 @@ template <class R> DDP_DEVICE_NOINLINE void job_run_unit(JobBoard<R> *b, int u, 
         const R e0 = warp_max(errs, 0, lane_), e1 = warp_max(errs, 1, lane_);
         if (lane_ == 0) { b->res[u][0] = e0; b->res[u][1] = e1; }
     } else {
-        Reg<R, 12> part;
+        Reg<R, 16> part;
         Reg<int, 4> badk;
         rows_unit(&b->ctx, u, u + 1, lane_, part, badk);
         DDP_UNROLL
         for (int e = 0; e < 4; e++) {
             if (e == u) {
-                R *pp = b->part + e * 96 + lane_;
-                pp[0] = part(lane_, 3 * e); pp[32] = part(lane_, 3 * e + 1); pp[64] = part(lane_, 3 * e + 2);
+                R *pp = b->part + e * 128 + lane_;
+                pp[0] = part(lane_, 4 * e); pp[32] = part(lane_, 4 * e + 1); pp[64] = part(lane_, 4 * e + 2); pp[96] = part(lane_, 4 * e + 3);
                 b->badl[e * 32 + lane_] = badk(lane_, e);
             }
         }
@@ -735,7 +737,7 @@ template <class R> DDP_DEVICE_NOINLINE void job_run(Traj<R> &t, const JobCtx<R> 
         seq = (unsigned)(++b->owner_seq);
         b->ctx = ctx;
         b->part = t.sm + Lay::MSC + 512;                 // behind forward_trial's knot ring [0, 480)
-        b->badl = (int *)(t.sm + Lay::MSC + 896);
+        b->badl = (int *)(t.sm + Lay::MSC + 1024);
         b->done = 0;
         __threadfence_block();
         *(volatile unsigned long long *)&b->word = ((unsigned long long)seq << 32) | ((unsigned long long)n << 16);
@@ -781,7 +783,7 @@ template <class R> DDP_DEVICE bool coop_has_helpers(const Traj<R> &t) {
 
 // Line-search rows of one 32-knot block: per-lane partials of the four units.  Alone (one call, the knot's data
 // loaded once) or, when a warp of the CTA is idle, as a job of four units; the partials are the same either way.
-template <class R> DDP_DEVICE void run_rows(Traj<R> &t, const JobCtx<R> &ctx, Reg<R, 12> &part, Reg<int, 4> &badk) {
+template <class R> DDP_DEVICE void run_rows(Traj<R> &t, const JobCtx<R> &ctx, Reg<R, 16> &part, Reg<int, 4> &badk) {
     const int lane_ = t.lane_;
 #if DDP_GPU
     if (coop_has_helpers(t)) {
@@ -789,8 +791,8 @@ template <class R> DDP_DEVICE void run_rows(Traj<R> &t, const JobCtx<R> &ctx, Re
         JobBoard<R> *b = (JobBoard<R> *)t.board;
         DDP_UNROLL
         for (int e = 0; e < 4; e++) {
-            const R *pp = b->part + e * 96 + lane_;
-            part(lane_, 3 * e) = pp[0]; part(lane_, 3 * e + 1) = pp[32]; part(lane_, 3 * e + 2) = pp[64];
+            const R *pp = b->part + e * 128 + lane_;
+            part(lane_, 4 * e) = pp[0]; part(lane_, 4 * e + 1) = pp[32]; part(lane_, 4 * e + 2) = pp[64]; part(lane_, 4 * e + 3) = pp[96];
             badk(lane_, e) = b->badl[e * 32 + lane_];
         }
         __syncwarp();
@@ -1270,7 +1272,7 @@ template <class R> DDP_DEVICE_NOINLINE void backward_pass(Traj<R> &t) {
 // =============================================================================================
 // Forward pass.
 // =============================================================================================
-template <class R> struct RollOut { R cost, costq, logcost, err; };
+template <class R> struct RollOut { R cost, costq, logcost, err, cmax; };   // cmax: largest constraint value of the candidate
 
 // Running product of barrier arguments with an occasional log, so that sum(log(.)) costs one log per ~dozens of rows.
 template <class R> struct LogProd {
@@ -1285,7 +1287,7 @@ template <class R> struct LogProd {
 
 template <class R> struct TrialAcc {
     LogProd<R> lg;
-    R e1;
+    R e1, cmax;   // cmax is a running maximum over ALL rows of the knot (never reset between units: max is order-free)
     int bad;
 };
 
@@ -1303,6 +1305,7 @@ DDP_DEVICE void trial_row(const RowCtx<R> &t, long long ro, R sv, R yv, R cold, 
         if (ynew < (R(1) - tau) * yv || snew < (R(1) - tau) * sv) A.bad = 1;
         t.sn[ro] = snew; t.yn[ro] = ynew;
         A.lg.mul(ynew); A.e1 += rabs(cnew + ynew);
+        A.cmax = rmax(A.cmax, cnew);
     } else {
         const R cinv = rrcp(cold);
         const R r = sv * cold + t.mu, D = sv * cinv;
@@ -1311,6 +1314,7 @@ DDP_DEVICE void trial_row(const RowCtx<R> &t, long long ro, R sv, R yv, R cold, 
         if (cnew > (R(1) - tau) * cold || snew < (R(1) - tau) * sv) A.bad = 1;
         t.sn[ro] = snew;
         A.lg.mul(-cnew);
+        A.cmax = rmax(A.cmax, cnew);
     }
 }
 
@@ -1330,7 +1334,7 @@ template <class R> DDP_DEVICE_NOINLINE void stage_knot(R *slot, const R *K, cons
 // part(3u..3u+2) = {stage cost, sum log(barrier argument), |c + y|_1}, badk(u) = this lane's knot if it fails the
 // fraction-to-boundary rule (ddp.cpp:683-687 / :699-703), else 0x7fffffff.
 template <class R>
-DDP_DEVICE_NOINLINE void rows_unit(const JobCtx<R> *cp_, int u0, int u1, int lane_, Reg<R, 12> &part, Reg<int, 4> &badk) {
+DDP_DEVICE_NOINLINE void rows_unit(const JobCtx<R> *cp_, int u0, int u1, int lane_, Reg<R, 16> &part, Reg<int, 4> &badk) {
     (void)lane_;
     const JobCtx<R> c = *cp_;
     const RowCtx<R> t = row_global(c.row);
@@ -1345,9 +1349,10 @@ DDP_DEVICE_NOINLINE void rows_unit(const JobCtx<R> *cp_, int u0, int u1, int lan
     FOR_LANES(lane) {
         const int i = c.base + lane;
         DDP_UNROLL
-        for (int e = 0; e < 12; e++) part(lane, e) = R(0);
-        DDP_UNROLL
-        for (int e = 0; e < 4; e++) badk(lane, e) = 0x7fffffff;
+        for (int e = 0; e < 4; e++) {
+            part(lane, 4 * e) = R(0); part(lane, 4 * e + 1) = R(0); part(lane, 4 * e + 2) = R(0); part(lane, 4 * e + 3) = R(-INFINITY);
+            badk(lane, e) = 0x7fffffff;
+        }
         if (i < N) {
             R zo[19], zn[19], v1[10], v2[19], tpo[6], tpn[6];
             DDP_UNROLL
@@ -1361,7 +1366,7 @@ DDP_DEVICE_NOINLINE void rows_unit(const JobCtx<R> *cp_, int u0, int u1, int lan
             const int P = t.nplanes[i];
             const double *pl = t.planes + (long long)i * t.PM * 4;
             TrialAcc<R> A;
-            A.lg.lp = R(1); A.lg.lsum = R(0); A.e1 = R(0); A.bad = 0;
+            A.lg.lp = R(1); A.lg.lsum = R(0); A.e1 = R(0); A.bad = 0; A.cmax = R(-INFINITY);
             R q_cost = R(0);
             DDP_NOUNROLL
             for (int g = 4 * u0; g < 16 && g < 4 * u1; g++) {   // g = 15: the time row and the stage cost
@@ -1423,11 +1428,12 @@ DDP_DEVICE_NOINLINE void rows_unit(const JobCtx<R> *cp_, int u0, int u1, int lan
                     DDP_UNROLL
                     for (int e = 0; e < 4; e++) {
                         if (e == uu) {
-                            part(lane, 3 * e) = q_cost; part(lane, 3 * e + 1) = A.lg.total(); part(lane, 3 * e + 2) = A.e1;
+                            part(lane, 4 * e) = q_cost; part(lane, 4 * e + 1) = A.lg.total(); part(lane, 4 * e + 2) = A.e1;
+                            part(lane, 4 * e + 3) = A.cmax;
                             if (A.bad) badk(lane, e) = i;
                         }
                     }
-                    A.lg.lp = R(1); A.lg.lsum = R(0); A.e1 = R(0); A.bad = 0;
+                    A.lg.lp = R(1); A.lg.lsum = R(0); A.e1 = R(0); A.bad = 0; A.cmax = R(-INFINITY);
                 }
             }
         }
@@ -1515,12 +1521,12 @@ template <class R> DDP_DEVICE_NOINLINE bool forward_trial_coop(Traj<R> &tt_, R a
     const int time_power = tt_.time_power;
     long long fwd_knots = 0, cyc_seq = 0;
     Reg<R, 1> xcur;
-    Reg<R, 3> acc;  // per-lane partials: stage cost, log barrier, |c+y|_1
+    Reg<R, 4> acc;  // per-lane partials: stage cost, log barrier, |c+y|_1, max c
     // Old point and gains of the next knots stream into a 4-deep shared-memory ring by cp.async, three knots ahead of
     // the recursion (the MSC scratch of the linearisation is free during the line search): slot = [K_i (100) | xu_i (20)].
     R *ring = sm + Lay::MSC;
     FOR_LANES(lane) {
-        acc(lane, 0) = R(0); acc(lane, 1) = R(0); acc(lane, 2) = R(0);
+        acc(lane, 0) = R(0); acc(lane, 1) = R(0); acc(lane, 2) = R(0); acc(lane, 3) = R(-INFINITY);
         xcur(lane, 0) = (lane >= 10 && lane < 19) ? xu[lane] : R(0);  // xnew[0] = xold[0]
         DDP_UNROLL
         for (int d = 0; d < 3; d++) {
@@ -1541,7 +1547,7 @@ template <class R> DDP_DEVICE_NOINLINE bool forward_trial_coop(Traj<R> &tt_, R a
             c.xu = xu; c.xun = xun; c.K = Kin; c.kdx = kdxo; c.H = nullptr; c.aux = nullptr;
             c.N = N; c.base = base; c.time_power = time_power; c.type = JOB_ROWS;
             c.w_snap = w_snap; c.w_time = w_time; c.alpha = alpha; c.tau = tau;
-            Reg<R, 12> part;
+            Reg<R, 16> part;
             Reg<int, 4> badk;
             run_rows(tt_, c, part, badk);
             Reg<int, 1> bmin;
@@ -1549,7 +1555,8 @@ template <class R> DDP_DEVICE_NOINLINE bool forward_trial_coop(Traj<R> &tt_, R a
                 int m = 0x7fffffff;
                 DDP_UNROLL
                 for (int u = 0; u < 4; u++) {
-                    acc(lane, 0) += part(lane, 3 * u); acc(lane, 1) += part(lane, 3 * u + 1); acc(lane, 2) += part(lane, 3 * u + 2);
+                    acc(lane, 0) += part(lane, 4 * u); acc(lane, 1) += part(lane, 4 * u + 1); acc(lane, 2) += part(lane, 4 * u + 2);
+                    acc(lane, 3) = rmax(acc(lane, 3), part(lane, 4 * u + 3));
                     if (badk(lane, u) < m) m = badk(lane, u);
                 }
                 bmin(lane, 0) = m;
@@ -1579,6 +1586,7 @@ template <class R> DDP_DEVICE_NOINLINE bool forward_trial_coop(Traj<R> &tt_, R a
     out.cost = qs + p;
     out.logcost = out.cost - t.mu * warp_sum(acc, 1, lane_);
     out.err = t.infeas ? rmax(tol, warp_sum(acc, 2, lane_)) : R(0);
+    out.cmax = warp_max(acc, 3, lane_);
     WARP_SYNC();
     return true;
 }
@@ -1601,12 +1609,12 @@ template <class R> DDP_DEVICE_NOINLINE bool forward_trial_solo(Traj<R> &tt_, R a
     const int time_power = tt_.time_power;
     long long fwd_knots = 0, cyc_seq = 0;
     Reg<R, 1> xcur, xn;
-    Reg<R, 3> acc;  // per-lane partials: stage cost, log barrier, |c+y|_1
+    Reg<R, 4> acc;  // per-lane partials: stage cost, log barrier, |c+y|_1, max c
     // Old point and gains of the next knots stream into a 4-deep shared-memory ring by cp.async, three knots ahead of
     // the recursion (the MSC scratch of the linearisation is free during the line search): slot = [K_i (100) | xu_i (20)].
     R *ring = sm + Lay::MSC;
     FOR_LANES(lane) {
-        acc(lane, 0) = R(0); acc(lane, 1) = R(0); acc(lane, 2) = R(0);
+        acc(lane, 0) = R(0); acc(lane, 1) = R(0); acc(lane, 2) = R(0); acc(lane, 3) = R(-INFINITY);
         xcur(lane, 0) = (lane >= 10 && lane < 19) ? xu[lane] : R(0);  // xnew[0] = xold[0]
         xn(lane, 0) = R(0);
         DDP_UNROLL
@@ -1684,7 +1692,7 @@ template <class R> DDP_DEVICE_NOINLINE bool forward_trial_solo(Traj<R> &tt_, R a
                 time_powers(zo[9], tpo);
                 time_powers(zn[9], tpn);
                 TrialAcc<R> A;
-                A.lg.lp = R(1); A.lg.lsum = R(0); A.e1 = R(0); A.bad = 0;
+                A.lg.lp = R(1); A.lg.lsum = R(0); A.e1 = R(0); A.bad = 0; A.cmax = R(-INFINITY);
                 const int P = t.nplanes[i];
                 const double *pl = t.planes + (long long)i * t.PM * 4;
                 DDP_NOUNROLL
@@ -1752,6 +1760,7 @@ template <class R> DDP_DEVICE_NOINLINE bool forward_trial_solo(Traj<R> &tt_, R a
                 }
                 acc(lane, 1) += A.lg.total();
                 acc(lane, 2) += A.e1;
+                acc(lane, 3) = rmax(acc(lane, 3), A.cmax);
             }
         }
         const int first = warp_min_int(badk, 0, lane_);
@@ -1778,6 +1787,7 @@ template <class R> DDP_DEVICE_NOINLINE bool forward_trial_solo(Traj<R> &tt_, R a
     out.cost = qs + p;
     out.logcost = out.cost - t.mu * warp_sum(acc, 1, lane_);
     out.err = t.infeas ? rmax(tol, warp_sum(acc, 2, lane_)) : R(0);
+    out.cmax = warp_max(acc, 3, lane_);
     WARP_SYNC();
     return true;
 }
@@ -1935,7 +1945,7 @@ template <class R> struct GBoard {
     int done;           // units finished
     int retired;        // last generation whose candidates the owner no longer needs
     int claimed_final;  // units that had been claimed when the last search on this board was closed
-    struct Res { int ok, slot; long long knots; R cost, costq, logcost, err; } res[GSPEC_UNITS];
+    struct Res { int ok, slot; long long knots; R cost, costq, logcost, err, cmax; } res[GSPEC_UNITS];
 };
 
 #if DDP_GPU
@@ -2032,7 +2042,7 @@ template <class R> DDP_DEVICE_NOINLINE void forward_pass(Traj<R> &t) {
             if (win >= 0) {
                 const typename GBoard<R>::Res *rs = &b->res[win];
                 ro.cost = *(volatile R *)&rs->cost; ro.costq = *(volatile R *)&rs->costq;
-                ro.logcost = *(volatile R *)&rs->logcost; ro.err = *(volatile R *)&rs->err;
+                ro.logcost = *(volatile R *)&rs->logcost; ro.err = *(volatile R *)&rs->err; ro.cmax = *(volatile R *)&rs->cmax;
                 const R *src = t.ws_all + (long long)(*(volatile int *)&rs->slot) * t.ws_stride;
                 warp_copy_global(t.xun, src + t.off_xun, (long long)(t.N + 1) * 20, lane_);
                 warp_copy_global(t.sn, src + t.off_sn, (long long)t.MCS * t.NP, lane_);
@@ -2065,6 +2075,7 @@ template <class R> DDP_DEVICE_NOINLINE void forward_pass(Traj<R> &t) {
         t.stepsize = R(0);
     } else {
         t.cost = ro.cost; t.costq = ro.costq; t.logcost = ro.logcost; t.err = ro.err;
+        t.cmax = ro.cmax; t.cmax_valid = 1;
         R *tmp;
         tmp = t.xu; t.xu = t.xun; t.xun = tmp;
         tmp = t.s; t.s = t.sn; t.sn = tmp;
@@ -2078,13 +2089,27 @@ template <class R> DDP_DEVICE_NOINLINE void forward_pass(Traj<R> &t) {
 #if DDP_GPU
 // A warp of a fully idle CTA: run line-search trials posted by the remaining solves until every trajectory is finished.
 template <class R>
-DDP_DEVICE_NOINLINE void gspec_helper_loop(const SolveArgs &A, R *sm, const R *tabs, R *ws, int slot, int lane_) {
+DDP_DEVICE_NOINLINE void gspec_helper_loop(const SolveArgs &A, R *sm, const R *tabs, R *ws, int slot, int lane_,
+                                           JobBoard<R> *cta_boards, BlockCtl *ctl, int wpb, int me) {
     GBoard<R> *boards = (GBoard<R> *)A.gboards;
     const int nboards = 2 * (int)(gridDim.x * (blockDim.x >> 5));
     const WsLay wl = ws_layout(A.N, A.PM, A.fcap);
     sm = as_shared(sm);
     if (lane_ == 0) atomicAdd(A.counter + 4, 1u);
     while (*(volatile unsigned int *)(A.counter + 3) < (unsigned)A.B) {
+        // row units of a trial that another warp of this CTA is running come first: they are short and someone waits for them
+        if (ctl != nullptr) {
+            bool found = false;
+            for (int w = 0; w < wpb; w++) {
+                if (w == me) continue;
+                const int u = job_claim(cta_boards + w, 0u);
+                if (u < 0) continue;
+                found = true;
+                job_run_unit(cta_boards + w, u, sm, lane_);
+                if (lane_ == 0) atomicAdd(A.counter + 2, 1u);
+            }
+            if (found) continue;
+        }
         // scan the claim words, 32 per step
         int bi = -1, unit = -1;
         unsigned seq = 0;
@@ -2120,7 +2145,7 @@ DDP_DEVICE_NOINLINE void gspec_helper_loop(const SolveArgs &A, R *sm, const R *t
         GBoard<R> *b = boards + bi;
         Traj<R> t = b->t;
         t.lane_ = lane_; t.sm = sm; t.tab = tabs + (t.minvo ? 180 : 0);
-        t.board = nullptr; t.ctl = nullptr; t.gb = nullptr;
+        t.board = ctl ? (void *)(cta_boards + me) : nullptr; t.ctl = ctl; t.wpb = wpb; t.gb = nullptr;   // rows go to idle warps of THIS CTA
         t.xun = ws + wl.xun; t.sn = ws + wl.sn; t.yn = ws + wl.yn; t.kdx = ws + wl.kdx;
         t.n_fwd_knots = 0; t.cyc_seq = 0;
         if (lane_ < 9) sm[Lay::XD + lane_] = b->xd[lane_];
@@ -2129,12 +2154,12 @@ DDP_DEVICE_NOINLINE void gspec_helper_loop(const SolveArgs &A, R *sm, const R *t
         R alpha = R(1);
         for (int k = 0; k < step; k++) alpha = alpha * R(0.5);
         RollOut<R> ro;
-        ro.cost = ro.costq = ro.logcost = ro.err = R(0);
-        const bool ok = forward_trial_solo(t, alpha, b->tau, ro);
+        ro.cost = ro.costq = ro.logcost = ro.err = ro.cmax = R(0);
+        const bool ok = run_trial(t, alpha, b->tau, ro);
         if (lane_ == 0) {
             typename GBoard<R>::Res *rs = &b->res[unit];
             rs->ok = ok ? 1 : 0; rs->slot = slot; rs->knots = t.n_fwd_knots;
-            rs->cost = ro.cost; rs->costq = ro.costq; rs->logcost = ro.logcost; rs->err = ro.err;
+            rs->cost = ro.cost; rs->costq = ro.costq; rs->logcost = ro.logcost; rs->err = ro.err; rs->cmax = ro.cmax;
             atomicAdd(A.counter + 6, 1u);
         }
         __threadfence();   // the candidate buffers and the result before the unit counts as done
@@ -2187,7 +2212,7 @@ template <class R> DDP_DEVICE_NOINLINE void solve_one(const SolveArgs &A, int st
     t.reg_base = cfg.zero_init ? R(1.6) : R(4.0);      // ddp.cpp:60-61
     t.n_bwd_sweeps = t.n_bwd_knots = t.n_fwd_trials = t.n_fwd_knots = 0;
     t.cyc_bwd = t.cyc_fwd = 0; t.cyc_ric = t.cyc_seq = 0; t.cyc_t0 = ddp_clock();
-    t.mu = R(0); t.step = 0; t.failed = 0; t.bfailed = 0; t.lin_valid = 0;
+    t.mu = R(0); t.step = 0; t.failed = 0; t.bfailed = 0; t.lin_valid = 0; t.cmax_valid = 0; t.cmax = R(0);
     const bool from_stage0 = (A.two_stage && st == 1);
     int infeas_in;
     if (from_stage0) infeas_in = A.out[0].infeas_out ? A.out[0].infeas_out[b] : 1;
@@ -2323,7 +2348,10 @@ template <class R> DDP_DEVICE_NOINLINE void solve_one(const SolveArgs &A, int st
             t.reg = R(0); t.bfailed = 0;
             t.lin_valid = 0;
         }
-        if (!scan_constraints(t, 1, R(2.0e-4), dummy0, dummy1)) {  // ddp.cpp:346-390 (hazard H8)
+        // any c >= 2e-4 at the current iterate (ddp.cpp:346-355, hazard H8)?  The accepted trial evaluated exactly these
+        // constraint values, so their maximum is at hand; a scan is only needed before the first accepted trial.
+        const bool violated = t.cmax_valid ? (t.cmax >= R(2.0e-4)) : scan_constraints(t, 1, R(2.0e-4), dummy0, dummy1);
+        if (!violated) {  // ddp.cpp:356-390
             if (cfg.zero_init) { infeas_out = 0; rtn = 2; break; }
             if (!cfg.zero_init && !cfg.line_init) {
                 const R dc = t.cost - cost_m2;
