@@ -55,7 +55,7 @@ class Stats(C.Structure):
 
 class TraceRow(C.Structure):
     _fields_ = [(n, C.c_double) for n in ("cost", "costq", "logcost", "err", "mu", "reg", "stepsize", "opterr")] + \
-               [(n, C.c_int32) for n in ("step", "fp_failed", "n_bwd", "pad")]
+               [(n, C.c_int32) for n in ("step", "fp_failed", "n_bwd", "t_us")]
 
 
 EXPORTS = ["direct_ddp_version", "direct_ddp_create", "direct_ddp_destroy", "direct_ddp_last_error",

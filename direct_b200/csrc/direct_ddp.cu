@@ -253,9 +253,10 @@ template <class R> int launch(H *h, SolveArgs &A, cudaStream_t s) {
     if (A.gspec) {
         const size_t nb = (size_t)2 * grid * wpb;
         if ((st = ensure(h, h->gboards, nb * sizeof(ddp::GBoard<R>)))) return st;
-        if ((st = ensure(h, h->gwords, nb * sizeof(unsigned long long)))) return st;
+        const size_t wbytes = nb * sizeof(unsigned long long) + ((nb + 31) / 32 + 1) * sizeof(unsigned int);   // words + bitmap
+        if ((st = ensure(h, h->gwords, wbytes))) return st;
         CK(cudaMemsetAsync(h->gboards.p, 0, nb * sizeof(ddp::GBoard<R>), s));
-        CK(cudaMemsetAsync(h->gwords.p, 0, nb * sizeof(unsigned long long), s));
+        CK(cudaMemsetAsync(h->gwords.p, 0, wbytes, s));
         A.gboards = h->gboards.p; A.gwords = (unsigned long long *)h->gwords.p;
     }
     if (h->opts.trace) {
@@ -621,7 +622,7 @@ int direct_ddp_last_trace(direct_ddp_handle h, direct_ddp_trace_row *rows, int c
         const double *r = &t[(size_t)i * 12];
         rows[i].cost = r[0]; rows[i].costq = r[1]; rows[i].logcost = r[2]; rows[i].err = r[3]; rows[i].mu = r[4];
         rows[i].reg = r[5]; rows[i].stepsize = r[6]; rows[i].opterr = r[7];
-        rows[i].step = (int)r[8]; rows[i].fp_failed = (int)r[9]; rows[i].n_bwd = (int)r[10]; rows[i].pad = 0;
+        rows[i].step = (int)r[8]; rows[i].fp_failed = (int)r[9]; rows[i].n_bwd = (int)r[10]; rows[i].t_us = (int)r[11];
     }
     *len = n;
     return 0;

@@ -124,7 +124,7 @@ struct SolveArgs {
                                  // [4] warps of fully idle CTAs, [5] speculative line searches posted, [6] remote trials run
     int gspec;                   // 1: warps of idle CTAs run line-search trials of the remaining solves ("Speculative line search")
     void *gboards;               // GBoard<R>[2 * slots]
-    unsigned long long *gwords;  // their claim words, [2 * slots]
+    unsigned long long *gwords;  // their claim words, [2 * slots], followed by a bitmap of the boards with unclaimed units
     double *trace;               // optional [cap][12] trace of trajectory 0 (last stage), or NULL
     int trace_cap;
     int *trace_len;
@@ -221,6 +221,8 @@ template <class R> struct Traj {
     // speculative line search over the warps of idle CTAs (null / 0: off)
     void *gb;                            // this slot's two GBoard<R>
     unsigned long long *gw;              // and their claim words
+    unsigned int *gbits;                 // bitmap of open boards (bit = board index)
+    int gindex;                          // index of this slot's first board
     unsigned int *gctr;                  // SolveArgs::counter
     R *ws_all;                           // workspace of slot 0
     long long ws_stride, off_xun, off_sn, off_yn, off_kdx;
@@ -1569,7 +1571,9 @@ template <class R> DDP_DEVICE_NOINLINE bool forward_trial_coop(Traj<R> &tt_, R a
     FOR_LANES(lane) { cp_wait<0>(); }   // nothing of the ring / staging may land after this trial
     WARP_SYNC();
     tt_.n_fwd_knots += fwd_knots;
+#ifndef DDP_SPEC_PROFILE
     tt_.cyc_seq += cyc_seq;
+#endif
     if (!ok) return false;
     // terminal cost (ddp.cpp:1289-1292) and totals
     Reg<R, 1> pt;
@@ -1770,7 +1774,9 @@ template <class R> DDP_DEVICE_NOINLINE bool forward_trial_solo(Traj<R> &tt_, R a
     FOR_LANES(lane) { cp_wait<0>(); }   // nothing of the ring / staging may land after this trial
     WARP_SYNC();
     tt_.n_fwd_knots += fwd_knots;
+#ifndef DDP_SPEC_PROFILE
     tt_.cyc_seq += cyc_seq;
+#endif
     if (!ok) return false;
     // terminal cost (ddp.cpp:1289-1292) and totals
     Reg<R, 1> pt;
@@ -1992,6 +1998,7 @@ template <class R> DDP_DEVICE_NOINLINE void forward_pass(Traj<R> &t) {
     if (gspec_ready(t)) {
         GBoard<R> *b = (GBoard<R> *)t.gb + t.gflip;
         unsigned long long *w = t.gw + t.gflip;
+        const int bidx = t.gindex + t.gflip;
         t.gflip ^= 1;
         int seq = 0;
         __threadfence();   // every lane's part of the iterate and the gains before the board is posted
@@ -2008,6 +2015,8 @@ template <class R> DDP_DEVICE_NOINLINE void forward_pass(Traj<R> &t) {
             b->tau = tau; b->done = 0; b->claimed_final = GSPEC_UNITS;
             __threadfence();   // the board before the claim word
             *(volatile unsigned long long *)w = ((unsigned long long)(unsigned)seq << 32) | ((unsigned long long)GSPEC_UNITS << 16);
+            __threadfence();
+            atomicOr(t.gbits + (bidx >> 5), 1u << (bidx & 31));
             atomicAdd(t.gctr + 5, 1u);
         }
         seq = __shfl_sync(0xffffffffu, seq, 0);
@@ -2017,7 +2026,14 @@ template <class R> DDP_DEVICE_NOINLINE void forward_pass(Traj<R> &t) {
         bool acc0 = run_trial(t, stepsize, tau, ro);
         if (acc0) acc0 = filter_try(t, ro.logcost, ro.err);
         int claimed = 0;
-        if (lane_ == 0) { claimed = gspec_close(w); *(volatile int *)&b->claimed_final = claimed; }
+#ifdef DDP_SPEC_PROFILE
+        const long long clk_w = ddp_clock();   // profiling build: the "sequential rollout" counter shows wait + copy time
+#endif
+        if (lane_ == 0) {
+            claimed = gspec_close(w);
+            *(volatile int *)&b->claimed_final = claimed;
+            atomicAnd(t.gbits + (bidx >> 5), ~(1u << (bidx & 31)));
+        }
         claimed = __shfl_sync(0xffffffffu, claimed, 0);
         if (acc0) {
             if (lane_ == 0) { __threadfence(); *(volatile int *)&b->retired = seq; }   // nobody's candidate is needed
@@ -2058,6 +2074,9 @@ template <class R> DDP_DEVICE_NOINLINE void forward_pass(Traj<R> &t) {
             if (lane_ == 0) { __threadfence(); *(volatile int *)&b->retired = seq; }
         }
         __syncwarp();
+#ifdef DDP_SPEC_PROFILE
+        t.cyc_seq += ddp_clock() - clk_w;
+#endif
     }
     if (failed)
 #endif
@@ -2110,37 +2129,48 @@ DDP_DEVICE_NOINLINE void gspec_helper_loop(const SolveArgs &A, R *sm, const R *t
             }
             if (found) continue;
         }
-        // scan the claim words, 32 per step
+        // find a board with unclaimed units in the bitmap (start position spread over the helpers), claim one unit
         int bi = -1, unit = -1;
         unsigned seq = 0;
-        for (int base = 0; base < nboards && bi < 0; base += 32) {
-            const int k = base + lane_;
-            unsigned long long wv = 0;
-            if (k < nboards) wv = *(volatile unsigned long long *)(A.gwords + k);
-            const bool open = (wv >> 32) != 0 && (int)(wv & 0xffff) < (int)((wv >> 16) & 0xffff);
-            unsigned m = __ballot_sync(0xffffffffu, open);
-            while (m && bi < 0) {
-                const int l = __ffs(m) - 1;
-                m &= m - 1;
-                const int cand = base + l;
-                int u = -1;
-                unsigned sq = 0;
-                if (lane_ == 0) {
-                    unsigned long long cur = *(volatile unsigned long long *)(A.gwords + cand);
-                    while (true) {
-                        const int n = (int)((cur >> 16) & 0xffff), nx = (int)(cur & 0xffff);
-                        if ((cur >> 32) == 0 || nx >= n) break;
-                        const unsigned long long old = atomicCAS(A.gwords + cand, cur, cur + 1);
-                        if (old == cur) { u = nx; sq = (unsigned)(cur >> 32); break; }
-                        cur = old;
+        {
+            const unsigned int *bits = (const unsigned int *)(A.gwords + nboards);
+            const int nwords = (nboards + 31) >> 5;
+            const int rot = (slot * 7) % nwords;
+            for (int base = 0; base < nwords && bi < 0; base += 32) {
+                int wi = base + lane_;
+                unsigned wv = 0;
+                if (wi < nwords) { wi = (wi + rot) % nwords; wv = *(volatile unsigned int *)(bits + wi); }
+                unsigned m = __ballot_sync(0xffffffffu, wv != 0);
+                while (m && bi < 0) {
+                    const int l = __ffs(m) - 1;
+                    m &= m - 1;
+                    unsigned word = __shfl_sync(0xffffffffu, wv, l);
+                    const int widx = __shfl_sync(0xffffffffu, wi, l);
+                    while (word && bi < 0) {
+                        const int bit = __ffs(word) - 1;
+                        word &= word - 1;
+                        const int cand = (widx << 5) + bit;
+                        if (cand >= nboards) continue;
+                        int u = -1;
+                        unsigned sq = 0;
+                        if (lane_ == 0) {
+                            unsigned long long cur = *(volatile unsigned long long *)(A.gwords + cand);
+                            while (true) {
+                                const int n = (int)((cur >> 16) & 0xffff), nx = (int)(cur & 0xffff);
+                                if ((cur >> 32) == 0 || nx >= n) break;
+                                const unsigned long long old = atomicCAS(A.gwords + cand, cur, cur + 1);
+                                if (old == cur) { u = nx; sq = (unsigned)(cur >> 32); break; }
+                                cur = old;
+                            }
+                        }
+                        u = __shfl_sync(0xffffffffu, u, 0);
+                        sq = __shfl_sync(0xffffffffu, sq, 0);
+                        if (u >= 0) { bi = cand; unit = u; seq = sq; }
                     }
                 }
-                u = __shfl_sync(0xffffffffu, u, 0);
-                sq = __shfl_sync(0xffffffffu, sq, 0);
-                if (u >= 0) { bi = cand; unit = u; seq = sq; }
             }
         }
-        if (bi < 0) { __nanosleep(2000); continue; }
+        if (bi < 0) { __nanosleep(500); continue; }
         __threadfence();   // acquire: the board and the owner's arrays as of the posting
         GBoard<R> *b = boards + bi;
         Traj<R> t = b->t;
@@ -2193,6 +2223,8 @@ template <class R> DDP_DEVICE_NOINLINE void solve_one(const SolveArgs &A, int st
         const long long slot = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
         t.gb = (GBoard<R> *)A.gboards + 2 * slot;
         t.gw = A.gwords + 2 * slot;
+        t.gindex = (int)(2 * slot);
+        t.gbits = (unsigned int *)(A.gwords + 2 * (long long)gridDim.x * (blockDim.x >> 5));
         t.ws_all = (R *)A.ws; t.ws_stride = A.ws_stride;
         t.off_xun = wl.xun; t.off_sn = wl.sn; t.off_yn = wl.yn; t.off_kdx = wl.kdx;
     }
@@ -2326,7 +2358,8 @@ template <class R> DDP_DEVICE_NOINLINE void solve_one(const SolveArgs &A, int st
                 if (lane == 0) {
                     double *tr = A.trace + (long long)trace_n * 12;
                     tr[0] = t.cost; tr[1] = t.costq; tr[2] = t.logcost; tr[3] = t.err; tr[4] = t.mu; tr[5] = t.reg;
-                    tr[6] = t.stepsize; tr[7] = t.opterr; tr[8] = t.step; tr[9] = t.failed; tr[10] = n_bwd; tr[11] = 0;
+                    tr[6] = t.stepsize; tr[7] = t.opterr; tr[8] = t.step; tr[9] = t.failed; tr[10] = n_bwd;
+                    tr[11] = (double)((ddp_clock() - t.cyc_t0) / 1965);   // microseconds at the nominal SM clock
                 }
             }
             trace_n++;

@@ -124,7 +124,8 @@ typedef struct direct_ddp_stats {
 
 typedef struct direct_ddp_trace_row {
     double cost, costq, logcost, err, mu, reg, stepsize, opterr;
-    int32_t step, fp_failed, n_bwd, pad;
+    int32_t step, fp_failed, n_bwd;
+    int32_t t_us;   /* device time at the end of the iteration, microseconds since the solve of this trajectory began */
 } direct_ddp_trace_row;
 
 typedef struct direct_ddp_handle_s *direct_ddp_handle;
