@@ -300,6 +300,11 @@ template <class R> DDP_DEVICE void fg_matrix(const R *tp, R *fg) {
     fg[6] = R(0); fg[7] = R(1); fg[8] = tp[1]; fg[9] = R(3) * tp[2]; fg[10] = R(4) * tp[3]; fg[11] = R(5) * tp[4];
     fg[12] = R(0); fg[13] = R(0); fg[14] = R(1); fg[15] = R(6) * tp[1]; fg[16] = R(12) * tp[2]; fg[17] = R(20) * tp[3];
 }
+// Row o of [F | G] by selects: indexing fg[] with a lane-dependent o would put the array into local memory.
+template <class R> DDP_DEVICE void fg_row(const R *fg, int o, R *c) {
+    DDP_UNROLL
+    for (int b = 0; b < 6; b++) c[b] = o == 0 ? fg[b] : (o == 1 ? fg[6 + b] : fg[12 + b]);
+}
 // fT = d x+/dT = (F' (x) I) x + (G' (x) I) u, ddp.cpp:930-935 and :1332.
 template <class R> DDP_DEVICE void ft_vector(const R *tp, const R *z, R *fT) {
     const R fp[18] = {R(0), R(1), tp[1], R(3) * tp[2], R(4) * tp[3], R(5) * tp[4],
@@ -1037,8 +1042,12 @@ template <class R> DDP_DEVICE_NOINLINE bool riccati(Traj<R> &t, R regadd, Reg<R,
     R *DDP_RESTRICT Kout = as_global(t.K);
     const R w_terminal = t.w_terminal;
     // terminal value function, ddp.cpp:1318-1323: Vx = P (x_N - x_d), Vxx = P = w_terminal I
+    // Nothing inside the knot loop may touch local memory: a local load shares its scoreboard with the global prefetch
+    // of the next knot's columns and would wait for it (profiles/r1h: 16 % of the recursion).  So the by-reference
+    // error accumulator is kept in a local copy and F/G entries are selected, not indexed, per lane.
+    Reg<R, 1> errl;
     FOR_LANES(lane) {
-        errq(lane, 0) = R(0);
+        errl(lane, 0) = R(0);
         for (int e = lane; e < 90; e += 32) {
             const R v = (e / 10 == e % 10 && e % 10 < 9) ? w_terminal : R(0);
             sm[Lay::S1 + e] = v; sm[Lay::S2 + e] = v;
@@ -1085,7 +1094,11 @@ template <class R> DDP_DEVICE_NOINLINE bool riccati(Traj<R> &t, R regadd, Reg<R,
                     for (int p = 0; p < 9; p++) tj[p] = sm[Lay::VX + p];
                 } else {
                     const int lj = lane < 9 ? 3 + lane / 3 : (lane - 10) / 3, aj = lane < 9 ? lane % 3 : (lane - 10) % 3;
-                    const R f0 = fg[lj], f1 = fg[6 + lj], f2 = fg[12 + lj];
+                    R f0 = fg[5], f1 = fg[11], f2 = fg[17];   // column lj of F|G by selects (a dynamic index would go through local memory)
+                    DDP_UNROLL
+                    for (int k = 4; k >= 0; k--) {
+                        if (lj == k) { f0 = fg[k]; f1 = fg[6 + k]; f2 = fg[12 + k]; }
+                    }
                     const R *V = sm + Lay::S2;   // V = (S + S^T)/2 (ddp.cpp:628), symmetrised by the writer below
                     DDP_UNROLL
                     for (int p = 0; p < 9; p++) {
@@ -1112,7 +1125,7 @@ template <class R> DDP_DEVICE_NOINLINE bool riccati(Traj<R> &t, R regadd, Reg<R,
                 R acc = R(0);
                 DDP_UNROLL
                 for (int q = 0; q < 9; q++) acc += sm[Lay::S2 + p * 10 + q] * fT[q];
-                sm[Lay::XH + p] = fT[p] * acc;
+                sm[Lay::XH + p] = sm[Lay::FTN + p] * acc;   // fT[p]: from shared memory, a dynamic register index would be local memory
             }
         }
         WARP_SYNC();
@@ -1126,10 +1139,10 @@ template <class R> DDP_DEVICE_NOINLINE bool riccati(Traj<R> &t, R regadd, Reg<R,
                 col(lane, 9) += hTT;
             }
             if (lane == 19) {   // |Qu|_inf, ddp.cpp:633
-                R e = errq(lane, 0);
+                R e = errl(lane, 0);
                 DDP_UNROLL
                 for (int r = 0; r < 10; r++) e = amax(e, rabs(col(lane, r)));
-                errq(lane, 0) = e;
+                errl(lane, 0) = e;
             }
         }
         // ---- ten Cholesky pivots over the u block -----------------------------------------------------------
@@ -1192,16 +1205,20 @@ template <class R> DDP_DEVICE_NOINLINE bool riccati(Traj<R> &t, R regadd, Reg<R,
             WARP_SYNC();
             FOR_LANES(lane) {
                 if (lane >= 10 && lane < 19) {
+                    const int qc = lane - 9;
+                    R kq[10];   // this lane's gain column, re-read from shared memory (keeping kx live across the block spilled it)
+                    DDP_UNROLL
+                    for (int p = 0; p < 10; p++) kq[p] = sm[Lay::KC + p * 10 + qc];
                     DDP_UNROLL
                     for (int r = 0; r < 9; r++) {
                         R acc = R(0);
                         DDP_UNROLL
-                        for (int p = 0; p < 10; p++) acc += sm[Lay::KC + p * 10 + (r + 1)] * kx(lane, p);
+                        for (int p = 0; p < 10; p++) acc += sm[Lay::KC + p * 10 + (r + 1)] * kq[p];
                         col(lane, r) -= regadd * acc;
                     }
                     R acc = R(0);
                     DDP_UNROLL
-                    for (int p = 0; p < 10; p++) acc += sm[Lay::KC + p * 10] * kx(lane, p);
+                    for (int p = 0; p < 10; p++) acc += sm[Lay::KC + p * 10] * kq[p];
                     col(lane, 9) -= regadd * acc;
                 }
             }
@@ -1225,6 +1242,7 @@ template <class R> DDP_DEVICE_NOINLINE bool riccati(Traj<R> &t, R regadd, Reg<R,
         }
         WARP_SYNC();
     }
+    FOR_LANES(lane) { errq(lane, 0) = errl(lane, 0); }
     t.n_bwd_knots += knots;
     return ok;
 }
@@ -1489,11 +1507,12 @@ DDP_DEVICE_NOINLINE void rollout_block(R *sm, const R *DDP_RESTRICT xu, R *DDP_R
             FOR_LANES(lane) {   // x+ = (F (x) I) x + (G (x) I) u (ddp.cpp:1062-1067)
                 if (lane >= 10 && lane < 19) {
                     const int o = (lane - 10) / 3, a = (lane - 10) % 3;
-                    R s1 = R(0), s2 = R(0);
+                    R s1 = R(0), s2 = R(0), fr[6];
+                    fg_row(fg, o, fr);
                     DDP_UNROLL
                     for (int b = 0; b < 3; b++) {
-                        if (b >= o) s1 += fg[o * 6 + b] * sm[Lay::ZN + 10 + 3 * b + a];
-                        s2 += fg[o * 6 + 3 + b] * sm[Lay::ZN + 3 * b + a];
+                        if (b >= o) s1 += fr[b] * sm[Lay::ZN + 10 + 3 * b + a];
+                        s2 += fr[3 + b] * sm[Lay::ZN + 3 * b + a];
                     }
                     xn(lane, 0) = s1 + s2;
                 }
@@ -1667,11 +1686,12 @@ template <class R> DDP_DEVICE_NOINLINE bool forward_trial_solo(Traj<R> &tt_, R a
             FOR_LANES(lane) {   // x+ = (F (x) I) x + (G (x) I) u (ddp.cpp:1062-1067)
                 if (lane >= 10 && lane < 19) {
                     const int o = (lane - 10) / 3, a = (lane - 10) % 3;
-                    R s1 = R(0), s2 = R(0);
+                    R s1 = R(0), s2 = R(0), fr[6];
+                    fg_row(fg, o, fr);
                     DDP_UNROLL
                     for (int b = 0; b < 3; b++) {
-                        if (b >= o) s1 += fg[o * 6 + b] * sm[Lay::ZN + 10 + 3 * b + a];
-                        s2 += fg[o * 6 + 3 + b] * sm[Lay::ZN + 3 * b + a];
+                        if (b >= o) s1 += fr[b] * sm[Lay::ZN + 10 + 3 * b + a];
+                        s2 += fr[3 + b] * sm[Lay::ZN + 3 * b + a];
                     }
                     xn(lane, 0) = s1 + s2;
                 }
@@ -1817,11 +1837,12 @@ template <class R> DDP_DEVICE_NOINLINE void initial_roll(Traj<R> &t) {
         FOR_LANES(lane) {
             if (lane >= 10 && lane < 19) {
                 const int o = (lane - 10) / 3, a = (lane - 10) % 3;
-                R s1 = R(0), s2 = R(0);
+                R s1 = R(0), s2 = R(0), fr[6];
+                fg_row(fg, o, fr);
                 DDP_UNROLL
                 for (int b = 0; b < 3; b++) {
-                    if (b >= o) s1 += fg[o * 6 + b] * sm[Lay::ZN + 10 + 3 * b + a];
-                    s2 += fg[o * 6 + 3 + b] * sm[Lay::ZN + 3 * b + a];
+                    if (b >= o) s1 += fr[b] * sm[Lay::ZN + 10 + 3 * b + a];
+                    s2 += fr[3 + b] * sm[Lay::ZN + 3 * b + a];
                 }
                 xn(lane, 0) = s1 + s2;
             }
