@@ -30,7 +30,7 @@ class Batch(C.Structure):
                 ("init_bez", C.c_void_p), ("infeas", C.c_void_p), ("infeas_all", C.c_int),
                 ("max_vel", C.c_double), ("max_acc", C.c_double), ("w_snap", C.c_double),
                 ("w_terminal", C.c_double), ("w_time", C.c_double), ("iter_max", C.c_int), ("time_power", C.c_int),
-                ("zero_init", C.c_int), ("line_init", C.c_int), ("minvo", C.c_int)]
+                ("zero_init", C.c_int), ("line_init", C.c_int), ("minvo", C.c_int), ("nknots", C.c_void_p)]
 
 
 class ResultC(C.Structure):
@@ -53,6 +53,12 @@ class Stats(C.Structure):
                 ("spec_searches", C.c_int64), ("spec_trials", C.c_int64)]
 
 
+class CorridorC(C.Structure):
+    """direct_ddp_corridor: msgs/msg/corridor.msg flattened (include/direct_ddp.h)."""
+    _fields_ = [("path_id", C.c_int), ("N", C.c_int), ("P_max", C.c_int), ("planes", C.POINTER(C.c_double)),
+                ("nplanes", C.POINTER(C.c_int32)), ("center", C.POINTER(C.c_double)), ("seed", C.POINTER(C.c_double))]
+
+
 class TraceRow(C.Structure):
     _fields_ = [(n, C.c_double) for n in ("cost", "costq", "logcost", "err", "mu", "reg", "stepsize", "opterr")] + \
                [(n, C.c_int32) for n in ("step", "fp_failed", "n_bwd", "t_us")]
@@ -61,7 +67,9 @@ class TraceRow(C.Structure):
 EXPORTS = ["direct_ddp_version", "direct_ddp_create", "direct_ddp_destroy", "direct_ddp_last_error",
            "direct_ddp_solve_batch", "direct_ddp_solve_batch_device", "direct_ddp_solve_two_stage",
            "direct_ddp_solve_two_stage_device", "direct_ddp_time_allocation_device", "direct_ddp_last_stats",
-           "direct_ddp_last_trace", "direct_ddp_measure_fma_peak", "direct_ddp_sample", "direct_ddp_sample_device"]
+           "direct_ddp_last_trace", "direct_ddp_measure_fma_peak", "direct_ddp_sample", "direct_ddp_sample_device",
+           "direct_ddp_corridor_read", "direct_ddp_corridor_write", "direct_ddp_corridor_free", "direct_ddp_replay",
+           "direct_ddp_replay_write", "direct_ddp_sm_clock_hz"]
 
 _lib = None
 
@@ -95,6 +103,14 @@ def load_library(build_if_missing: bool = True):
         lib.direct_ddp_measure_fma_peak.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]
         lib.direct_ddp_sample.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 5
         lib.direct_ddp_sample_device.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 6
+        lib.direct_ddp_corridor_read.argtypes = [C.c_char_p, C.POINTER(C.POINTER(CorridorC))]
+        lib.direct_ddp_corridor_write.argtypes = [C.c_char_p, C.POINTER(CorridorC)]
+        lib.direct_ddp_corridor_free.argtypes = [C.POINTER(CorridorC)]
+        lib.direct_ddp_corridor_free.restype = None
+        lib.direct_ddp_replay.argtypes = [C.c_void_p, C.POINTER(CorridorC), C.c_int, C.c_int, C.POINTER(TwoStage), C.c_double,
+                                          C.c_double, C.c_void_p]
+        lib.direct_ddp_replay_write.argtypes = [C.c_char_p, C.c_void_p, C.c_int]
+        lib.direct_ddp_sm_clock_hz.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         _lib = lib
     return _lib
 
@@ -167,7 +183,7 @@ class Solver:
 
     @staticmethod
     def batch_struct(pb: ProblemBatch, keep: list, *, init_bez=None, durations=None, infeas=1, zero_init=1, line_init=0,
-                     minvo=0, w_snap=1.0, w_terminal=1.0, w_time=1.0, iter_max=50, time_power=2) -> Batch:
+                     minvo=0, w_snap=1.0, w_terminal=1.0, w_time=1.0, iter_max=50, time_power=2, nknots=None) -> Batch:
         dur = np.ascontiguousarray(pb.durations if durations is None else durations, dtype=np.float64)
         ib = None if init_bez is None else np.ascontiguousarray(init_bez, dtype=np.float64)
         inf_arr, inf_all = None, 0
@@ -175,10 +191,11 @@ class Solver:
             inf_all = int(infeas)
         else:
             inf_arr = np.ascontiguousarray(infeas, dtype=np.int32)
-        keep.extend([dur, ib, inf_arr])
+        nk = None if nknots is None else np.ascontiguousarray(nknots, dtype=np.int32)
+        keep.extend([dur, ib, inf_arr, nk])
         return Batch(pb.B, pb.N, pb.P_max, _ptr(pb.planes), _ptr(pb.nplanes), _ptr(dur), _ptr(pb.seeds), _ptr(pb.x0),
                      _ptr(pb.xd), _ptr(ib), _ptr(inf_arr), inf_all, pb.max_vel, pb.max_acc, w_snap, w_terminal, w_time,
-                     iter_max, time_power, int(zero_init), int(line_init), int(minvo))
+                     iter_max, time_power, int(zero_init), int(line_init), int(minvo), _ptr(nk))
 
     # ---- host-buffer entry points (the drop-in path: H2D + solve + D2H inside the call) ----------------
     def solve_batch(self, pb: ProblemBatch, **kw) -> HostResult:
@@ -190,9 +207,9 @@ class Solver:
         return out
 
     def solve_two_stage(self, pb: ProblemBatch, stage0=None, stage1=None, time_power=TIME_POWER, want_stage0=True,
-                        out0: HostResult | None = None, out1: HostResult | None = None):
+                        out0: HostResult | None = None, out1: HostResult | None = None, nknots=None):
         keep = []
-        b = self.batch_struct(pb, keep)
+        b = self.batch_struct(pb, keep, nknots=nknots)
         ts = two_stage_opts(stage0, stage1, time_power)
         r0 = out0 if out0 is not None else (HostResult(pb.B, pb.N) if want_stage0 else None)
         r1 = out1 if out1 is not None else HostResult(pb.B, pb.N)
@@ -227,6 +244,16 @@ class Solver:
     def sample_device(self, B, N, S, bez, tim, pos, vel, acc, stream: int = 0):
         self._check(self.lib.direct_ddp_sample_device(self.h, B, N, S, bez, tim, pos, vel, acc, C.c_void_p(stream)))
 
+    def replay(self, corridor: "Corridor", n_min: int = 2, n_max: int | None = None, stage0=None, stage1=None,
+               time_power=TIME_POWER, max_vel: float = 2.0, max_acc: float = 2.0) -> np.ndarray:
+        """corridorRecCallBack's comparison loop (teach_repeat_planner.cpp:309-350) as one ragged batch -> rows [n][12]."""
+        n_max = corridor.N if n_max is None else n_max
+        rows = np.zeros((n_max - n_min + 1, 12))
+        ts = two_stage_opts(stage0, stage1, time_power)
+        cs = corridor.c_struct()
+        self._check(self.lib.direct_ddp_replay(self.h, C.byref(cs), n_min, n_max, C.byref(ts), max_vel, max_acc, _ptr(rows)))
+        return rows
+
     def stats(self) -> Stats:
         s = Stats()
         self._check(self.lib.direct_ddp_last_stats(self.h, C.byref(s)))
@@ -242,3 +269,48 @@ class Solver:
         n = C.c_int(0)
         self._check(self.lib.direct_ddp_last_trace(self.h, rows, cap, C.byref(n)))
         return [{f: getattr(rows[k], f) for f, _ in TraceRow._fields_} for k in range(n.value)]
+
+
+class Corridor:
+    """A recorded corridor (msgs/msg/corridor.msg as readCorridorMsg flattens it, teach_repeat_planner.cpp:385-410)."""
+
+    def __init__(self, path_id, planes, nplanes, center, seed):
+        self.path_id = int(path_id)
+        self.planes = np.ascontiguousarray(planes, dtype=np.float64)     # (N, P_max, 4)
+        self.nplanes = np.ascontiguousarray(nplanes, dtype=np.int32)     # (N,)
+        self.center = np.ascontiguousarray(center, dtype=np.float64)     # (N, 3)
+        self.seed = np.ascontiguousarray(seed, dtype=np.float64)         # (N, 3)
+        self.N, self.P_max = self.planes.shape[0], self.planes.shape[1]
+
+    def c_struct(self) -> CorridorC:
+        dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int32)
+        return CorridorC(self.path_id, self.N, self.P_max, self.planes.ctypes.data_as(dp), self.nplanes.ctypes.data_as(ip),
+                         self.center.ctypes.data_as(dp), self.seed.ctypes.data_as(dp))
+
+    def write(self, path: str):
+        cs = self.c_struct()
+        st = load_library().direct_ddp_corridor_write(path.encode(), C.byref(cs))
+        if st:
+            raise DirectDdpError(f"direct_ddp_corridor_write failed with status {st}")
+
+    @staticmethod
+    def read(path: str) -> "Corridor":
+        lib = load_library()
+        p = C.POINTER(CorridorC)()
+        st = lib.direct_ddp_corridor_read(path.encode(), C.byref(p))
+        if st:
+            raise DirectDdpError(f"direct_ddp_corridor_read failed with status {st}")
+        c = p.contents
+        N, PM = c.N, c.P_max
+        out = Corridor(c.path_id, np.ctypeslib.as_array(c.planes, (N, PM, 4)).copy(), np.ctypeslib.as_array(c.nplanes, (N,)).copy(),
+                       np.ctypeslib.as_array(c.center, (N, 3)).copy(), np.ctypeslib.as_array(c.seed, (N, 3)).copy())
+        lib.direct_ddp_corridor_free(p)
+        return out
+
+
+def write_replay_rows(path: str, rows: np.ndarray):
+    """The reference's result file, one "%d %f x11" line per prefix (teach_repeat_planner.cpp:347)."""
+    rows = np.ascontiguousarray(rows, dtype=np.float64)
+    st = load_library().direct_ddp_replay_write(path.encode(), _ptr(rows), rows.shape[0])
+    if st:
+        raise DirectDdpError(f"direct_ddp_replay_write failed with status {st}")

@@ -150,7 +150,7 @@ struct direct_ddp_handle_s {
     std::string err;
     direct_ddp_stats stats;
     // grow-only device buffers
-    DevBuf planes, nplanes, durations, seeds, x0, xd, init_bez, infeas;
+    DevBuf planes, nplanes, durations, seeds, x0, xd, init_bez, infeas, nknots;
     DevBuf o_int[2], o_cost[2], o_xf[2], o_pc[2], o_bz[2], o_pt[2], o_jk[2], o_st[2];
     DevBuf ws, counter, tabs, bez_tmp, time_tmp, trace, trace_len, scratch_i, gboards, gwords;
     const long long *last_stats_dev = nullptr;  // device [B][4] of the last solve (stage 1 / single)
@@ -299,6 +299,7 @@ int solve_device(H *h, const direct_ddp_batch *in, const direct_ddp_two_stage *t
     A.B = in->B; A.N = in->N; A.PM = in->P_max;
     A.planes = in->planes; A.nplanes = in->nplanes; A.durations = in->durations; A.seeds = in->seeds;
     A.x0 = in->x0; A.xd = in->xd; A.max_vel = in->max_vel; A.max_acc = in->max_acc;
+    A.nknots = in->nknots;
     if (ts) {
         if ((st = validate_cfg(h, ts->time_power, 0, ts->iter_max0))) return st;
         if ((st = validate_cfg(h, ts->time_power, 0, ts->iter_max))) return st;
@@ -399,6 +400,11 @@ int solve_host(H *h, const direct_ddp_batch *in, const direct_ddp_two_stage *ts,
     UP(durations, durations, (size_t)B * N * 8, double)
     UP(x0, x0, (size_t)B * 72, double)
     UP(xd, xd, (size_t)B * 72, double)
+    if (in->nknots) {
+        for (int b = 0; b < B; b++)
+            if (in->nknots[b] < 1 || in->nknots[b] > N) { h->err = "nknots must be in [1, N]"; return DIRECT_DDP_ERR_ARG; }
+    }
+    UP(nknots, nknots, (size_t)B * 4, int32_t)
     if (!ts) {
         UP(init_bez, init_bez, (size_t)B * N * 144, double)
         UP(infeas, infeas, (size_t)B * 4, int32_t)
@@ -412,6 +418,14 @@ int solve_host(H *h, const direct_ddp_batch *in, const direct_ddp_two_stage *ts,
     direct_ddp_result dev0, dev1;
     if ((st = mirror_result(h, 0, ts ? out0 : nullptr, B, N, &dev0))) return st;
     if ((st = mirror_result(h, 1, out1, B, N, &dev1))) return st;
+    if (in->nknots) {   // ragged batch: entries past a trajectory's own knot count come back as zeros
+        for (direct_ddp_result *dv : {&dev0, &dev1}) {
+            if (dv->poly_coeff) CK(cudaMemsetAsync(dv->poly_coeff, 0, (size_t)B * N * 144, s));
+            if (dv->bez_coeff) CK(cudaMemsetAsync(dv->bez_coeff, 0, (size_t)B * N * 144, s));
+            if (dv->poly_time) CK(cudaMemsetAsync(dv->poly_time, 0, (size_t)B * N * 8, s));
+            if (dv->jerk) CK(cudaMemsetAsync(dv->jerk, 0, (size_t)B * N * 8, s));
+        }
+    }
     if ((st = solve_device(h, &d, ts, (ts && out0) ? &dev0 : nullptr, &dev1, s))) return st;
     CK(cudaEventRecord(h->ev[4], s));
     if (ts && out0 && (st = download_result(h, out0, &dev0, B, N, s, &d2h))) return st;
@@ -466,7 +480,7 @@ void direct_ddp_destroy(direct_ddp_handle h) {
     if (!h) return;
     if (h->sm_count > 0) {
         cudaSetDevice(h->opts.device);
-        DevBuf *bufs[] = {&h->planes, &h->nplanes, &h->durations, &h->seeds, &h->x0, &h->xd, &h->init_bez, &h->infeas,
+        DevBuf *bufs[] = {&h->planes, &h->nplanes, &h->durations, &h->seeds, &h->x0, &h->xd, &h->init_bez, &h->infeas, &h->nknots,
                           &h->ws, &h->counter, &h->tabs, &h->bez_tmp, &h->time_tmp, &h->trace, &h->trace_len, &h->scratch_i,
                           &h->gboards, &h->gwords};
         for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
@@ -577,6 +591,15 @@ int direct_ddp_measure_fma_peak(direct_ddp_handle h, int precision, double *tflo
     }
     *tflops = 2.0 * 8.0 * (double)iters * blocks * threads / (best * 1e-3) / 1e12;
     return 0;
+}
+
+int direct_ddp_sm_clock_hz(direct_ddp_handle h, double *hz) {
+    REQUIRE_DEVICE(h)
+    if (!hz) return DIRECT_DDP_ERR_ARG;
+    int khz = 0;
+    CK(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, h->opts.device));
+    *hz = 1000.0 * khz;
+    return DIRECT_DDP_OK;
 }
 
 int direct_ddp_last_stats(direct_ddp_handle h, direct_ddp_stats *out) {

@@ -111,6 +111,7 @@ struct SolveArgs {
     const int32_t *nplanes;
     const double *durations, *seeds, *x0, *xd, *init_bez;
     const int32_t *infeas;
+    const int32_t *nknots;       // [B] knots of each trajectory (1 .. N), or null: all N
     double max_vel, max_acc;
     StageCfg cfg[2];
     int coop;          // 1: idle warps of a CTA help its remaining solves (tail balancing)
@@ -2233,8 +2234,11 @@ template <class R> DDP_DEVICE_NOINLINE void solve_one(const SolveArgs &A, int st
     const StageCfg &cfg = A.cfg[st];
     sm = as_shared(sm);
     tabs = as_shared(tabs);
-    const int N = A.N;
-    const WsLay wl = ws_layout(N, A.PM, A.fcap);
+    // NS = knots per trajectory in the caller's arrays (their stride); N = knots of THIS trajectory (ragged batches, e.g. the
+    // prefixes of a recorded corridor, teach_repeat_planner.cpp:316-350).  The workspace is laid out for NS.
+    const int NS = A.N;
+    const int N = A.nknots ? A.nknots[b] : A.N;
+    const WsLay wl = ws_layout(NS, A.PM, A.fcap);
     Traj<R> t;
     t.N = N; t.PM = A.PM; t.NP = wl.NP; t.MCS = wl.MCS; t.lane_ = lane_;
     t.board = board; t.ctl = ctl; t.wpb = wpb;
@@ -2250,8 +2254,8 @@ template <class R> DDP_DEVICE_NOINLINE void solve_one(const SolveArgs &A, int st
         t.off_xun = wl.xun; t.off_sn = wl.sn; t.off_yn = wl.yn; t.off_kdx = wl.kdx;
     }
 #endif
-    t.planes = A.planes + (long long)b * N * A.PM * 4;
-    t.nplanes = A.nplanes + (long long)b * N;
+    t.planes = A.planes + (long long)b * NS * A.PM * 4;
+    t.nplanes = A.nplanes + (long long)b * NS;
     t.sm = sm;
     t.tab = tabs + (cfg.minvo ? 180 : 0);
     t.xu = ws + wl.xu; t.xun = ws + wl.xun; t.K = ws + wl.K; t.kdx = ws + wl.kdx; t.aux = ws + wl.aux; t.H = ws + wl.H;
@@ -2271,11 +2275,11 @@ template <class R> DDP_DEVICE_NOINLINE void solve_one(const SolveArgs &A, int st
     if (from_stage0) infeas_in = A.out[0].infeas_out ? A.out[0].infeas_out[b] : 1;
     else infeas_in = A.two_stage ? 1 : (A.infeas ? A.infeas[b] : cfg.infeas_all);
     t.infeas = infeas_in;
-    const double *dur = A.durations + (long long)b * N;
-    const double *ibez = A.init_bez ? A.init_bez + (long long)b * N * 18 : nullptr;
+    const double *dur = A.durations + (long long)b * NS;
+    const double *ibez = A.init_bez ? A.init_bez + (long long)b * NS * 18 : nullptr;
     if (from_stage0) {
-        ibez = A.bez_tmp + (long long)b * N * 18;
-        if (A.out[0].rtn[b] == 2) dur = A.time_tmp + (long long)b * N;  // UpdateTime, teach_repeat_planner.cpp:911-912
+        ibez = A.bez_tmp + (long long)b * NS * 18;
+        if (A.out[0].rtn[b] == 2) dur = A.time_tmp + (long long)b * NS;  // UpdateTime, teach_repeat_planner.cpp:911-912
     }
 
     // ---- setup (ddp.cpp:104-250), lane <-> knot --------------------------------------------------------
@@ -2317,8 +2321,8 @@ template <class R> DDP_DEVICE_NOINLINE void solve_one(const SolveArgs &A, int st
                 R p1[3];
                 DDP_UNROLL
                 for (int a = 0; a < 3; a++) {
-                    z[10 + a] = (i == 0) ? (R)A.x0[(long long)b * 9 + a] : (R)A.seeds[((long long)b * N + i) * 3 + a];
-                    p1[a] = (i == N - 1) ? (R)A.xd[(long long)b * 9 + a] : (R)A.seeds[((long long)b * N + i + 1) * 3 + a];
+                    z[10 + a] = (i == 0) ? (R)A.x0[(long long)b * 9 + a] : (R)A.seeds[((long long)b * NS + i) * 3 + a];
+                    p1[a] = (i == N - 1) ? (R)A.xd[(long long)b * 9 + a] : (R)A.seeds[((long long)b * NS + i + 1) * 3 + a];
                 }
                 z[9] = u[9];
                 int vio = 1, cnt = 0;
@@ -2453,9 +2457,9 @@ template <class R> DDP_DEVICE_NOINLINE void solve_one(const SolveArgs &A, int st
             time_powers(T, tp);
             rmat<R>(0, tp, m);
             rmat_times_u(m, z, mu9);
-            if (O.jerk) O.jerk[(long long)b * N + i] = (double)dot9(z, mu9);  // finalroll, ddp.cpp:1624-1634
-            if (O.poly_time) O.poly_time[(long long)b * N + i] = (double)T;
-            if (carry) A.time_tmp[(long long)b * N + i] = (double)T;
+            if (O.jerk) O.jerk[(long long)b * NS + i] = (double)dot9(z, mu9);  // finalroll, ddp.cpp:1624-1634
+            if (O.poly_time) O.poly_time[(long long)b * NS + i] = (double)T;
+            if (carry) A.time_tmp[(long long)b * NS + i] = (double)T;
             DDP_UNROLL
             for (int l = 0; l < 6; l++) {
                 DDP_UNROLL
@@ -2463,7 +2467,7 @@ template <class R> DDP_DEVICE_NOINLINE void solve_one(const SolveArgs &A, int st
                     // PolyCoeff row = [Ek_inv * x, u[0:9]] (ddp.cpp:814-823); index l*3+a
                     R pc = z[zidx(l, a)];
                     if (l == 2) pc = pc * R(0.5);
-                    if (O.poly_coeff) O.poly_coeff[((long long)b * N + i) * 18 + l * 3 + a] = (double)pc;
+                    if (O.poly_coeff) O.poly_coeff[((long long)b * NS + i) * 18 + l * 3 + a] = (double)pc;
                 }
             }
             // BezCoeff = (1/T) * Bezier control points (poly2bezFunc, ddp.cpp:799-812: the inverse of
@@ -2481,8 +2485,8 @@ template <class R> DDP_DEVICE_NOINLINE void solve_one(const SolveArgs &A, int st
                         pw = pw * T;
                     }
                     const double bzv = (double)accv;
-                    if (O.bez_coeff) O.bez_coeff[((long long)b * N + i) * 18 + a * 6 + j] = bzv;
-                    if (carry) A.bez_tmp[((long long)b * N + i) * 18 + a * 6 + j] = bzv;
+                    if (O.bez_coeff) O.bez_coeff[((long long)b * NS + i) * 18 + a * 6 + j] = bzv;
+                    if (carry) A.bez_tmp[((long long)b * NS + i) * 18 + a * 6 + j] = bzv;
                 }
             }
         }

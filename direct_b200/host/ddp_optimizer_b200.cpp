@@ -25,6 +25,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <mutex>
+#include <cstring>
 #include <vector>
 
 #include "direct_ddp.h"
@@ -107,6 +108,7 @@ int ddpTrajOptimizer::polyCurveGeneration(
     }
 
     direct_ddp_batch in;
+    std::memset(&in, 0, sizeof in);   // fields added to the ABI later (nknots, ...) default to 'not used'
     in.B = 1; in.N = N; in.P_max = P_max;
     in.planes = planes.data(); in.nplanes = nplanes.data(); in.durations = durations.data();
     in.seeds = line_init_flag ? seeds.data() : nullptr;

@@ -76,6 +76,10 @@ typedef struct direct_ddp_batch {
     int time_power;          /* 1 or 2 (anything else is undefined behaviour in the reference,
                                 ddp_optimizer.cpp:1294-1305; rejected here)                         */
     int zero_init, line_init, minvo;
+    const int32_t *nknots;   /* [B] knots of each trajectory, each in [1, N], or NULL (= N for all): ragged batches such
+                                as the prefixes 2..64 of a recorded corridor (teach_repeat_planner.cpp:316-350).  All
+                                per-knot arrays keep the stride N; entries past a trajectory's own count are ignored on
+                                input and left untouched on output.                                              */
 } direct_ddp_batch;
 
 /* Outputs, one entry per trajectory; any pointer may be NULL to skip that output.
@@ -164,6 +168,32 @@ int direct_ddp_sample_device(direct_ddp_handle h, int B, int N, int S, const dou
 /* The same with host buffers (H2D, kernel, D2H inside the call). */
 int direct_ddp_sample(direct_ddp_handle h, int B, int N, int S, const double *bez_coeff, const double *poly_time,
                       double *pos, double *vel, double *acc);
+
+/* ---- recorded corridors and the authors' comparison loop (direct_b200/host/corridor_replay.cpp) ----------------------
+ * direct_ddp_corridor = msgs/msg/corridor.msg flattened as readCorridorMsg does (teach_repeat_planner.cpp:385-410);
+ * the on-disk form is a plain-text dump of the message:
+ *     corridor <path_id> <N>
+ *     polyhedron <cx> <cy> <cz> <sx> <sy> <sz> <P>       N times, each followed by P lines "<a> <b> <c> <d>"
+ * direct_ddp_replay = corridorRecCallBack's loop with alg 0 (teach_repeat_planner.cpp:309-350): the prefixes
+ * n = n_min .. n_max of the corridor are planned by fastTrajPlanning's protocol (:792-951) as ONE ragged batch;
+ * rows[(n - n_min)][12] = {n, compTime, sum allocTime, sum initAllocTime, rtn0, iter_used0, jerkCost0, rtn, iter_used,
+ * jerkCost, terminalNorm, 0 | -1}, the columns of teach_repeat_planner.cpp:347; direct_ddp_replay_write prints them in
+ * the reference's "%d %f ... %f" format. */
+typedef struct direct_ddp_corridor {
+    int path_id, N, P_max;
+    double *planes;   /* [N][P_max][4], rows past nplanes[i] hold the always-inactive plane (0,0,0,-1) */
+    int32_t *nplanes; /* [N] */
+    double *center;   /* [N][3] polyhedron.center */
+    double *seed;     /* [N][3] polyhedron.seed_coord */
+} direct_ddp_corridor;
+int direct_ddp_corridor_read(const char *path, direct_ddp_corridor **out);
+int direct_ddp_corridor_write(const char *path, const direct_ddp_corridor *c);
+void direct_ddp_corridor_free(direct_ddp_corridor *c);
+int direct_ddp_replay(direct_ddp_handle h, const direct_ddp_corridor *c, int n_min, int n_max, const direct_ddp_two_stage *ts,
+                      double max_vel, double max_acc, double *rows);
+int direct_ddp_replay_write(const char *path, const double *rows, int nrows);
+/* SM clock of the handle's device in Hz (converts the cycle counts of direct_ddp_result::stats into seconds). */
+int direct_ddp_sm_clock_hz(direct_ddp_handle h, double *hz);
 
 int direct_ddp_last_stats(direct_ddp_handle h, direct_ddp_stats *out);
 /* Register-resident FMA throughput of the device (TFLOP/s, 2 flops per FMA) for DIRECT_DDP_FP64 or

@@ -1,0 +1,101 @@
+"""Recorded-corridor loader and the authors' comparison loop: direct_b200/host/corridor_replay.cpp.
+CPU: dump round trip and result-file format.  GPU: ragged batches equal per-prefix solves, replay rows equal the oracle."""
+import numpy as np
+import pytest
+
+from direct_b200 import make_batch
+from direct_b200.capi import Corridor, Solver, write_replay_rows
+from direct_b200.problems import ProblemBatch, time_allocation
+
+
+def recorded(n=24, kind="poly", first=7):
+    """A synthetic 'recorded' corridor: the cells of one generated problem; polyhedron.center = centre of the box part."""
+    pb = make_batch(1, n, kind, first=first)
+    pl = pb.planes[0]
+    center = np.stack([(-pl[:, 2 * a, 3] + pl[:, 2 * a + 1, 3]) / 2 for a in range(3)], axis=-1)
+    return Corridor(42, pl, pb.nplanes[0], center, pb.seeds[0])
+
+
+def prefix_problem(c: Corridor, n: int) -> ProblemBatch:
+    """fastTrajPlanning's setup for the first n polyhedra (teach_repeat_planner.cpp:805-842)."""
+    pts = np.concatenate([c.center[:1], c.seed[1:n], c.center[n - 1:n]], axis=0)[None]
+    x0, xd = np.zeros((1, 9)), np.zeros((1, 9))
+    x0[0, :3], xd[0, :3] = c.center[0], c.center[n - 1]
+    return ProblemBatch(1, n, c.P_max, np.ascontiguousarray(c.planes[None, :n]), np.ascontiguousarray(c.nplanes[None, :n]),
+                        time_allocation(pts, 2.0, 2.0), np.ascontiguousarray(c.seed[None, :n]), x0, xd)
+
+
+def test_corridor_dump_round_trip(tmp_path):
+    c = recorded()
+    p = str(tmp_path / "corridor.txt")
+    c.write(p)
+    d = Corridor.read(p)
+    assert d.path_id == 42 and d.N == c.N and d.P_max == int(c.nplanes.max())
+    assert (d.nplanes == c.nplanes).all() and (d.center == c.center).all() and (d.seed == c.seed).all()
+    for i in range(c.N):
+        k = c.nplanes[i]
+        assert (d.planes[i, :k] == c.planes[i, :k]).all()
+        assert (d.planes[i, k:] == np.array([0, 0, 0, -1.0])).all()   # inactive padding, teach_repeat_planner.cpp:867-879
+    with pytest.raises(Exception):
+        Corridor.read(str(tmp_path / "missing.txt"))
+
+
+def test_replay_result_file_format(tmp_path):
+    rows = np.array([[2, 0.0123, 3.5, 4.25, 2, 5, 10.5, 1, 9, 8.25, 1e-9, 0], [3, 0.02, 5.5, 6.25, 2, 6, 11.5, 0, 100, 9.25, 2e-3, -1]])
+    p = str(tmp_path / "alg0path42")
+    write_replay_rows(p, rows)
+    lines = open(p).read().strip().split("\n")
+    assert lines[0] == "%d %f %f %f %f %f %f %f %f %f %f %f" % (2, *rows[0, 1:])   # teach_repeat_planner.cpp:347
+    assert len(lines) == 2 and lines[1].split()[0] == "3" and lines[1].split()[-1] == "-1.000000"
+
+
+@pytest.mark.gpu
+def test_gpu_ragged_batch_equals_uniform_solves():
+    c = recorded(n=20)
+    ns = [2, 3, 7, 12, 20]
+    B, N = len(ns), max(ns)
+    planes = np.zeros((B, N, c.P_max, 4)); planes[..., 3] = -1.0
+    nplanes = np.zeros((B, N), np.int32)
+    dur, seeds, x0, xd = np.ones((B, N)), np.zeros((B, N, 3)), np.zeros((B, 9)), np.zeros((B, 9))
+    singles = []
+    for b, n in enumerate(ns):
+        q = prefix_problem(c, n)
+        singles.append(q)
+        planes[b, :n], nplanes[b, :n], dur[b, :n], seeds[b, :n], x0[b], xd[b] = q.planes[0], q.nplanes[0], q.durations[0], q.seeds[0], q.x0[0], q.xd[0]
+    pb = ProblemBatch(B, N, c.P_max, planes, nplanes, dur, seeds, x0, xd)
+    s = Solver(0, "fp64")
+    g0, g1 = s.solve_two_stage(pb, nknots=np.array(ns, np.int32))
+    for b, n in enumerate(ns):
+        u0, u1 = s.solve_two_stage(singles[b])
+        assert g0.rtn[b] == u0.rtn[0] and g1.rtn[b] == u1.rtn[0] and g1.iters[b] == u1.iters[0]
+        for f in ("poly_time", "bez_coeff", "poly_coeff", "jerk"):
+            assert np.array_equal(getattr(g1, f)[b, :n], getattr(u1, f)[0]), (f, n)   # same arithmetic: same bits
+            assert (getattr(g1, f)[b, n:] == 0).all()                                  # untouched tail comes back as zeros
+        assert g1.cost[b] == u1.cost[0] and np.array_equal(g1.x_final[b], u1.x_final[0])
+    with pytest.raises(Exception):
+        s.solve_two_stage(pb, nknots=np.array([0] * B, np.int32))
+    s.close()
+
+
+@pytest.mark.gpu
+def test_gpu_replay_rows_match_oracle(oracle, tmp_path):
+    c = recorded(n=24)
+    p = str(tmp_path / "corridor.txt")
+    c.write(p)
+    c = Corridor.read(p)
+    s = Solver(0, "fp64")
+    rows = s.replay(c, 2, 24)
+    s.close()
+    assert rows.shape == (23, 12) and (rows[:, 0] == np.arange(2, 25)).all()
+    good = 0
+    for k, n in enumerate(range(2, 25)):
+        q = prefix_problem(c, n)
+        a0, a1 = oracle.two_stage_batch(q)
+        want = [a1.poly_time.sum(), q.durations.sum(), a0.rtn[0], a0.iters[0], a0.jerk.sum(), a1.rtn[0], a1.iters[0], a1.jerk.sum(),
+                float(((a1.x_final[0] - q.xd[0]) ** 2).sum()), -1.0 if (a1.poly_time < 0).any() else 0.0]
+        got = rows[k, 2:]
+        assert np.isfinite(rows[k]).all() and rows[k, 1] > 0     # compTime: device time of the two solves
+        assert got[1] == pytest.approx(want[1], rel=1e-12)        # initTimeAllocation, teach_repeat_planner.cpp:583-639
+        ok = all(abs(g - w) <= 1e-5 * max(1.0, abs(w)) for g, w in zip(got, want))
+        good += ok
+    assert good >= 21, good   # rel 1e-5 on every column; at most two chaotic prefixes tolerated
