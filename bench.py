@@ -338,6 +338,7 @@ def main():
                         "rollouts_per_solve": st.fwd_trials / B, "grid_blocks": st.grid_blocks,
                         "block_threads": st.block_threads, "smem_bytes_per_block": st.smem_bytes_per_block,
                         "warp_slots": st.workspace_slots, "coop_jobs": int(st.coop_jobs), "helper_units": int(st.helper_units),
+                        "spec_searches": int(st.spec_searches), "spec_trials": int(st.spec_trials),
                         "cycle_share_bwd": float(cyc[0] / max(1, cyc[2])),
                         "cycle_share_linesearch": float(cyc[1] / max(1, cyc[2]))},
     }

@@ -397,6 +397,18 @@ template <class R> DDP_DEVICE RowCtx<R> row_global(RowCtx<R> c) {
     return c;
 }
 
+// First row of row group g of knot i into the one-deep pipeline registers (slack, dual slack, plane), issued while the
+// previous group is being finished so that the group's basis rows are computed under the load latency.
+template <class R>
+DDP_DEVICE void first_row_load(const RowCtx<R> &t, const double *pl, int P, int g, int i, R &s_n, R &y_n, R *n_n) {
+    if (g < 15 && (g >= 6 || P > 0)) {
+        const long long ro = (long long)row_slot(g, 0, t.PM) * t.NP + i;
+        s_n = t.s[ro];
+        if (t.infeas) y_n = t.y[ro];
+        if (g < 6) load_plane(pl, 0, n_n);
+    }
+}
+
 // Visit every constraint row of knot i at the point z (constraint VALUES only; computecminvo,
 // ddp.cpp:1132-1285): f(row slot, c).
 template <class R, class F> DDP_DEVICE void visit_rows(const RowCtx<R> &t, int i, const R *z, F &&f) {
@@ -868,6 +880,8 @@ template <class R> DDP_DEVICE_NOINLINE void linearize_solo(Traj<R> &tt_, Reg<R, 
                 // ---- pass 1: rows -> weights -> per-group blocks.  One rolled loop over the 15 row groups and one over
                 // the rows of a group (a single copy of the row code: the kernel is instruction-fetch bound,
                 // profiles/r1c); the slack of row r+1 is loaded while row r is processed. ------------------------
+                R s_n = R(0), y_n = R(1), n_n[4] = {R(0), R(0), R(0), R(0)};   // pipeline registers, see first_row_load
+                first_row_load(t, pl, P, 0, i, s_n, y_n, n_n);
                 DDP_NOUNROLL
                 for (int g = 0; g < 15; g++) {
                     const int shift = group_shift(g), nr = g < 6 ? P : 6;
@@ -881,13 +895,6 @@ template <class R> DDP_DEVICE_NOINLINE void linearize_solo(Traj<R> &tt_, Reg<R, 
                     // one-deep software pipeline: slack (and plane) of row r+1 are loaded while row r is processed.  Deeper
                     // pipelines / two-row unrolling were measured slower at full occupancy: the kernel is bound by
                     // instruction fetch and every extra copy of the row body costs more than the latency it hides.
-                    R s_n = R(0), y_n = R(1), n_n[4] = {R(0), R(0), R(0), R(0)};
-                    if (nr > 0) {
-                        const long long ro = (long long)row_slot(g, 0, t.PM) * t.NP + i;
-                        s_n = t.s[ro];
-                        if (t.infeas) y_n = t.y[ro];
-                        if (g < 6) load_plane(pl, 0, n_n);
-                    }
                     DDP_NOUNROLL
                     for (int r = 0; r < nr; r++) {
                         const R sv = s_n, yv = y_n;
@@ -915,6 +922,7 @@ template <class R> DDP_DEVICE_NOINLINE void linearize_solo(Traj<R> &tt_, Reg<R, 
                         gv[0] += gw * n[0]; gv[1] += gw * n[1]; gv[2] += gw * n[2];
                         tt += dt * tc; gt += gtc;
                     }
+                    first_row_load(t, pl, P, g + 1, i, s_n, y_n, n_n);
                     if (g < 6) {
                         DDP_UNROLL
                         for (int e = 0; e < 6; e++) msc[(g * 6 + e) * 32] = M[e];
@@ -1085,8 +1093,10 @@ template <class R> DDP_DEVICE_NOINLINE bool riccati(Traj<R> &t, R regadd, Reg<R,
             pre(lane, 0) = R(0);
             if (i > 0) {   // prefetch the next knot's column, fT and time while this one is eliminated
                 if (lane < 20) load20(Hin + (long long)(i - 1) * 400 + lane * 20, &nxt(lane, 0));
-                if (lane < 9) pre(lane, 0) = aux[(long long)(i - 1) * 12 + lane];
-                else if (lane == 9) pre(lane, 0) = xu[(long long)(i - 1) * 20 + 9];
+                // one load through a selected address: two predicated loads into the same register made the second wait
+                // for the first (write-after-write), a full global-load latency per knot (profiles/r1h)
+                const R *psrc = lane < 9 ? aux + (long long)(i - 1) * 12 + lane : xu + (long long)(i - 1) * 20 + 9;
+                if (lane < 10) pre(lane, 0) = *psrc;
             }
             if (lane < 20 && lane != 9) {
                 R tj[9];
@@ -1720,6 +1730,8 @@ template <class R> DDP_DEVICE_NOINLINE bool forward_trial_solo(Traj<R> &tt_, R a
                 A.lg.lp = R(1); A.lg.lsum = R(0); A.e1 = R(0); A.bad = 0; A.cmax = R(-INFINITY);
                 const int P = t.nplanes[i];
                 const double *pl = t.planes + (long long)i * t.PM * 4;
+                R s_n = R(0), y_n = R(1), n_n[4] = {R(0), R(0), R(0), R(0)};   // pipeline registers, see first_row_load
+                first_row_load(t, pl, P, 0, i, s_n, y_n, n_n);
                 DDP_NOUNROLL
                 for (int g = 0; g < 15; g++) {   // one copy of the row code for all groups (see linearize)
                     const int shift = group_shift(g), nr = g < 6 ? P : 6;
@@ -1732,13 +1744,6 @@ template <class R> DDP_DEVICE_NOINLINE bool forward_trial_solo(Traj<R> &tt_, R a
                     for (int a = 0; a < 3; a++) {
                         co[a] = dot_axis<R, 0>(b, zo, a); cd[a] = dot_axis<R, 0>(bd, zo, a); cn[a] = dot_axis<R, 0>(bn, zn, a);
                         j1[a] = dot_axis<R, 3>(b, v1, a); j2[a] = dot_axis<R, 0>(b, v2, a);
-                    }
-                    R s_n = R(0), y_n = R(1), n_n[4] = {R(0), R(0), R(0), R(0)};   // one-deep pipeline, see linearize
-                    if (nr > 0) {
-                        const long long ro = (long long)row_slot(g, 0, t.PM) * t.NP + i;
-                        s_n = t.s[ro];
-                        if (t.infeas) y_n = t.y[ro];
-                        if (g < 6) load_plane(pl, 0, n_n);
                     }
                     DDP_NOUNROLL
                     for (int r = 0; r < nr; r++) {
@@ -1762,6 +1767,7 @@ template <class R> DDP_DEVICE_NOINLINE bool forward_trial_solo(Traj<R> &tt_, R a
                         const R jv2 = ((n[0] * j2[0] + n[1] * j2[1]) + n[2] * j2[2]) + tc * v2[9];
                         trial_row(t, ro_cur, sv, yv, cold, cnew, jv1, jv2, alpha, tau, A);
                     }
+                    first_row_load(t, pl, P, g + 1, i, s_n, y_n, n_n);
                     if ((g & 3) == 3) {   // end of unit g / 4 (see rows_unit): bank its partials, restart the accumulators
                         acc(lane, 1) += A.lg.total();
                         acc(lane, 2) += A.e1;
