@@ -13,7 +13,9 @@
 #include <vector>
 
 #include "../../include/direct_ddp.h"
+#include "../../include/direct_gddp.h"
 #include "ipddp_solver.h"
+#include "gddp.cuh"
 
 #ifndef DDP_MAX_THREADS
 #define DDP_MAX_THREADS 128  // four trajectories (warps) per CTA: up to three helpers for the last solve of a CTA
@@ -153,6 +155,7 @@ struct direct_ddp_handle_s {
     DevBuf planes, nplanes, durations, seeds, x0, xd, init_bez, infeas, nknots;
     DevBuf o_int[2], o_cost[2], o_xf[2], o_pc[2], o_bz[2], o_pt[2], o_jk[2], o_st[2];
     DevBuf ws, counter, tabs, bez_tmp, time_tmp, trace, trace_len, scratch_i, gboards, gwords;
+    DevBuf gd[8];   // generic DDP (gddp.cuh): x0, xg, u_init, ints, cost, x, u, stats
     const long long *last_stats_dev = nullptr;  // device [B][4] of the last solve (stage 1 / single)
     const long long *last_stats_dev0 = nullptr; // stage 0 when two-stage
     int last_B = 0;
@@ -484,6 +487,7 @@ void direct_ddp_destroy(direct_ddp_handle h) {
                           &h->ws, &h->counter, &h->tabs, &h->bez_tmp, &h->time_tmp, &h->trace, &h->trace_len, &h->scratch_i,
                           &h->gboards, &h->gwords};
         for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
+        for (DevBuf &b : h->gd) if (b.p) cudaFree(b.p);
         for (int k = 0; k < 2; k++) {
             DevBuf *ob[] = {&h->o_int[k], &h->o_cost[k], &h->o_xf[k], &h->o_pc[k], &h->o_bz[k], &h->o_pt[k], &h->o_jk[k], &h->o_st[k]};
             for (DevBuf *b : ob) if (b->p) cudaFree(b->p);
@@ -652,3 +656,118 @@ int direct_ddp_last_trace(direct_ddp_handle h, direct_ddp_trace_row *rows, int c
 }
 
 }  // extern "C"
+
+
+// ---- generic unconstrained DDP (include/direct_gddp.h, gddp.cuh) ---------------------------------------------------------
+namespace {
+
+template <int MODEL, class R> int gddp_launch(H *h, const direct_gddp_problem *in, const direct_gddp_result *out, cudaStream_t s) {
+    using D = gddp::Dim<MODEL>;
+    gddp::Args<R> A;
+    memset(&A, 0, sizeof A);
+    A.B = in->B; A.N = in->N; A.iter_max = in->iter_max; A.dt = (R)in->dt; A.tol = (R)in->tol;
+    A.x0 = in->x0; A.xg = in->xg; A.u_init = in->u_init;
+    for (int a = 0; a < D::NX; a++) { A.q[a] = (R)in->q[a]; A.qf[a] = (R)in->qf[a]; }
+    for (int m = 0; m < D::NU; m++) { A.r[m] = (R)in->r[m]; A.uh[m] = (R)in->uh[m]; }
+    A.rtn = out->rtn; A.iters = out->iters; A.cost = out->cost; A.x = out->x; A.u = out->u; A.stats = (long long *)out->stats;
+    const int threads = 128, wpb = threads / 32;
+    const size_t smem = (size_t)wpb * gddp::Smem<MODEL>::TOTAL * sizeof(R);
+    auto kern = gddp::gddp_kernel<MODEL, R>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
+    if (per_sm < 1) { h->err = "gddp kernel does not fit on an SM"; return DIRECT_DDP_ERR_CUDA; }
+    long long grid = (long long)per_sm * h->sm_count;
+    const long long need = ((long long)in->B + wpb - 1) / wpb;
+    if (grid > need) grid = need;
+    const gddp::Ws<MODEL, R> wl(in->N);
+    A.ws_stride = wl.total;
+    int st = ensure(h, h->ws, (size_t)grid * wpb * wl.total * sizeof(R));
+    if (st) return st;
+    A.ws = (R *)h->ws.p;
+    if ((st = ensure(h, h->counter, 64))) return st;
+    CK(cudaMemsetAsync(h->counter.p, 0, 64, s));
+    A.counter = (unsigned int *)h->counter.p;
+    CK(cudaEventRecord(h->ev[2], s));
+    kern<<<(unsigned)grid, threads, smem, s>>>(A);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(h->ev[3], s));
+    h->stats.kernel_launches = 1;
+    h->stats.grid_blocks = (int)grid; h->stats.block_threads = threads;
+    h->stats.smem_bytes_per_block = (int)smem; h->stats.workspace_slots = (int)(grid * wpb);
+    h->last_stats_dev = nullptr; h->last_stats_dev0 = nullptr; h->last_B = 0; h->stats_valid = false;
+    return 0;
+}
+
+int gddp_validate(H *h, const direct_gddp_problem *in, const direct_gddp_result *out) {
+    if (!in || !out) { h->err = "problem or result is NULL"; return DIRECT_DDP_ERR_ARG; }
+    if (in->model != DIRECT_GDDP_DINT6 && in->model != DIRECT_GDDP_QUAD12) { h->err = "unknown model"; return DIRECT_DDP_ERR_ARG; }
+    if (in->B <= 0 || in->N <= 0 || in->iter_max < 0 || !(in->dt > 0.0)) { h->err = "B, N, dt must be positive"; return DIRECT_DDP_ERR_ARG; }
+    if (!in->x0 || !in->xg || !out->rtn || !out->iters || !out->cost || !out->x || !out->u) { h->err = "missing pointer"; return DIRECT_DDP_ERR_ARG; }
+    return 0;
+}
+
+int gddp_dispatch(H *h, const direct_gddp_problem *in, const direct_gddp_result *out, cudaStream_t s) {
+    const bool f32 = h->opts.precision == DIRECT_DDP_FP32;
+    if (in->model == DIRECT_GDDP_QUAD12) return f32 ? gddp_launch<1, float>(h, in, out, s) : gddp_launch<1, double>(h, in, out, s);
+    return f32 ? gddp_launch<0, float>(h, in, out, s) : gddp_launch<0, double>(h, in, out, s);
+}
+
+}  // namespace
+
+extern "C" int direct_gddp_solve_device(direct_ddp_handle h, const direct_gddp_problem *in, direct_gddp_result *out, void *stream) {
+    REQUIRE_DEVICE(h)
+    int st = gddp_validate(h, in, out);
+    if (st) return st;
+    CK(cudaSetDevice(h->opts.device));
+    return gddp_dispatch(h, in, out, stream ? (cudaStream_t)stream : h->stream);
+}
+
+extern "C" int direct_gddp_solve(direct_ddp_handle h, const direct_gddp_problem *in, direct_gddp_result *out) {
+    REQUIRE_DEVICE(h)
+    int st = gddp_validate(h, in, out);
+    if (st) return st;
+    CK(cudaSetDevice(h->opts.device));
+    cudaStream_t s = h->stream;
+    const int nx = in->model == DIRECT_GDDP_QUAD12 ? 12 : 6, nu = in->model == DIRECT_GDDP_QUAD12 ? 4 : 3;
+    const size_t B = (size_t)in->B, N = (size_t)in->N;
+    direct_gddp_problem d = *in;
+    direct_gddp_result r;
+    memset(&r, 0, sizeof r);
+    int64_t h2d = 0, d2h = 0;
+    CK(cudaEventRecord(h->ev[0], s));
+    const size_t nb_x0 = B * nx * 8, nb_u = B * N * nu * 8, nb_x = B * (N + 1) * nx * 8;
+    if ((st = ensure(h, h->gd[0], nb_x0)) || (st = ensure(h, h->gd[1], nb_x0))) return st;
+    CK(cudaMemcpyAsync(h->gd[0].p, in->x0, nb_x0, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(h->gd[1].p, in->xg, nb_x0, cudaMemcpyHostToDevice, s));
+    d.x0 = (const double *)h->gd[0].p; d.xg = (const double *)h->gd[1].p;
+    h2d += 2 * (int64_t)nb_x0;
+    if (in->u_init) {
+        if ((st = ensure(h, h->gd[2], nb_u))) return st;
+        CK(cudaMemcpyAsync(h->gd[2].p, in->u_init, nb_u, cudaMemcpyHostToDevice, s));
+        d.u_init = (const double *)h->gd[2].p;
+        h2d += (int64_t)nb_u;
+    }
+    if ((st = ensure(h, h->gd[3], B * 8)) || (st = ensure(h, h->gd[4], B * 8)) || (st = ensure(h, h->gd[5], nb_x)) ||
+        (st = ensure(h, h->gd[6], nb_u)) || (st = ensure(h, h->gd[7], B * 32))) return st;
+    r.rtn = (int32_t *)h->gd[3].p; r.iters = (int32_t *)h->gd[3].p + B; r.cost = (double *)h->gd[4].p;
+    r.x = (double *)h->gd[5].p; r.u = (double *)h->gd[6].p; r.stats = (int64_t *)h->gd[7].p;
+    CK(cudaEventRecord(h->ev[1], s));
+    if ((st = gddp_dispatch(h, &d, &r, s))) return st;
+    CK(cudaEventRecord(h->ev[4], s));
+    CK(cudaMemcpyAsync(out->rtn, r.rtn, B * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(out->iters, r.iters, B * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(out->cost, r.cost, B * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(out->x, r.x, nb_x, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(out->u, r.u, nb_u, cudaMemcpyDeviceToHost, s));
+    d2h += (int64_t)(B * 16 + nb_x + nb_u);
+    if (out->stats) { CK(cudaMemcpyAsync(out->stats, r.stats, B * 32, cudaMemcpyDeviceToHost, s)); d2h += (int64_t)B * 32; }
+    CK(cudaEventRecord(h->ev[5], s));
+    CK(cudaStreamSynchronize(s));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, h->ev[0], h->ev[1])); h->stats.h2d_ms = ms;
+    CK(cudaEventElapsedTime(&ms, h->ev[2], h->ev[3])); h->stats.kernel_ms = ms;
+    CK(cudaEventElapsedTime(&ms, h->ev[4], h->ev[5])); h->stats.d2h_ms = ms;
+    h->stats.h2d_bytes = h2d; h->stats.d2h_bytes = d2h;
+    return DIRECT_DDP_OK;
+}

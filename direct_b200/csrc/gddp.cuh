@@ -1,0 +1,414 @@
+// gddp.cuh -- generic unconstrained batched DDP for sm_100a (model (B) of SURVEY.md section 8(d); include/direct_gddp.h).
+//
+// One warp owns one trajectory for the whole solve (persistent kernel, atomic work queue).  The backward sweep keeps the
+// augmented matrix  [Qxx Qxu Qx; Qux Quu Qu]  one COLUMN PER LANE in registers (z order [x(nx); u(nu)], lane nz holds the
+// gradient column): per knot every lane builds its column a_j of [A | B] from the analytic Jacobian (selects, no
+// indexing), forms w_j = Vxx a_j, and the matrix entries Q[r][j] = a_r . w_j from the columns published in shared memory;
+// the nu control rows are then eliminated by right-looking Cholesky pivots (pivot broadcast by shuffle, multipliers through
+// shared memory), the gains come from one nu x nu back-substitution per lane, and the trailing block IS the new Vxx, Vx
+// (Schur complement with the regularised Quu).  No Jacobian, no Q matrix and no value function ever touches HBM; per knot
+// the sweep reads nx + nu numbers and writes nu (nx + 1) gains.  The rollout keeps the state in registers of every lane.
+// Arithmetic type R = float (BASELINE.json's fp32 configuration) or double.
+#ifndef DIRECT_B200_GDDP_CUH_
+#define DIRECT_B200_GDDP_CUH_
+
+namespace gddp {
+
+template <class R> struct Args {
+    int B, N, iter_max;
+    R dt, tol;
+    const double *x0, *xg, *u_init;
+    R q[12], qf[12], r[4], uh[4];
+    int32_t *rtn, *iters;
+    double *cost, *x, *u;
+    long long *stats;
+    R *ws;
+    long long ws_stride;
+    unsigned int *counter;
+};
+
+template <int MODEL> struct Dim {
+    static constexpr int NX = MODEL == 1 ? 12 : 6;
+    static constexpr int NU = MODEL == 1 ? 4 : 3;
+    static constexpr int NZ = NX + NU;
+};
+
+__device__ __forceinline__ float g_sin(float x) { return sinf(x); }
+__device__ __forceinline__ double g_sin(double x) { return sin(x); }
+__device__ __forceinline__ float g_cos(float x) { return cosf(x); }
+__device__ __forceinline__ double g_cos(double x) { return cos(x); }
+__device__ __forceinline__ float g_rsqrt(float x) { return 1.0f / sqrtf(x); }
+__device__ __forceinline__ double g_rsqrt(double x) { return 1.0 / sqrt(x); }
+__device__ __forceinline__ float g_abs(float x) { return fabsf(x); }
+__device__ __forceinline__ double g_abs(double x) { return fabs(x); }
+template <class R> __device__ __forceinline__ R sel3(R a, R b, R c, int k) { return k == 0 ? a : (k == 1 ? b : c); }
+
+// ---- models: continuous dynamics f(x, u), evaluated identically by every lane (uniform registers) ---------------------
+template <int MODEL, class R> struct Model;
+
+template <class R> struct Model<0, R> {   // 3D double integrator
+    static __device__ __forceinline__ void f(const R *x, const R *u, R *fx) {
+#pragma unroll
+        for (int a = 0; a < 3; a++) { fx[a] = x[3 + a]; fx[3 + a] = u[a]; }
+    }
+    // column j of [A | B] = [I + dt df/dx | dt df/du]
+    static __device__ __forceinline__ void column(const R *, const R *, R dt, int j, R *a) {
+#pragma unroll
+        for (int r = 0; r < 6; r++) a[r] = (r == j) ? R(1) : R(0);
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+            if (j == 3 + r) a[r] += dt;      // dp/dv
+            if (j == 6 + r) a[3 + r] = dt;   // dv/da
+        }
+    }
+};
+
+template <class R> struct Model<1, R> {   // rigid-body quadrotor, Euler angles (Quadrotor.cpp:15-20 constants)
+    static __device__ __forceinline__ void f(const R *x, const R *u, R *fx) {
+        const R m = R(0.98), g = R(9.81), Jx = R(2.64e-3), Jy = R(2.64e-3), Jz = R(4.96e-3);
+        const R ph = x[6], th = x[7], ps = x[8], p = x[9], q = x[10], r = x[11];
+        const R sp = g_sin(ph), cp = g_cos(ph), st = g_sin(th), ct = g_cos(th), ss = g_sin(ps), cs = g_cos(ps);
+        const R tt = st / ct, ict = R(1) / ct, fm = u[0] / m;
+        fx[0] = x[3]; fx[1] = x[4]; fx[2] = x[5];
+        fx[3] = fm * (cp * st * cs + sp * ss); fx[4] = fm * (cp * st * ss - sp * cs); fx[5] = fm * (cp * ct) - g;
+        const R sqcr = sp * q + cp * r, cqsr = cp * q - sp * r;
+        fx[6] = p + tt * sqcr; fx[7] = cqsr; fx[8] = sqcr * ict;
+        fx[9] = (u[1] - (Jz - Jy) * q * r) / Jx; fx[10] = (u[2] - (Jx - Jz) * p * r) / Jy; fx[11] = (u[3] - (Jy - Jx) * p * q) / Jz;
+    }
+    static __device__ __forceinline__ void column(const R *x, const R *u, R dt, int j, R *a) {
+        const R m = R(0.98), Jx = R(2.64e-3), Jy = R(2.64e-3), Jz = R(4.96e-3);
+        const R ph = x[6], th = x[7], ps = x[8], p = x[9], q = x[10], r = x[11];
+        const R sp = g_sin(ph), cp = g_cos(ph), st = g_sin(th), ct = g_cos(th), ss = g_sin(ps), cs = g_cos(ps);
+        const R tt = st / ct, ict = R(1) / ct, fm = u[0] / m;
+        const R sqcr = sp * q + cp * r, cqsr = cp * q - sp * r;
+        const int grp = j / 3, k = j - 3 * grp;
+#pragma unroll
+        for (int rr = 0; rr < 12; rr++) a[rr] = (rr == j) ? R(1) : R(0);
+        if (grp == 1) {   // velocity columns: dp/dv
+#pragma unroll
+            for (int rr = 0; rr < 3; rr++) if (rr == k) a[rr] += dt;
+        } else if (grp == 2) {   // attitude columns: dv/d(rpy), d(rpy rates)/d(rpy)
+            const R b0 = sel3(-sp * st * cs + cp * ss, cp * ct * cs, -cp * st * ss + sp * cs, k);
+            const R b1 = sel3(-sp * st * ss - cp * cs, cp * ct * ss, cp * st * cs + sp * ss, k);
+            const R b2 = sel3(-sp * ct, -cp * st, R(0), k);
+            a[3] += dt * (fm * b0); a[4] += dt * (fm * b1); a[5] += dt * (fm * b2);
+            a[6] += dt * sel3(tt * cqsr, sqcr * ict * ict, R(0), k);
+            a[7] += dt * sel3(-sqcr, R(0), R(0), k);
+            a[8] += dt * sel3(cqsr * ict, sqcr * st * ict * ict, R(0), k);
+        } else if (grp == 3) {   // body-rate columns: d(rpy rates)/d(omega), d(omega dot)/d(omega)
+            a[6] += dt * sel3(R(1), sp * tt, cp * tt, k);
+            a[7] += dt * sel3(R(0), cp, -sp, k);
+            a[8] += dt * sel3(R(0), sp * ict, cp * ict, k);
+            a[9] += dt * sel3(R(0), -(Jz - Jy) * r / Jx, -(Jz - Jy) * q / Jx, k);
+            a[10] += dt * sel3(-(Jx - Jz) * r / Jy, R(0), -(Jx - Jz) * p / Jy, k);
+            a[11] += dt * sel3(-(Jy - Jx) * q / Jz, -(Jy - Jx) * p / Jz, R(0), k);
+        } else if (j == 12) {    // thrust column
+            a[3] = dt * ((cp * st * cs + sp * ss) / m); a[4] = dt * ((cp * st * ss - sp * cs) / m); a[5] = dt * ((cp * ct) / m);
+        } else if (j > 12) {     // torque columns
+            a[9] = j == 13 ? dt * (R(1) / Jx) : R(0); a[10] = j == 14 ? dt * (R(1) / Jy) : R(0); a[11] = j == 15 ? dt * (R(1) / Jz) : R(0);
+        }
+    }
+};
+
+// Per-warp shared scratch (elements of R).
+template <int MODEL> struct Smem {
+    using D = Dim<MODEL>;
+    enum {
+        V0 = 0,                                  // value-function Hessian, two buffers used alternately
+        V1 = D::NX * D::NX,
+        S = 2 * D::NX * D::NX,                   // unsymmetrised Schur complement
+        VX = 3 * D::NX * D::NX,                  // V_x
+        AC = VX + D::NX,                         // published columns of [A | B]: AC[j * NX + k]
+        LM = AC + D::NZ * D::NX,                 // multipliers of the nu pivots: LM[p * (NZ + 1) + lane]
+        XU = LM + D::NU * (D::NZ + 1),           // current knot's [x; u] (and the rollout's staging)
+        TOTAL = ((XU + D::NZ + 3) / 4) * 4
+    };
+};
+
+template <int MODEL, class R> struct Ws {
+    using D = Dim<MODEL>;
+    long long xb, xn, ub, un, K, kf, total;
+    __host__ __device__ explicit Ws(int N) {
+        long long o = 0;
+        xb = o; o += (long long)(N + 1) * D::NX;
+        xn = o; o += (long long)(N + 1) * D::NX;
+        ub = o; o += (long long)N * D::NU;
+        un = o; o += (long long)N * D::NU;
+        K = o; o += (long long)N * D::NU * D::NX;
+        kf = o; o += (long long)N * D::NU;
+        total = (o + 3) & ~3LL;
+    }
+};
+
+// Closed-loop rollout from x0 with controls ub + alpha k + K (x - xb) (K == nullptr: open loop with the controls in `un`).
+template <int MODEL, class R>
+__device__ __noinline__ R rollout(const Args<R> &A, int b, int lane, R *sm, const R *xb, const R *ub, const R *K, const R *kf, R alpha,
+                                  R *xn, R *un) {
+    using D = Dim<MODEL>;
+    constexpr int NX = D::NX, NU = D::NU;
+    R x[NX], xg[NX];
+#pragma unroll
+    for (int a = 0; a < NX; a++) { x[a] = (R)A.x0[(long long)b * NX + a]; xg[a] = (R)A.xg[(long long)b * NX + a]; }
+    if (lane < NX) xn[lane] = x[lane];
+    R J = R(0);
+    R *st = sm + Smem<MODEL>::XU;
+    for (int i = 0; i < A.N; i++) {
+        R u[NU];
+        if (K) {
+            // lanes 0..NU-1 each form one control; the old state comes through shared memory
+            if (lane < NX) st[lane] = xb[(long long)i * NX + lane];
+            __syncwarp();
+            R v = R(0);
+            if (lane < NU) {
+                v = ub[(long long)i * NU + lane] + alpha * kf[(long long)i * NU + lane];
+                const R *Kr = K + ((long long)i * NU + lane) * NX;
+#pragma unroll
+                for (int a = 0; a < NX; a++) v += Kr[a] * (x[a] - st[a]);
+            }
+#pragma unroll
+            for (int m = 0; m < NU; m++) u[m] = __shfl_sync(0xffffffffu, v, m);
+            __syncwarp();
+        } else {
+#pragma unroll
+            for (int m = 0; m < NU; m++) u[m] = un[(long long)i * NU + m];
+        }
+        if (lane < NU) {
+            R um = u[0];
+#pragma unroll
+            for (int m = 1; m < NU; m++) if (lane == m) um = u[m];
+            un[(long long)i * NU + lane] = um;
+        }
+        R c = R(0);
+#pragma unroll
+        for (int a = 0; a < NX; a++) { const R d = x[a] - xg[a]; c += A.q[a] * d * d; }
+#pragma unroll
+        for (int m = 0; m < NU; m++) { const R d = u[m] - A.uh[m]; c += A.r[m] * d * d; }
+        J += R(0.5) * A.dt * c;
+        R fx[NX];
+        Model<MODEL, R>::f(x, u, fx);
+#pragma unroll
+        for (int a = 0; a < NX; a++) x[a] = x[a] + A.dt * fx[a];
+        if (lane < NX) {
+            R xv = x[0];
+#pragma unroll
+            for (int a = 1; a < NX; a++) if (lane == a) xv = x[a];
+            xn[(long long)(i + 1) * NX + lane] = xv;
+        }
+    }
+    R c = R(0);
+#pragma unroll
+    for (int a = 0; a < NX; a++) { const R d = x[a] - xg[a]; c += A.qf[a] * d * d; }
+    return J + R(0.5) * c;
+}
+
+// Backward sweep with the regularised Quu.  Returns false when a pivot is not positive; *dV1 = sum_i k_i' Qu_i.
+template <int MODEL, class R>
+__device__ __noinline__ bool sweep(const Args<R> &A, int b, int lane, R *sm, const R *xb, const R *ub, R rho, R *K, R *kf, R *dV1,
+                                   long long *knots) {
+    using D = Dim<MODEL>;
+    using SM = Smem<MODEL>;
+    constexpr int NX = D::NX, NU = D::NU, NZ = D::NZ;
+    const int N = A.N;
+    R xg[NX];
+#pragma unroll
+    for (int a = 0; a < NX; a++) xg[a] = (R)A.xg[(long long)b * NX + a];
+    // terminal value function
+    for (int e = lane; e < NX * NX; e += 32) sm[SM::V0 + e] = (e / NX == e % NX) ? A.qf[e % NX] : R(0);
+    if (lane < NX) {
+        R qfl = A.qf[0], xgl = xg[0];
+#pragma unroll
+        for (int a = 1; a < NX; a++) if (lane == a) { qfl = A.qf[a]; xgl = xg[a]; }
+        sm[SM::VX + lane] = qfl * (xb[(long long)N * NX + lane] - xgl);
+    }
+    // this lane's cost weights: Hessian diagonal entry of its own column
+    R wdiag = R(0);
+#pragma unroll
+    for (int a = 0; a < NX; a++) if (lane == a) wdiag = A.dt * A.q[a];
+#pragma unroll
+    for (int m = 0; m < NU; m++) if (lane == NX + m) wdiag = A.dt * A.r[m] + rho;
+    R dv = R(0);
+    int vb = 0;   // which V buffer holds the current value function
+    bool ok = true;
+    R nxt = R(0);
+    if (lane < NX) nxt = xb[(long long)(N - 1) * NX + lane];
+    else if (lane < NZ) nxt = ub[(long long)(N - 1) * NU + lane - NX];
+    __syncwarp();
+    for (int i = N - 1; i >= 0; i--) {
+        (*knots)++;
+        // ---- the knot's point, uniform in every lane; the next knot's is fetched meanwhile -------------------------
+        if (lane < NZ) sm[SM::XU + lane] = nxt;
+        if (i > 0) {
+            if (lane < NX) nxt = xb[(long long)(i - 1) * NX + lane];
+            else if (lane < NZ) nxt = ub[(long long)(i - 1) * NU + lane - NX];
+        }
+        __syncwarp();
+        R x[NX], u[NU];
+#pragma unroll
+        for (int a = 0; a < NX; a++) x[a] = sm[SM::XU + a];
+#pragma unroll
+        for (int m = 0; m < NU; m++) u[m] = sm[SM::XU + NX + m];
+        // ---- column of [A | B], w = Vxx a (gradient lane: w = Vx) ------------------------------------------------------
+        R a[NX], w[NX];
+        const R *V = sm + (vb ? SM::V1 : SM::V0);
+        if (lane < NZ) {
+            Model<MODEL, R>::column(x, u, A.dt, lane, a);
+#pragma unroll
+            for (int r = 0; r < NX; r++) {
+                R acc = R(0);
+#pragma unroll
+                for (int k = 0; k < NX; k++) acc += V[r * NX + k] * a[k];
+                w[r] = acc;
+            }
+#pragma unroll
+            for (int k = 0; k < NX; k++) sm[SM::AC + lane * NX + k] = a[k];
+        } else {
+#pragma unroll
+            for (int r = 0; r < NX; r++) w[r] = sm[SM::VX + r];
+        }
+        __syncwarp();
+        // ---- Q[r][lane] = a_r . w  (+ cost terms) ------------------------------------------------------------------------
+        R qc[NZ];
+#pragma unroll
+        for (int r = 0; r < NZ; r++) {
+            R acc = R(0);
+#pragma unroll
+            for (int k = 0; k < NX; k++) acc += sm[SM::AC + r * NX + k] * w[k];
+            qc[r] = acc;
+        }
+        if (lane < NZ) {
+#pragma unroll
+            for (int r = 0; r < NZ; r++) if (lane == r) qc[r] += wdiag;
+        } else if (lane == NZ) {
+#pragma unroll
+            for (int r = 0; r < NX; r++) qc[r] += A.dt * A.q[r] * (x[r] - xg[r]);
+#pragma unroll
+            for (int m = 0; m < NU; m++) qc[NX + m] += A.dt * A.r[m] * (u[m] - A.uh[m]);
+        }
+        // ---- eliminate the nu control rows --------------------------------------------------------------------------------
+        R mp[NU];
+#pragma unroll
+        for (int p = 0; p < NU; p++) {
+            const R d = __shfl_sync(0xffffffffu, qc[NX + p], NX + p);
+            if (!(d > R(0))) { ok = false; break; }
+            const R ri = g_rsqrt(d);
+            const R m = (lane == NX + p) ? d * ri : qc[NX + p] * ri;
+            mp[p] = m;
+            if (lane <= NZ) sm[SM::LM + p * (NZ + 1) + lane] = m;
+            __syncwarp();
+            const R *Lm = sm + SM::LM + p * (NZ + 1);
+#pragma unroll
+            for (int r = 0; r < NZ; r++) qc[r] -= Lm[r] * m;
+            if (lane == NZ) dv -= m * m;
+        }
+        if (!ok) break;
+        // ---- gains: L' z = y with y = this lane's multipliers; [k | K] = -z ------------------------------------------------
+        if (lane < NX || lane == NZ) {
+            R z[NU];
+#pragma unroll
+            for (int p = NU - 1; p >= 0; p--) {
+                R s = mp[p];
+#pragma unroll
+                for (int t = p + 1; t < NU; t++) s -= sm[SM::LM + p * (NZ + 1) + NX + t] * z[t];
+                z[p] = s / sm[SM::LM + p * (NZ + 1) + NX + p];
+            }
+            if (lane < NX) {
+#pragma unroll
+                for (int m = 0; m < NU; m++) K[((long long)i * NU + m) * NX + lane] = -z[m];
+            } else {
+#pragma unroll
+                for (int m = 0; m < NU; m++) kf[(long long)i * NU + m] = -z[m];
+            }
+        }
+        // ---- the trailing block is the new value function: Vx (gradient lane), Vxx = sym(.) --------------------------------
+        if (lane < NX) {
+#pragma unroll
+            for (int r = 0; r < NX; r++) sm[SM::S + r * NX + lane] = qc[r];
+        } else if (lane == NZ) {
+#pragma unroll
+            for (int r = 0; r < NX; r++) sm[SM::VX + r] = qc[r];
+        }
+        __syncwarp();
+        if (lane < NX) {
+            R *Vn = sm + (vb ? SM::V0 : SM::V1);
+#pragma unroll
+            for (int r = 0; r < NX; r++) Vn[lane * NX + r] = R(0.5) * (qc[r] + sm[SM::S + lane * NX + r]);
+        }
+        vb ^= 1;
+        __syncwarp();
+    }
+    *dV1 = __shfl_sync(0xffffffffu, dv, NZ);
+    return ok;
+}
+
+template <int MODEL, class R> __global__ void __launch_bounds__(128) gddp_kernel(Args<R> A) {
+    using D = Dim<MODEL>;
+    constexpr int NX = D::NX, NU = D::NU;
+    extern __shared__ __align__(16) unsigned char gsm_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    R *sm = reinterpret_cast<R *>(gsm_raw) + warp * Smem<MODEL>::TOTAL;
+    const Ws<MODEL, R> wl(A.N);
+    R *ws = A.ws + ((long long)blockIdx.x * wpb + warp) * A.ws_stride;
+    const int N = A.N;
+    while (true) {
+        unsigned int b = 0;
+        if (lane == 0) b = atomicAdd(A.counter, 1u);
+        b = __shfl_sync(0xffffffffu, b, 0);
+        if (b >= (unsigned int)A.B) break;
+        const long long clk0 = clock64();
+        R *xb = ws + wl.xb, *xn = ws + wl.xn, *ub = ws + wl.ub, *un = ws + wl.un, *K = ws + wl.K, *kf = ws + wl.kf;
+        for (int e = lane; e < N * NU; e += 32) un[e] = A.u_init ? (R)A.u_init[(long long)b * N * NU + e] : A.uh[e % NU];
+        __syncwarp();
+        R J = rollout<MODEL, R>(A, (int)b, lane, sm, nullptr, nullptr, nullptr, nullptr, R(0), xb, un);
+        { R *t = ub; ub = un; un = t; }
+        __syncwarp();
+        R rho = R(0);
+        int rtn = 0, iter = 0;
+        long long sweeps = 0, rollouts = 1, knots = 0;
+        for (iter = 0; iter < A.iter_max; iter++) {
+            bool ok = false;
+            R dV1 = R(0);
+            while (true) {
+                sweeps++;
+                ok = sweep<MODEL, R>(A, (int)b, lane, sm, xb, ub, rho, K, kf, &dV1, &knots);
+                __syncwarp();
+                if (ok) break;
+                rho = rho * R(4) > R(1e-6) ? rho * R(4) : R(1e-6);
+                if (rho > R(1e10)) break;
+            }
+            if (!ok) { rtn = -4; break; }
+            if (-dV1 <= A.tol * (R(1) + g_abs(J))) { rtn = 1; break; }
+            bool accepted = false;
+            R Jn = R(0), alpha = R(1);
+            for (int s = 0; s < 11; s++, alpha *= R(0.5)) {
+                rollouts++;
+                Jn = rollout<MODEL, R>(A, (int)b, lane, sm, xb, ub, K, kf, alpha, xn, un);
+                __syncwarp();
+                if (Jn < J) { accepted = true; break; }
+            }
+            if (!accepted) {
+                rho = rho * R(4) > R(1e-6) ? rho * R(4) : R(1e-6);
+                if (rho > R(1e10)) { rtn = -4; break; }
+                continue;
+            }
+            const R dJ = J - Jn;
+            J = Jn;
+            { R *t = xb; xb = xn; xn = t; t = ub; ub = un; un = t; }
+            rho = rho / R(4);
+            if (rho < R(1e-9)) rho = R(0);
+            if (dJ <= A.tol * (R(1) + g_abs(J))) { rtn = 1; iter++; break; }
+        }
+        if (lane == 0) {
+            A.rtn[b] = rtn; A.iters[b] = iter; A.cost[b] = (double)J;
+            if (A.stats) {
+                long long *S = A.stats + (long long)b * 4;
+                S[0] = sweeps; S[1] = rollouts; S[2] = knots; S[3] = clock64() - clk0;
+            }
+        }
+        for (int e = lane; e < (N + 1) * NX; e += 32) A.x[(long long)b * (N + 1) * NX + e] = (double)xb[e];
+        for (int e = lane; e < N * NU; e += 32) A.u[(long long)b * N * NU + e] = (double)ub[e];
+        __syncwarp();
+    }
+}
+
+}  // namespace gddp
+#endif
