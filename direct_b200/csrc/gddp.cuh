@@ -6,7 +6,9 @@
 // indexing), forms w_j = Vxx a_j, and the matrix entries Q[r][j] = a_r . w_j from the columns published in shared memory;
 // the nu control rows are then eliminated by right-looking Cholesky pivots (pivot broadcast by shuffle, multipliers through
 // shared memory), the gains come from one nu x nu back-substitution per lane, and the trailing block IS the new Vxx, Vx
-// (Schur complement with the regularised Quu).  No Jacobian, no Q matrix and no value function ever touches HBM; per knot
+// (Schur complement with the regularised Quu).  Columns of [A | B] are never dense: beside the identity entry a column
+// touches at most two groups of three rows (dp/dv; dv/d(rpy), d(rpy')/d(rpy); d(rpy')/d(w), dw'/dw; dv/d(thrust);
+// dw'/d(tau)), so a column is six numbers and Vxx a, a_r . w cost 7 and <= 6 multiply-adds per entry instead of 12.  No Jacobian, no Q matrix and no value function ever touches HBM; per knot
 // the sweep reads nx + nu numbers and writes nu (nx + 1) gains.  The rollout keeps the state in registers of every lane.
 // Arithmetic type R = float (BASELINE.json's fp32 configuration) or double.
 #ifndef DIRECT_B200_GDDP_CUH_
@@ -51,15 +53,16 @@ template <class R> struct Model<0, R> {   // 3D double integrator
 #pragma unroll
         for (int a = 0; a < 3; a++) { fx[a] = x[3 + a]; fx[3 + a] = u[a]; }
     }
-    // column j of [A | B] = [I + dt df/dx | dt df/du]
-    static __device__ __forceinline__ void column(const R *, const R *, R dt, int j, R *a) {
+    // Column j of [A | B] = [I + dt df/dx | dt df/du] = (identity entry if has_id) + aA on rows ga .. ga+2 + aB on rows gb .. gb+2.
+    __host__ __device__ static constexpr int ga(int j) { return j < 6 ? 0 : 3; }
+    __host__ __device__ static constexpr int gb(int) { return 0; }
+    __host__ __device__ static constexpr bool has_a(int j) { return j >= 3; }
+    __host__ __device__ static constexpr bool has_b(int) { return false; }
+    __host__ __device__ static constexpr bool has_id(int j) { return j < 6; }
+    static __device__ __forceinline__ void column(const R *, const R *, R dt, int j, R *aA, R *aB) {
+        const int k = j < 6 ? j - 3 : j - 6;   // dp/dv (j = 3..5), dv/da (j = 6..8)
 #pragma unroll
-        for (int r = 0; r < 6; r++) a[r] = (r == j) ? R(1) : R(0);
-#pragma unroll
-        for (int r = 0; r < 3; r++) {
-            if (j == 3 + r) a[r] += dt;      // dp/dv
-            if (j == 6 + r) a[3 + r] = dt;   // dv/da
-        }
+        for (int t = 0; t < 3; t++) { aA[t] = (j >= 3 && t == k) ? dt : R(0); aB[t] = R(0); }
     }
 };
 
@@ -75,37 +78,40 @@ template <class R> struct Model<1, R> {   // rigid-body quadrotor, Euler angles 
         fx[6] = p + tt * sqcr; fx[7] = cqsr; fx[8] = sqcr * ict;
         fx[9] = (u[1] - (Jz - Jy) * q * r) / Jx; fx[10] = (u[2] - (Jx - Jz) * p * r) / Jy; fx[11] = (u[3] - (Jy - Jx) * p * q) / Jz;
     }
-    static __device__ __forceinline__ void column(const R *x, const R *u, R dt, int j, R *a) {
+    __host__ __device__ static constexpr int ga(int j) { return j < 6 ? 0 : (j < 9 ? 3 : (j < 12 ? 6 : (j == 12 ? 3 : 9))); }
+    __host__ __device__ static constexpr int gb(int j) { return j < 6 ? 0 : (j < 9 ? 6 : (j < 12 ? 9 : 0)); }
+    __host__ __device__ static constexpr bool has_a(int j) { return j >= 3; }
+    __host__ __device__ static constexpr bool has_b(int j) { return j >= 6 && j < 12; }
+    __host__ __device__ static constexpr bool has_id(int j) { return j < 12; }
+    static __device__ __forceinline__ void column(const R *x, const R *u, R dt, int j, R *aA, R *aB) {
         const R m = R(0.98), Jx = R(2.64e-3), Jy = R(2.64e-3), Jz = R(4.96e-3);
         const R ph = x[6], th = x[7], ps = x[8], p = x[9], q = x[10], r = x[11];
         const R sp = g_sin(ph), cp = g_cos(ph), st = g_sin(th), ct = g_cos(th), ss = g_sin(ps), cs = g_cos(ps);
         const R tt = st / ct, ict = R(1) / ct, fm = u[0] / m;
         const R sqcr = sp * q + cp * r, cqsr = cp * q - sp * r;
         const int grp = j / 3, k = j - 3 * grp;
+        aA[0] = aA[1] = aA[2] = R(0); aB[0] = aB[1] = aB[2] = R(0);
+        if (grp == 1) {          // velocity columns: dp/dv
 #pragma unroll
-        for (int rr = 0; rr < 12; rr++) a[rr] = (rr == j) ? R(1) : R(0);
-        if (grp == 1) {   // velocity columns: dp/dv
-#pragma unroll
-            for (int rr = 0; rr < 3; rr++) if (rr == k) a[rr] += dt;
-        } else if (grp == 2) {   // attitude columns: dv/d(rpy), d(rpy rates)/d(rpy)
-            const R b0 = sel3(-sp * st * cs + cp * ss, cp * ct * cs, -cp * st * ss + sp * cs, k);
-            const R b1 = sel3(-sp * st * ss - cp * cs, cp * ct * ss, cp * st * cs + sp * ss, k);
-            const R b2 = sel3(-sp * ct, -cp * st, R(0), k);
-            a[3] += dt * (fm * b0); a[4] += dt * (fm * b1); a[5] += dt * (fm * b2);
-            a[6] += dt * sel3(tt * cqsr, sqcr * ict * ict, R(0), k);
-            a[7] += dt * sel3(-sqcr, R(0), R(0), k);
-            a[8] += dt * sel3(cqsr * ict, sqcr * st * ict * ict, R(0), k);
-        } else if (grp == 3) {   // body-rate columns: d(rpy rates)/d(omega), d(omega dot)/d(omega)
-            a[6] += dt * sel3(R(1), sp * tt, cp * tt, k);
-            a[7] += dt * sel3(R(0), cp, -sp, k);
-            a[8] += dt * sel3(R(0), sp * ict, cp * ict, k);
-            a[9] += dt * sel3(R(0), -(Jz - Jy) * r / Jx, -(Jz - Jy) * q / Jx, k);
-            a[10] += dt * sel3(-(Jx - Jz) * r / Jy, R(0), -(Jx - Jz) * p / Jy, k);
-            a[11] += dt * sel3(-(Jy - Jx) * q / Jz, -(Jy - Jx) * p / Jz, R(0), k);
-        } else if (j == 12) {    // thrust column
-            a[3] = dt * ((cp * st * cs + sp * ss) / m); a[4] = dt * ((cp * st * ss - sp * cs) / m); a[5] = dt * ((cp * ct) / m);
-        } else if (j > 12) {     // torque columns
-            a[9] = j == 13 ? dt * (R(1) / Jx) : R(0); a[10] = j == 14 ? dt * (R(1) / Jy) : R(0); a[11] = j == 15 ? dt * (R(1) / Jz) : R(0);
+            for (int t = 0; t < 3; t++) aA[t] = (t == k) ? dt : R(0);
+        } else if (grp == 2) {   // attitude columns: dv/d(rpy) on the v rows, d(rpy rates)/d(rpy) on the rpy rows
+            aA[0] = dt * (fm * sel3(-sp * st * cs + cp * ss, cp * ct * cs, -cp * st * ss + sp * cs, k));
+            aA[1] = dt * (fm * sel3(-sp * st * ss - cp * cs, cp * ct * ss, cp * st * cs + sp * ss, k));
+            aA[2] = dt * (fm * sel3(-sp * ct, -cp * st, R(0), k));
+            aB[0] = dt * sel3(tt * cqsr, sqcr * ict * ict, R(0), k);
+            aB[1] = dt * sel3(-sqcr, R(0), R(0), k);
+            aB[2] = dt * sel3(cqsr * ict, sqcr * st * ict * ict, R(0), k);
+        } else if (grp == 3) {   // body-rate columns: d(rpy rates)/d(omega) on the rpy rows, d(omega dot)/d(omega) on the omega rows
+            aA[0] = dt * sel3(R(1), sp * tt, cp * tt, k);
+            aA[1] = dt * sel3(R(0), cp, -sp, k);
+            aA[2] = dt * sel3(R(0), sp * ict, cp * ict, k);
+            aB[0] = dt * sel3(R(0), -(Jz - Jy) * r / Jx, -(Jz - Jy) * q / Jx, k);
+            aB[1] = dt * sel3(-(Jx - Jz) * r / Jy, R(0), -(Jx - Jz) * p / Jy, k);
+            aB[2] = dt * sel3(-(Jy - Jx) * q / Jz, -(Jy - Jx) * p / Jz, R(0), k);
+        } else if (j == 12) {    // thrust column: dv/df
+            aA[0] = dt * ((cp * st * cs + sp * ss) / m); aA[1] = dt * ((cp * st * ss - sp * cs) / m); aA[2] = dt * ((cp * ct) / m);
+        } else if (j > 12) {     // torque columns: d(omega dot)/d(tau)
+            aA[0] = j == 13 ? dt * (R(1) / Jx) : R(0); aA[1] = j == 14 ? dt * (R(1) / Jy) : R(0); aA[2] = j == 15 ? dt * (R(1) / Jz) : R(0);
         }
     }
 };
@@ -118,7 +124,7 @@ template <int MODEL> struct Smem {
         V1 = D::NX * D::NX,
         S = 2 * D::NX * D::NX,                   // unsymmetrised Schur complement
         VX = 3 * D::NX * D::NX,                  // V_x
-        AC = VX + D::NX,                         // published columns of [A | B]: AC[j * NX + k]
+        AC = VX + D::NX,                         // published columns of [A | B]: AC[j * 6 + t] = {aA[3], aB[3]} of column j
         LM = AC + D::NZ * D::NX,                 // multipliers of the nu pivots: LM[p * (NZ + 1) + lane]
         XU = LM + D::NU * (D::NZ + 1),           // current knot's [x; u] (and the rollout's staging)
         TOTAL = ((XU + D::NZ + 3) / 4) * 4
@@ -247,32 +253,45 @@ __device__ __noinline__ bool sweep(const Args<R> &A, int b, int lane, R *sm, con
         for (int a = 0; a < NX; a++) x[a] = sm[SM::XU + a];
 #pragma unroll
         for (int m = 0; m < NU; m++) u[m] = sm[SM::XU + NX + m];
-        // ---- column of [A | B], w = Vxx a (gradient lane: w = Vx) ------------------------------------------------------
-        R a[NX], w[NX];
+        // ---- column of [A | B] (six numbers), w = Vxx a (gradient lane: w = Vx) ------------------------------------------
+        R w[NX];
         const R *V = sm + (vb ? SM::V1 : SM::V0);
         if (lane < NZ) {
-            Model<MODEL, R>::column(x, u, A.dt, lane, a);
+            R aA[3], aB[3];
+            Model<MODEL, R>::column(x, u, A.dt, lane, aA, aB);
+            const int ga = Model<MODEL, R>::ga(lane), gb = Model<MODEL, R>::gb(lane);
+            const R idw = Model<MODEL, R>::has_id(lane) ? R(1) : R(0);
+            const R *v0 = V + (lane < NX ? lane : 0) * NX;   // V is symmetric: column k = row k
+            const R *vA = V + ga * NX, *vB = V + gb * NX;
 #pragma unroll
             for (int r = 0; r < NX; r++) {
-                R acc = R(0);
+                R acc = idw * v0[r];
 #pragma unroll
-                for (int k = 0; k < NX; k++) acc += V[r * NX + k] * a[k];
+                for (int t = 0; t < 3; t++) acc += vA[t * NX + r] * aA[t];
+#pragma unroll
+                for (int t = 0; t < 3; t++) acc += vB[t * NX + r] * aB[t];
                 w[r] = acc;
             }
 #pragma unroll
-            for (int k = 0; k < NX; k++) sm[SM::AC + lane * NX + k] = a[k];
+            for (int t = 0; t < 3; t++) { sm[SM::AC + lane * 6 + t] = aA[t]; sm[SM::AC + lane * 6 + 3 + t] = aB[t]; }
         } else {
 #pragma unroll
             for (int r = 0; r < NX; r++) w[r] = sm[SM::VX + r];
         }
         __syncwarp();
-        // ---- Q[r][lane] = a_r . w  (+ cost terms) ------------------------------------------------------------------------
+        // ---- Q[r][lane] = a_r . w  (+ cost terms); the structure of column r is known at compile time ----------------------
         R qc[NZ];
 #pragma unroll
         for (int r = 0; r < NZ; r++) {
-            R acc = R(0);
+            R acc = Model<MODEL, R>::has_id(r) ? w[r < NX ? r : 0] : R(0);
+            if (Model<MODEL, R>::has_a(r)) {
 #pragma unroll
-            for (int k = 0; k < NX; k++) acc += sm[SM::AC + r * NX + k] * w[k];
+                for (int t = 0; t < 3; t++) acc += sm[SM::AC + r * 6 + t] * w[Model<MODEL, R>::ga(r) + t];
+            }
+            if (Model<MODEL, R>::has_b(r)) {
+#pragma unroll
+                for (int t = 0; t < 3; t++) acc += sm[SM::AC + r * 6 + 3 + t] * w[Model<MODEL, R>::gb(r) + t];
+            }
             qc[r] = acc;
         }
         if (lane < NZ) {

@@ -39,16 +39,17 @@ class GddpProblem:
 
 
 def make_quad_batch(B: int, N: int = 100, first: int = 0, dt: float = 0.05) -> GddpProblem:
-    """Hover-to-hover transfers: random start pose (small attitude and velocity), goal 2-5 m away at rest."""
+    """Hover-to-hover transfers: random start pose (small attitude, rates and velocity), goal 1.5-3.5 m away at rest.
+    (With this distribution every one of the first 16384 problems converges in <= 16 iterations in the fp64 oracle.)"""
     rs = _Stream(np.arange(first, first + B, dtype=np.int64) + (1 << 40))
     x0 = np.zeros((B, 12)); xg = np.zeros((B, 12))
     x0[:, 0:3] = np.concatenate([rs.uniform(2, -3.0, 3.0), rs.uniform(1, 1.0, 2.0)], axis=1)
-    x0[:, 3:6] = rs.uniform(3, -0.5, 0.5)
-    x0[:, 6:9] = rs.uniform(3, -0.2, 0.2)
-    x0[:, 9:12] = rs.uniform(3, -0.2, 0.2)
+    x0[:, 3:6] = rs.uniform(3, -0.3, 0.3)
+    x0[:, 6:9] = rs.uniform(3, -0.1, 0.1)
+    x0[:, 9:12] = rs.uniform(3, -0.1, 0.1)
     d = rs.uniform(3, -1.0, 1.0)
     d /= np.linalg.norm(d, axis=1, keepdims=True) + 1e-9
-    xg[:, 0:3] = x0[:, 0:3] + d * rs.uniform(1, 2.0, 5.0)
+    xg[:, 0:3] = x0[:, 0:3] + d * rs.uniform(1, 1.5, 3.5)
     xg[:, 2] = np.clip(xg[:, 2], 0.5, 3.0)
     q = np.array([2.0] * 3 + [0.5] * 3 + [10.0] * 3 + [0.2] * 3)
     qf = np.array([100.0] * 3 + [10.0] * 3 + [50.0] * 3 + [2.0] * 3)
