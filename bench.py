@@ -151,6 +151,72 @@ def workload_config(args, per_gpu):
             "l2": "256 MiB buffer written between timed steps (L2 flush); the per-warp workspaces (1 GB) exceed L2 anyway"}
 
 
+def model_b_report(capi, torch, dev, local_rank, flush, steps, with_cpu):
+    """SURVEY.md section 8(d) config 2, model (B): BASELINE.json's literal 12-state / 4-input quadrotor, fp32, batch 4096 x
+    100 knots, unconstrained DDP (include/direct_gddp.h).  The reference has no such model: NO reference
+    parity, checker = oracle/gddp_oracle.c.  Reported next to the headline, never instead of it."""
+    import dataclasses
+    from direct_b200 import gddp
+    B, N = 4096, 100
+    gp = dataclasses.replace(gddp.make_quad_batch(B, N), tol=1e-5)
+    solver = capi.Solver(local_rank, "fp32")
+    t = {k: torch.from_numpy(getattr(gp, k)).to(dev) for k in ("x0", "xg")}
+    o = dict(rtn=torch.zeros(B, dtype=torch.int32, device=dev), iters=torch.zeros(B, dtype=torch.int32, device=dev),
+             cost=torch.zeros(B, dtype=torch.float64, device=dev), x=torch.zeros(B, N + 1, 12, dtype=torch.float64, device=dev),
+             u=torch.zeros(B, N, 4, dtype=torch.float64, device=dev), stats=torch.zeros(B, 4, dtype=torch.int64, device=dev))
+    pc = gddp.problem_struct(gp, t["x0"].data_ptr(), t["xg"].data_ptr(), 0)
+    oc = gddp.ResultC(*[o[n].data_ptr() for n, _ in gddp.ResultC._fields_])
+    stream = torch.cuda.current_stream().cuda_stream
+    for _ in range(3):
+        flush.fill_(1)
+        gddp.solve_device(solver, pc, oc, stream)
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for k in range(steps):
+        flush.fill_(k & 255)
+        ev[k][0].record()
+        gddp.solve_device(solver, pc, oc, stream)
+        ev[k][1].record()
+    torch.cuda.synchronize()
+    ms = sum(a.elapsed_time(b) for a, b in ev) / steps
+    stats = o["stats"].cpu().numpy()
+    rtn = o["rtn"].cpu().numpy()
+    knots = int(stats[:, 2].sum())
+    fl = gddp.bwd_flops_per_knot(12, 4)
+    peak = solver.fma_peak_tflops("fp32")
+    t0 = time.perf_counter()
+    e2e_n = 3
+    for _ in range(e2e_n):
+        flush.fill_(2)
+        hres = gddp.solve(solver, gp)      # host buffers: H2D + solve + D2H inside the call
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / e2e_n
+    st = solver.stats()
+    out = {"workload": f"unconstrained DDP, {B} x {N}-knot 12-state/4-input rigid-body quadrotor (explicit Euler, dt 0.05), hover-to-hover "
+                       "transfers of 1.5-3.5 m; model (B) of SURVEY.md 8(d): the reference has no such model, parity unpinned",
+           "dtype": "f32", "value": B / ms * 1e3, "unit": "solves/s", "ms_per_step": ms, "gpu_launches": steps,
+           "e2e": {"value": B / e2e_s, "unit": "solves/s", "h2d_bytes_per_step": int(st.h2d_bytes), "d2h_bytes_per_step": int(st.d2h_bytes),
+                   "ms_per_step": e2e_s * 1e3},
+           "roofline": {"bound": "fp32_fma", "achieved": fl * knots / (ms * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
+                        "frac": fl * knots / (ms * 1e-3) / 1e12 / peak if peak else None, "traffic": None,
+                        "flops_per_bwd_knot": fl, "bwd_knots_per_launch": knots},
+           "solve_stats": {"converged_frac": float((rtn == 1).mean()), "mean_iters": float(o["iters"].float().mean().item()),
+                           "bwd_sweeps_per_solve": float(stats[:, 0].mean()), "rollouts_per_solve": float(stats[:, 1].mean())}}
+    if with_cpu:
+        from oracle import gddp_py as G   # checker / CPU baseline only
+        cores = host_cores()
+        t0 = time.perf_counter()
+        a = G.solve_batch(gp, nthreads=cores)
+        cpu_s = time.perf_counter() - t0
+        okm = (a.rtn == 1) & (hres.rtn == 1)
+        rel = np.abs(hres.cost[okm] - a.cost[okm]) / np.abs(a.cost[okm])
+        out["cpu_baseline"] = {"value": B / cpu_s, "unit": "solves/s", "cores": cores, "kind": "port",
+                               "sample": f"all {B} problems, fp64 C oracle (oracle/gddp_oracle.c), {cores} OpenMP threads"}
+        out["parity_sample"] = {"n": int(okm.sum()), "tol": 1e-3, "frac_within_tol": float((rel <= 1e-3).mean())}
+    solver.close()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -164,6 +230,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=4096)
     ap.add_argument("--ref-sample", type=int, default=48)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-model-b", action="store_true", help="skip the secondary 12-state quadrotor (model (B)) report")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -359,6 +426,12 @@ def main():
                                 "sample": f"first {smp} trajectories of rank 0's batch, two-stage protocol, {cores} OpenMP threads, "
                                           "fp64 C restatement of ddp_optimizer.cpp (oracle/ipddp_oracle.c)"}
         line["parity_sample"] = {"n": int(smp), "tol": tol, "frac_within_tol": float(ok.mean())}
+    if rank == 0 and world == 1 and not args.no_model_b:
+        try:
+            line["model_b_quadrotor12_fp32"] = model_b_report(capi, torch, dev, local_rank, flush, max(3, min(args.steps, 10)),
+                                                              not args.no_cpu_baseline)
+        except Exception as e:   # the headline line must not depend on the secondary report
+            line["model_b_quadrotor12_fp32"] = {"error": repr(e)}
     if rank == 0:
         print(json.dumps(line))
     if world > 1:

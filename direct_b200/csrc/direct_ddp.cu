@@ -720,7 +720,7 @@ extern "C" int direct_gddp_solve_device(direct_ddp_handle h, const direct_gddp_p
     int st = gddp_validate(h, in, out);
     if (st) return st;
     CK(cudaSetDevice(h->opts.device));
-    return gddp_dispatch(h, in, out, stream ? (cudaStream_t)stream : h->stream);
+    return gddp_dispatch(h, in, out, (cudaStream_t)stream);   // NULL = the default stream, as in direct_ddp_solve_batch_device
 }
 
 extern "C" int direct_gddp_solve(direct_ddp_handle h, const direct_gddp_problem *in, direct_gddp_result *out) {
