@@ -33,13 +33,17 @@ template <int MODEL> struct Dim {
     static constexpr int NX = MODEL == 1 ? 12 : 6;
     static constexpr int NU = MODEL == 1 ? 4 : 3;
     static constexpr int NZ = NX + NU;
+    static constexpr int NT = MODEL == 1 ? 6 : 0;   // transcendentals of the point cached next to it: sin/cos of roll, pitch, yaw
+    static constexpr int XS = NX + NT;              // stride of a stored point [x; trig]
 };
 
 __device__ __forceinline__ float g_sin(float x) { return sinf(x); }
 __device__ __forceinline__ double g_sin(double x) { return sin(x); }
 __device__ __forceinline__ float g_cos(float x) { return cosf(x); }
 __device__ __forceinline__ double g_cos(double x) { return cos(x); }
-__device__ __forceinline__ float g_rsqrt(float x) { return 1.0f / sqrtf(x); }
+__device__ __forceinline__ float g_rsqrt(float x) { return rsqrtf(x); }
+__device__ __forceinline__ void g_sincos(float x, float *s, float *c) { sincosf(x, s, c); }
+__device__ __forceinline__ void g_sincos(double x, double *s, double *c) { sincos(x, s, c); }
 __device__ __forceinline__ double g_rsqrt(double x) { return 1.0 / sqrt(x); }
 __device__ __forceinline__ float g_abs(float x) { return fabsf(x); }
 __device__ __forceinline__ double g_abs(double x) { return fabs(x); }
@@ -49,7 +53,8 @@ template <class R> __device__ __forceinline__ R sel3(R a, R b, R c, int k) { ret
 template <int MODEL, class R> struct Model;
 
 template <class R> struct Model<0, R> {   // 3D double integrator
-    static __device__ __forceinline__ void f(const R *x, const R *u, R *fx) {
+    static __device__ __forceinline__ void trig(const R *, int, R *) {}
+    static __device__ __forceinline__ void f(const R *x, const R *u, const R *, R *fx) {
 #pragma unroll
         for (int a = 0; a < 3; a++) { fx[a] = x[3 + a]; fx[3 + a] = u[a]; }
     }
@@ -59,7 +64,7 @@ template <class R> struct Model<0, R> {   // 3D double integrator
     __host__ __device__ static constexpr bool has_a(int j) { return j >= 3; }
     __host__ __device__ static constexpr bool has_b(int) { return false; }
     __host__ __device__ static constexpr bool has_id(int j) { return j < 6; }
-    static __device__ __forceinline__ void column(const R *, const R *, R dt, int j, R *aA, R *aB) {
+    static __device__ __forceinline__ void column(const R *, const R *, const R *, R dt, int j, R *aA, R *aB) {
         const int k = j < 6 ? j - 3 : j - 6;   // dp/dv (j = 3..5), dv/da (j = 6..8)
 #pragma unroll
         for (int t = 0; t < 3; t++) { aA[t] = (j >= 3 && t == k) ? dt : R(0); aB[t] = R(0); }
@@ -67,10 +72,18 @@ template <class R> struct Model<0, R> {   // 3D double integrator
 };
 
 template <class R> struct Model<1, R> {   // rigid-body quadrotor, Euler angles (Quadrotor.cpp:15-20 constants)
-    static __device__ __forceinline__ void f(const R *x, const R *u, R *fx) {
+    // tg = {sin, cos} of roll, pitch, yaw: one sincos per angle in lanes 0..2, broadcast (every lane needs all six)
+    static __device__ __forceinline__ void trig(const R *x, int lane, R *tg) {
+        const R ang = lane == 0 ? x[6] : (lane == 1 ? x[7] : x[8]);
+        R s, c;
+        g_sincos(ang, &s, &c);
+#pragma unroll
+        for (int t = 0; t < 3; t++) { tg[2 * t] = __shfl_sync(0xffffffffu, s, t); tg[2 * t + 1] = __shfl_sync(0xffffffffu, c, t); }
+    }
+    static __device__ __forceinline__ void f(const R *x, const R *u, const R *tg, R *fx) {
         const R m = R(0.98), g = R(9.81), Jx = R(2.64e-3), Jy = R(2.64e-3), Jz = R(4.96e-3);
-        const R ph = x[6], th = x[7], ps = x[8], p = x[9], q = x[10], r = x[11];
-        const R sp = g_sin(ph), cp = g_cos(ph), st = g_sin(th), ct = g_cos(th), ss = g_sin(ps), cs = g_cos(ps);
+        const R p = x[9], q = x[10], r = x[11];
+        const R sp = tg[0], cp = tg[1], st = tg[2], ct = tg[3], ss = tg[4], cs = tg[5];
         const R tt = st / ct, ict = R(1) / ct, fm = u[0] / m;
         fx[0] = x[3]; fx[1] = x[4]; fx[2] = x[5];
         fx[3] = fm * (cp * st * cs + sp * ss); fx[4] = fm * (cp * st * ss - sp * cs); fx[5] = fm * (cp * ct) - g;
@@ -83,10 +96,10 @@ template <class R> struct Model<1, R> {   // rigid-body quadrotor, Euler angles 
     __host__ __device__ static constexpr bool has_a(int j) { return j >= 3; }
     __host__ __device__ static constexpr bool has_b(int j) { return j >= 6 && j < 12; }
     __host__ __device__ static constexpr bool has_id(int j) { return j < 12; }
-    static __device__ __forceinline__ void column(const R *x, const R *u, R dt, int j, R *aA, R *aB) {
+    static __device__ __forceinline__ void column(const R *x, const R *u, const R *tg, R dt, int j, R *aA, R *aB) {
         const R m = R(0.98), Jx = R(2.64e-3), Jy = R(2.64e-3), Jz = R(4.96e-3);
-        const R ph = x[6], th = x[7], ps = x[8], p = x[9], q = x[10], r = x[11];
-        const R sp = g_sin(ph), cp = g_cos(ph), st = g_sin(th), ct = g_cos(th), ss = g_sin(ps), cs = g_cos(ps);
+        const R p = x[9], q = x[10], r = x[11];
+        const R sp = tg[0], cp = tg[1], st = tg[2], ct = tg[3], ss = tg[4], cs = tg[5];
         const R tt = st / ct, ict = R(1) / ct, fm = u[0] / m;
         const R sqcr = sp * q + cp * r, cqsr = cp * q - sp * r;
         const int grp = j / 3, k = j - 3 * grp;
@@ -126,8 +139,8 @@ template <int MODEL> struct Smem {
         VX = 3 * D::NX * D::NX,                  // V_x
         AC = VX + D::NX,                         // published columns of [A | B]: AC[j * 6 + t] = {aA[3], aB[3]} of column j
         LM = AC + D::NZ * D::NX,                 // multipliers of the nu pivots: LM[p * (NZ + 1) + lane]
-        XU = LM + D::NU * (D::NZ + 1),           // current knot's [x; u] (and the rollout's staging)
-        TOTAL = ((XU + D::NZ + 3) / 4) * 4
+        XU = LM + D::NU * (D::NZ + 1),           // current knot's [x; trig; u] (and the rollout's staging)
+        TOTAL = ((XU + D::XS + D::NU + 3) / 4) * 4
     };
 };
 
@@ -136,8 +149,8 @@ template <int MODEL, class R> struct Ws {
     long long xb, xn, ub, un, K, kf, total;
     __host__ __device__ explicit Ws(int N) {
         long long o = 0;
-        xb = o; o += (long long)(N + 1) * D::NX;
-        xn = o; o += (long long)(N + 1) * D::NX;
+        xb = o; o += (long long)(N + 1) * D::XS;
+        xn = o; o += (long long)(N + 1) * D::XS;
         ub = o; o += (long long)N * D::NU;
         un = o; o += (long long)N * D::NU;
         K = o; o += (long long)N * D::NU * D::NX;
@@ -151,8 +164,8 @@ template <int MODEL, class R>
 __device__ __noinline__ R rollout(const Args<R> &A, int b, int lane, R *sm, const R *xb, const R *ub, const R *K, const R *kf, R alpha,
                                   R *xn, R *un) {
     using D = Dim<MODEL>;
-    constexpr int NX = D::NX, NU = D::NU;
-    R x[NX], xg[NX];
+    constexpr int NX = D::NX, NU = D::NU, NT = D::NT, XS = D::XS;
+    R x[NX], xg[NX], tg[NT > 0 ? NT : 1];
 #pragma unroll
     for (int a = 0; a < NX; a++) { x[a] = (R)A.x0[(long long)b * NX + a]; xg[a] = (R)A.xg[(long long)b * NX + a]; }
     if (lane < NX) xn[lane] = x[lane];
@@ -162,7 +175,7 @@ __device__ __noinline__ R rollout(const Args<R> &A, int b, int lane, R *sm, cons
         R u[NU];
         if (K) {
             // lanes 0..NU-1 each form one control; the old state comes through shared memory
-            if (lane < NX) st[lane] = xb[(long long)i * NX + lane];
+            if (lane < NX) st[lane] = xb[(long long)i * XS + lane];
             __syncwarp();
             R v = R(0);
             if (lane < NU) {
@@ -191,14 +204,21 @@ __device__ __noinline__ R rollout(const Args<R> &A, int b, int lane, R *sm, cons
         for (int m = 0; m < NU; m++) { const R d = u[m] - A.uh[m]; c += A.r[m] * d * d; }
         J += R(0.5) * A.dt * c;
         R fx[NX];
-        Model<MODEL, R>::f(x, u, fx);
+        Model<MODEL, R>::trig(x, lane, tg);
+        if (NT > 0 && lane < NT) {   // the sweep linearises at this point: keep its sin/cos next to it
+            R tv = tg[0];
+#pragma unroll
+            for (int a = 1; a < NT; a++) if (lane == a) tv = tg[a];
+            xn[(long long)i * XS + NX + lane] = tv;
+        }
+        Model<MODEL, R>::f(x, u, tg, fx);
 #pragma unroll
         for (int a = 0; a < NX; a++) x[a] = x[a] + A.dt * fx[a];
         if (lane < NX) {
             R xv = x[0];
 #pragma unroll
             for (int a = 1; a < NX; a++) if (lane == a) xv = x[a];
-            xn[(long long)(i + 1) * NX + lane] = xv;
+            xn[(long long)(i + 1) * XS + lane] = xv;
         }
     }
     R c = R(0);
@@ -213,7 +233,7 @@ __device__ __noinline__ bool sweep(const Args<R> &A, int b, int lane, R *sm, con
                                    long long *knots) {
     using D = Dim<MODEL>;
     using SM = Smem<MODEL>;
-    constexpr int NX = D::NX, NU = D::NU, NZ = D::NZ;
+    constexpr int NX = D::NX, NU = D::NU, NZ = D::NZ, NT = D::NT, XS = D::XS;
     const int N = A.N;
     R xg[NX];
 #pragma unroll
@@ -224,7 +244,7 @@ __device__ __noinline__ bool sweep(const Args<R> &A, int b, int lane, R *sm, con
         R qfl = A.qf[0], xgl = xg[0];
 #pragma unroll
         for (int a = 1; a < NX; a++) if (lane == a) { qfl = A.qf[a]; xgl = xg[a]; }
-        sm[SM::VX + lane] = qfl * (xb[(long long)N * NX + lane] - xgl);
+        sm[SM::VX + lane] = qfl * (xb[(long long)N * XS + lane] - xgl);
     }
     // this lane's cost weights: Hessian diagonal entry of its own column
     R wdiag = R(0);
@@ -236,29 +256,31 @@ __device__ __noinline__ bool sweep(const Args<R> &A, int b, int lane, R *sm, con
     int vb = 0;   // which V buffer holds the current value function
     bool ok = true;
     R nxt = R(0);
-    if (lane < NX) nxt = xb[(long long)(N - 1) * NX + lane];
-    else if (lane < NZ) nxt = ub[(long long)(N - 1) * NU + lane - NX];
+    if (lane < XS) nxt = xb[(long long)(N - 1) * XS + lane];
+    else if (lane < XS + NU) nxt = ub[(long long)(N - 1) * NU + lane - XS];
     __syncwarp();
     for (int i = N - 1; i >= 0; i--) {
         (*knots)++;
         // ---- the knot's point, uniform in every lane; the next knot's is fetched meanwhile -------------------------
-        if (lane < NZ) sm[SM::XU + lane] = nxt;
+        if (lane < XS + NU) sm[SM::XU + lane] = nxt;
         if (i > 0) {
-            if (lane < NX) nxt = xb[(long long)(i - 1) * NX + lane];
-            else if (lane < NZ) nxt = ub[(long long)(i - 1) * NU + lane - NX];
+            if (lane < XS) nxt = xb[(long long)(i - 1) * XS + lane];
+            else if (lane < XS + NU) nxt = ub[(long long)(i - 1) * NU + lane - XS];
         }
         __syncwarp();
-        R x[NX], u[NU];
+        R x[NX], u[NU], tg[NT > 0 ? NT : 1];
 #pragma unroll
         for (int a = 0; a < NX; a++) x[a] = sm[SM::XU + a];
 #pragma unroll
-        for (int m = 0; m < NU; m++) u[m] = sm[SM::XU + NX + m];
+        for (int a = 0; a < NT; a++) tg[a] = sm[SM::XU + NX + a];   // sin/cos cached by the rollout that produced the point
+#pragma unroll
+        for (int m = 0; m < NU; m++) u[m] = sm[SM::XU + XS + m];
         // ---- column of [A | B] (six numbers), w = Vxx a (gradient lane: w = Vx) ------------------------------------------
         R w[NX];
         const R *V = sm + (vb ? SM::V1 : SM::V0);
         if (lane < NZ) {
             R aA[3], aB[3];
-            Model<MODEL, R>::column(x, u, A.dt, lane, aA, aB);
+            Model<MODEL, R>::column(x, u, tg, A.dt, lane, aA, aB);
             const int ga = Model<MODEL, R>::ga(lane), gb = Model<MODEL, R>::gb(lane);
             const R idw = Model<MODEL, R>::has_id(lane) ? R(1) : R(0);
             const R *v0 = V + (lane < NX ? lane : 0) * NX;   // V is symmetric: column k = row k
@@ -316,7 +338,7 @@ __device__ __noinline__ bool sweep(const Args<R> &A, int b, int lane, R *sm, con
             __syncwarp();
             const R *Lm = sm + SM::LM + p * (NZ + 1);
 #pragma unroll
-            for (int r = 0; r < NZ; r++) qc[r] -= Lm[r] * m;
+            for (int r = 0; r < NZ; r++) if (r < NX || r > NX + p) qc[r] -= Lm[r] * m;   // eliminated rows are never read again
             if (lane == NZ) dv -= m * m;
         }
         if (!ok) break;
@@ -423,7 +445,7 @@ template <int MODEL, class R> __global__ void __launch_bounds__(128) gddp_kernel
                 S[0] = sweeps; S[1] = rollouts; S[2] = knots; S[3] = clock64() - clk0;
             }
         }
-        for (int e = lane; e < (N + 1) * NX; e += 32) A.x[(long long)b * (N + 1) * NX + e] = (double)xb[e];
+        for (int e = lane; e < (N + 1) * NX; e += 32) A.x[(long long)b * (N + 1) * NX + e] = (double)xb[(long long)(e / NX) * D::XS + e % NX];
         for (int e = lane; e < N * NU; e += 32) A.u[(long long)b * N * NU + e] = (double)ub[e];
         __syncwarp();
     }
