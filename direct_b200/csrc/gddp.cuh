@@ -161,7 +161,7 @@ template <int MODEL, class R> struct Ws {
 
 // Closed-loop rollout from x0 with controls ub + alpha k + K (x - xb) (K == nullptr: open loop with the controls in `un`).
 template <int MODEL, class R>
-__device__ __noinline__ R rollout(const Args<R> &A, int b, int lane, R *sm, const R *xb, const R *ub, const R *K, const R *kf, R alpha,
+__device__ __forceinline__ R rollout(const Args<R> &A, int b, int lane, R *sm, const R *xb, const R *ub, const R *K, const R *kf, R alpha,
                                   R *xn, R *un) {
     using D = Dim<MODEL>;
     constexpr int NX = D::NX, NU = D::NU, NT = D::NT, XS = D::XS;
@@ -229,7 +229,7 @@ __device__ __noinline__ R rollout(const Args<R> &A, int b, int lane, R *sm, cons
 
 // Backward sweep with the regularised Quu.  Returns false when a pivot is not positive; *dV1 = sum_i k_i' Qu_i.
 template <int MODEL, class R>
-__device__ __noinline__ bool sweep(const Args<R> &A, int b, int lane, R *sm, const R *xb, const R *ub, R rho, R *K, R *kf, R *dV1,
+__device__ __forceinline__ bool sweep(const Args<R> &A, int b, int lane, R *sm, const R *xb, const R *ub, R rho, R *K, R *kf, R *dV1,
                                    long long *knots) {
     using D = Dim<MODEL>;
     using SM = Smem<MODEL>;
@@ -259,8 +259,9 @@ __device__ __noinline__ bool sweep(const Args<R> &A, int b, int lane, R *sm, con
     if (lane < XS) nxt = xb[(long long)(N - 1) * XS + lane];
     else if (lane < XS + NU) nxt = ub[(long long)(N - 1) * NU + lane - XS];
     __syncwarp();
+    long long nk = 0;   // local counter: a by-pointer counter would be a local-memory read-modify-write per knot
     for (int i = N - 1; i >= 0; i--) {
-        (*knots)++;
+        nk++;
         // ---- the knot's point, uniform in every lane; the next knot's is fetched meanwhile -------------------------
         if (lane < XS + NU) sm[SM::XU + lane] = nxt;
         if (i > 0) {
@@ -378,10 +379,16 @@ __device__ __noinline__ bool sweep(const Args<R> &A, int b, int lane, R *sm, con
         __syncwarp();
     }
     *dV1 = __shfl_sync(0xffffffffu, dv, NZ);
+    *knots += nk;
     return ok;
 }
 
-template <int MODEL, class R> __global__ void __launch_bounds__(128) gddp_kernel(Args<R> A) {
+// Resident CTAs per SM: the sweep is latency-bound, so occupancy pays until the register cap starts to spill.  Measured
+// on B200 (fp32, B = 4096 / 65536, k solves/s): 2 CTAs (157 registers) 555 / 669, 4 CTAs (128) 803 / 1070, 5 CTAs (96) 758 / 1125.
+#ifndef GDDP_MIN_BLOCKS
+#define GDDP_MIN_BLOCKS (sizeof(R) == 4 ? 4 : 2)
+#endif
+template <int MODEL, class R> __global__ void __launch_bounds__(128, GDDP_MIN_BLOCKS) gddp_kernel(Args<R> A) {
     using D = Dim<MODEL>;
     constexpr int NX = D::NX, NU = D::NU;
     extern __shared__ __align__(16) unsigned char gsm_raw[];
