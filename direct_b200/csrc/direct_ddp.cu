@@ -14,8 +14,10 @@
 
 #include "../../include/direct_ddp.h"
 #include "../../include/direct_gddp.h"
+#include "../../include/direct_voxel.h"
 #include "ipddp_solver.h"
 #include "gddp.cuh"
+#include "voxel.cuh"
 
 #ifndef DDP_MAX_THREADS
 #define DDP_MAX_THREADS 128  // four trajectories (warps) per CTA: up to three helpers for the last solve of a CTA
@@ -156,6 +158,9 @@ struct direct_ddp_handle_s {
     DevBuf o_int[2], o_cost[2], o_xf[2], o_pc[2], o_bz[2], o_pt[2], o_jk[2], o_st[2];
     DevBuf ws, counter, tabs, bez_tmp, time_tmp, trace, trace_len, scratch_i, gboards, gwords;
     DevBuf gd[8];   // generic DDP (gddp.cuh): x0, xg, u_init, ints, cost, x, u, stats
+    DevBuf vx[16];  // voxel kernels (voxel.cuh): occupied, inside, candidates, cluster, can_can, can_clu, vertices, result,
+                    // claim, loop candidates, conflict rows, loop can_clu, ctl, use, invalid, phase timers
+    int vx_coop_blocks = 0;   // co-resident CTAs of cluster_loop_kernel
     const long long *last_stats_dev = nullptr;  // device [B][4] of the last solve (stage 1 / single)
     const long long *last_stats_dev0 = nullptr; // stage 0 when two-stage
     int last_B = 0;
@@ -488,6 +493,7 @@ void direct_ddp_destroy(direct_ddp_handle h) {
                           &h->gboards, &h->gwords};
         for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
         for (DevBuf &b : h->gd) if (b.p) cudaFree(b.p);
+        for (DevBuf &b : h->vx) if (b.p) cudaFree(b.p);
         for (int k = 0; k < 2; k++) {
             DevBuf *ob[] = {&h->o_int[k], &h->o_cost[k], &h->o_xf[k], &h->o_pc[k], &h->o_bz[k], &h->o_pt[k], &h->o_jk[k], &h->o_st[k]};
             for (DevBuf *b : ob) if (b->p) cudaFree(b->p);
@@ -769,5 +775,264 @@ extern "C" int direct_gddp_solve(direct_ddp_handle h, const direct_gddp_problem 
     CK(cudaEventElapsedTime(&ms, h->ev[2], h->ev[3])); h->stats.kernel_ms = ms;
     CK(cudaEventElapsedTime(&ms, h->ev[4], h->ev[5])); h->stats.d2h_ms = ms;
     h->stats.h2d_bytes = h2d; h->stats.d2h_bytes = d2h;
+    return DIRECT_DDP_OK;
+}
+
+
+// ---- voxel-map kernels (include/direct_voxel.h, voxel.cuh) ----------------------------------------------------------------
+namespace {
+int voxel_validate(H *h, const direct_voxel_map *m) {
+    if (!m || !m->occupied || m->nx <= 0 || m->ny <= 0 || m->nz <= 0) { h->err = "bad voxel map"; return DIRECT_DDP_ERR_ARG; }
+    if ((long long)m->nx * m->ny * m->nz > 0x7fffffffLL) { h->err = "voxel map too large for 32-bit cell indices"; return DIRECT_DDP_ERR_ARG; }
+    return 0;
+}
+}  // namespace
+
+extern "C" int direct_voxel_convex_test_device(direct_ddp_handle h, const direct_voxel_map *map, const int32_t *cand, int C,
+                                               const int32_t *clu, int K, uint8_t *can_can, uint8_t *can_clu, void *stream) {
+    REQUIRE_DEVICE(h)
+    int st = voxel_validate(h, map);
+    if (st) return st;
+    if (!map->inside || C < 0 || K < 0 || (C > 0 && (!cand || !can_can || !can_clu)) || (K > 0 && !clu)) { h->err = "missing pointer"; return DIRECT_DDP_ERR_ARG; }
+    CK(cudaSetDevice(h->opts.device));
+    cudaStream_t s = (cudaStream_t)stream;
+    CK(cudaEventRecord(h->ev[2], s));
+    if (C > 0) {
+        const int threads = 256, wpb = threads / 32;
+        long long grid = ((long long)C + wpb - 1) / wpb;
+        const long long cap = (long long)h->sm_count * 8;   // 2048 threads per SM: a persistent grid, warps stride over the candidates
+        if (grid > cap) grid = cap;
+        voxel::convex_test_kernel<<<(unsigned)grid, threads, 0, s>>>(map->occupied, map->inside, map->ny * map->nz, map->nz, cand, C, clu, K,
+                                                                     can_can, can_clu);
+        CK(cudaGetLastError());
+    }
+    CK(cudaEventRecord(h->ev[3], s));
+    h->stats.kernel_launches = C > 0 ? 1 : 0;
+    h->last_stats_dev = nullptr; h->last_stats_dev0 = nullptr; h->last_B = 0; h->stats_valid = false;
+    return DIRECT_DDP_OK;
+}
+
+extern "C" int direct_voxel_cube_inflation_device(direct_ddp_handle h, const direct_voxel_map *map, const int32_t *vertex_idx, int dir,
+                                                  int inf_step, int32_t *result, void *stream) {
+    REQUIRE_DEVICE(h)
+    int st = voxel_validate(h, map);
+    if (st) return st;
+    if (!vertex_idx || !result || dir < 0 || dir > 5 || inf_step < 0) { h->err = "bad inflation argument"; return DIRECT_DDP_ERR_ARG; }
+    CK(cudaSetDevice(h->opts.device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const int32_t one = 1;
+    CK(cudaMemcpyAsync(result, &one, sizeof one, cudaMemcpyHostToDevice, s));
+    CK(cudaEventRecord(h->ev[2], s));
+    // the face of a box inside the map has at most max(nx ny, nx nz, ny nz) cells; blocks stride over it
+    voxel::cube_inflation_kernel<<<h->sm_count, 256, 0, s>>>(map->occupied, map->ny * map->nz, map->nz, vertex_idx, dir, inf_step, result);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(h->ev[3], s));
+    h->stats.kernel_launches = 1;
+    h->last_stats_dev = nullptr; h->last_stats_dev0 = nullptr; h->last_B = 0; h->stats_valid = false;
+    return DIRECT_DDP_OK;
+}
+
+namespace {
+int voxel_upload_map(H *h, const direct_voxel_map *map, direct_voxel_map *d, cudaStream_t s, bool need_inside) {
+    const size_t cells = (size_t)map->nx * map->ny * map->nz;
+    int st;
+    if ((st = ensure(h, h->vx[0], cells))) return st;
+    CK(cudaMemcpyAsync(h->vx[0].p, map->occupied, cells, cudaMemcpyHostToDevice, s));
+    *d = *map;
+    d->occupied = (const uint8_t *)h->vx[0].p;
+    d->inside = nullptr;
+    if (need_inside) {
+        if ((st = ensure(h, h->vx[1], cells))) return st;
+        CK(cudaMemcpyAsync(h->vx[1].p, map->inside, cells, cudaMemcpyHostToDevice, s));
+        d->inside = (const uint8_t *)h->vx[1].p;
+    }
+    return 0;
+}
+}  // namespace
+
+extern "C" int direct_voxel_convex_test(direct_ddp_handle h, const direct_voxel_map *map, const int32_t *cand, int C, const int32_t *clu,
+                                        int K, uint8_t *can_can, uint8_t *can_clu) {
+    REQUIRE_DEVICE(h)
+    int st = voxel_validate(h, map);
+    if (st) return st;
+    if (!map->inside || C < 0 || K < 0 || (C > 0 && (!cand || !can_can || !can_clu)) || (K > 0 && !clu)) { h->err = "missing pointer"; return DIRECT_DDP_ERR_ARG; }
+    CK(cudaSetDevice(h->opts.device));
+    cudaStream_t s = h->stream;
+    direct_voxel_map d;
+    CK(cudaEventRecord(h->ev[0], s));
+    if ((st = voxel_upload_map(h, map, &d, s, true))) return st;
+    const size_t ncc = (size_t)C * ((size_t)C + 1) / 2;
+    if ((st = ensure(h, h->vx[2], (size_t)C * 12)) || (st = ensure(h, h->vx[3], (size_t)K * 12)) || (st = ensure(h, h->vx[4], ncc)) ||
+        (st = ensure(h, h->vx[5], (size_t)C))) return st;
+    if (C > 0) CK(cudaMemcpyAsync(h->vx[2].p, cand, (size_t)C * 12, cudaMemcpyHostToDevice, s));
+    if (K > 0) CK(cudaMemcpyAsync(h->vx[3].p, clu, (size_t)K * 12, cudaMemcpyHostToDevice, s));
+    if (ncc > 0) CK(cudaMemcpyAsync(h->vx[4].p, can_can, ncc, cudaMemcpyHostToDevice, s));   // entries the kernel never writes keep the caller's bytes
+    CK(cudaEventRecord(h->ev[1], s));
+    if ((st = direct_voxel_convex_test_device(h, &d, (const int32_t *)h->vx[2].p, C, (const int32_t *)h->vx[3].p, K, (uint8_t *)h->vx[4].p,
+                                              (uint8_t *)h->vx[5].p, s))) return st;
+    CK(cudaEventRecord(h->ev[4], s));
+    if (ncc > 0) CK(cudaMemcpyAsync(can_can, h->vx[4].p, ncc, cudaMemcpyDeviceToHost, s));
+    if (C > 0) CK(cudaMemcpyAsync(can_clu, h->vx[5].p, (size_t)C, cudaMemcpyDeviceToHost, s));
+    CK(cudaEventRecord(h->ev[5], s));
+    CK(cudaStreamSynchronize(s));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, h->ev[0], h->ev[1])); h->stats.h2d_ms = ms;
+    CK(cudaEventElapsedTime(&ms, h->ev[2], h->ev[3])); h->stats.kernel_ms = ms;
+    CK(cudaEventElapsedTime(&ms, h->ev[4], h->ev[5])); h->stats.d2h_ms = ms;
+    return DIRECT_DDP_OK;
+}
+
+extern "C" int direct_voxel_cube_inflation(direct_ddp_handle h, const direct_voxel_map *map, const int32_t *vertex_idx, int dir, int inf_step,
+                                           int32_t *result) {
+    REQUIRE_DEVICE(h)
+    int st = voxel_validate(h, map);
+    if (st) return st;
+    if (!vertex_idx || !result) { h->err = "missing pointer"; return DIRECT_DDP_ERR_ARG; }
+    CK(cudaSetDevice(h->opts.device));
+    cudaStream_t s = h->stream;
+    direct_voxel_map d;
+    if ((st = voxel_upload_map(h, map, &d, s, false))) return st;
+    if ((st = ensure(h, h->vx[6], 96)) || (st = ensure(h, h->vx[7], 16))) return st;
+    CK(cudaMemcpyAsync(h->vx[6].p, vertex_idx, 96, cudaMemcpyHostToDevice, s));
+    if ((st = direct_voxel_cube_inflation_device(h, &d, (const int32_t *)h->vx[6].p, dir, inf_step, (int32_t *)h->vx[7].p, s))) return st;
+    CK(cudaMemcpyAsync(result, h->vx[7].p, 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, h->ev[2], h->ev[3])); h->stats.kernel_ms = ms;
+    return DIRECT_DDP_OK;
+}
+
+extern "C" int direct_voxel_inflate_box_device(direct_ddp_handle h, const direct_voxel_map *map, int32_t *vertex_idx, int inf_step,
+                                               int itr_inflate_max, int32_t *iters, void *stream) {
+    REQUIRE_DEVICE(h)
+    int st = voxel_validate(h, map);
+    if (st) return st;
+    if (!vertex_idx || inf_step != 1 || itr_inflate_max < 0) { h->err = "bad inflation argument (inf_step must be 1)"; return DIRECT_DDP_ERR_ARG; }
+    CK(cudaSetDevice(h->opts.device));
+    cudaStream_t s = (cudaStream_t)stream;
+    CK(cudaEventRecord(h->ev[2], s));
+    voxel::inflate_box_kernel<<<1, 1024, 0, s>>>(map->occupied, map->nx, map->ny, map->nz, vertex_idx, inf_step, itr_inflate_max, iters);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(h->ev[3], s));
+    h->stats.kernel_launches = 1;
+    h->last_stats_dev = nullptr; h->last_stats_dev0 = nullptr; h->last_B = 0; h->stats_valid = false;
+    return DIRECT_DDP_OK;
+}
+
+extern "C" int direct_voxel_inflate_box(direct_ddp_handle h, const direct_voxel_map *map, int32_t *vertex_idx, int inf_step,
+                                        int itr_inflate_max, int32_t *iters) {
+    REQUIRE_DEVICE(h)
+    int st = voxel_validate(h, map);
+    if (st) return st;
+    if (!vertex_idx) { h->err = "missing pointer"; return DIRECT_DDP_ERR_ARG; }
+    CK(cudaSetDevice(h->opts.device));
+    cudaStream_t s = h->stream;
+    direct_voxel_map d;
+    if ((st = voxel_upload_map(h, map, &d, s, false))) return st;
+    if ((st = ensure(h, h->vx[6], 96)) || (st = ensure(h, h->vx[7], 16))) return st;
+    CK(cudaMemcpyAsync(h->vx[6].p, vertex_idx, 96, cudaMemcpyHostToDevice, s));
+    if ((st = direct_voxel_inflate_box_device(h, &d, (int32_t *)h->vx[6].p, inf_step, itr_inflate_max, (int32_t *)h->vx[7].p, s))) return st;
+    int32_t it = 0;
+    CK(cudaMemcpyAsync(vertex_idx, h->vx[6].p, 96, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(&it, h->vx[7].p, 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (iters) *iters = it;
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, h->ev[2], h->ev[3])); h->stats.kernel_ms = ms;
+    return DIRECT_DDP_OK;
+}
+
+extern "C" int direct_voxel_cluster_device(direct_ddp_handle h, const direct_voxel_map *map, uint8_t *use, uint8_t *invalid,
+                                           int32_t *cluster_xyz, int32_t *ctl, int cap, int cand_cap, int itr_cluster_max, void *stream) {
+    REQUIRE_DEVICE(h)
+    int st = voxel_validate(h, map);
+    if (st) return st;
+    if (!map->inside || !use || !invalid || !cluster_xyz || !ctl || cap <= 0 || cand_cap <= 0 || cand_cap > 32 * voxel::ACC_WORDS ||
+        itr_cluster_max < 0) { h->err = "bad clustering argument (cand_cap <= 32768)"; return DIRECT_DDP_ERR_ARG; }
+    CK(cudaSetDevice(h->opts.device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t cells = (size_t)map->nx * map->ny * map->nz;
+    const bool fresh_claims = h->vx[8].cap < cells * 4;
+    if ((st = ensure(h, h->vx[8], cells * 4)) || (st = ensure(h, h->vx[9], (size_t)cand_cap * 12)) ||
+        (st = ensure(h, h->vx[10], (size_t)cand_cap * ((cand_cap + 31) / 32) * 4)) || (st = ensure(h, h->vx[11], (size_t)cand_cap))) return st;
+    // the kernel hands every claim word back empty; only a new (or regrown) array needs the fill
+    if (fresh_claims) CK(cudaMemsetAsync(h->vx[8].p, 0x7f, h->vx[8].cap, s));
+    if (h->vx_coop_blocks == 0) {
+        int per_sm = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, voxel::cluster_loop_kernel, 256, 0));
+        if (per_sm < 1) { h->err = "cluster_loop_kernel does not fit an SM"; return DIRECT_DDP_ERR_CUDA; }
+        h->vx_coop_blocks = per_sm * h->sm_count;
+    }
+    const uint8_t *occ = map->occupied, *inside = map->inside;
+    int *claim = (int *)h->vx[8].p, *cand = (int *)h->vx[9].p;
+    unsigned *conflict = (unsigned *)h->vx[10].p;
+    uint8_t *can_clu = (uint8_t *)h->vx[11].p;
+    int nx = map->nx, ny = map->ny, nz = map->nz;
+    voxel::ClusterCtl *c = (voxel::ClusterCtl *)ctl;
+    if ((st = ensure(h, h->vx[15], 64))) return st;
+    unsigned long long *phase_ns = (unsigned long long *)h->vx[15].p;
+    CK(cudaMemsetAsync(phase_ns, 0, 64, s));
+    void *args[] = {&occ, &inside, &use, &invalid, &claim, &nx, &ny, &nz, &cluster_xyz, &cap, &cand, &cand_cap, &conflict, &can_clu,
+                    &itr_cluster_max, &c, &phase_ns};
+    CK(cudaEventRecord(h->ev[2], s));
+    CK(cudaLaunchCooperativeKernel((const void *)voxel::cluster_loop_kernel, dim3(h->vx_coop_blocks), dim3(256), args, 0, s));
+    CK(cudaEventRecord(h->ev[3], s));
+    h->stats.kernel_launches = 1;
+    h->last_stats_dev = nullptr; h->last_stats_dev0 = nullptr; h->last_B = 0; h->stats_valid = false;
+    return DIRECT_DDP_OK;
+}
+
+extern "C" int direct_voxel_cluster(direct_ddp_handle h, const direct_voxel_map *map, uint8_t *use, uint8_t *invalid, int32_t *cluster_xyz,
+                                    int32_t *cluster_num, int cap, int cand_cap, int itr_cluster_max, int32_t *iters) {
+    REQUIRE_DEVICE(h)
+    int st = voxel_validate(h, map);
+    if (st) return st;
+    if (!map->inside || !use || !invalid || !cluster_xyz || !cluster_num || *cluster_num < 0 || *cluster_num > cap) {
+        h->err = "bad clustering argument"; return DIRECT_DDP_ERR_ARG;
+    }
+    CK(cudaSetDevice(h->opts.device));
+    cudaStream_t s = h->stream;
+    const size_t cells = (size_t)map->nx * map->ny * map->nz;
+    direct_voxel_map d;
+    CK(cudaEventRecord(h->ev[0], s));
+    if ((st = voxel_upload_map(h, map, &d, s, true))) return st;
+    if ((st = ensure(h, h->vx[12], 32)) || (st = ensure(h, h->vx[13], cells)) || (st = ensure(h, h->vx[14], cells)) ||
+        (st = ensure(h, h->vx[3], (size_t)cap * 12))) return st;
+    int32_t ctl[8] = {*cluster_num, 0, 0, 0, 0, 0, 0, 0};
+    CK(cudaMemcpyAsync(h->vx[12].p, ctl, 32, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(h->vx[13].p, use, cells, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(h->vx[14].p, invalid, cells, cudaMemcpyHostToDevice, s));
+    if (*cluster_num > 0) CK(cudaMemcpyAsync(h->vx[3].p, cluster_xyz, (size_t)*cluster_num * 12, cudaMemcpyHostToDevice, s));
+    CK(cudaEventRecord(h->ev[1], s));
+    if ((st = direct_voxel_cluster_device(h, &d, (uint8_t *)h->vx[13].p, (uint8_t *)h->vx[14].p, (int32_t *)h->vx[3].p, (int32_t *)h->vx[12].p,
+                                          cap, cand_cap, itr_cluster_max, s))) return st;
+    CK(cudaEventRecord(h->ev[4], s));
+    CK(cudaMemcpyAsync(ctl, h->vx[12].p, 32, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (ctl[2] != 0) { h->err = "cluster or candidate capacity exceeded"; return DIRECT_DDP_ERR_ARG; }
+    CK(cudaMemcpyAsync(use, h->vx[13].p, cells, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(invalid, h->vx[14].p, cells, cudaMemcpyDeviceToHost, s));
+    if (ctl[0] > 0) CK(cudaMemcpyAsync(cluster_xyz, h->vx[3].p, (size_t)ctl[0] * 12, cudaMemcpyDeviceToHost, s));
+    CK(cudaEventRecord(h->ev[5], s));
+    CK(cudaStreamSynchronize(s));
+    *cluster_num = ctl[0];
+    if (iters) *iters = ctl[1];
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, h->ev[0], h->ev[1])); h->stats.h2d_ms = ms;
+    CK(cudaEventElapsedTime(&ms, h->ev[2], h->ev[3])); h->stats.kernel_ms = ms;
+    CK(cudaEventElapsedTime(&ms, h->ev[4], h->ev[5])); h->stats.d2h_ms = ms;
+    return DIRECT_DDP_OK;
+}
+
+// Device time of the phases of the last direct_voxel_cluster[_device] launch on this handle, summed over its iterations (ms):
+// claims, ordered compaction, cluster rays, candidate rays, acceptance scan.  Synchronises the handle's device.
+extern "C" int direct_voxel_cluster_phases(direct_ddp_handle h, double ms[5]) {
+    REQUIRE_DEVICE(h)
+    if (!ms || !h->vx[15].p) { h->err = "no clustering launch on this handle yet"; return DIRECT_DDP_ERR_ARG; }
+    CK(cudaSetDevice(h->opts.device));
+    unsigned long long ns[8];
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(ns, h->vx[15].p, 64, cudaMemcpyDeviceToHost));
+    for (int k = 0; k < 5; k++) ms[k] = (double)ns[k] * 1e-6;
     return DIRECT_DDP_OK;
 }

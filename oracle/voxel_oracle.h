@@ -1,0 +1,36 @@
+/* voxel_oracle.h -- CPU restatement of the reference's voxel-map CUDA kernels and of the host loops around them
+ * (polyhedron_generator/src/cluster_engine.cu, cluster_server.cu).  TEST INFRASTRUCTURE ONLY (see voxel_oracle.c). */
+#ifndef VOXEL_ORACLE_H_
+#define VOXEL_ORACLE_H_
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* paraConvexTest + paraResultCheck (cluster_engine.cu:70-180, :37-67).  can_can: [C (C + 1) / 2] (only the entries the
+ * reference writes are touched), can_clu: [C]. */
+void voxel_oracle_convex_test(const uint8_t *occ, const uint8_t *inside, int ny, int nz, const int32_t *cand, int C,
+                              const int32_t *clu, int K, uint8_t *can_can, uint8_t *can_clu);
+
+/* paraCubeInflation (cluster_engine.cu:185-349).  max_threads > 0 restates the reference's fixed <<<128, 128>>> launch
+ * (cluster_server.cu:170-171: only the first max_threads cells of the face are looked at); 0 = every cell. */
+int voxel_oracle_cube_inflation(const uint8_t *occ, int ny, int nz, const int32_t *vertex_idx, int dir, int inf_step,
+                                long long max_threads);
+
+/* cubeInflation_gpu (cluster_server.cu:343-440): the six-direction loop until the box stops growing. vertex_idx[24] in/out.
+ * Returns the number of outer iterations run. */
+int voxel_oracle_inflate_box(const uint8_t *occ, int nx, int ny, int nz, int32_t *vertex_idx, int inf_step, int itr_inflate_max);
+
+/* polytopeCluster_gpu (cluster_server.cu:556-767) with every can_can entry read from the kernel's own output (the reference
+ * downloads C (C - 1) / 2 entries and indexes up to C (C + 1) / 2 - 2: its last candidate row is stale host memory).
+ * cluster_xyz [cap][3] holds cluster_num voxels on entry (all of them active), more on return; inside / use / invalid are
+ * the reference's per-voxel flag arrays (inside is read only).  Returns the new cluster size, or -1 when cap or cand_cap
+ * would be exceeded.  iters_out (optional): iterations run. */
+int voxel_oracle_cluster(const uint8_t *occ, const uint8_t *inside, uint8_t *use, uint8_t *invalid, int nx, int ny, int nz,
+                         int32_t *cluster_xyz, int cluster_num, int cap, int cand_cap, int itr_cluster_max, int *iters_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,84 @@
+"""Voxel-map kernels on one B200: direct_b200's kernels next to the reference's own CUDA kernels (oracle/_ref/libvoxel_ref.so,
+cluster_engine.cu compiled unmodified for sm_100a, the reference's launch shapes) on the same inputs, results compared byte for byte.
+    python tools/voxel_report.py [--map 200 200 40] [--pillars 160] [--out gpurun_out/voxel_report.json]"""
+import argparse, json, sys, time
+import numpy as np
+sys.path.insert(0, ".")
+sys.path.insert(0, "tests/golden")
+from direct_b200 import voxel as X          # noqa: E402
+from direct_b200.capi import Solver         # noqa: E402
+from oracle import voxel_py as V            # noqa: E402  (checker + reference kernels)
+import make_voxel_golden as MG              # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--map", type=int, nargs=3, default=[200, 200, 40])
+ap.add_argument("--pillars", type=int, default=160)
+ap.add_argument("--reps", type=int, default=5)
+ap.add_argument("--itr", type=int, default=8)
+ap.add_argument("--out", default="")
+a = ap.parse_args()
+shape = tuple(a.map)
+cell = (shape[0] // 2, shape[1] // 2, shape[2] * 3 // 8)
+occ = X.make_map(shape, a.pillars, 6, clear=(*cell, 6))
+s = Solver(0, "fp64")
+rep = {"map": list(shape), "occupied_frac": float(occ.mean())}
+
+# 1. box inflation: one fused launch against the reference's launch + synchronise + copy per direction
+v0 = X.box_vertices(*cell, *cell)
+best = 1e9
+for _ in range(a.reps):
+    t = time.perf_counter(); gv, gi = X.inflate_box(s, occ, v0, 1000); wall = time.perf_counter() - t
+    best = min(best, s.stats().kernel_ms)
+rv, ri, rsec = V.ref_inflate_box(occ, v0, 1000)
+rsec = min([rsec] + [V.ref_inflate_box(occ, v0, 1000)[2] for _ in range(a.reps - 1)])
+assert np.array_equal(gv, rv) and gi == ri
+rep["inflate_box"] = {"box": list(X.box_bounds(gv)), "outer_iters": gi, "fused_kernel_ms": best, "reference_loop_ms": rsec * 1e3,
+                      "speedup": rsec * 1e3 / best}
+print(f"inflate_box: box {X.box_bounds(gv)} after {gi} iterations; fused launch {best:.3f} ms, reference's stepwise loop {rsec * 1e3:.3f} ms "
+      f"({rsec * 1e3 / best:.1f}x)")
+
+# 2. convex test on the candidates of the first clustering iterations
+v20, _ = X.inflate_box(s, occ, v0, 20)
+inside, use, shell = X.cube_shell(shape, v20)
+cand = MG.first_candidates(occ, inside, use, shell)
+Cn, K = len(cand), len(shell)
+rays = Cn * (Cn - 1) // 2 + Cn * K
+l1 = 0   # sum of |d|_1 over the rays: an upper bound of the voxels a ray visits (it may stop early at an `inside` voxel)
+for t in range(Cn):
+    c = cand[t].astype(np.int64)
+    l1 += int(np.abs(shell.astype(np.int64) - c).sum()) + int(np.abs(cand[:t].astype(np.int64) - c).sum())
+best = 1e9
+for _ in range(a.reps):
+    gc, gl = X.convex_test(s, occ, inside, cand, shell)
+    best = min(best, s.stats().kernel_ms)
+rbest = 1e9
+for _ in range(a.reps):
+    rc, rl, rms = V.ref_convex_test(occ, inside, cand, shell)
+    rbest = min(rbest, rms)
+assert np.array_equal(gc, rc) and np.array_equal(gl, rl)
+rep["convex_test"] = {"candidates": Cn, "cluster": K, "rays": rays, "voxel_steps_upper_bound": int(l1), "kernel_ms": best,
+                      "reference_kernels_ms": rbest, "speedup": rbest / best, "rays_per_s": rays / (best * 1e-3),
+                      "voxel_steps_per_s_upper_bound": float(l1) / (best * 1e-3), "identical_to_reference_kernels": True}
+print(f"convex_test: {Cn} candidates x ({Cn} + {K} cluster voxels) = {rays} rays, <= {l1} voxel steps: {best:.3f} ms "
+      f"({rays / best / 1e6:.2f} G rays/s) against {rbest:.3f} ms for paraConvexTest + paraResultCheck ({rbest / best:.1f}x), identical bytes")
+
+# 3. the whole clustering loop in one cooperative launch
+inv0 = np.zeros_like(occ)
+best = 1e9
+for _ in range(a.reps):
+    t = time.perf_counter(); clu, use1, inv1, it = X.cluster(s, occ, inside, use, inv0, shell, 50000, 10000, a.itr); wall = time.perf_counter() - t
+    if s.stats().kernel_ms < best:
+        best, phases = s.stats().kernel_ms, X.cluster_phases(s)
+rep["cluster_loop"] = {"phases_ms": phases, "initial": K, "final": int(len(clu)), "iterations": it, "rejected": int(inv1.sum()), "kernel_ms": best,
+                       "host_call_ms": wall * 1e3}
+print(f"cluster loop: {K} -> {len(clu)} voxels in {it} iterations ({int(inv1.sum())} rejected): {best:.3f} ms in one launch "
+      f"(host-buffer call {wall * 1e3:.1f} ms with the map, flag and cluster copies)")
+print("   phases (ms, summed over the iterations): " + ", ".join(f"{k} {v:.3f}" for k, v in phases.items()))
+if shape[0] * shape[1] * shape[2] <= 200 * 200 * 40 and a.itr <= 3:
+    t = time.perf_counter(); o = V.cluster(occ, inside, use, inv0, shell, 50000, 10000, a.itr); ot = time.perf_counter() - t
+    assert np.array_equal(o[0], clu) and np.array_equal(o[2], inv1) and o[3] == it
+    rep["cluster_loop"]["cpu_oracle_s"] = ot
+    print(f"   = sequential CPU oracle ({ot:.2f} s), voxel for voxel")
+if a.out:
+    json.dump(rep, open(a.out, "w"), indent=1)
+s.close()
