@@ -158,8 +158,8 @@ struct direct_ddp_handle_s {
     DevBuf o_int[2], o_cost[2], o_xf[2], o_pc[2], o_bz[2], o_pt[2], o_jk[2], o_st[2];
     DevBuf ws, counter, tabs, bez_tmp, time_tmp, trace, trace_len, scratch_i, gboards, gwords;
     DevBuf gd[8];   // generic DDP (gddp.cuh): x0, xg, u_init, ints, cost, x, u, stats
-    DevBuf vx[16];  // voxel kernels (voxel.cuh): occupied, inside, candidates, cluster, can_can, can_clu, vertices, result,
-                    // claim, loop candidates, conflict rows, loop can_clu, ctl, use, invalid, phase timers
+    DevBuf vx[19];  // voxel kernels (voxel.cuh): occupied, inside, candidates, cluster, can_can, can_clu, vertices, result,
+                    // claim, loop candidates, conflict rows, loop can_clu, ctl, use, invalid, phase timers, merged map, segment counts, reciprocal table
     int vx_coop_blocks = 0;   // co-resident CTAs of cluster_loop_kernel
     const long long *last_stats_dev = nullptr;  // device [B][4] of the last solve (stage 1 / single)
     const long long *last_stats_dev0 = nullptr; // stage 0 when two-stage
@@ -781,6 +781,16 @@ extern "C" int direct_gddp_solve(direct_ddp_handle h, const direct_gddp_problem 
 
 // ---- voxel-map kernels (include/direct_voxel.h, voxel.cuh) ----------------------------------------------------------------
 namespace {
+int voxel_rcp_table(H *h, cudaStream_t s) {
+    if (h->vx[18].p) return 0;
+    int st = ensure(h, h->vx[18], sizeof(double) * voxel::RCP_N);
+    if (st) return st;
+    voxel::rcp_table_kernel<<<voxel::RCP_N / 256, 256, 0, s>>>((double *)h->vx[18].p);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(s));   // later launches may come on other streams
+    return 0;
+}
+
 int voxel_validate(H *h, const direct_voxel_map *m) {
     if (!m || !m->occupied || m->nx <= 0 || m->ny <= 0 || m->nz <= 0) { h->err = "bad voxel map"; return DIRECT_DDP_ERR_ARG; }
     if ((long long)m->nx * m->ny * m->nz > 0x7fffffffLL) { h->err = "voxel map too large for 32-bit cell indices"; return DIRECT_DDP_ERR_ARG; }
@@ -798,16 +808,21 @@ extern "C" int direct_voxel_convex_test_device(direct_ddp_handle h, const direct
     cudaStream_t s = (cudaStream_t)stream;
     CK(cudaEventRecord(h->ev[2], s));
     if (C > 0) {
-        const int threads = 256, wpb = threads / 32;
-        long long grid = ((long long)C + wpb - 1) / wpb;
-        const long long cap = (long long)h->sm_count * 8;   // 2048 threads per SM: a persistent grid, warps stride over the candidates
+        const int threads = 256;
+        const long long tasks = (long long)C * ((C - 1 + K + 31) / 32);
+        long long grid = (tasks + 7) / 8;
+        const long long cap = (long long)h->sm_count * 8;   // 2048 threads per SM: a persistent grid, warps stride over the tasks
         if (grid > cap) grid = cap;
-        voxel::convex_test_kernel<<<(unsigned)grid, threads, 0, s>>>(map->occupied, map->inside, map->ny * map->nz, map->nz, cand, C, clu, K,
+        if (grid < 1) grid = 1;
+        const size_t cells = (size_t)map->nx * map->ny * map->nz;
+        if ((st = ensure(h, h->vx[16], cells)) || (st = voxel_rcp_table(h, s))) return st;   // merged map (bit 0 occupied, bit 1 inside)
+        voxel::merge_map_kernel<<<h->sm_count * 4, 256, 0, s>>>(map->occupied, map->inside, (uint8_t *)h->vx[16].p, cells, can_clu, C);
+        voxel::convex_test_kernel<<<(unsigned)grid, threads, 0, s>>>((const uint8_t *)h->vx[16].p, (const double *)h->vx[18].p, map->ny * map->nz, map->nz, cand, C, clu, K,
                                                                      can_can, can_clu);
         CK(cudaGetLastError());
     }
     CK(cudaEventRecord(h->ev[3], s));
-    h->stats.kernel_launches = C > 0 ? 1 : 0;
+    h->stats.kernel_launches = C > 0 ? 2 : 0;
     h->last_stats_dev = nullptr; h->last_stats_dev0 = nullptr; h->last_B = 0; h->stats_valid = false;
     return DIRECT_DDP_OK;
 }
@@ -953,10 +968,13 @@ extern "C" int direct_voxel_cluster_device(direct_ddp_handle h, const direct_vox
     cudaStream_t s = (cudaStream_t)stream;
     const size_t cells = (size_t)map->nx * map->ny * map->nz;
     const bool fresh_claims = h->vx[8].cap < cells * 4;
+    const size_t conflict_bytes = (size_t)cand_cap * ((cand_cap + 31) / 32) * 4;
+    const bool fresh_conflict = h->vx[10].cap < conflict_bytes;
     if ((st = ensure(h, h->vx[8], cells * 4)) || (st = ensure(h, h->vx[9], (size_t)cand_cap * 12)) ||
         (st = ensure(h, h->vx[10], (size_t)cand_cap * ((cand_cap + 31) / 32) * 4)) || (st = ensure(h, h->vx[11], (size_t)cand_cap))) return st;
     // the kernel hands every claim word back empty; only a new (or regrown) array needs the fill
     if (fresh_claims) CK(cudaMemsetAsync(h->vx[8].p, 0x7f, h->vx[8].cap, s));
+    if (fresh_conflict) CK(cudaMemsetAsync(h->vx[10].p, 0, h->vx[10].cap, s));   // rows of rejected candidates are read (and ignored)
     if (h->vx_coop_blocks == 0) {
         int per_sm = 0;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, voxel::cluster_loop_kernel, 256, 0));
@@ -972,12 +990,18 @@ extern "C" int direct_voxel_cluster_device(direct_ddp_handle h, const direct_vox
     if ((st = ensure(h, h->vx[15], 64))) return st;
     unsigned long long *phase_ns = (unsigned long long *)h->vx[15].p;
     CK(cudaMemsetAsync(phase_ns, 0, 64, s));
-    void *args[] = {&occ, &inside, &use, &invalid, &claim, &nx, &ny, &nz, &cluster_xyz, &cap, &cand, &cand_cap, &conflict, &can_clu,
-                    &itr_cluster_max, &c, &phase_ns};
+    if ((st = ensure(h, h->vx[16], cells)) || (st = ensure(h, h->vx[17], ((size_t)26 * (size_t)(cap > cand_cap ? cap : cand_cap) / 128 + 2) * 4))) return st;
+    if ((st = voxel_rcp_table(h, s))) return st;
+    int *seg_count = (int *)h->vx[17].p;
+    const double *rcp = (const double *)h->vx[18].p;
+    const uint8_t *merged = (const uint8_t *)h->vx[16].p;
     CK(cudaEventRecord(h->ev[2], s));
+    voxel::merge_map_kernel<<<h->sm_count * 4, 256, 0, s>>>(occ, inside, (uint8_t *)h->vx[16].p, cells, nullptr, 0);
+    void *args[] = {&occ, &inside, &merged, &rcp, &use, &invalid, &claim, &nx, &ny, &nz, &cluster_xyz, &cap, &cand, &cand_cap, &conflict, &can_clu,
+                    &seg_count, &itr_cluster_max, &c, &phase_ns};
     CK(cudaLaunchCooperativeKernel((const void *)voxel::cluster_loop_kernel, dim3(h->vx_coop_blocks), dim3(256), args, 0, s));
     CK(cudaEventRecord(h->ev[3], s));
-    h->stats.kernel_launches = 1;
+    h->stats.kernel_launches = 2;
     h->last_stats_dev = nullptr; h->last_stats_dev0 = nullptr; h->last_B = 0; h->stats_valid = false;
     return DIRECT_DDP_OK;
 }

@@ -15,57 +15,101 @@
 namespace voxel {
 namespace cg = cooperative_groups;
 
-// Smallest positive t with s + t ds integer, for s = 0.5 (cluster_engine.cu:19-35: mod(+-0.5, 1) = 0.5).
-__device__ __forceinline__ double intbound_half(int ds) {
-    if (ds == 0) return 99999.0;
-    const int a = ds < 0 ? -ds : ds;
-    return (1 - 0.5) / a;
+// 1 / k for k = 1 .. RCP_N - 1, correctly rounded fp64 quotients (IEEE division gives the same bits on the host and on the device);
+// filled once per handle.  The reference's per-ray quotients are tDelta = step / d = 1 / |d| and tMax = (1 - 0.5) / |d| (cluster_engine.cu
+// :19-35 with s = mod(+-0.5, 1) = 0.5), and 0.5 / |d| is exactly half of 1 / |d|: three table reads replace six fp64 divisions, same bits.
+constexpr int RCP_N = 4096;
+__global__ void rcp_table_kernel(double *rcp) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < RCP_N) rcp[k] = k == 0 ? 0.0 : 1.0 / (double)k;
+}
+__device__ __forceinline__ double rcp_abs(const double *__restrict__ rcp, int d) {
+    const int a = d < 0 ? -d : d;
+    return a < RCP_N ? __ldg(rcp + a) : 1.0 / (double)a;
+}
+
+// Merged map: bit 0 = occupied (map_data > 0), bit 1 = inside (inside_data > 0).  One byte gather per ray step instead of two.
+__global__ void merge_map_kernel(const uint8_t *__restrict__ occ, const uint8_t *__restrict__ inside, uint8_t *__restrict__ merged, size_t cells,
+                                 uint8_t *ones, int n_ones) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < cells; i += (size_t)gridDim.x * blockDim.x) {
+        merged[i] = (uint8_t)((occ[i] > 0 ? 1 : 0) | (inside[i] > 0 ? 2 : 0));
+        if (i < (size_t)n_ones) ones[i] = 1;   // can_clu of the convex test starts true
+    }
 }
 
 // true = the ray from (x, y, z) to (ex, ey, ez) is free (paraConvexTest's d_result[tid], cluster_engine.cu:104-176).
-__device__ __forceinline__ bool ray_free(const uint8_t *__restrict__ occ, const uint8_t *__restrict__ inside, int yz, int nz,
-                                         int x, int y, int z, int ex, int ey, int ez) {
+// The walk takes the reference's decisions in the reference's order (same fp64 tMax additions and comparisons).  Two things are
+// arranged differently.  (1) The walk reaches its end voxel after exactly |dx| + |dy| + |dz| steps (axis a crosses its last
+// boundary at t = 1 - 0.5 / |d_a| < 1 and its next one only at t > 1; the margin 0.5 / |d| is 13 orders of magnitude above the
+// rounding of the additions), so "position == end" is a step counter.  (2) The reference's loop waits for each voxel before it
+// takes the next step (the exit tests depend on the load); here the next LOOK steps are taken first, their voxels are fetched
+// together and then examined in order - steps past the end are not taken, so nothing outside the ray is ever read.
+constexpr int LOOK = 4;
+__device__ __forceinline__ bool ray_free(const uint8_t *__restrict__ m, const double *__restrict__ rcp, int yz, int nz, int x, int y, int z,
+                                         int ex, int ey, int ez) {
     const int dx = ex - x, dy = ey - y, dz = ez - z;
     const int sx = dx == 0 ? 0 : (dx < 0 ? -1 : 1), sy = dy == 0 ? 0 : (dy < 0 ? -1 : 1), sz = dz == 0 ? 0 : (dz < 0 ? -1 : 1);
-    double tx = intbound_half(dx), ty = intbound_half(dy), tz = intbound_half(dz);
-    const double ddx = ((double)sx) / dx, ddy = ((double)sy) / dy, ddz = ((double)sz) / dz;
+    // an axis with d = 0 is never stepped (its tMax is the reference's 99999); its delta is never added
+    const double ddx = rcp_abs(rcp, dx), ddy = rcp_abs(rcp, dy), ddz = rcp_abs(rcp, dz);
+    double tx = dx == 0 ? 99999.0 : 0.5 * ddx, ty = dy == 0 ? 99999.0 : 0.5 * ddy, tz = dz == 0 ? 99999.0 : 0.5 * ddz;
+    int rem = (dx < 0 ? -dx : dx) + (dy < 0 ? -dy : dy) + (dz < 0 ? -dz : dz);
+    int idx = x * yz + y * nz + z;
+    const int ix = sx * yz, iy = sy * nz, iz = sz;
     bool free_ray = true;
-    while (true) {
-        if (x == ex && y == ey && z == ez) break;
-        if (tx < ty) {
-            if (tx < tz) { x += sx; tx += ddx; }
-            else { z += sz; tz += ddz; }
-        } else {
-            if (ty < tz) { y += sy; ty += ddy; }
-            else { z += sz; tz += ddz; }
+    while (rem > 0) {
+        uint8_t v[LOOK];
+        int left[LOOK];
+#pragma unroll
+        for (int u = 0; u < LOOK; u++) {
+            if (rem > 0) {
+                if (tx < ty) {
+                    if (tx < tz) { idx += ix; tx += ddx; }
+                    else { idx += iz; tz += ddz; }
+                } else {
+                    if (ty < tz) { idx += iy; ty += ddy; }
+                    else { idx += iz; tz += ddz; }
+                }
+                rem--;
+            }
+            left[u] = rem;
+            v[u] = m[idx];
         }
-        const int idx = x * yz + y * nz + z;
-        if (inside[idx] > 0) return free_ray;
-        if (x == ex && y == ey && z == ez) break;
-        if (occ[idx] > 0) free_ray = false;
+#pragma unroll
+        for (int u = 0; u < LOOK; u++) {
+            if (v[u] & 2) return free_ray;        // an inside voxel of the cluster: stop tracing
+            if (left[u] == 0) return free_ray;    // the target itself is not examined
+            if (v[u] & 1) free_ray = false;
+        }
     }
     return free_ray;
 }
 
-__global__ void __launch_bounds__(256) convex_test_kernel(const uint8_t *__restrict__ occ, const uint8_t *__restrict__ inside, int yz, int nz,
+// A task = one candidate x 32 consecutive targets (earlier candidates first, then the cluster voxels), chunk-major; can_clu is preset
+// to 1 (merge_map_kernel) and cleared by any task that finds a blocked cluster ray; cluster tasks of a candidate already cleared are
+// skipped (their rays decide nothing).
+__global__ void __launch_bounds__(256) convex_test_kernel(const uint8_t *__restrict__ merged, const double *__restrict__ rcp, int yz, int nz,
                                                           const int *__restrict__ cand, int C, const int *__restrict__ clu, int K,
-                                                          uint8_t *__restrict__ can_can, uint8_t *__restrict__ can_clu) {
+                                                          uint8_t *__restrict__ can_can, uint8_t *can_clu) {
     const int lane = threadIdx.x & 31;
-    const int warps = (gridDim.x * blockDim.x) >> 5;
-    // heaviest candidates (most earlier candidates to test against) first
-    for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < C; w += warps) {
-        const int t = C - 1 - w;
-        const int x = cand[3 * t], y = cand[3 * t + 1], z = cand[3 * t + 2];
-        const long long bias = (long long)t * (t + 1) / 2;   // the reference's packing: n (n - 1) / 2 with n = t + 1
-        bool all_clu = true;
-        for (int j = lane; j < t + K; j += 32) {
+    const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const int chunks = (C - 1 + K + 31) >> 5;
+    // task = chunk * C + r, walked with stride `warps`: (chunk, r) advance by (warps / C, warps % C) with a carry - no division per task
+    const long long first = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int dq = (int)(warps / C), dr = (int)(warps % C);
+    int chunk = (int)(first / C), r = (int)(first % C);
+    for (; chunk < chunks; chunk += dq, r += dr) {
+        if (r >= C) { r -= C; chunk++; if (chunk >= chunks) break; }
+        const int t = C - 1 - r, jb = chunk * 32, j = jb + lane;
+        if (jb >= t + K) continue;                                        // warp-uniform
+        if (jb >= t && !((volatile uint8_t *)can_clu)[t]) continue;       // warp-uniform
+        bool clu_ok = true;
+        if (j < t + K) {
             const int *e = j < t ? cand + 3 * j : clu + 3 * (j - t);
-            const bool ok = ray_free(occ, inside, yz, nz, x, y, z, e[0], e[1], e[2]);
-            if (j < t) can_can[bias + j] = ok ? 1 : 0;
-            else all_clu = all_clu && ok;
+            const bool ok = ray_free(merged, rcp, yz, nz, cand[3 * t], cand[3 * t + 1], cand[3 * t + 2], e[0], e[1], e[2]);
+            if (j < t) can_can[(long long)t * (t + 1) / 2 + j] = ok ? 1 : 0;   // the reference's packing: n (n - 1) / 2 with n = t + 1
+            else clu_ok = ok;
         }
-        all_clu = __all_sync(0xffffffffu, all_clu);
-        if (lane == 0) can_clu[t] = all_clu ? 1 : 0;
+        if (!__all_sync(0xffffffffu, clu_ok) && lane == 0) can_clu[t] = 0;
     }
 }
 
@@ -167,12 +211,13 @@ __global__ void __launch_bounds__(1024) inflate_box_kernel(const uint8_t *__rest
 // upload.  Here the whole loop stays on the device; phases are separated by grid barriers:
 //   1a  every (active voxel, neighbour) pair claims its free neighbour cell with atomicMin(key = 26 i + k): the smallest key is
 //       the pair that reaches the cell first in the reference's nested loops (cluster_server.cu:573-626);
-//   1b  CTA 0 compacts the winning pairs in key order -> the reference's candidate list, element for element;
-//   2a  one warp per candidate: rays to the cluster voxels, stop at the first blocked one (can_clu);
-//   2b  one warp per SURVIVING candidate: rays to the earlier surviving candidates; the 32 results of a warp step are one ballot
+//   1b  the winning pairs are compacted in key order (per-segment counts, barrier, bases) -> the reference's candidate list,
+//       element for element;
+//   2a  one warp per (candidate, 32 cluster voxels): rays to the cluster voxels, candidates already found blocked are skipped (can_clu);
+//   2b  one warp per (SURVIVING candidate, 32 earlier surviving candidates); the 32 results of a warp step are one ballot
 //       word of that candidate's conflict bit-row (a candidate that failed 2a is rejected whatever its rays say and is never in
 //       the accepted set, so its rays decide nothing: cluster_server.cu:696-711);
-//   3   warp 0 of CTA 0 walks the candidates in order: accepted <=> can_clu and (conflict row & accepted bit-set) == 0; accepted
+//   3   CTA 0 walks the candidates in order, 32 at a time: accepted <=> can_clu and (conflict row & accepted bit-set) == 0; accepted
 //       voxels are appended to the cluster (they are the next iteration's active set), the others marked invalid.
 // The reference reads the last candidate's can_can row from stale host memory (it downloads C (C - 1) / 2 entries and indexes up
 // to C (C + 1) / 2 - 2); here every row is the kernel's own result, as in oracle/voxel_oracle.c.
@@ -195,13 +240,12 @@ __device__ __forceinline__ bool neighbour_cell(const int *__restrict__ xyz, int 
     return !(x < 0 || x > nx - 1 || y < 0 || y > ny - 1 || z < 0 || z > nz - 1);
 }
 
-__global__ void __launch_bounds__(256) cluster_loop_kernel(const uint8_t *__restrict__ occ, const uint8_t *__restrict__ inside, uint8_t *use,
+__global__ void __launch_bounds__(256) cluster_loop_kernel(const uint8_t *__restrict__ occ, const uint8_t *__restrict__ inside, const uint8_t *__restrict__ merged, const double *__restrict__ rcp, uint8_t *use,
                                                            uint8_t *invalid, int *claim, int nx, int ny, int nz, int *cluster_xyz, int cap,
-                                                           int *cand, int cand_cap, unsigned *conflict, uint8_t *can_clu, int itr_cluster_max,
+                                                           int *cand, int cand_cap, unsigned *conflict, uint8_t *can_clu, int *seg_count, int itr_cluster_max,
                                                            ClusterCtl *ctl, unsigned long long *phase_ns) {
     cg::grid_group grid = cg::this_grid();
     __shared__ unsigned acc[ACC_WORDS];
-    __shared__ int warp_sum[8];
     const int yz = ny * nz, lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x, gthreads = (long long)gridDim.x * blockDim.x;
     const int gwarp = (int)(gtid >> 5), gwarps = (int)(gthreads >> 5);
@@ -235,98 +279,140 @@ __global__ void __launch_bounds__(256) cluster_loop_kernel(const uint8_t *__rest
         }
         grid.sync();
         mark(0);
-        // 1b: ordered compaction by CTA 0 (each thread owns a contiguous range of keys)
-        if (blockIdx.x == 0) {
-            const long long P = 26LL * A, chunk = (P + blockDim.x - 1) / blockDim.x;
-            const long long lo = chunk * threadIdx.x, hi = lo + chunk < P ? lo + chunk : P;
+        // 1b: ordered compaction, grid-wide.  A warp owns segments of 128 consecutive keys (four per lane): count the winning keys of
+        // each segment, barrier, then every segment finds its base (sum of the counts before it) and writes its winners in key order.
+        const long long P = 26LL * A;
+        const int nseg = (int)((P + 127) >> 7);
+        for (int sg = gwarp; sg < nseg; sg += gwarps) {
             int mine = 0;
-            for (long long p = lo; p < hi; p++) {
+            for (int q = 0; q < 4; q++) {
+                const long long p = ((long long)sg << 7) + 4 * lane + q;
                 int x, y, z;
-                if (!neighbour_cell(act, (int)(p / 26), (int)(p % 26), nx, ny, nz, x, y, z)) continue;
-                mine += claim[x * yz + y * nz + z] == (int)p;
+                if (p < P && neighbour_cell(act, (int)(p / 26), (int)(p % 26), nx, ny, nz, x, y, z)) mine += claim[x * yz + y * nz + z] == (int)p;
+            }
+            for (int d = 16; d > 0; d >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, d);
+            if (lane == 0) seg_count[sg] = mine;
+        }
+        if (blockIdx.x == 0) for (int w = threadIdx.x; w < ACC_WORDS; w += blockDim.x) acc[w] = 0;
+        grid.sync();
+        for (int sg = gwarp; sg < nseg; sg += gwarps) {
+            int base = 0;
+            for (int q = lane; q < sg; q += 32) base += seg_count[q];
+            for (int d = 16; d > 0; d >>= 1) base += __shfl_xor_sync(0xffffffffu, base, d);
+            int cell[4], mine = 0;
+            for (int q = 0; q < 4; q++) {
+                const long long p = ((long long)sg << 7) + 4 * lane + q;
+                int x, y, z;
+                cell[q] = -1;
+                if (p < P && neighbour_cell(act, (int)(p / 26), (int)(p % 26), nx, ny, nz, x, y, z) && claim[x * yz + y * nz + z] == (int)p) {
+                    cell[q] = x * yz + y * nz + z; mine++;
+                }
             }
             int incl = mine;
             for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += o; }
-            if (lane == 31) warp_sum[wib] = incl;
-            __syncthreads();
-            int base = 0, total = 0;
-            for (int w = 0; w < (int)(blockDim.x >> 5); w++) { if (w < wib) base += warp_sum[w]; total += warp_sum[w]; }
             int at = base + incl - mine;
-            const bool fits = total <= cand_cap;
-            for (long long p = lo; p < hi; p++) {
-                int x, y, z;
-                if (!neighbour_cell(act, (int)(p / 26), (int)(p % 26), nx, ny, nz, x, y, z)) continue;
-                const int idx = x * yz + y * nz + z;
-                if (claim[idx] != (int)p) continue;
-                claim[idx] = CLAIM_EMPTY;
-                if (fits) { cand[3 * at] = x; cand[3 * at + 1] = y; cand[3 * at + 2] = z; use[idx] = 1; at++; }
+            for (int q = 0; q < 4; q++) {
+                if (cell[q] < 0) continue;
+                claim[cell[q]] = CLAIM_EMPTY;
+                if (at < cand_cap) {
+                    const int x = cell[q] / yz, r = cell[q] - x * yz;
+                    cand[3 * at] = x; cand[3 * at + 1] = r / nz; cand[3 * at + 2] = r % nz;
+                    use[cell[q]] = 1; can_clu[at] = 1;
+                }
+                at++;
             }
-            if (threadIdx.x == 0) { ctl->cand_num = fits ? total : 0; if (!fits) ctl->status = -1; }
-            for (int w = threadIdx.x; w < ACC_WORDS; w += blockDim.x) acc[w] = 0;
-            __syncthreads();
+            if (sg == nseg - 1 && lane == 31) {   // incl of the last lane of the last segment closes the count
+                const int total = base + incl;
+                ctl->cand_num = total <= cand_cap ? total : 0;
+                if (total > cand_cap) ctl->status = -1;
+            }
         }
+        if (nseg == 0 && gtid == 0) ctl->cand_num = 0;
         grid.sync();
         mark(1);
         const int C = ctl->cand_num;
         if (C == 0) break;   // cluster_server.cu:652 (or overflow)
         const int W = (C + 31) >> 5;
-        // 2a: candidate -> cluster rays
-        for (int t = gwarp; t < C; t += gwarps) {
-            const int x = cand[3 * t], y = cand[3 * t + 1], z = cand[3 * t + 2];
-            bool ok = true;
-            for (int jb = 0; jb < K && ok; jb += 32) {
-                const int j = jb + lane;
-                const bool mine_ok = j < K ? ray_free(occ, inside, yz, nz, x, y, z, cluster_xyz[3 * j], cluster_xyz[3 * j + 1], cluster_xyz[3 * j + 2]) : true;
-                ok = __all_sync(0xffffffffu, mine_ok);
+        // 2a: candidate -> cluster rays.  A task = one candidate x 32 cluster voxels, chunk-major so that a candidate found blocked in
+        // an early chunk is skipped by the later ones (the stores of 0 and the skip test race benignly: a late skip only costs rays).
+        {
+            const int chunks = (K + 31) >> 5;
+            const int dq = gwarps / C, dr = gwarps % C;
+            int chunk = gwarp / C, r = gwarp % C;
+            for (; chunk < chunks; chunk += dq, r += dr) {   // task = chunk * C + r, stride gwarps, no division per task
+                if (r >= C) { r -= C; chunk++; if (chunk >= chunks) break; }
+                const int t = r, j = chunk * 32 + lane;
+                if (!((volatile uint8_t *)can_clu)[t]) continue;   // warp-uniform: one address
+                bool ok = true;
+                if (j < K) ok = ray_free(merged, rcp, yz, nz, cand[3 * t], cand[3 * t + 1], cand[3 * t + 2], cluster_xyz[3 * j], cluster_xyz[3 * j + 1], cluster_xyz[3 * j + 2]);
+                if (!__all_sync(0xffffffffu, ok) && lane == 0) can_clu[t] = 0;
             }
-            if (lane == 0) can_clu[t] = ok ? 1 : 0;
         }
         grid.sync();
         mark(2);
-        // 2b: surviving candidate -> earlier surviving candidates, heaviest rows first
-        for (int w = gwarp; w < C; w += gwarps) {
-            const int t = C - 1 - w;
-            if (!can_clu[t]) continue;
-            const int x = cand[3 * t], y = cand[3 * t + 1], z = cand[3 * t + 2];
-            for (int jb = 0; jb < t; jb += 32) {
-                const int j = jb + lane;
+        // 2b: surviving candidate -> earlier surviving candidates.  A task = one candidate x 32 earlier candidates = one conflict word.
+        {
+            const int chunks = (C + 31) >> 5;
+            const int dq = gwarps / C, dr = gwarps % C;
+            int chunk = gwarp / C, r = gwarp % C;
+            for (; chunk < chunks; chunk += dq, r += dr) {
+                if (r >= C) { r -= C; chunk++; if (chunk >= chunks) break; }
+                const int t = C - 1 - r, jb = chunk * 32, j = jb + lane;
+                if (jb >= t || !can_clu[t]) continue;   // warp-uniform
                 bool blocked = false;
-                if (j < t && can_clu[j]) blocked = !ray_free(occ, inside, yz, nz, x, y, z, cand[3 * j], cand[3 * j + 1], cand[3 * j + 2]);
+                if (j < t && can_clu[j]) blocked = !ray_free(merged, rcp, yz, nz, cand[3 * t], cand[3 * t + 1], cand[3 * t + 2], cand[3 * j], cand[3 * j + 1], cand[3 * j + 2]);
                 const unsigned word = __ballot_sync(0xffffffffu, blocked);
                 if (lane == 0) conflict[(size_t)t * W + (jb >> 5)] = word;
             }
         }
         grid.sync();
         mark(3);
-        // 3: acceptance scan (cluster_server.cu:693-737) by CTA 0, 32 candidates at a time: the conflicts with candidates accepted in
-        // EARLIER groups are reduced by the whole CTA (rows read in parallel), the order dependence inside a group is resolved by
-        // warp 0 from the group's diagonal conflict word in registers (32 shuffle steps, no memory on the dependent chain).
+        // 3: acceptance scan (cluster_server.cu:693-737) by CTA 0, 32 candidates (one group) at a time.  Warp 0 resolves group g: the
+        // order dependence inside the group from the group's diagonal conflict word, in registers (a few ballot rounds, no memory on
+        // the dependent chain).  Meanwhile the other warps reduce, for group g + 1, the conflicts with everything accepted in groups < g
+        // (rows read in parallel); the one word they cannot know yet - group g itself - is a single AND for warp 0 in the next round.
         if (blockIdx.x == 0) {
-            __shared__ unsigned prehit;
+            __shared__ unsigned prehit[2];
             int n = K, overflow = 0;   // maintained by warp 0 (uniform across its lanes)
-            for (int b = 0; b < C; b += 32) {
-                if (threadIdx.x == 0) prehit = 0;
-                __syncthreads();
-                const int gw = b >> 5;   // words of earlier groups
-                for (int q = wib; q < 32; q += (int)(blockDim.x >> 5)) {
-                    const int i = b + q;
-                    if (i >= C || !can_clu[i]) continue;   // warp-uniform
-                    bool hit = false;
-                    for (int w = lane; w < gw; w += 32) hit |= (conflict[(size_t)i * W + w] & acc[w]) != 0;
-                    if (__any_sync(0xffffffffu, hit) && lane == 0) atomicOr(&prehit, 1u << q);
-                }
-                __syncthreads();
+            if (threadIdx.x < 2) prehit[threadIdx.x] = 0;
+            unsigned pf_cc = 0, pf_prev = 0, pf_diag = 0;
+            int pf_x = 0, pf_y = 0, pf_z = 0;
+            if (wib == 0 && lane < C) {   // group 0
+                pf_cc = can_clu[lane]; pf_diag = lane > 0 ? conflict[(size_t)lane * W] : 0u;
+                pf_x = cand[3 * lane]; pf_y = cand[3 * lane + 1]; pf_z = cand[3 * lane + 2];
+            }
+            __syncthreads();
+            const int groups = (C + 31) >> 5;
+            for (int g = 0; g < groups; g++) {
                 if (wib == 0) {
-                    const int i = b + lane;
+                    const int i = g * 32 + lane;
                     const bool valid = i < C;
-                    const bool alive = valid && can_clu[i] && !((prehit >> lane) & 1u);
-                    const unsigned diag = (alive && lane > 0) ? conflict[(size_t)i * W + gw] : 0u;   // bits j - b < lane
-                    int x = 0, y = 0, z = 0;
-                    if (valid) { x = cand[3 * i]; y = cand[3 * i + 1]; z = cand[3 * i + 2]; }
-                    unsigned accmask = 0;
-                    for (int k = 0; k < 32; k++) {
-                        const bool ok = alive && (diag & accmask) == 0;
-                        if (__shfl_sync(0xffffffffu, (int)ok, k)) accmask |= 1u << k;
+                    // this group's words were fetched during the previous round (pf_*); fetch the next group's now, off the chain
+                    const unsigned cc = pf_cc, prev = pf_prev, dg = pf_diag;
+                    const int x = pf_x, y = pf_y, z = pf_z;
+                    {
+                        const int i2 = i + 32;
+                        if (i2 < C) {
+                            pf_cc = can_clu[i2]; pf_prev = conflict[(size_t)i2 * W + g]; pf_diag = lane > 0 ? conflict[(size_t)i2 * W + g + 1] : 0u;
+                            pf_x = cand[3 * i2]; pf_y = cand[3 * i2 + 1]; pf_z = cand[3 * i2 + 2];
+                        } else pf_cc = 0;
+                    }
+                    bool alive = valid && cc && !((prehit[g & 1] >> lane) & 1u);
+                    __syncwarp();
+                    if (lane == 0) prehit[g & 1] = 0;   // free for group g + 2 (written after the next barrier)
+                    if (alive && g > 0) alive = (prev & acc[g - 1]) == 0;
+                    const unsigned diag = alive ? dg : 0u;   // bits j - 32 g < lane
+                    // greedy in lane order without a 32-step chain: per round a lane is rejected when it conflicts with an accepted
+                    // lane, accepted when it conflicts with no accepted and no still-undecided lower lane; the lowest undecided lane
+                    // always decides, so the loop ends, usually after two or three rounds
+                    unsigned accmask = 0, und = __ballot_sync(0xffffffffu, alive);
+                    const unsigned lower = (1u << lane) - 1u;
+                    while (und) {
+                        const bool me = (und >> lane) & 1u;
+                        const bool rej = me && (diag & accmask) != 0;
+                        const bool acc_now = me && !rej && (diag & und & lower) == 0;
+                        const unsigned a = __ballot_sync(0xffffffffu, acc_now), r = __ballot_sync(0xffffffffu, rej);
+                        accmask |= a; und &= ~(a | r);
                     }
                     const bool mine = (accmask >> lane) & 1u;
                     const int at = n + __popc(accmask & ((1u << lane) - 1u));
@@ -334,9 +420,28 @@ __global__ void __launch_bounds__(256) cluster_loop_kernel(const uint8_t *__rest
                     if (mine && fits) { cluster_xyz[3 * at] = x; cluster_xyz[3 * at + 1] = y; cluster_xyz[3 * at + 2] = z; }
                     else if (valid) invalid[x * yz + y * nz + z] = 1;
                     const unsigned kept = __ballot_sync(0xffffffffu, mine && fits);
-                    if (lane == 0) acc[gw] = kept;
+                    if (lane == 0) acc[g] = kept;
                     n += __popc(kept);
                     if (kept != accmask) overflow = 1;
+                } else if (g >= 1 && g + 1 < groups) {
+                    // 32 rows x g words of group g + 1, flat over the helper threads, eight independent reads in flight per thread
+                    // (rows of candidates that failed 2a hold stale words: warp 0 ignores their bits)
+                    const int items = 32 * g, th = (int)threadIdx.x - 32, nh = (int)blockDim.x - 32;
+                    for (int base = th; base < items; base += nh * 8) {
+                        unsigned v[8];
+#pragma unroll
+                        for (int u = 0; u < 8; u++) {
+                            const int idx = base + u * nh;
+                            v[u] = 0;
+                            if (idx < items) {
+                                const int q = idx / g, w = idx - q * g, i = (g + 1) * 32 + q;
+                                if (i < C) v[u] = conflict[(size_t)i * W + w] & acc[w];
+                            }
+                        }
+#pragma unroll
+                        for (int u = 0; u < 8; u++)
+                            if (v[u]) atomicOr(&prehit[(g + 1) & 1], 1u << ((base + u * nh) / g));
+                    }
                 }
                 __syncthreads();
             }
