@@ -17,6 +17,7 @@
 #include "../../include/direct_voxel.h"
 #include "ipddp_solver.h"
 #include "gddp.cuh"
+#include "gddp_pair.cuh"
 #include "voxel.cuh"
 
 #ifndef DDP_MAX_THREADS
@@ -676,19 +677,22 @@ template <int MODEL, class R> int gddp_launch(H *h, const direct_gddp_problem *i
     for (int a = 0; a < D::NX; a++) { A.q[a] = (R)in->q[a]; A.qf[a] = (R)in->qf[a]; }
     for (int m = 0; m < D::NU; m++) { A.r[m] = (R)in->r[m]; A.uh[m] = (R)in->uh[m]; }
     A.rtn = out->rtn; A.iters = out->iters; A.cost = out->cost; A.x = out->x; A.u = out->u; A.stats = (long long *)out->stats;
+    // two trajectories per warp (gddp_pair.cuh) unless DIRECT_GDDP_PAIR=0 asks for the one-per-warp kernel (tuning / comparison)
+    const char *pe = getenv("DIRECT_GDDP_PAIR");
+    const int tpw = (pe && atoi(pe) == 0) ? 1 : 2;
     const int threads = 128, wpb = threads / 32;
-    const size_t smem = (size_t)wpb * gddp::Smem<MODEL>::TOTAL * sizeof(R);
-    auto kern = gddp::gddp_kernel<MODEL, R>;
+    const size_t smem = (size_t)wpb * tpw * gddp::Smem<MODEL>::TOTAL * sizeof(R);
+    auto kern = tpw == 2 ? gddp::gddp_pair_kernel<MODEL, R> : gddp::gddp_kernel<MODEL, R>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
     if (per_sm < 1) { h->err = "gddp kernel does not fit on an SM"; return DIRECT_DDP_ERR_CUDA; }
     long long grid = (long long)per_sm * h->sm_count;
-    const long long need = ((long long)in->B + wpb - 1) / wpb;
+    const long long need = ((long long)in->B + wpb * tpw - 1) / (wpb * tpw);
     if (grid > need) grid = need;
     const gddp::Ws<MODEL, R> wl(in->N);
     A.ws_stride = wl.total;
-    int st = ensure(h, h->ws, (size_t)grid * wpb * wl.total * sizeof(R));
+    int st = ensure(h, h->ws, (size_t)grid * wpb * tpw * wl.total * sizeof(R));
     if (st) return st;
     A.ws = (R *)h->ws.p;
     if ((st = ensure(h, h->counter, 64))) return st;
@@ -700,7 +704,7 @@ template <int MODEL, class R> int gddp_launch(H *h, const direct_gddp_problem *i
     CK(cudaEventRecord(h->ev[3], s));
     h->stats.kernel_launches = 1;
     h->stats.grid_blocks = (int)grid; h->stats.block_threads = threads;
-    h->stats.smem_bytes_per_block = (int)smem; h->stats.workspace_slots = (int)(grid * wpb);
+    h->stats.smem_bytes_per_block = (int)smem; h->stats.workspace_slots = (int)(grid * wpb * tpw);
     h->last_stats_dev = nullptr; h->last_stats_dev0 = nullptr; h->last_B = 0; h->stats_valid = false;
     return 0;
 }

@@ -1,0 +1,8 @@
+# Round-end verification on one B200: full GPU suite, smoke, bench (both arms), launch list of the bench command.
+set -x
+timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -15 > gpurun_out/final_pytest.log; cat gpurun_out/final_pytest.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -5 | tee gpurun_out/final_smoke.log
+timeout 900 python bench.py > gpurun_out/bench_final.json 2> gpurun_out/bench_final.err; cat gpurun_out/bench_final.json; tail -3 gpurun_out/bench_final.err
+timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_final_ref.json 2> gpurun_out/bench_final_ref.err; cat gpurun_out/bench_final_ref.json
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_r1j.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/b_ncu_r1j.log 2>&1
+tail -2 gpurun_out/b_ncu_r1j.log
