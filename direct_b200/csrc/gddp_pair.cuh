@@ -47,17 +47,42 @@ __device__ __forceinline__ R rollout2(const Args<R> &A, int b, int hl, bool act,
     if (act && hl < NX) xn[hl] = pick<NX>(x, hl);
     R J = R(0);
     R *st = sm + Smem<MODEL>::XU;
+    // the knot's old state, control, feedforward and gain row are fetched one knot ahead (the recursion would otherwise wait for
+    // them at every knot: they were 14 % of the kernel's stall samples)
+    R stn = R(0), ubn = R(0), kfn = R(0), Kn[NX];
+#pragma unroll
+    for (int a = 0; a < NX; a++) Kn[a] = R(0);
+    if (closed) {
+        if (hl < NX) stn = xb[hl];
+        if (hl < NU) {
+            ubn = ub[hl]; kfn = kf[hl];
+#pragma unroll
+            for (int a = 0; a < NX; a++) Kn[a] = K[(long long)hl * NX + a];
+        }
+    }
     for (int i = 0; i < A.N; i++) {
         R u[NU];
         if (closed) {
-            if (hl < NX) st[hl] = xb[(long long)i * XS + hl];
+            if (hl < NX) st[hl] = stn;
+            const R ubc = ubn, kfc = kfn;
+            R Kc[NX];
+#pragma unroll
+            for (int a = 0; a < NX; a++) Kc[a] = Kn[a];
+            if (i + 1 < A.N) {
+                if (hl < NX) stn = xb[(long long)(i + 1) * XS + hl];
+                if (hl < NU) {
+                    ubn = ub[(long long)(i + 1) * NU + hl]; kfn = kf[(long long)(i + 1) * NU + hl];
+                    const R *Kr = K + ((long long)(i + 1) * NU + hl) * NX;
+#pragma unroll
+                    for (int a = 0; a < NX; a++) Kn[a] = Kr[a];
+                }
+            }
             __syncwarp();
             R v = R(0);
             if (hl < NU) {
-                v = ub[(long long)i * NU + hl] + alpha * kf[(long long)i * NU + hl];
-                const R *Kr = K + ((long long)i * NU + hl) * NX;
+                v = ubc + alpha * kfc;
 #pragma unroll
-                for (int a = 0; a < NX; a++) v += Kr[a] * (x[a] - st[a]);
+                for (int a = 0; a < NX; a++) v += Kc[a] * (x[a] - st[a]);
             }
 #pragma unroll
             for (int m = 0; m < NU; m++) u[m] = shfl16(v, m);
@@ -191,7 +216,7 @@ __device__ __forceinline__ bool sweep2(const Args<R> &A, int b, int hl, bool act
 #pragma unroll
         for (int r = 0; r < NZ; r++) if (hl == r) qc[r] += wdiag;
         // ---- eliminate the nu control rows -------------------------------------------------------------------------------------
-        R mp[NU], mg[NU];
+        R mp[NU], mg[NU], rip[NU];
 #pragma unroll
         for (int p = 0; p < NU; p++) {
             const R d = shfl16(qc[NX + p], NX + p);
@@ -199,7 +224,7 @@ __device__ __forceinline__ bool sweep2(const Args<R> &A, int b, int hl, bool act
             const R ri = g_rsqrt(d);
             const R m = (hl == NX + p) ? d * ri : qc[NX + p] * ri;
             const R gp = shfl16(g, NX + p) * ri;   // the gradient column's multiplier
-            mp[p] = m; mg[p] = gp;
+            mp[p] = m; mg[p] = gp; rip[p] = ri;
             if (hl < NZ) sm[SM::LM + p * (NZ + 1) + hl] = m;
             __syncwarp();
             const R *Lm = sm + SM::LM + p * (NZ + 1);
@@ -218,8 +243,7 @@ __device__ __forceinline__ bool sweep2(const Args<R> &A, int b, int hl, bool act
                 R s = mp[p], sg = mg[p];
 #pragma unroll
                 for (int t = p + 1; t < NU; t++) { const R l = sm[SM::LM + p * (NZ + 1) + NX + t]; s -= l * z[t]; sg -= l * zg[t]; }
-                const R dd = sm[SM::LM + p * (NZ + 1) + NX + p];
-                z[p] = s / dd; zg[p] = sg / dd;
+                z[p] = s * rip[p]; zg[p] = sg * rip[p];   // 1 / L[p][p] = 1 / sqrt(d) is the pivot's rsqrt
             }
             if (st && hl < NX) {
 #pragma unroll
