@@ -81,15 +81,17 @@ template <class R> struct Model<1, R> {   // rigid-body quadrotor, Euler angles 
         for (int t = 0; t < 3; t++) { tg[2 * t] = __shfl_sync(0xffffffffu, s, t); tg[2 * t + 1] = __shfl_sync(0xffffffffu, c, t); }
     }
     static __device__ __forceinline__ void f(const R *x, const R *u, const R *tg, R *fx) {
+        // divisions by the constants are multiplications by their (compile-time) reciprocals; one division per point (1 / cos pitch)
         const R m = R(0.98), g = R(9.81), Jx = R(2.64e-3), Jy = R(2.64e-3), Jz = R(4.96e-3);
+        const R im = R(1) / m, iJx = R(1) / Jx, iJy = R(1) / Jy, iJz = R(1) / Jz;
         const R p = x[9], q = x[10], r = x[11];
         const R sp = tg[0], cp = tg[1], st = tg[2], ct = tg[3], ss = tg[4], cs = tg[5];
-        const R tt = st / ct, ict = R(1) / ct, fm = u[0] / m;
+        const R ict = R(1) / ct, tt = st * ict, fm = u[0] * im;
         fx[0] = x[3]; fx[1] = x[4]; fx[2] = x[5];
         fx[3] = fm * (cp * st * cs + sp * ss); fx[4] = fm * (cp * st * ss - sp * cs); fx[5] = fm * (cp * ct) - g;
         const R sqcr = sp * q + cp * r, cqsr = cp * q - sp * r;
         fx[6] = p + tt * sqcr; fx[7] = cqsr; fx[8] = sqcr * ict;
-        fx[9] = (u[1] - (Jz - Jy) * q * r) / Jx; fx[10] = (u[2] - (Jx - Jz) * p * r) / Jy; fx[11] = (u[3] - (Jy - Jx) * p * q) / Jz;
+        fx[9] = (u[1] - (Jz - Jy) * q * r) * iJx; fx[10] = (u[2] - (Jx - Jz) * p * r) * iJy; fx[11] = (u[3] - (Jy - Jx) * p * q) * iJz;
     }
     __host__ __device__ static constexpr int ga(int j) { return j < 6 ? 0 : (j < 9 ? 3 : (j < 12 ? 6 : (j == 12 ? 3 : 9))); }
     __host__ __device__ static constexpr int gb(int j) { return j < 6 ? 0 : (j < 9 ? 6 : (j < 12 ? 9 : 0)); }
@@ -98,9 +100,10 @@ template <class R> struct Model<1, R> {   // rigid-body quadrotor, Euler angles 
     __host__ __device__ static constexpr bool has_id(int j) { return j < 12; }
     static __device__ __forceinline__ void column(const R *x, const R *u, const R *tg, R dt, int j, R *aA, R *aB) {
         const R m = R(0.98), Jx = R(2.64e-3), Jy = R(2.64e-3), Jz = R(4.96e-3);
+        const R im = R(1) / m, iJx = R(1) / Jx, iJy = R(1) / Jy, iJz = R(1) / Jz;
         const R p = x[9], q = x[10], r = x[11];
         const R sp = tg[0], cp = tg[1], st = tg[2], ct = tg[3], ss = tg[4], cs = tg[5];
-        const R tt = st / ct, ict = R(1) / ct, fm = u[0] / m;
+        const R ict = R(1) / ct, tt = st * ict, fm = u[0] * im;
         const R sqcr = sp * q + cp * r, cqsr = cp * q - sp * r;
         const int grp = j / 3, k = j - 3 * grp;
         aA[0] = aA[1] = aA[2] = R(0); aB[0] = aB[1] = aB[2] = R(0);
@@ -118,13 +121,13 @@ template <class R> struct Model<1, R> {   // rigid-body quadrotor, Euler angles 
             aA[0] = dt * sel3(R(1), sp * tt, cp * tt, k);
             aA[1] = dt * sel3(R(0), cp, -sp, k);
             aA[2] = dt * sel3(R(0), sp * ict, cp * ict, k);
-            aB[0] = dt * sel3(R(0), -(Jz - Jy) * r / Jx, -(Jz - Jy) * q / Jx, k);
-            aB[1] = dt * sel3(-(Jx - Jz) * r / Jy, R(0), -(Jx - Jz) * p / Jy, k);
-            aB[2] = dt * sel3(-(Jy - Jx) * q / Jz, -(Jy - Jx) * p / Jz, R(0), k);
+            aB[0] = dt * sel3(R(0), -(Jz - Jy) * r * iJx, -(Jz - Jy) * q * iJx, k);
+            aB[1] = dt * sel3(-(Jx - Jz) * r * iJy, R(0), -(Jx - Jz) * p * iJy, k);
+            aB[2] = dt * sel3(-(Jy - Jx) * q * iJz, -(Jy - Jx) * p * iJz, R(0), k);
         } else if (j == 12) {    // thrust column: dv/df
-            aA[0] = dt * ((cp * st * cs + sp * ss) / m); aA[1] = dt * ((cp * st * ss - sp * cs) / m); aA[2] = dt * ((cp * ct) / m);
+            aA[0] = dt * ((cp * st * cs + sp * ss) * im); aA[1] = dt * ((cp * st * ss - sp * cs) * im); aA[2] = dt * ((cp * ct) * im);
         } else if (j > 12) {     // torque columns: d(omega dot)/d(tau)
-            aA[0] = j == 13 ? dt * (R(1) / Jx) : R(0); aA[1] = j == 14 ? dt * (R(1) / Jy) : R(0); aA[2] = j == 15 ? dt * (R(1) / Jz) : R(0);
+            aA[0] = j == 13 ? dt * iJx : R(0); aA[1] = j == 14 ? dt * iJy : R(0); aA[2] = j == 15 ? dt * iJz : R(0);
         }
     }
 };
