@@ -681,7 +681,7 @@ template <int MODEL, class R> int gddp_launch(H *h, const direct_gddp_problem *i
     const char *pe = getenv("DIRECT_GDDP_PAIR");
     const int tpw = (pe && atoi(pe) == 0) ? 1 : 2;
     const int threads = 128, wpb = threads / 32;
-    const size_t smem = (size_t)wpb * tpw * gddp::Smem<MODEL>::TOTAL * sizeof(R);
+    const size_t smem = (size_t)wpb * (tpw == 2 ? 2 * gddp::SmemP<MODEL>::TOTAL : gddp::Smem<MODEL>::TOTAL) * sizeof(R);
     auto kern = tpw == 2 ? gddp::gddp_pair_kernel<MODEL, R> : gddp::gddp_kernel<MODEL, R>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;

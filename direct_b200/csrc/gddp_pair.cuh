@@ -27,6 +27,25 @@ template <int MODEL, class R> __device__ __forceinline__ void trig16(const R *x,
     }
 }
 
+// Per-half shared scratch.  Rows of V and of the unsymmetrised Schur complement are padded to NX + 1 elements: lane k reads / writes row k,
+// and an odd row stride puts the 16 lanes of a half on 16 different banks (stride 12 gave two-way conflicts on every access).  TOTAL is
+// 16 mod 32, so the two halves of a warp, which execute every access together, use complementary banks.
+template <int MODEL> struct SmemP {
+    using D = Dim<MODEL>;
+    enum {
+        LD = D::NX + 1,
+        V0 = 0,
+        V1 = D::NX * LD,
+        S = 2 * D::NX * LD,
+        VX = 3 * D::NX * LD,
+        AC = VX + D::NX,
+        LM = AC + D::NZ * 6,
+        XU = LM + D::NU * (D::NZ + 1),
+        END = XU + D::XS + D::NU,
+        TOTAL = ((END + 15) / 32) * 32 + 16
+    };
+};
+
 // Register array element selected by a lane index (a select chain: no local memory).
 template <int n, class R> __device__ __forceinline__ R pick(const R *v, int k) {
     R r = v[0];
@@ -46,7 +65,7 @@ __device__ __forceinline__ R rollout2(const Args<R> &A, int b, int hl, bool act,
     for (int a = 0; a < NX; a++) { x[a] = (R)A.x0[(long long)b * NX + a]; xg[a] = (R)A.xg[(long long)b * NX + a]; }
     if (act && hl < NX) xn[hl] = pick<NX>(x, hl);
     R J = R(0);
-    R *st = sm + Smem<MODEL>::XU;
+    R *st = sm + SmemP<MODEL>::XU;
     // the knot's old state, control, feedforward and gain row are fetched one knot ahead (the recursion would otherwise wait for
     // them at every knot: they were 14 % of the kernel's stall samples)
     R stn = R(0), ubn = R(0), kfn = R(0), Kn[NX];
@@ -118,15 +137,15 @@ template <int MODEL, class R>
 __device__ __forceinline__ bool sweep2(const Args<R> &A, int b, int hl, bool act, R *sm, const R *xb, const R *ub, R rho, R *K, R *kf, R *dV1,
                                        long long *knots) {
     using D = Dim<MODEL>;
-    using SM = Smem<MODEL>;
+    using SM = SmemP<MODEL>;
     using M = Model<MODEL, R>;
-    constexpr int NX = D::NX, NU = D::NU, NZ = D::NZ, NT = D::NT, XS = D::XS, NP = XS + NU;   // NP entries of a staged point
+    constexpr int NX = D::NX, NU = D::NU, NZ = D::NZ, NT = D::NT, XS = D::XS, NP = XS + NU, LD = SM::LD;   // NP entries of a staged point
     static_assert(NZ <= 16 && NP <= 32, "a trajectory must fit a half-warp");
     const int N = A.N;
     R xg[NX];
 #pragma unroll
     for (int a = 0; a < NX; a++) xg[a] = (R)A.xg[(long long)b * NX + a];
-    for (int e = hl; e < NX * NX; e += 16) sm[SM::V0 + e] = (e / NX == e % NX) ? A.qf[e % NX] : R(0);
+    for (int e = hl; e < NX * NX; e += 16) sm[SM::V0 + (e / NX) * LD + e % NX] = (e / NX == e % NX) ? A.qf[e % NX] : R(0);
     if (hl < NX) sm[SM::VX + hl] = pick<NX>(A.qf, hl) * (xb[(long long)N * XS + hl] - pick<NX>(xg, hl));
     // this lane's row: Hessian diagonal entry, weight and target of the cost gradient, where its own z entry sits in the staged point
     R wdiag = R(0), gw = R(0), gt = R(0);
@@ -169,15 +188,15 @@ __device__ __forceinline__ bool sweep2(const Args<R> &A, int b, int hl, bool act
             const int ga = M::ga(hl), gb = M::gb(hl);
             const bool id = M::has_id(hl);
             const R idw = id ? R(1) : R(0);
-            const R *v0 = V + (hl < NX ? hl : 0) * NX;
-            const R *vA = V + ga * NX, *vB = V + gb * NX;
+            const R *v0 = V + (hl < NX ? hl : 0) * LD;
+            const R *vA = V + ga * LD, *vB = V + gb * LD;
 #pragma unroll
             for (int r = 0; r < NX; r++) {
                 R acc = idw * v0[r];
 #pragma unroll
-                for (int t = 0; t < 3; t++) acc += vA[t * NX + r] * aA[t];
+                for (int t = 0; t < 3; t++) acc += vA[t * LD + r] * aA[t];
 #pragma unroll
-                for (int t = 0; t < 3; t++) acc += vB[t * NX + r] * aB[t];
+                for (int t = 0; t < 3; t++) acc += vB[t * LD + r] * aB[t];
                 w[r] = acc;
             }
 #pragma unroll
@@ -254,14 +273,14 @@ __device__ __forceinline__ bool sweep2(const Args<R> &A, int b, int hl, bool act
         // ---- the trailing block is the new value function ----------------------------------------------------------------------
         if (hl < NX) {
 #pragma unroll
-            for (int r = 0; r < NX; r++) sm[SM::S + r * NX + hl] = qc[r];
+            for (int r = 0; r < NX; r++) sm[SM::S + r * LD + hl] = qc[r];
             sm[SM::VX + hl] = g;
         }
         __syncwarp();
         if (hl < NX) {
             R *Vn = sm + (vb ? SM::V0 : SM::V1);
 #pragma unroll
-            for (int r = 0; r < NX; r++) Vn[hl * NX + r] = R(0.5) * (qc[r] + sm[SM::S + hl * NX + r]);
+            for (int r = 0; r < NX; r++) Vn[hl * LD + r] = R(0.5) * (qc[r] + sm[SM::S + hl * LD + r]);
         }
         vb ^= 1;
         __syncwarp();
@@ -279,7 +298,7 @@ template <int MODEL, class R> __global__ void __launch_bounds__(128, GDDP_PAIR_M
     constexpr int NX = D::NX, NU = D::NU;
     extern __shared__ __align__(16) unsigned char gsm_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5, sub = lane >> 4, hl = lane & 15;
-    R *sm = reinterpret_cast<R *>(gsm_raw) + (warp * 2 + sub) * Smem<MODEL>::TOTAL;
+    R *sm = reinterpret_cast<R *>(gsm_raw) + (warp * 2 + sub) * SmemP<MODEL>::TOTAL;
     const Ws<MODEL, R> wl(A.N);
     R *ws = A.ws + (((long long)blockIdx.x * wpb + warp) * 2 + sub) * A.ws_stride;
     const int N = A.N;
