@@ -184,11 +184,22 @@ def model_b_report(capi, torch, dev, local_rank, flush, steps, with_cpu):
     knots = int(stats[:, 2].sum())
     fl = gddp.bwd_flops_per_knot(12, 4)
     peak = solver.fma_peak_tflops("fp32")
+    # e2e: the host-buffer C-ABI call from / into pinned host memory (H2D + solve + D2H inside the call)
+    hres = gddp.GddpResult(B, N, 12, 4)
+    pins = []
+    for name in ("rtn", "iters", "cost", "x", "u", "stats"):
+        a = getattr(hres, name)
+        tp = torch.empty(a.shape, dtype=torch.from_numpy(a).dtype, pin_memory=True)
+        pins.append(tp)
+        setattr(hres, name, tp.numpy())
+    gpin = dataclasses.replace(gp, x0=torch.from_numpy(gp.x0).pin_memory().numpy(), xg=torch.from_numpy(gp.xg).pin_memory().numpy())
+    gddp.solve(solver, gpin, hres)         # warm-up (staging buffers of the handle)
+    torch.cuda.synchronize()
+    e2e_n = max(3, steps)
     t0 = time.perf_counter()
-    e2e_n = 3
     for _ in range(e2e_n):
         flush.fill_(2)
-        hres = gddp.solve(solver, gp)      # host buffers: H2D + solve + D2H inside the call
+        gddp.solve(solver, gpin, hres)
     torch.cuda.synchronize()
     e2e_s = (time.perf_counter() - t0) / e2e_n
     st = solver.stats()

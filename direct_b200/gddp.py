@@ -104,11 +104,13 @@ def problem_struct(gp: GddpProblem, x0_ptr=None, xg_ptr=None, u_init_ptr=None) -
     return p
 
 
-def solve(solver, gp: GddpProblem) -> GddpResult:
-    """Host-buffer call through the C-ABI on `solver` (a direct_b200.capi.Solver: device, precision, stream)."""
+def solve(solver, gp: GddpProblem, out: GddpResult | None = None) -> GddpResult:
+    """Host-buffer call through the C-ABI on `solver` (a direct_b200.capi.Solver: device, precision, stream).  `out`: a result whose
+    arrays the caller owns (e.g. views of pinned memory); a fresh pageable one is allocated otherwise."""
     lib = solver.lib
     lib.direct_gddp_solve.argtypes = [C.c_void_p, C.POINTER(ProblemC), C.POINTER(ResultC)]
-    out = GddpResult(gp.B, gp.N, gp.nx, gp.nu)
+    if out is None:
+        out = GddpResult(gp.B, gp.N, gp.nx, gp.nu)
     p, o = problem_struct(gp), out.c_struct()
     solver._check(lib.direct_gddp_solve(solver.h, C.byref(p), C.byref(o)))
     return out

@@ -6,3 +6,11 @@ timeout 900 python bench.py > gpurun_out/bench_final.json 2> gpurun_out/bench_fi
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_final_ref.json 2> gpurun_out/bench_final_ref.err; cat gpurun_out/bench_final_ref.json
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_r1j.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/b_ncu_r1j.log 2>&1
 tail -2 gpurun_out/b_ncu_r1j.log
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:gddp_pair -c 1 -o gpurun_out/prof_gddp_pair -f python tools/gddp_report.py --reps 1 > gpurun_out/ncu_gddp_pair.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:gddp_pair -c 1 -o gpurun_out/prof_gddp_pair64k -f python tools/gddp_report.py --reps 1 --batch 65536 > gpurun_out/ncu_gddp_pair64k.log 2>&1
+timeout 200 python tools/gddp_report.py | tee gpurun_out/gddp_final.log
+timeout 200 python tools/gddp_report.py --batch 16384 | tee -a gpurun_out/gddp_final.log
+timeout 200 python tools/gddp_report.py --batch 65536 --reps 3 | tee -a gpurun_out/gddp_final.log
+timeout 200 python tools/gddp_report.py --precision fp64 | tee -a gpurun_out/gddp_final.log
+timeout 200 python tools/gddp_report.py --knots 200 | tee -a gpurun_out/gddp_final.log
+timeout 200 python tools/gddp_report.py --model dint --knots 50 | tee -a gpurun_out/gddp_final.log
