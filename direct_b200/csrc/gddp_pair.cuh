@@ -7,7 +7,8 @@
 // one shuffle and one multiply-add instead of a 17th lane.  The two halves of a warp run two trajectories of a pair in lockstep
 // (same code, width-16 shuffles, stores predicated per half); a half that has converged, or whose line search has accepted,
 // idles until its partner catches up (measured on the bench problems: 92 % of the pair's steps are useful for both halves).
-// Same arithmetic, in the same order, as gddp.cuh; the checker is the same oracle (oracle/gddp_oracle.c, parity unpinned).
+// Same arithmetic, in the same order, as gddp.cuh (one difference: the gains are multiplied by the pivot's rsqrt instead of divided by
+// its square root); the checker is the same oracle (oracle/gddp_oracle.c, parity unpinned).
 #ifndef DIRECT_B200_GDDP_PAIR_CUH_
 #define DIRECT_B200_GDDP_PAIR_CUH_
 

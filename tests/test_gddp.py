@@ -155,3 +155,41 @@ def test_gpu_double_integrator_config0(G):
 
 def G_threads():
     return max(1, len(os.sched_getaffinity(0)))
+
+
+@pytest.mark.gpu
+def test_gpu_pair_kernel_ragged_batches_and_single_kernel_agree(G, monkeypatch):
+    """Two trajectories share a warp (gddp_pair.cuh): odd batches leave a half-warp without a trajectory, a batch of one leaves a whole
+    half idle, and a pair's halves finish at different iterations.  Every batch size must give, trajectory for trajectory, the
+    decisions of the one-trajectory-per-warp kernel (DIRECT_GDDP_PAIR=0; same arithmetic except that the gains are multiplied by the
+    pivot's rsqrt instead of divided by its square root) and its numbers to 1e-9, results that do not depend on the partner (bit for
+    bit), and what the oracle gives within 1e-5."""
+    from direct_b200.capi import Solver
+    full = make_quad_batch(67, 60)
+    u0 = np.tile(np.array([0.98 * 9.81, 0.0, 0.0, 0.0]), (67, 60, 1)) + 0.01 * np.sin(np.arange(67 * 60 * 4)).reshape(67, 60, 4)
+    full = dataclasses.replace(full, u_init=np.ascontiguousarray(u0))     # warm-start controls: the u_init path of both kernels
+    a = G.solve_batch(full, nthreads=G_threads())
+    assert len(set(a.iters.tolist())) > 2                                  # partners do finish at different iterations
+    s = Solver(0, "fp64")
+    res = {}
+    for B in (1, 2, 3, 66, 67):
+        gp = full.slice(0, B)
+        monkeypatch.setenv("DIRECT_GDDP_PAIR", "1")
+        p = gddp.solve(s, gp)
+        monkeypatch.setenv("DIRECT_GDDP_PAIR", "0")
+        q = gddp.solve(s, gp)
+        assert np.array_equal(p.rtn, q.rtn) and np.array_equal(p.iters, q.iters)
+        assert np.array_equal(p.stats[:, :3], q.stats[:, :3])             # sweeps, rollouts, backward knots
+        for f in ("cost", "x", "u"):
+            assert np.abs(getattr(p, f) - getattr(q, f)).max() <= 1e-9 * max(1.0, np.abs(getattr(q, f)).max()), (B, f)
+        res[B] = p
+    monkeypatch.delenv("DIRECT_GDDP_PAIR")
+    s.close()
+    g = res[67]
+    for B in (1, 2, 3, 66):                                                # a trajectory's result does not depend on its partner
+        for f in ("rtn", "iters", "cost", "x", "u"):
+            assert np.array_equal(getattr(res[B], f), getattr(g, f)[:B]), (B, f)
+    ok = _screen(a)
+    same = ok & (g.rtn == a.rtn) & (g.iters == a.iters)
+    assert same.mean() > 0.9
+    assert (np.abs(g.cost[same] - a.cost[same]) / np.abs(a.cost[same])).max() < 1e-5
