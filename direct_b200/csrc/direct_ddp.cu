@@ -1064,3 +1064,59 @@ extern "C" int direct_voxel_cluster_phases(direct_ddp_handle h, double ms[5]) {
     for (int k = 0; k < 5; k++) ms[k] = (double)ns[k] * 1e-6;
     return DIRECT_DDP_OK;
 }
+
+extern "C" int direct_voxel_polytope(direct_ddp_handle h, const direct_voxel_map *map, const int32_t seed_xyz[3], int itr_inflate_max,
+                                     int itr_cluster_max, int cap, int cand_cap, int32_t *cluster_xyz, int32_t *cluster_num, int32_t *iters,
+                                     int32_t *vertex_idx, uint8_t *inside, uint8_t *use, uint8_t *invalid) {
+    REQUIRE_DEVICE(h)
+    int st = voxel_validate(h, map);
+    if (st) return st;
+    if (!seed_xyz || !cluster_xyz || !cluster_num || cap <= 0 || seed_xyz[0] < 0 || seed_xyz[0] >= map->nx || seed_xyz[1] < 0 ||
+        seed_xyz[1] >= map->ny || seed_xyz[2] < 0 || seed_xyz[2] >= map->nz) { h->err = "bad polytope argument (seed outside the map?)"; return DIRECT_DDP_ERR_ARG; }
+    CK(cudaSetDevice(h->opts.device));
+    cudaStream_t s = h->stream;
+    const size_t cells = (size_t)map->nx * map->ny * map->nz;
+    direct_voxel_map d;
+    CK(cudaEventRecord(h->ev[0], s));
+    if ((st = voxel_upload_map(h, map, &d, s, false))) return st;
+    if ((st = ensure(h, h->vx[1], cells)) || (st = ensure(h, h->vx[13], cells)) || (st = ensure(h, h->vx[14], cells)) ||
+        (st = ensure(h, h->vx[3], (size_t)cap * 12)) || (st = ensure(h, h->vx[6], 96)) || (st = ensure(h, h->vx[7], 16)) ||
+        (st = ensure(h, h->vx[12], 32))) return st;
+    d.inside = (const uint8_t *)h->vx[1].p;
+    int32_t v[24], ctl[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int k = 0; k < 8; k++) { v[k] = seed_xyz[0]; v[8 + k] = seed_xyz[1]; v[16 + k] = seed_xyz[2]; }   // cluster_server.cu:793-800
+    CK(cudaMemcpyAsync(h->vx[6].p, v, 96, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(h->vx[12].p, ctl, 32, cudaMemcpyHostToDevice, s));
+    CK(cudaEventRecord(h->ev[1], s));
+    CK(cudaMemsetAsync(h->vx[1].p, 0, cells, s));    // flagClear
+    CK(cudaMemsetAsync(h->vx[13].p, 0, cells, s));
+    CK(cudaMemsetAsync(h->vx[14].p, 0, cells, s));
+    if ((st = direct_voxel_inflate_box_device(h, &d, (int32_t *)h->vx[6].p, 1, itr_inflate_max, (int32_t *)h->vx[7].p, s))) return st;
+    voxel::cube_shell_kernel<<<h->sm_count * 2, 256, 0, s>>>((const int *)h->vx[6].p, map->ny, map->nz, (uint8_t *)h->vx[1].p, (uint8_t *)h->vx[13].p,
+                                                            (int *)h->vx[3].p, cap, (voxel::ClusterCtl *)h->vx[12].p);
+    CK(cudaGetLastError());
+    if (cand_cap > 0 && itr_cluster_max >= 0) {
+        if ((st = direct_voxel_cluster_device(h, &d, (uint8_t *)h->vx[13].p, (uint8_t *)h->vx[14].p, (int32_t *)h->vx[3].p, (int32_t *)h->vx[12].p,
+                                              cap, cand_cap, itr_cluster_max, s))) return st;
+    }
+    CK(cudaMemcpyAsync(ctl, h->vx[12].p, 32, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(v, h->vx[6].p, 96, cudaMemcpyDeviceToHost, s));
+    int32_t it_inf = 0;
+    CK(cudaMemcpyAsync(&it_inf, h->vx[7].p, 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (ctl[2] != 0) { h->err = "cluster or candidate capacity exceeded"; return DIRECT_DDP_ERR_ARG; }
+    CK(cudaMemcpyAsync(cluster_xyz, h->vx[3].p, (size_t)ctl[0] * 12, cudaMemcpyDeviceToHost, s));
+    if (inside) CK(cudaMemcpyAsync(inside, h->vx[1].p, cells, cudaMemcpyDeviceToHost, s));
+    if (use) CK(cudaMemcpyAsync(use, h->vx[13].p, cells, cudaMemcpyDeviceToHost, s));
+    if (invalid) CK(cudaMemcpyAsync(invalid, h->vx[14].p, cells, cudaMemcpyDeviceToHost, s));
+    CK(cudaEventRecord(h->ev[5], s));
+    CK(cudaStreamSynchronize(s));
+    *cluster_num = ctl[0];
+    if (iters) { iters[0] = it_inf; iters[1] = ctl[1]; }
+    if (vertex_idx) memcpy(vertex_idx, v, 96);
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, h->ev[0], h->ev[1])); h->stats.h2d_ms = ms;
+    CK(cudaEventElapsedTime(&ms, h->ev[1], h->ev[3])); h->stats.kernel_ms = ms;   // memsets + inflation + shell + clustering
+    h->stats.kernel_launches = 4;
+    return DIRECT_DDP_OK;
+}

@@ -228,6 +228,8 @@ struct ClusterCtl {
     int active_begin;   // scratch: the active voxels are cluster_xyz[active_begin .. cluster_num)
     int cand_num;       // scratch
     int accepted;       // scratch
+    int skip;           // in: non-zero = do nothing (the degenerate box of polygonGeneration, cluster_server.cu:911-920)
+    int pad;
 };
 
 constexpr int CLAIM_EMPTY = 0x7f7f7f7f;   // cudaMemset(0x7f)
@@ -250,6 +252,7 @@ __global__ void __launch_bounds__(256) cluster_loop_kernel(const uint8_t *__rest
     const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x, gthreads = (long long)gridDim.x * blockDim.x;
     const int gwarp = (int)(gtid >> 5), gwarps = (int)(gthreads >> 5);
 
+    if (ctl->skip) return;   // uniform: nobody has reached a grid barrier
     if (gtid == 0) { ctl->active_begin = 0; ctl->iters = 0; ctl->status = 0; }
     for (long long i = gtid; i < ctl->cluster_num; i += gthreads)
         use[cluster_xyz[3 * i] * yz + cluster_xyz[3 * i + 1] * nz + cluster_xyz[3 * i + 2]] = 1;   // cluster_server.cu:583
@@ -455,6 +458,52 @@ __global__ void __launch_bounds__(256) cluster_loop_kernel(const uint8_t *__rest
         if (ctl->status != 0 || ctl->accepted == 0) break;   // cluster_server.cu:739
         itr++;
         if (gtid == 0) ctl->iters = itr;
+    }
+}
+
+// ---- polygonGeneration between its two stages (cluster_server.cu:822-920), one launch ----------------------------------------------
+// The voxels of the inflated box become `inside` and `use`; those with a neighbour outside the box are the initial cluster and lose
+// their `inside` flag.  After flagClear the `inside` flags are exactly the box, so "every one of the 26 neighbours is inside" is "the
+// voxel is not on the box's boundary", and the position of a boundary voxel in the reference's x, y, z scan is a closed form: no
+// compaction pass.  ctl->cluster_num = number of boundary voxels (a one-voxel box gets no use flag, :839-845), ctl->skip = the degenerate test of :911 (a box one voxel thick: the boundary is the result).  Flags must be
+// zero on entry (flagClear, :39-45).
+__device__ __forceinline__ long long shell_before_slab(long long a, long long ny, long long nz, long long nxb) {
+    // boundary voxels in x-slabs 0 .. a-1 of an nxb x ny x nz box
+    const long long full = ny * nz, ring = full - (ny > 2 ? ny - 2 : 0) * (nz > 2 ? nz - 2 : 0);
+    long long n = 0;
+    if (a > 0) n += full;                                              // slab 0
+    if (a > 1) n += (a - 1 < nxb - 1 ? a - 1 : nxb - 2) * ring;        // slabs 1 .. min(a, nxb - 1) - 1
+    if (a > nxb - 1 && nxb > 1) n += full;                             // slab nxb - 1
+    return n;
+}
+__global__ void cube_shell_kernel(const int *__restrict__ v, int ny_map, int nz_map, uint8_t *inside, uint8_t *use, int *cluster_xyz, int cap,
+                                  ClusterCtl *ctl) {
+    const int x0 = v[7], x1 = v[1], y0 = v[8 + 7], y1 = v[8 + 1], z0 = v[16 + 7], z1 = v[16 + 1];
+    const long long bx = x1 - x0 + 1, by = y1 - y0 + 1, bz = z1 - z0 + 1, cells = bx * by * bz;
+    const int yz = ny_map * nz_map;
+    for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < cells; c += (long long)gridDim.x * blockDim.x) {
+        const long long a = c / (by * bz), rem = c - a * by * bz, b = rem / bz, k = rem - b * bz;
+        const int x = x0 + (int)a, y = y0 + (int)b, z = z0 + (int)k, idx = x * yz + y * nz_map + z;
+        const bool edge_x = a == 0 || a == bx - 1, edge_y = b == 0 || b == by - 1, edge_z = k == 0 || k == bz - 1;
+        const bool boundary = edge_x || edge_y || edge_z;
+        inside[idx] = boundary ? 0 : 1;   // (:889-892 clears the flag of every boundary voxel, the one-voxel box included)
+        if (cells > 1) use[idx] = 1;
+        if (!boundary) continue;
+        long long rank = shell_before_slab(a, by, bz, bx);
+        if (edge_x) rank += b * bz + k;                                // a full slab
+        else {                                                         // an inner slab: full rows y0 / y1, two ends otherwise
+            if (b > 0) rank += bz;                                                       // row 0
+            if (b > 1) rank += (b - 1 < by - 1 ? b - 1 : by - 2) * (bz > 1 ? 2 : 1);   // rows 1 .. b - 1: their two end voxels
+            rank += edge_y ? k : (k == 0 ? 0 : 1);
+        }
+        if (rank < cap) { cluster_xyz[3 * rank] = x; cluster_xyz[3 * rank + 1] = y; cluster_xyz[3 * rank + 2] = z; }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        const long long n = cells == 1 ? 1 : shell_before_slab(bx, by, bz, bx);
+        ctl->cluster_num = n <= cap ? (int)n : 0;
+        ctl->iters = 0;
+        ctl->status = n <= cap ? 0 : -1;
+        ctl->skip = (bx == 1 || by == 1 || bz == 1 || n > cap) ? 1 : 0;
     }
 }
 

@@ -12,7 +12,7 @@ import numpy as np
 
 VOXEL_EXPORTS = ["direct_voxel_convex_test", "direct_voxel_convex_test_device", "direct_voxel_cube_inflation",
                  "direct_voxel_cube_inflation_device", "direct_voxel_inflate_box", "direct_voxel_inflate_box_device",
-                 "direct_voxel_cluster", "direct_voxel_cluster_device", "direct_voxel_cluster_phases"]
+                 "direct_voxel_cluster", "direct_voxel_cluster_device", "direct_voxel_cluster_phases", "direct_voxel_polytope"]
 
 
 class MapC(C.Structure):
@@ -76,6 +76,20 @@ def cluster(solver, occ, inside, use, invalid, cluster_xyz, cap: int, cand_cap: 
     solver._check(solver.lib.direct_voxel_cluster(solver.h, C.byref(m), C.c_void_p(use.ctypes.data), C.c_void_p(invalid.ctypes.data),
                                                   C.c_void_p(buf.ctypes.data), C.byref(n), cap, cand_cap, itr_cluster_max, C.byref(it)))
     return buf[:n.value].copy(), use, invalid, it.value
+
+
+def polytope(solver, occ, seed, itr_inflate_max: int, itr_cluster_max: int, cap: int, cand_cap: int, flags: bool = True) -> dict:
+    """cudaPolytopeGeneration::polygonGeneration for a one-voxel seed, four launches, no host round trip in between.
+    Returns dict(cluster [n][3], vertex_idx [24], iters [inflation, clustering], inside, use, invalid (None unless flags))."""
+    keep = []
+    m = _map_struct(occ, None, keep)
+    seed = np.ascontiguousarray(seed, dtype=np.int32); assert seed.size == 3
+    buf = np.zeros((cap, 3), np.int32); n = C.c_int32(0); it = (C.c_int32 * 2)(); v = np.zeros(24, np.int32)
+    fl = [np.zeros(np.shape(occ), np.uint8) if flags else None for _ in range(3)]
+    solver._check(solver.lib.direct_voxel_polytope(solver.h, C.byref(m), C.c_void_p(seed.ctypes.data), itr_inflate_max, itr_cluster_max, cap, cand_cap,
+                                                   C.c_void_p(buf.ctypes.data), C.byref(n), it, C.c_void_p(v.ctypes.data),
+                                                   *[C.c_void_p(f.ctypes.data) if f is not None else None for f in fl]))
+    return dict(cluster=buf[:n.value].copy(), vertex_idx=v, iters=[it[0], it[1]], inside=fl[0], use=fl[1], invalid=fl[2])
 
 
 def cluster_phases(solver) -> dict:

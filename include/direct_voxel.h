@@ -69,6 +69,18 @@ int direct_voxel_cluster(direct_ddp_handle h, const direct_voxel_map *map, uint8
 int direct_voxel_cluster_device(direct_ddp_handle h, const direct_voxel_map *map, uint8_t *use, uint8_t *invalid, int32_t *cluster_xyz,
                                 int32_t *ctl, int cap, int cand_cap, int itr_cluster_max, void *stream);
 
+/* cudaPolytopeGeneration::polygonGeneration (cluster_server.cu:769-966) for a one-voxel seed, the case the node uses per path point:
+ * flagClear, box inflation from the seed (<= itr_inflate_max outer iterations), the box's voxels -> inside / use flags and its boundary
+ * voxels -> initial cluster, then (unless the box is one voxel thick, :911-920) the clustering loop (<= itr_cluster_max iterations).
+ * Four launches on one stream, nothing but the seed goes up and nothing but the result comes down.  cluster_xyz [cap][3] receives the
+ * *cluster_num voxels of the polytope in the reference's order; inside / use / invalid ([nx ny nz], optional, may be NULL) receive the
+ * reference's flag arrays; vertex_idx [24] (optional) the inflated box.  (Seeds of several voxels are not accepted: the reference's
+ * bounding box of such a seed is -100000 .. 100000, cluster_server.cu:804-816.) */
+int direct_voxel_polytope(direct_ddp_handle h, const direct_voxel_map *map /* inside ignored */, const int32_t seed_xyz[3],
+                          int itr_inflate_max, int itr_cluster_max, int cap, int cand_cap, int32_t *cluster_xyz, int32_t *cluster_num,
+                          int32_t *iters /* optional [2]: inflation, clustering */, int32_t *vertex_idx, uint8_t *inside, uint8_t *use,
+                          uint8_t *invalid);
+
 /* Device time (ms) of the five phases of the last clustering launch on this handle, summed over its iterations: neighbour claims,
  * ordered candidate compaction, candidate -> cluster rays, candidate -> candidate rays, acceptance scan. */
 int direct_voxel_cluster_phases(direct_ddp_handle h, double ms[5]);

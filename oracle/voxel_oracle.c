@@ -184,3 +184,45 @@ int voxel_oracle_cluster(const uint8_t *occ, const uint8_t *inside, uint8_t *use
     if (iters_out) *iters_out = itr;
     return status ? status : cluster_num;
 }
+
+int voxel_oracle_polytope(const uint8_t *occ, int nx, int ny, int nz, const int32_t seed[3], int itr_inflate_max, int itr_cluster_max,
+                          int cap, int cand_cap, int32_t *cluster_xyz, int32_t *v, int *iters, uint8_t *inside, uint8_t *use,
+                          uint8_t *invalid) {
+    const int yz = ny * nz;
+    const size_t cells = (size_t)nx * ny * nz;
+    memset(use, 0, cells); memset(invalid, 0, cells); memset(inside, 0, cells);   /* flagClear, :39-45 */
+    for (int k = 0; k < 8; k++) { v[k] = seed[0]; v[8 + k] = seed[1]; v[16 + k] = seed[2]; }   /* :793-800 */
+    iters[0] = voxel_oracle_inflate_box(occ, nx, ny, nz, v, 1, itr_inflate_max);   /* cubeInflation_*: inf_step = 1 */
+    iters[1] = 0;
+    /* getVoxelsInCube, :79-98 */
+    long long ncube = 0;
+    for (int x = v[7]; x <= v[1]; x++) for (int y = v[8 + 7]; y <= v[8 + 1]; y++) for (int z = v[16 + 7]; z <= v[16 + 1]; z++) {
+        inside[x * yz + y * nz + z] = 1;
+        ncube++;
+    }
+    int n = 0;
+    if (ncube == 1) {   /* :839-845 */
+        if (cap < 1) return -1;
+        cluster_xyz[0] = v[7]; cluster_xyz[1] = v[8 + 7]; cluster_xyz[2] = v[16 + 7];
+        n = 1;
+    } else {            /* :846-886 */
+        for (int x = v[7]; x <= v[1]; x++) for (int y = v[8 + 7]; y <= v[8 + 1]; y++) for (int z = v[16 + 7]; z <= v[16 + 1]; z++) {
+            use[x * yz + y * nz + z] = 1;
+            int is_inside = 1;
+            for (int dx = -1; dx < 2; dx++) for (int dy = -1; dy < 2; dy++) for (int dz = -1; dz < 2; dz++) {
+                if (dx == 0 && dy == 0 && dz == 0) continue;
+                int tx = x + dx, ty = y + dy, tz = z + dz;
+                if (tx >= 0 && tx < nx && ty >= 0 && ty < ny && tz >= 0 && tz < nz) is_inside *= inside[tx * yz + ty * nz + tz];
+                else is_inside = 0;
+            }
+            if (is_inside < 1) {
+                if (n >= cap) return -1;
+                cluster_xyz[3 * n] = x; cluster_xyz[3 * n + 1] = y; cluster_xyz[3 * n + 2] = z;
+                n++;
+            }
+        }
+    }
+    for (int i = 0; i < n; i++) inside[cluster_xyz[3 * i] * yz + cluster_xyz[3 * i + 1] * nz + cluster_xyz[3 * i + 2]] = 0;   /* :889-892 */
+    if (abs(v[7] - v[1]) == 0 || abs(v[8 + 7] - v[8 + 1]) == 0 || abs(v[16 + 7] - v[16 + 1]) == 0) return n;   /* :911-920 */
+    return voxel_oracle_cluster(occ, inside, use, invalid, nx, ny, nz, cluster_xyz, n, cap, cand_cap, itr_cluster_max, &iters[1]);
+}

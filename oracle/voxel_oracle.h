@@ -30,6 +30,13 @@ int voxel_oracle_inflate_box(const uint8_t *occ, int nx, int ny, int nz, int32_t
 int voxel_oracle_cluster(const uint8_t *occ, const uint8_t *inside, uint8_t *use, uint8_t *invalid, int nx, int ny, int nz,
                          int32_t *cluster_xyz, int cluster_num, int cap, int cand_cap, int itr_cluster_max, int *iters_out);
 
+/* polygonGeneration (cluster_server.cu:769-966) for a one-voxel seed: flagClear, box inflation, getVoxelsInCube + boundary extraction
+ * (:834-895, restated with the reference's 26-neighbour product), degenerate test (:911-920), clustering.  inside / use / invalid
+ * [nx ny nz] are outputs; vertex_idx [24] out; iters [2] out (inflation, clustering).  Returns the cluster size or -1. */
+int voxel_oracle_polytope(const uint8_t *occ, int nx, int ny, int nz, const int32_t seed[3], int itr_inflate_max, int itr_cluster_max,
+                          int cap, int cand_cap, int32_t *cluster_xyz, int32_t *vertex_idx, int *iters, uint8_t *inside, uint8_t *use,
+                          uint8_t *invalid);
+
 #ifdef __cplusplus
 }
 #endif

@@ -79,6 +79,19 @@ def cluster(occ, inside, use, invalid, cluster_xyz, cap, cand_cap, itr_cluster_m
     return buf[:n].copy(), use, invalid, it.value
 
 
+def polytope(occ, seed, itr_inflate_max, itr_cluster_max, cap, cand_cap):
+    """Returns dict(cluster, vertex_idx, iters, inside, use, invalid)."""
+    occ = np.ascontiguousarray(occ, np.uint8)
+    seed = _i32(seed); buf = np.zeros((cap, 3), np.int32); v = np.zeros(24, np.int32); it = (C.c_int * 2)()
+    fl = [np.zeros(occ.shape, np.uint8) for _ in range(3)]
+    n = lib().voxel_oracle_polytope(C.c_void_p(occ.ctypes.data), *occ.shape, C.c_void_p(seed.ctypes.data), itr_inflate_max, itr_cluster_max,
+                                    cap, cand_cap, C.c_void_p(buf.ctypes.data), C.c_void_p(v.ctypes.data), it,
+                                    *[C.c_void_p(f.ctypes.data) for f in fl])
+    if n < 0:
+        raise RuntimeError("cluster or candidate capacity exceeded")
+    return dict(cluster=buf[:n].copy(), vertex_idx=v, iters=[it[0], it[1]], inside=fl[0], use=fl[1], invalid=fl[2])
+
+
 # ---- the reference's own kernels (GPU box only) ---------------------------------------------------------------------------------
 _ref = None
 

@@ -300,3 +300,52 @@ def test_gpu_cluster_full_size_properties(solver):
     # deterministic: a second run gives the same cluster in the same order
     clu2, _, _, it2 = X.cluster(solver, occ, inside, use, inv0, shell, 50000, 10000, 8)
     assert np.array_equal(clu, clu2) and it == it2
+
+
+# ---- polygonGeneration as a whole (cluster_server.cu:769-966) ---------------------------------------------------------------------------
+POLY_CASES = [  # shape, pillars, map seed, seed voxel, itr_inflate_max, itr_cluster_max
+    ((40, 36, 14), 16, 9, (20, 18, 6), 20, 3),
+    ((24, 20, 10), 8, 2, (12, 10, 4), 3, 20),
+    ((30, 30, 30), 10, 5, (0, 15, 29), 20, 4),      # seed in a corner region: the box runs into the map boundary
+    ((60, 60, 20), 30, 6, (30, 30, 8), 20, 6),
+    ((24, 20, 10), 8, 2, (12, 10, 4), 0, 5),        # no inflation: a one-voxel box is degenerate, the seed is the polytope
+]
+
+
+def _slab_map():
+    occ = np.ones((20, 20, 8), np.uint8)
+    occ[2:18, 2:18, 3] = 0                           # a corridor one voxel high: the box is one voxel thick (degenerate, :911-920)
+    return occ
+
+
+def test_oracle_polytope_equals_its_parts():
+    for shape, pillars, mseed, cell, inf, clu in POLY_CASES[:3]:
+        occ = X.make_map(shape, pillars, mseed, clear=(*cell, 2))
+        r = V.polytope(occ, cell, inf, clu, 40000, 8000)
+        v, it = V.inflate_box(occ, X.box_vertices(*cell, *cell), inf)
+        inside, use, shell = X.cube_shell(shape, v)               # numpy statement of :834-895
+        c = V.cluster(occ, inside, use, np.zeros_like(occ), shell, 40000, 8000, clu)
+        assert np.array_equal(r["vertex_idx"], v) and r["iters"] == [it, c[3]]
+        assert np.array_equal(r["cluster"], c[0]) and np.array_equal(r["use"], c[1]) and np.array_equal(r["invalid"], c[2])
+        assert np.array_equal(r["inside"], inside)
+    r = V.polytope(_slab_map(), (10, 10, 3), 20, 5, 4000, 800)
+    assert len(r["cluster"]) == 16 * 16 and r["iters"][1] == 0 and r["invalid"].sum() == 0
+
+
+@pytest.mark.gpu
+def test_gpu_polytope_matches_oracle(solver):
+    cases = [(X.make_map(shape, pillars, mseed, clear=(*cell, 2)), cell, inf, clu) for shape, pillars, mseed, cell, inf, clu in POLY_CASES]
+    cases.append((_slab_map(), (10, 10, 3), 20, 5))
+    cases.append((np.zeros((12, 9, 7), np.uint8), (5, 4, 3), 50, 5))          # empty map: the box is the whole map, nothing to cluster
+    for occ, cell, inf, clu in cases:
+        g = X.polytope(solver, occ, cell, inf, clu, 40000, 8000)
+        o = V.polytope(occ, cell, inf, clu, 40000, 8000)
+        assert np.array_equal(g["vertex_idx"], o["vertex_idx"]) and g["iters"] == o["iters"], (occ.shape, cell)
+        assert np.array_equal(g["cluster"], o["cluster"]), (occ.shape, cell, len(g["cluster"]), len(o["cluster"]))
+        for f in ("inside", "use", "invalid"):
+            assert np.array_equal(g[f], o[f]), (occ.shape, cell, f)
+    from direct_b200 import capi
+    with pytest.raises(capi.DirectDdpError):
+        X.polytope(solver, cases[0][0], (99, 0, 0), 5, 5, 1000, 1000)          # seed outside the map
+    with pytest.raises(capi.DirectDdpError):
+        X.polytope(solver, cases[0][0], cases[0][1], 20, 3, 100, 8000)         # cluster capacity below the box's boundary

@@ -79,6 +79,15 @@ if shape[0] * shape[1] * shape[2] <= 200 * 200 * 40 and a.itr <= 3:
     assert np.array_equal(o[0], clu) and np.array_equal(o[2], inv1) and o[3] == it
     rep["cluster_loop"]["cpu_oracle_s"] = ot
     print(f"   = sequential CPU oracle ({ot:.2f} s), voxel for voxel")
+# 4. polygonGeneration as a whole (flagClear, inflation, boundary extraction, clustering): four launches, no host round trip
+best = 1e9
+for _ in range(a.reps):
+    t = time.perf_counter(); pg = X.polytope(s, occ, cell, 20, a.itr, 50000, 10000, flags=False); wall = time.perf_counter() - t
+    best = min(best, s.stats().kernel_ms)
+assert np.array_equal(pg["cluster"], clu)
+rep["polytope"] = {"voxels": int(len(pg["cluster"])), "iters": pg["iters"], "device_ms": best, "host_call_ms": wall * 1e3}
+print(f"polytope (polygonGeneration, seed {cell}): {len(pg['cluster'])} voxels, {pg['iters'][0]} inflation + {pg['iters'][1]} clustering iterations: "
+      f"{best:.3f} ms on the device, {wall * 1e3:.1f} ms for the host call (map upload, cluster download)")
 if a.out:
     json.dump(rep, open(a.out, "w"), indent=1)
 s.close()
