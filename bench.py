@@ -140,7 +140,7 @@ def reference_arm(args):
                          "port_value": port_value},
         "e2e": {"value": value, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def workload_config(args, per_gpu):
@@ -228,7 +228,24 @@ def model_b_report(capi, torch, dev, local_rank, flush, steps, with_cpu):
     return out
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict) -> None:
+    """The one JSON line of this process, on the process's original stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    # stdout carries exactly one JSON line: whatever libraries print on fd 1 (NCCL's version banner under torchrun) goes to stderr
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -444,7 +461,7 @@ def main():
         except Exception as e:   # the headline line must not depend on the secondary report
             line["model_b_quadrotor12_fp32"] = {"error": repr(e)}
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
