@@ -203,13 +203,20 @@ def model_b_report(capi, torch, dev, local_rank, flush, steps, with_cpu):
     torch.cuda.synchronize()
     e2e_s = (time.perf_counter() - t0) / e2e_n
     st = solver.stats()
+    traffic, traffic_src = None, None
+    try:   # dram bytes of gddp_pair_kernel per launch, one ncu --set full capture of this workload (profiles/)
+        prof = json.load(open(os.path.join(ROOT, "profiles", "latest_ncu_model_b.json")))
+        if prof.get("workload") == f"{B}x{N} quad fp32":
+            traffic, traffic_src = prof["dram_bytes_per_launch"], prof["source"]
+    except Exception:
+        pass
     out = {"workload": f"unconstrained DDP, {B} x {N}-knot 12-state/4-input rigid-body quadrotor (explicit Euler, dt 0.05), hover-to-hover "
                        "transfers of 1.5-3.5 m; model (B) of SURVEY.md 8(d): the reference has no such model, parity unpinned",
            "dtype": "f32", "value": B / ms * 1e3, "unit": "solves/s", "ms_per_step": ms, "gpu_launches": steps,
            "e2e": {"value": B / e2e_s, "unit": "solves/s", "h2d_bytes_per_step": int(st.h2d_bytes), "d2h_bytes_per_step": int(st.d2h_bytes),
                    "ms_per_step": e2e_s * 1e3},
            "roofline": {"bound": "fp32_fma", "achieved": fl * knots / (ms * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
-                        "frac": fl * knots / (ms * 1e-3) / 1e12 / peak if peak else None, "traffic": None,
+                        "frac": fl * knots / (ms * 1e-3) / 1e12 / peak if peak else None, "traffic": traffic, "traffic_source": traffic_src,
                         "flops_per_bwd_knot": fl, "bwd_knots_per_launch": knots},
            "solve_stats": {"converged_frac": float((rtn == 1).mean()), "mean_iters": float(o["iters"].float().mean().item()),
                            "bwd_sweeps_per_solve": float(stats[:, 0].mean()), "rollouts_per_solve": float(stats[:, 1].mean())}}
