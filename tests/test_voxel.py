@@ -354,3 +354,46 @@ def test_gpu_polytope_matches_oracle(solver):
         X.polytope(solver, cases[0][0], (99, 0, 0), 5, 5, 1000, 1000)          # seed outside the map
     with pytest.raises(capi.DirectDdpError):
         X.polytope(solver, cases[0][0], cases[0][1], 20, 3, 100, 8000)         # cluster capacity below the box's boundary
+
+
+def test_closed_form_boundary_rank_of_cube_shell_kernel():
+    """cube_shell_kernel (direct_b200/csrc/voxel.cuh) places a boundary voxel of the inflated box at its position in the reference's
+    x, y, z scan (cluster_server.cu:848-886) by a closed form instead of a compaction pass.  The same formula, stated here in Python,
+    against the scan itself for every box shape up to 6 x 6 x 6 (thin and one-voxel boxes included); the GPU suite checks the kernel."""
+    import itertools
+
+    def before_slab(a, ny, nz, nxb):
+        full = ny * nz
+        ring = full - (ny - 2 if ny > 2 else 0) * (nz - 2 if nz > 2 else 0)
+        n = 0
+        if a > 0:
+            n += full
+        if a > 1:
+            n += (a - 1 if a - 1 < nxb - 1 else nxb - 2) * ring
+        if a > nxb - 1 and nxb > 1:
+            n += full
+        return n
+
+    def rank(a, b, k, bx, by, bz):
+        ex, ey, ez = a in (0, bx - 1), b in (0, by - 1), k in (0, bz - 1)
+        if not (ex or ey or ez):
+            return None
+        r = before_slab(a, by, bz, bx)
+        if ex:
+            return r + b * bz + k
+        if b > 0:
+            r += bz
+        if b > 1:
+            r += (b - 1) * (2 if bz > 1 else 1)
+        return r + (k if ey else (0 if k == 0 else 1))
+
+    for bx, by, bz in itertools.product(range(1, 7), repeat=3):
+        scan = [(a, b, k) for a in range(bx) for b in range(by) for k in range(bz)
+                if a in (0, bx - 1) or b in (0, by - 1) or k in (0, bz - 1)]
+        got = {}
+        for a, b, k in itertools.product(range(bx), range(by), range(bz)):
+            r = rank(a, b, k, bx, by, bz)
+            if r is not None:
+                assert r not in got
+                got[r] = (a, b, k)
+        assert [got[i] for i in range(len(scan))] == scan and before_slab(bx, by, bz, bx) == len(scan), (bx, by, bz)
