@@ -397,3 +397,38 @@ def test_closed_form_boundary_rank_of_cube_shell_kernel():
                 assert r not in got
                 got[r] = (a, b, k)
         assert [got[i] for i in range(len(scan))] == scan and before_slab(bx, by, bz, bx) == len(scan), (bx, by, bz)
+
+
+def test_group_of_32_acceptance_scan_equals_the_sequential_scan():
+    """cluster_loop_kernel's phase 3 resolves the reference's order-dependent acceptance scan (cluster_server.cu:693-737) 32 candidates at
+    a time: conflicts with groups already resolved come as one bit per candidate (prehit + the previous group's word), the dependence
+    inside a group is settled by rounds of 'rejected if it conflicts with an accepted lane, accepted if it conflicts with no accepted
+    and no still-undecided lower lane'.  The same procedure in Python against the plain sequential scan on random conflict sets."""
+    rng = np.random.default_rng(7)
+    for trial in range(60):
+        C = int(rng.integers(1, 150))
+        can_clu = rng.random(C) < rng.choice([0.3, 0.7, 1.0])
+        dens = rng.choice([0.0, 0.02, 0.2, 0.6])
+        conflict = np.tril(rng.random((C, C)) < dens, k=-1)           # conflict[i][j], j < i: the ray between i and j is blocked
+        conflict &= can_clu[None, :] & can_clu[:, None]               # phase 2b only traces rays between surviving candidates
+        seq = np.zeros(C, bool)
+        for i in range(C):
+            seq[i] = can_clu[i] and not (conflict[i, :i] & seq[:i]).any()
+        acc = np.zeros(C, bool)
+        for b in range(0, C, 32):
+            lanes = range(b, min(b + 32, C))
+            alive = {i: bool(can_clu[i]) and not (conflict[i, :b] & acc[:b]).any() for i in lanes}
+            und = {i for i in lanes if alive[i]}
+            accepted = set()
+            rounds = 0
+            while und:
+                rounds += 1
+                rej = {i for i in und if any(conflict[i, j] for j in accepted)}
+                now = {i for i in und - rej if not any(conflict[i, j] for j in und if j < i)}
+                assert rej or now                                     # the lowest undecided lane always decides
+                accepted |= now
+                und -= rej | now
+            assert rounds <= 32
+            for i in accepted:
+                acc[i] = True
+        assert np.array_equal(acc, seq), trial
