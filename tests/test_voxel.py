@@ -432,3 +432,32 @@ def test_group_of_32_acceptance_scan_equals_the_sequential_scan():
             for i in accepted:
                 acc[i] = True
         assert np.array_equal(acc, seq), trial
+
+
+def test_ray_walk_reaches_its_target_after_exactly_l1_steps_and_lookahead_reads_nothing_else():
+    """voxel.cuh's ray walk replaces the reference's 'position == end' tests by a step counter (|dx| + |dy| + |dz| steps) and examines the
+    voxels in groups of four fetched ahead.  Checked here on the reference's own fp64 walk (py_ray's arithmetic): the walk is at its
+    target after exactly that many steps and not before, for axis-aligned, diagonal, tie-prone and random directions up to the node's
+    map size - so the look-ahead never steps past the target and the counter is the reference's test."""
+    rng = np.random.default_rng(3)
+    dirs = [(d, 0, 0) for d in (1, -7, 333)] + [(5, 5, 5), (-9, 9, 0), (1, 3, 9), (3, 1, -9), (2, 4, 8), (6, -3, 2), (333, 333, 33), (1, 1, 332)]
+    dirs += [tuple(int(v) for v in rng.integers(-333, 334, 3)) for _ in range(1500)]
+    dirs += [tuple(int(v) for v in rng.integers(-6, 7, 3)) for _ in range(1500)]
+    for d in dirs:
+        if d == (0, 0, 0):
+            continue
+        step = [(t > 0) - (t < 0) for t in d]
+        tmax = [99999.0 if t == 0 else 0.5 / abs(t) for t in d]
+        delta = [0.0 if t == 0 else 1.0 / abs(t) for t in d]          # the kernel's table: 1 / |d|; tMax = 0.5 * (1 / |d|) exactly
+        assert all(t == 0 or 0.5 / abs(t) == 0.5 * (1.0 / abs(t)) for t in d)
+        p = [0, 0, 0]
+        n = sum(abs(t) for t in d)
+        for s in range(n):
+            assert p != list(d), (d, s)
+            if tmax[0] < tmax[1]:
+                k = 0 if tmax[0] < tmax[2] else 2
+            else:
+                k = 1 if tmax[1] < tmax[2] else 2
+            assert d[k] != 0                                          # an axis with d = 0 is never stepped
+            p[k] += step[k]; tmax[k] += delta[k]
+        assert p == list(d), d
