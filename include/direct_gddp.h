@@ -16,6 +16,8 @@
  *   quad12: x = [p, v, (roll, pitch, yaw), body rates], u = [thrust, tau_x, tau_y, tau_z];  dint6: x = [p, v], u = a
  *   iteration, regularisation schedule, stopping rules: oracle/gddp_oracle.c header.
  * Handles, status codes and the precision option are those of direct_ddp.h.  No CPU fallback.
+ * Kernel: two trajectories per warp (direct_b200/csrc/gddp_pair.cuh); the environment variable DIRECT_GDDP_PAIR=0 selects the
+ * one-trajectory-per-warp kernel (gddp.cuh) for comparison - same decisions, numbers equal to 1e-9.
  */
 #ifndef DIRECT_GDDP_H_
 #define DIRECT_GDDP_H_
