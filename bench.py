@@ -124,20 +124,36 @@ def reference_arm(args):
     dt = (time.perf_counter() - t0) / args.steps
     value = sample / dt
     # the dense C restatement for context (no per-call allocation: faster than the reference's Eigen code)
+    port_sample = max(sample, args.port_sample)   # a throughput figure needs many more trajectories than threads (heavy tail)
+    pbp = pb if port_sample == sample else make_batch(port_sample, args.knots, args.kind)
+    O.two_stage_batch(pbp.slice(0, min(port_sample, 4 * cores)), nthreads=cores)   # warm-up
     t0 = time.perf_counter()
-    O.two_stage_batch(pb, nthreads=cores)
-    port_value = sample / (time.perf_counter() - t0)
-    kind = "reference" if use_ref else "port"
+    for _ in range(args.steps):
+        O.two_stage_batch(pbp, nthreads=cores)
+    port_value = port_sample * args.steps / (time.perf_counter() - t0)
+    # The reference's translation unit is compiled here against oracle/shim/Eigen/Dense, an eager stand-in for Eigen3 (the real
+    # library is not in this image) that allocates far more than Eigen's expression templates would: it UNDERSTATES the
+    # reference's speed.  The allocation-free C restatement of the same algorithm OVERSTATES it.  The arm's value is the
+    # faster of the two, so that a ratio computed from it can only be conservative; both numbers are on the line.
+    ref_value = value if use_ref else None
+    if port_value >= value:
+        value, kind, dt, sample = port_value, "port", port_sample / port_value, port_sample
+    else:
+        kind = "reference"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": dict(workload_config(args, per_gpu=args.batch), reference_sample_per_step=sample),
         "cpu_baseline": {"value": value, "unit": "solves/s", "cores": cores, "kind": kind,
-                         "sample": f"first {sample} trajectories of the workload per step, {cores} OpenMP threads, "
-                                   + ("reference ddp_optimizer.cpp compiled unmodified against oracle/shim (eager Eigen stand-in)"
-                                      if use_ref else "C restatement (oracle/ipddp_oracle.c)"),
-                         "port_value": port_value},
+                         "sample": f"first {sample} trajectories of the workload per step ({args.ref_sample} for the reference's translation "
+                                   f"unit, {port_sample} for the C restatement), {cores} OpenMP threads; value = the faster of "
+                                   "(a) the reference's ddp_optimizer.cpp compiled unmodified against oracle/shim (eager Eigen stand-in) "
+                                   "and (b) the allocation-free C restatement oracle/ipddp_oracle.c",
+                         "reference_tu_value": ref_value, "port_value": port_value,
+                         "linear_algebra_stand_in": bool(use_ref),
+                         "note": "reference_tu_value is a LOWER bound of the reference's speed (stand-in Eigen), port_value an UPPER "
+                                 "bound (no per-call allocation, ddp_optimizer.cpp:479-504 copies absent)"},
         "e2e": {"value": value, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit(line)
@@ -264,6 +280,8 @@ def main():
     ap.add_argument("--precision", default="fp64", choices=["fp64", "fp32"])
     ap.add_argument("--cpu-sample", type=int, default=4096)
     ap.add_argument("--ref-sample", type=int, default=48)
+    ap.add_argument("--port-sample", type=int, default=1024, help="trajectories per step of the C restatement in --impl reference")
+    ap.add_argument("--screen-sample", type=int, default=1024, help="trajectories of the parity sample run through the conditioning screen")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-model-b", action="store_true", help="skip the secondary 12-state quadrotor (model (B)) report")
     args = ap.parse_args()
@@ -461,6 +479,29 @@ def main():
                                 "sample": f"first {smp} trajectories of rank 0's batch, two-stage protocol, {cores} OpenMP threads, "
                                           "fp64 C restatement of ddp_optimizer.cpp (oracle/ipddp_oracle.c)"}
         line["parity_sample"] = {"n": int(smp), "tol": tol, "frac_within_tol": float(ok.mean())}
+        # Conditioning screen (tests/conftest.py): the trajectories on which the ORACLE moves by more than a tenth of the tolerance
+        # under four 2^-48 relative input perturbations.  Parity is claimed on the rest; the screened ones are bounded by the
+        # oracle's own spread (same return code as one of its five runs, cost inside their min..max widened by 10 %).
+        nscr = min(args.screen_sample, smp)
+        if nscr > 0:
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            from conftest import perturbed_batches
+            ssub = pb.slice(0, nscr)
+            runs = [a1] + [O.two_stage_batch(q, nthreads=cores)[1] for q in perturbed_batches(ssub)]
+            cond = np.ones(nscr, dtype=bool)
+            for r in runs[1:]:
+                cond &= (r.rtn == a1.rtn[:nscr]) & (r.iters == a1.iters[:nscr]) & \
+                        (np.abs(r.cost - a1.cost[:nscr]) <= 0.1 * tol * np.abs(a1.cost[:nscr])) & \
+                        (np.max(np.abs(r.poly_time - a1.poly_time[:nscr]), axis=1) <= 0.1 * tol * np.max(np.abs(a1.poly_time[:nscr]), axis=1))
+            cs = np.stack([r.cost[:nscr] for r in runs]); rs = np.stack([r.rtn[:nscr] for r in runs])
+            lo, hi = cs.min(0), cs.max(0)
+            inside = (g_cost[:nscr] >= lo - 0.1 * np.abs(lo)) & (g_cost[:nscr] <= hi + 0.1 * np.abs(hi)) & (rs == g_rtn[:nscr][None]).any(0)
+            line["parity_sample"].update({
+                "screen_n": int(nscr), "frac_screened": float((~cond).mean()),
+                "frac_conditioned_within_tol": float(ok[:nscr][cond].mean()) if cond.any() else None,
+                "screened_out_inside_oracle_spread": float(inside[~cond].mean()) if (~cond).any() else None,
+                "screen": "oracle alone: 4 input perturbations of 2^-48 relative; screened = oracle cost / segment times move by > tol/10 or "
+                          "its return code / iteration count changes"})
     if rank == 0 and world == 1 and not args.no_model_b:
         try:
             line["model_b_quadrotor12_fp32"] = model_b_report(capi, torch, dev, local_rank, flush, max(3, min(args.steps, 10)),

@@ -1,6 +1,7 @@
 """Build recipe of libdirect_ddp_b200.so (hand-written CUDA for sm_100a + the C-ABI), in-tree."""
 from __future__ import annotations
 
+import glob
 import os
 import shutil
 import subprocess
@@ -8,8 +9,8 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "libdirect_ddp_b200.so")
 SOURCES = [os.path.join(HERE, "csrc", "direct_ddp.cu"), os.path.join(HERE, "host", "corridor_replay.cpp")]
-DEPS = SOURCES + [os.path.join(HERE, "csrc", f) for f in ("ipddp_solver.h", "simt.h", "gddp.cuh", "voxel.cuh")] + \
-    [os.path.join(HERE, "..", "include", f) for f in ("direct_ddp.h", "direct_gddp.h", "direct_voxel.h")]
+DEPS = SOURCES + sorted(glob.glob(os.path.join(HERE, "csrc", "*.h")) + glob.glob(os.path.join(HERE, "csrc", "*.cuh")) +
+                        glob.glob(os.path.join(HERE, "..", "include", "*.h")))
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--shared", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 

@@ -195,7 +195,7 @@ int ensure(H *h, DevBuf &b, size_t bytes) {
 int validate(H *h, const direct_ddp_batch *in) {
     if (!in) { h->err = "batch is NULL"; return DIRECT_DDP_ERR_ARG; }
     if (in->B <= 0 || in->N <= 0) { h->err = "B and N must be positive"; return DIRECT_DDP_ERR_ARG; }
-    if (in->P_max < 0 || in->P_max > DIRECT_DDP_MAX_PLANES) { h->err = "P_max must be in [0, 32]"; return DIRECT_DDP_ERR_ARG; }
+    if (in->P_max < 0 || in->P_max > DIRECT_DDP_MAX_PLANES) { h->err = "P_max must be in [0, DIRECT_DDP_MAX_PLANES]"; return DIRECT_DDP_ERR_ARG; }
     if (!in->planes || !in->nplanes || !in->durations || !in->x0 || !in->xd) { h->err = "missing input pointer"; return DIRECT_DDP_ERR_ARG; }
     return 0;
 }
@@ -328,6 +328,7 @@ int solve_device(H *h, const direct_ddp_batch *in, const direct_ddp_two_stage *t
         }
     } else {
         if ((st = validate_cfg(h, in->time_power, in->line_init, in->iter_max))) return st;
+        if (in->line_init && !in->seeds) { h->err = "line_init needs seeds"; return DIRECT_DDP_ERR_ARG; }   // ddp_optimizer.cpp:195-247
         A.two_stage = 0;
         A.init_bez = in->init_bez; A.infeas = in->infeas;
         fill_cfg(A.cfg[0], in->w_snap, in->w_terminal, in->w_time, in->iter_max, in->time_power, in->zero_init,
@@ -404,6 +405,8 @@ int solve_host(H *h, const direct_ddp_batch *in, const direct_ddp_two_stage *ts,
         d.field = (const type *)h->buf.p;                                                                    \
         h2d += (int64_t)(bytes);                                                                             \
     }
+    for (size_t e = 0; e < (size_t)B * N; e++)   // a count past P_max would read past the polytope's rows on the device
+        if (in->nplanes[e] < 0 || in->nplanes[e] > PM) { h->err = "nplanes must be in [0, P_max]"; return DIRECT_DDP_ERR_ARG; }
     UP(planes, planes, (size_t)B * N * PM * 32, double)
     UP(nplanes, nplanes, (size_t)B * N * 4, int32_t)
     UP(durations, durations, (size_t)B * N * 8, double)
@@ -652,11 +655,14 @@ int direct_ddp_last_trace(direct_ddp_handle h, direct_ddp_trace_row *rows, int c
     if (n > cap) n = cap;
     std::vector<double> t((size_t)n * 12 + 1);
     if (n > 0) CK(cudaMemcpy(t.data(), h->trace.p, (size_t)n * 12 * sizeof(double), cudaMemcpyDeviceToHost));
+    int khz = 0;
+    CK(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, h->opts.device));
+    const double cyc_per_us = khz > 0 ? khz / 1000.0 : 1965.0;
     for (int i = 0; i < n; i++) {
         const double *r = &t[(size_t)i * 12];
         rows[i].cost = r[0]; rows[i].costq = r[1]; rows[i].logcost = r[2]; rows[i].err = r[3]; rows[i].mu = r[4];
         rows[i].reg = r[5]; rows[i].stepsize = r[6]; rows[i].opterr = r[7];
-        rows[i].step = (int)r[8]; rows[i].fp_failed = (int)r[9]; rows[i].n_bwd = (int)r[10]; rows[i].t_us = (int)r[11];
+        rows[i].step = (int)r[8]; rows[i].fp_failed = (int)r[9]; rows[i].n_bwd = (int)r[10]; rows[i].t_us = (int)(r[11] / cyc_per_us);
     }
     *len = n;
     return 0;

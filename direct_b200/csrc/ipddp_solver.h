@@ -2390,7 +2390,7 @@ template <class R> DDP_DEVICE_NOINLINE void solve_one(const SolveArgs &A, int st
                     double *tr = A.trace + (long long)trace_n * 12;
                     tr[0] = t.cost; tr[1] = t.costq; tr[2] = t.logcost; tr[3] = t.err; tr[4] = t.mu; tr[5] = t.reg;
                     tr[6] = t.stepsize; tr[7] = t.opterr; tr[8] = t.step; tr[9] = t.failed; tr[10] = n_bwd;
-                    tr[11] = (double)((ddp_clock() - t.cyc_t0) / 1965);   // microseconds at the nominal SM clock
+                    tr[11] = (double)(ddp_clock() - t.cyc_t0);   // SM cycles since the solve began; the host converts with the device's clock
                 }
             }
             trace_n++;

@@ -21,6 +21,7 @@
 //   getCompTime                         <- wall clock around the call, like ddp_optimizer.cpp:30,414-416
 #include <global_planner/ddp_optimizer.h>
 
+#include <algorithm>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -139,7 +140,14 @@ int ddpTrajOptimizer::polyCurveGeneration(
             std::fprintf(stderr, "direct_ddp_b200: %s (status %d)\n", direct_ddp_last_error(S.h), status);
         }
     }
-    if (status != DIRECT_DDP_OK) return -100;
+    if (status != DIRECT_DDP_OK) {
+        // The caller (teach_repeat_planner.cpp:899-944) does not know this value and goes on to call the getters: leave
+        // every member they read in a defined state (zeros of the right size, the start state as "final" state).
+        std::fill(pc.begin(), pc.end(), 0.0); std::fill(bz.begin(), bz.end(), 0.0);
+        std::fill(ptime.begin(), ptime.end(), 0.0); std::fill(jerk.begin(), jerk.end(), 0.0);
+        for (int q = 0; q < 9; q++) x_final[q] = x0[q];
+        rtn = -100; cost = 0.0; iters = 0; infeas_out = infeas ? 1 : 0; line_failed_out = 1;
+    }
 
     // ---- results -> the members the inline getters read (ddp_optimizer.h:299-340) ------------------------
     PolyCoeff = Eigen::MatrixXd::Zero(N, 18);

@@ -11,6 +11,8 @@ N overlapping convex cells along that polyline:
   * ``kind="box"``   axis-aligned boxes, P = 6 planes per cell
   * ``kind="poly"``  box + U{0..8} random cutting planes, P <= 14 (ragged; padded with the
                      always-inactive plane (0,0,0,-1), the trick teach_repeat_planner.cpp:867-879 uses)
+  * ``kind="poly40"`` box + U{0..34} cutting planes, P <= 40: polytopes with more planes than a warp has lanes
+                     (cdd H-representations have no bound, poly_utils.cpp:127-166)
 
 Planes are unit outward normals with ``n.x + d <= 0`` inside (poly_utils.cpp:156-166).  Initial
 segment times come from the reference's trapezoidal rule (teach_repeat_planner.cpp:583-639).
@@ -93,8 +95,9 @@ def time_allocation(points: np.ndarray, max_vel: float, max_acc: float) -> np.nd
 def make_batch(B: int, N: int, kind: str = "box", first: int = 0, max_vel: float = 2.0,
                max_acc: float = 2.0) -> ProblemBatch:
     """Problems ``first .. first+B-1`` of the infinite deterministic family."""
-    if kind not in ("box", "poly"):
-        raise ValueError("kind must be 'box' or 'poly'")
+    if kind not in ("box", "poly", "poly40"):
+        raise ValueError("kind must be 'box', 'poly' or 'poly40'")
+    max_cuts = {"box": 0, "poly": 8, "poly40": 34}[kind]
     ids = np.arange(first, first + B, dtype=np.int64)
     rs = _Stream(ids)
     # --- tour waypoints (ring goals) --------------------------------------------------------
@@ -122,7 +125,7 @@ def make_batch(B: int, N: int, kind: str = "box", first: int = 0, max_vel: float
     seeds = pts[:, :N].copy()
     jit = rs.uniform(3 * N, -0.2, 0.2).reshape(B, N, 3)
     centre = seeds + jit * w[:, :N, None]
-    P_max = 6 if kind == "box" else 14
+    P_max = 6 + max_cuts
     planes = np.zeros((B, N, P_max, 4))
     planes[..., 3] = -1.0  # inactive padding: c = -1 always
     for a in range(3):
@@ -131,14 +134,15 @@ def make_batch(B: int, N: int, kind: str = "box", first: int = 0, max_vel: float
         planes[:, :, 2 * a + 1, a] = -1.0
         planes[:, :, 2 * a + 1, 3] = centre[:, :, a] - w[:, :N]
     nplanes = np.full((B, N), 6, dtype=np.int32)
-    if kind == "poly":
-        ncut = np.floor(rs.uniform(N, 0.0, 9.0)).astype(np.int32).clip(0, 8)
-        dirs = rs.uniform(N * 8 * 3, -1.0, 1.0).reshape(B, N, 8, 3)
-        rho = rs.uniform(N * 8, 0.8, 1.1).reshape(B, N, 8)
+    if max_cuts:
+        mc = max_cuts
+        ncut = np.floor(rs.uniform(N, 0.0, mc + 1.0)).astype(np.int32).clip(0, mc)
+        dirs = rs.uniform(N * mc * 3, -1.0, 1.0).reshape(B, N, mc, 3)
+        rho = rs.uniform(N * mc, 0.8, 1.1).reshape(B, N, mc)
         nrm = np.linalg.norm(dirs, axis=-1, keepdims=True)
         nrm = np.where(nrm < 1e-3, 1.0, nrm)
         dirs = dirs / nrm
-        for k in range(8):
+        for k in range(mc):
             on = ncut > k
             n = dirs[:, :, k]
             # plane through seed + rho*w*n with outward normal n

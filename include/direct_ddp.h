@@ -33,7 +33,7 @@ extern "C" {
 
 enum {
     DIRECT_DDP_OK = 0,
-    DIRECT_DDP_ERR_ARG = -1,     /* bad argument (NULL, N<=0, P>32, time_power not in {1,2}, ...) */
+    DIRECT_DDP_ERR_ARG = -1,     /* bad argument (NULL, N<=0, nplanes > P_max, time_power not in {1,2}, ...) */
     DIRECT_DDP_ERR_CUDA = -2,    /* CUDA runtime error / no device                               */
     DIRECT_DDP_ERR_NOMEM = -3,
     DIRECT_DDP_ERR_UNSUPPORTED = -4
@@ -41,7 +41,10 @@ enum {
 
 enum { DIRECT_DDP_FP64 = 0, DIRECT_DDP_FP32 = 1 };
 
-#define DIRECT_DDP_MAX_PLANES 32 /* planes per polytope handled by one warp (lane <-> plane) */
+/* Planes per polytope: no algorithmic limit (the reference has none, m_c = 6 P + 55 rows per knot,
+ * ddp_optimizer.cpp:145, :1181-1187); the row loops of the kernel walk a polytope's planes one after the other and the
+ * per-slot workspace grows linearly with P_max.  The constant is a sanity bound on the argument only. */
+#define DIRECT_DDP_MAX_PLANES 4096
 
 typedef struct direct_ddp_opts {
     int device;          /* CUDA device ordinal                                                    */
@@ -62,7 +65,7 @@ typedef struct direct_ddp_opts {
 typedef struct direct_ddp_batch {
     int B, N, P_max;
     const double *planes;    /* [B][N][P_max][4]                                                    */
-    const int32_t *nplanes;  /* [B][N], each in [0, P_max], P_max <= DIRECT_DDP_MAX_PLANES          */
+    const int32_t *nplanes;  /* [B][N], each in [0, P_max] (checked by the host entry points)          */
     const double *durations; /* [B][N]                                                              */
     const double *seeds;     /* [B][N][3] or NULL                                                   */
     const double *x0;        /* [B][9] = [pos.row(0), vel.row(0), acc.row(0)] (ddp_optimizer.cpp:115-121) */

@@ -32,7 +32,7 @@ def load_golden(name):
     return pb, d
 
 
-GOLDEN_TWO_STAGE = ["box_n5", "poly_n12", "box_n50_single", "poly_n30_minvo", "box_n8_timepower1", "box_n100"]
+GOLDEN_TWO_STAGE = ["box_n5", "poly_n12", "box_n50_single", "poly_n30_minvo", "box_n8_timepower1", "box_n100", "poly40_n10"]
 OUT_FIELDS = ("cost", "poly_coeff", "bez_coeff", "poly_time")
 
 
@@ -51,12 +51,16 @@ def oracle():
 # outputs by far more than 1e-5 -- the oracle built with -ffp-contract=fast disagrees with itself on those,
 # and so would the reference rebuilt with other compiler flags.  No implementation with a different rounding
 # sequence can promise 1e-5 there.  The screen below finds them with the oracle alone: a trajectory is
-# "conditioned" when four 2^-48-relative input perturbations leave every oracle output within 1e-7 relative
-# and every discrete outcome unchanged.  Parity (<= 1e-5, identical rtn / iteration counts) is asserted on
-# ALL conditioned trajectories; the others are checked for validity of what is returned.
+# "conditioned" when four 2^-48-relative input perturbations leave every oracle output within 1e-6 relative
+# (a tenth of the parity tolerance) and every discrete outcome unchanged.  Parity (<= 1e-5, identical rtn /
+# iteration counts) is asserted on ALL conditioned trajectories; the others are bounded by
+# assert_screened_out_bounded (same return codes as the oracle's own runs, valid, cost inside the oracle's own
+# spread).  Measured pass fractions of the test batches (oracle alone, this container): 64 x 33 box 0.969,
+# 48 x 50 poly 0.917 (4 trajectories on which the oracle disagrees with itself at 1e-5), 32 x 100 poly 0.969,
+# 8 x 200 box 1.0, 24 x 30 poly40 0.917, the 128-trajectory sample of the 4096 x 100 bench batch 0.977.
 # ---------------------------------------------------------------------------------------------------------
 PERTURB_EPS = 2.0 ** -48
-SCREEN_TOL = 1e-7
+SCREEN_TOL = 1e-6
 
 
 def _row_rel(a, b):
@@ -82,15 +86,46 @@ def perturbed_batches(pb):
             mk(x0=pb.x0 * (1 + e), xd=pb.xd * (1 - e)), mk(planes=np.ascontiguousarray(pb.planes * (1 + e)))]
 
 
-def conditioned_mask_two_stage(oracle, pb, base=None, nthreads=None):
-    """(mask, (a0, a1)): trajectories on which the oracle's two-stage result is insensitive to 1-ulp inputs."""
+SCREEN_FLOOR = 0.90        # at least this fraction of every small test batch must pass the screen (measured 0.917 - 1.0)
+SCREEN_FLOOR_FULL = 0.95   # ... and of the sample of the full-size bench batch (measured 0.977)
+
+
+def conditioned_mask_two_stage(oracle, pb, base=None, nthreads=None, keep=None):
+    """(mask, (a0, a1)): trajectories on which the oracle's two-stage result is insensitive to 1-ulp inputs.
+    `keep` (a list) receives the oracle's perturbed runs [(p0, p1), ...] for assert_screened_out_bounded."""
     nt = nthreads or oracle.max_threads()
     a0, a1 = base if base is not None else oracle.two_stage_batch(pb, nthreads=nt)
     ok = np.ones(pb.B, dtype=bool)
     for q in perturbed_batches(pb):
         p0, p1 = oracle.two_stage_batch(q, nthreads=nt)
         ok &= ~results_differ(p0, a0, SCREEN_TOL) & ~results_differ(p1, a1, SCREEN_TOL)
+        if keep is not None:
+            keep.append((p0, p1))
     return ok, (a0, a1)
+
+
+def assert_screened_out_bounded(oracle, pb, ok, base, got, perturbed=None, slack=0.10):
+    """The trajectories the screen sets aside are not exempt: on each of them the device result must (i) end with a
+    return code that the oracle itself produces under its four 2^-48 input perturbations (or the unperturbed run),
+    (ii) be a valid result (assert_valid_result: finite, inside the corridor when converged), and (iii) have a final
+    cost inside the oracle's own min..max over those five runs widened by `slack` (10 %) -- i.e. the device lands no
+    further from the oracle than the oracle lands from itself."""
+    if ok.all():
+        return
+    if perturbed is None:
+        perturbed = []
+        conditioned_mask_two_stage(oracle, pb, base=base, keep=perturbed)
+    idx = np.nonzero(~ok)[0]
+    for st in (0, 1):
+        runs = [base[st]] + [p[st] for p in perturbed]
+        rt = np.stack([r.rtn[idx] for r in runs])            # (5, k)
+        cs = np.stack([r.cost[idx] for r in runs])
+        g = got[st]
+        assert np.isfinite(g.cost[idx]).all()
+        for j, i in enumerate(idx):
+            assert g.rtn[i] in set(rt[:, j].tolist()), (st, int(i), int(g.rtn[i]), rt[:, j])
+            lo, hi = cs[:, j].min(), cs[:, j].max()
+            assert lo - slack * abs(lo) <= g.cost[i] <= hi + slack * abs(hi), (st, int(i), g.cost[i], lo, hi)
 
 
 def assert_valid_result(pb, r):

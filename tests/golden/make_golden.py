@@ -30,6 +30,7 @@ CASES = {
     "poly_n30_minvo": (3, 30, "poly", 90, {"minvo": 1}),
     "box_n8_timepower1": (3, 8, "box", 300, {"time_power": 1}),
     "box_n100": (2, 100, "box", 1000, {}),
+    "poly40_n10": (3, 10, "poly40", 700, {}),         # polytopes with up to 40 planes (m_c = 6 P + 55 up to 295 rows per knot)
 }
 
 
@@ -71,6 +72,9 @@ def line_init_case():
 if __name__ == "__main__":
     if not O.ref_available():
         O.build(ref=True)
+    only = sys.argv[1:]   # optional: names of the cases to (re)generate; default all
     for name, (B, N, kind, first, ov) in CASES.items():
-        run_case(name, B, N, kind, first, ov)
-    line_init_case()
+        if not only or name in only:
+            run_case(name, B, N, kind, first, ov)
+    if not only or "box_n6_lineinit" in only:
+        line_init_case()

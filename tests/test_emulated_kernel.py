@@ -4,8 +4,8 @@ GPU-less container; the shipped path is tested by test_gpu_parity.py through the
 import numpy as np
 import pytest
 
-from conftest import (GOLDEN_TWO_STAGE, OUT_FIELDS, assert_valid_result, conditioned_mask_two_stage, load_golden, rel_err,
-                      results_differ)
+from conftest import (GOLDEN_TWO_STAGE, OUT_FIELDS, SCREEN_FLOOR, assert_screened_out_bounded, assert_valid_result,
+                      conditioned_mask_two_stage, load_golden, rel_err, results_differ)
 from direct_b200.problems import STAGE0, STAGE1, make_batch
 
 TOL64 = 1e-5   # north_star: <= 1e-5 relative in fp64
@@ -61,13 +61,15 @@ def test_emulated_kernel_parity_on_conditioned_trajectories(emu, oracle):
     oracle; its iterates separate from ANY differently-rounded evaluation around iteration 33): every
     trajectory that passes the conditioning screen matches to 1e-5, the rest are still valid results."""
     pb = make_batch(64, 33, "box", first=2033)
-    ok, (a0, a1) = conditioned_mask_two_stage(oracle, pb, nthreads=4)
-    assert 0.7 <= ok.mean() < 1.0 and not ok[44]
+    pert = []
+    ok, (a0, a1) = conditioned_mask_two_stage(oracle, pb, nthreads=4, keep=pert)
+    assert SCREEN_FLOOR <= ok.mean() < 1.0 and not ok[44]
     e0, e1 = emu.two_stage_batch(pb)
     for a, e in ((a0, e0), (a1, e1)):
         bad = results_differ(e, a, TOL64, OUT_FIELDS + ("jerk", "x_final")) & ok
         assert not bad.any(), np.nonzero(bad)[0]
         assert_valid_result(pb, e)
+    assert_screened_out_bounded(oracle, pb, ok, (a0, a1), (e0, e1), perturbed=pert)
 
 
 def test_emulated_fp32_smoke(emu, oracle):

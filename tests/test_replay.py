@@ -97,5 +97,10 @@ def test_gpu_replay_rows_match_oracle(oracle, tmp_path):
         assert np.isfinite(rows[k]).all() and rows[k, 1] > 0     # compTime: device time of the two solves
         assert got[1] == pytest.approx(want[1], rel=1e-12)        # initTimeAllocation, teach_repeat_planner.cpp:583-639
         ok = all(abs(g - w) <= 1e-5 * max(1.0, abs(w)) for g, w in zip(got, want))
+        if not ok:   # allowed only where the oracle disagrees with itself under 2^-48 input perturbations (conftest.py screen)
+            from conftest import conditioned_mask_two_stage
+            cond, _ = conditioned_mask_two_stage(oracle, q, base=(a0, a1))
+            assert not cond[0], (n, got, want)
+            assert got[5] in (0, 1, -3, -4) and np.isfinite(got).all()
         good += ok
-    assert good >= 21, good   # rel 1e-5 on every column; at most two chaotic prefixes tolerated
+    assert good >= 21, good   # rel 1e-5 on every column; at most two chaotic prefixes (each verified chaotic above)
