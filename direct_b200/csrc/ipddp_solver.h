@@ -152,9 +152,15 @@ struct Lay {
         RI = 574,   // riccati: 1/sqrt(pivot) of the ten Cholesky pivots
         MSC = 584,  // per-lane 3x3 blocks M_g of the linearisation: MSC[e*32+lane], e < 63.  During the line search
                     // (no linearisation in flight) the same area holds forward_trial's knot ring [0, 480).
-        TOTAL = 584 + 63 * 32
+        TOTAL = 584 + 63 * 32,
+        // Line search, behind the knot ring [0, 480) and the job partials [512, 1152) of MSC: the slack-row ring of the row
+        // phase (RowRing below).  Offsets are multiples of 16 bytes for float and double.
+        RB = 584 + 1152,            // mbarriers of the RING_NB batches (8 bytes each)
+        RS = 584 + 1160,            // slack rows s:      RING_ROWS x 32
+        RY = 584 + 1160 + 12 * 32   // dual slack rows y: RING_ROWS x 32   (ends at 584 + 1928 <= TOTAL)
     };
 };
+enum { RING_BATCH = 4, RING_NB = 3, RING_ROWS = RING_BATCH * RING_NB };
 DDP_HD int smem_elems_per_warp(int /*pm*/) { return Lay::TOTAL; }
 
 // Workspace slot layout (elements of Real).  Row arrays (s, y and their trial copies) are stored
@@ -480,6 +486,14 @@ DDP_DEVICE void lin_diag_group(const R *tab, int g, const R *tp, R m0, R m1, R m
 // bit for bit - is the same with or without helpers.
 // =============================================================================================
 enum { JOB_LIN = 1, JOB_ROWS = 2, JOB_MAX_UNITS = 16 };
+// Idle warps poll the boards with an exponentially growing nanosleep between polls (profiles/r1h: with a fixed 400-500 ns the
+// polling loops executed as many warp instructions as the solves themselves and competed with the tail's owners for issue slots).
+#ifndef DDP_IDLE_NS_MIN
+#define DDP_IDLE_NS_MIN 250u
+#endif
+#ifndef DDP_IDLE_NS_MAX
+#define DDP_IDLE_NS_MAX 4000u
+#endif
 template <class R> struct JobCtx {   // everything a unit needs; copied to registers by whoever runs the unit
     RowCtx<R> row;
     const R *xu, *xun, *K, *kdx;
@@ -741,6 +755,7 @@ template <class R> DDP_DEVICE_NOINLINE void job_run_unit(JobBoard<R> *b, int u, 
             }
         }
     }
+    fence_async_all();       // the slack rows this unit wrote are read by the owner's bulk copies (RowRing) in the next trial
     __threadfence_block();   // the unit's global and shared writes are visible to the CTA before it counts as done
     __syncwarp();
     if (lane_ == 0) atomicAdd(&b->done, 1);
@@ -777,6 +792,7 @@ template <class R> DDP_DEVICE_NOINLINE void job_run(Traj<R> &t, const JobCtx<R> 
 // A warp without a trajectory serves the boards of its CTA until no warp of the CTA owns one any more.
 template <class R>
 DDP_DEVICE_NOINLINE void helper_loop(JobBoard<R> *boards, BlockCtl *ctl, int wpb, int me, R *sm, int lane_, unsigned int *units_ctr) {
+    unsigned idle_ns = DDP_IDLE_NS_MIN;   // parked, not spinning: the sleep doubles while there is nothing to do
     while (*(volatile int *)&ctl->active_owners > 0) {
         bool found = false;
         for (int w = 0; w < wpb; w++) {
@@ -787,7 +803,8 @@ DDP_DEVICE_NOINLINE void helper_loop(JobBoard<R> *boards, BlockCtl *ctl, int wpb
             job_run_unit(boards + w, u, sm, lane_);
             if (lane_ == 0) atomicAdd(units_ctr, 1u);
         }
-        if (!found) __nanosleep(400);
+        if (found) idle_ns = DDP_IDLE_NS_MIN;
+        else { __nanosleep(idle_ns); if (idle_ns < DDP_IDLE_NS_MAX) idle_ns *= 2; }
     }
 }
 #endif
@@ -1471,6 +1488,56 @@ DDP_DEVICE_NOINLINE void rows_unit(const JobCtx<R> *cp_, int u0, int u1, int lan
     }
 }
 
+// =============================================================================================
+// Slack-row ring (TMA).  The row phase of a line-search trial walks the 6 P + 55 constraint rows of 32 knots (lane <-> knot)
+// and needs, for every row, the 32 slack values s (and dual slacks y in the infeasible phase) of those knots: one 256-byte
+// line per row and array, [row slot][knot] in the workspace, row slots in visit order.  Loading them with one LDG per lane
+// and row left the loop waiting on global-memory latency (profiles/r1h: 17 % of all stall samples sit on those loads, L1
+// prefetch or not).  Here ONE lane hands whole batches of RING_BATCH rows to the copy engine (cp.async.bulk, completion on an
+// mbarrier) RING_NB batches = RING_ROWS rows ahead of their use; the lanes read the values from shared memory.
+// Everything is warp-uniform: the visit sequence is  (position group g < 6: rows 0 .. Pw-1, Pw = most planes of any of the 32
+// knots) , (6 rows of each velocity / acceleration group) , time row;  lanes whose polytope has fewer planes skip the body.
+// GPU only: the lane-by-lane CPU emulation reads the rows straight from the workspace (same arithmetic).
+// =============================================================================================
+template <class R> struct RowRing {
+    int Pw;                    // most planes of any knot of the block: 6 Pw + 55 rows in the sequence
+    int pslot, pg, pr, issued; // producer: workspace row slot / position group / row in group of the next row to issue, rows issued
+};
+#if DDP_GPU
+template <class R> DDP_DEVICE void ring_issue_batch(RowRing<R> &q, const RowCtx<R> &t, R *sm, int base, int bslot, int lane_) {
+    const int left = 6 * q.Pw + 55 - q.issued;
+    const int n = left < RING_BATCH ? left : RING_BATCH;
+    if (n <= 0) return;
+    unsigned long long *bar = reinterpret_cast<unsigned long long *>(sm + Lay::RB) + bslot;
+    const unsigned row_bytes = 32u * (unsigned)sizeof(R);
+    if (lane_ == 0) mbar_expect_tx(bar, (unsigned)n * row_bytes * (t.infeas ? 2u : 1u));
+    for (int k = 0; k < n; k++) {
+        if (lane_ == 0) {
+            const long long go = (long long)q.pslot * t.NP + base;
+            bulk_g2s(sm + Lay::RS + (bslot * RING_BATCH + k) * 32, t.s + go, row_bytes, bar);
+            if (t.infeas) bulk_g2s(sm + Lay::RY + (bslot * RING_BATCH + k) * 32, t.y + go, row_bytes, bar);
+        }
+        // next row in visit order: position groups own PM slots each and use Pw of them, the rest is contiguous
+        q.pslot++; q.issued++;
+        if (q.pg < 6 && ++q.pr == q.Pw) { q.pg++; q.pr = 0; q.pslot = q.pg * t.PM; }
+    }
+}
+// Start the ring for the 32-knot block at `base`: barriers re-armed (every copy of the previous block has been consumed),
+// first RING_NB batches in flight.  Called before the block's state recursion so that the rows are there when it ends.
+template <class R>
+DDP_DEVICE void ring_start(RowRing<R> &q, const RowCtx<R> &t, R *sm, int base, int Pw, int lane_) {
+    q.Pw = Pw; q.issued = 0; q.pr = 0;
+    q.pg = Pw > 0 ? 0 : 6; q.pslot = Pw > 0 ? 0 : 6 * t.PM;
+    __syncwarp();
+    if (lane_ < RING_NB) mbar_init(reinterpret_cast<unsigned long long *>(sm + Lay::RB) + lane_, 1);
+    fence_async_all();    // the barriers, whatever generic stores last touched the ring area, and the st.global that wrote the slack
+                          // rows (this warp's lanes or, through the job board, helper warps) before the copy engine reads them
+    __syncwarp();
+    DDP_UNROLL
+    for (int b = 0; b < RING_NB; b++) ring_issue_batch(q, t, sm, base, b, lane_);
+}
+#endif
+
 // Closed-loop state / control recursion over knots base .. base+nk-1 of a line-search trial (ddp.cpp:689-697, :1062-1067):
 // lanes 0-9 own u, lanes 10-18 own x.  Out of line on purpose: inside forward_trial the register allocator spilled this
 // loop's state around the calls of the row phase.  xcur carries the state across blocks.
@@ -1505,7 +1572,7 @@ DDP_DEVICE_NOINLINE void rollout_block(R *sm, const R *DDP_RESTRICT xu, R *DDP_R
                     R kdx = R(0);
                     DDP_UNROLL
                     for (int b = 0; b < 9; b++) kdx += Kr[1 + b] * sm[Lay::DX + b];
-                    const R un = (slot[100 + lane] + alpha * Kr[0]) + kdx;
+                    const R un = step_u(slot[100 + lane], alpha, Kr[0], kdx);
                     sm[Lay::ZN + lane] = un;
                     xun[(long long)i * 20 + lane] = un;
                     kdxo[(long long)i * 10 + lane] = kdx;
@@ -1658,6 +1725,14 @@ template <class R> DDP_DEVICE_NOINLINE bool forward_trial_solo(Traj<R> &tt_, R a
         }
     }
     bool ok = true;
+    // planes of this lane's knot of the block and the most planes of any knot of the block (warp-uniform row sequence)
+    Reg<int, 1> Pl;
+    FOR_LANES(lane) { Pl(lane, 0) = lane < N ? t.nplanes[lane] : 0; }
+    int Pw = warp_max_int(Pl, 0, lane_);
+#if DDP_GPU
+    RowRing<R> rq;
+    ring_start(rq, t, sm, 0, Pw, lane_);   // the first rows of block 0 travel while its state recursion runs
+#endif
     for (int base = 0; base < N && ok; base += 32) {
         const int nk = N - base < 32 ? N - base : 32;
         const long long clk_s = ddp_clock();
@@ -1684,7 +1759,7 @@ template <class R> DDP_DEVICE_NOINLINE bool forward_trial_solo(Traj<R> &tt_, R a
                     R kdx = R(0);
                     DDP_UNROLL
                     for (int b = 0; b < 9; b++) kdx += Kr[1 + b] * sm[Lay::DX + b];
-                    const R un = (slot[100 + lane] + alpha * Kr[0]) + kdx;
+                    const R un = step_u(slot[100 + lane], alpha, Kr[0], kdx);
                     sm[Lay::ZN + lane] = un;
                     xun[(long long)i * 20 + lane] = un;
                     kdxo[(long long)i * 10 + lane] = kdx;
@@ -1711,92 +1786,142 @@ template <class R> DDP_DEVICE_NOINLINE bool forward_trial_solo(Traj<R> &tt_, R a
             FOR_LANES(lane) { xcur(lane, 0) = xn(lane, 0); }
         }
         cyc_seq += ddp_clock() - clk_s;
-        // ---- rows of knots base .. base+nk-1, lane <-> knot ---------------------------------------------
+        // ---- rows of knots base .. base+nk-1, lane <-> knot; slack rows from the TMA ring (RowRing) ---------------
         Reg<int, 1> badk;
         FOR_LANES(lane) {
             const int i = base + lane;
+            const bool live = i < N;
+            const int il = live ? i : N - 1;   // lanes past the end run along on the last knot and never store / accumulate
             badk(lane, 0) = 0x7fffffff;
-            if (i < N) {
-                R zo[19], zn[19], v1[10], v2[19], tpo[6], tpn[6];
+            {
+                // Live across the 15 groups: the old point zo and the new STATE zx in registers; the feed-forward v1 and the
+                // closed-loop part v2 of the nine coefficient controls wait in shared memory (the job-partial area of MSC, idle
+                // while a warp works alone), their T entries and the two segment times stay in registers.  The new controls and
+                // the state step are re-formed per group with the recursion's own expression (step_u: same bits), the powers
+                // of T per group as well: every value kept live here is a register the row loop below cannot use (the
+                // 15 per-group constants co..j2 used to be spilled and re-read from local memory in every row).
+                R zo[19], zx[9];
                 DDP_UNROLL
-                for (int e = 0; e < 19; e++) { zo[e] = xu[(long long)i * 20 + e]; zn[e] = xun[(long long)i * 20 + e]; }
+                for (int e = 0; e < 19; e++) zo[e] = xu[(long long)il * 20 + e];
                 DDP_UNROLL
-                for (int e = 0; e < 10; e++) { v1[e] = Kin[(long long)i * 100 + e * 10]; v2[e] = kdxo[(long long)i * 10 + e]; }
+                for (int e = 0; e < 9; e++) zx[e] = xun[(long long)il * 20 + 10 + e];
+                R *vst = sm + Lay::MSC + 512 + lane;   // vst[e * 32]: v1[e], vst[(9 + e) * 32]: v2[e], e < 9
                 DDP_UNROLL
-                for (int e = 10; e < 19; e++) v2[e] = zn[e] - zo[e];
-                time_powers(zo[9], tpo);
-                time_powers(zn[9], tpn);
+                for (int e = 0; e < 9; e++) { vst[e * 32] = Kin[(long long)il * 100 + e * 10]; vst[(9 + e) * 32] = kdxo[(long long)il * 10 + e]; }
+                const R v1T = Kin[(long long)il * 100 + 90], v2T = kdxo[(long long)il * 10 + 9];
+                const R Tn = step_u(zo[9], alpha, v1T, v2T);   // = xun[9] (ddp.cpp:689/:695, rollout above)
                 TrialAcc<R> A;
                 A.lg.lp = R(1); A.lg.lsum = R(0); A.e1 = R(0); A.bad = 0; A.cmax = R(-INFINITY);
-                const int P = t.nplanes[i];
-                const double *pl = t.planes + (long long)i * t.PM * 4;
-                R s_n = R(0), y_n = R(1), n_n[4] = {R(0), R(0), R(0), R(0)};   // pipeline registers, see first_row_load
-                first_row_load(t, pl, P, 0, i, s_n, y_n, n_n);
+                const int P = live ? Pl(lane, 0) : 0;
+                const double *pl = t.planes + (long long)il * t.PM * 4;
+                R n_n[4] = {R(0), R(0), R(0), R(0)};   // plane of the next row, loaded one row ahead
+                if (P > 0) load_plane(pl, 0, n_n);
+#if DDP_GPU
+                int cbatch = 0, cphase = 0, cin = 0;   // consumer: batch slot, that slot's phase, row in batch
+#endif
                 DDP_NOUNROLL
-                for (int g = 0; g < 15; g++) {   // one copy of the row code for all groups (see linearize)
-                    const int shift = group_shift(g), nr = g < 6 ? P : 6;
+                for (int g = 0; g < 16; g++) {   // one copy of the row code for all groups (see linearize); g = 15: the time row
+                    const int shift = group_shift(g), nr = g < 6 ? P : (g < 15 ? (live ? 6 : 0) : (live ? 1 : 0));
+                    const int nrw = g < 6 ? Pw : (g < 15 ? 6 : 1);
                     const R lim = g < 11 ? t.max_vel : t.max_acc;
-                    R b[6], bd[6], bn[6], co[3], cd[3], cn[3], j1[3], j2[3];
-                    basis_row_rt(tab + g * 6, shift, tpo, b);
-                    basis_row_rt(tab + 90 + g * 6, shift + 1, tpo, bd);
-                    basis_row_rt(tab + g * 6, shift, tpn, bn);
-                    DDP_UNROLL
-                    for (int a = 0; a < 3; a++) {
-                        co[a] = dot_axis<R, 0>(b, zo, a); cd[a] = dot_axis<R, 0>(bd, zo, a); cn[a] = dot_axis<R, 0>(bn, zn, a);
-                        j1[a] = dot_axis<R, 3>(b, v1, a); j2[a] = dot_axis<R, 0>(b, v2, a);
+                    R co[3], cd[3], cn[3], j1[3], j2[3];
+                    if (g < 15) {
+                        R b[6], bd[6], bn[6], tpo[6], tpn[6];
+                        time_powers(zo[9], tpo);
+                        time_powers(Tn, tpn);
+                        basis_row_rt(tab + g * 6, shift, tpo, b);
+                        basis_row_rt(tab + 90 + g * 6, shift + 1, tpo, bd);
+                        basis_row_rt(tab + g * 6, shift, tpn, bn);
+                        DDP_UNROLL
+                        for (int a = 0; a < 3; a++) {
+                            co[a] = dot_axis<R, 0>(b, zo, a); cd[a] = dot_axis<R, 0>(bd, zo, a);
+                            // new point [(uo + alpha ku) + Ku dx ; xn] and step [Ku dx ; xn - xo], orders l = 0..2 are the state
+                            R accn = R(0), acc2 = R(0), acc1 = R(0);
+                            DDP_UNROLL
+                            for (int l = 0; l < 3; l++) {
+                                accn += bn[l] * zx[3 * l + a];
+                                acc2 += b[l] * (zx[3 * l + a] - zo[10 + 3 * l + a]);
+                            }
+                            DDP_UNROLL
+                            for (int l = 3; l < 6; l++) {
+                                const int e = 3 * (l - 3) + a;
+                                const R k1 = vst[e * 32], k2 = vst[(9 + e) * 32];
+                                accn += bn[l] * step_u(zo[e], alpha, k1, k2);
+                                acc2 += b[l] * k2;
+                                acc1 += b[l] * k1;
+                            }
+                            cn[a] = accn; j2[a] = acc2; j1[a] = acc1;
+                        }
+                    } else {   // the time row -T + 0.3 <= 0 (ddp.cpp:1279) as a row with n = (1, 0, 0 | 0.3): one copy of the row code
+                        co[0] = -zo[9]; cn[0] = -Tn; cd[0] = R(0); j1[0] = -v1T; j2[0] = -v2T;
+                        co[1] = co[2] = cn[1] = cn[2] = cd[1] = cd[2] = j1[1] = j1[2] = j2[1] = j2[2] = R(0);
                     }
                     DDP_NOUNROLL
-                    for (int r = 0; r < nr; r++) {
-                        const R sv = s_n, yv = y_n;
-                        const long long ro_cur = (long long)row_slot(g, r, t.PM) * t.NP + i;
+                    for (int r = 0; r < nrw; r++) {
+                        const long long ro_cur = (long long)(g < 15 ? row_slot(g, r, t.PM) : 6 * t.PM + 54) * t.NP + i;
+#if DDP_GPU
+                        if (cin == 0) mbar_wait(reinterpret_cast<unsigned long long *>(sm + Lay::RB) + cbatch, (unsigned)cphase);
+                        const R sv = sm[Lay::RS + (cbatch * RING_BATCH + cin) * 32 + lane];
+                        const R yv = t.infeas ? sm[Lay::RY + (cbatch * RING_BATCH + cin) * 32 + lane] : R(1);
+#else
+                        const R sv = r < nr ? t.s[ro_cur] : R(0), yv = (r < nr && t.infeas) ? t.y[ro_cur] : R(1);
+#endif
                         R n[4];
                         if (g < 6) { n[0] = n_n[0]; n[1] = n_n[1]; n[2] = n_n[2]; n[3] = n_n[3]; }
-                        else fixed_row(r, lim, n);
-                        prefetch_l1(t.s + ro_cur + ROW_PREFETCH * t.NP);
-                        if (t.infeas) prefetch_l1(t.y + ro_cur + ROW_PREFETCH * t.NP);
-                        if (r + 1 < nr) {
-                            const long long ro = ro_cur + t.NP;
-                            s_n = t.s[ro];
-                            if (t.infeas) y_n = t.y[ro];
-                            if (g < 6) load_plane(pl, r + 1, n_n);
+                        else if (g < 15) fixed_row(r, lim, n);
+                        else { n[0] = R(1); n[1] = R(0); n[2] = R(0); n[3] = R(0.3); }
+                        if (g < 6 && r + 1 < nr) load_plane(pl, r + 1, n_n);
+                        if (r < nr) {
+                            const R cold = ((n[0] * co[0] + n[1] * co[1]) + n[2] * co[2]) + n[3] - t.margin;
+                            const R cnew = ((n[0] * cn[0] + n[1] * cn[1]) + n[2] * cn[2]) + n[3] - t.margin;
+                            const R tc = (n[0] * cd[0] + n[1] * cd[1]) + n[2] * cd[2];
+                            const R jv1 = ((n[0] * j1[0] + n[1] * j1[1]) + n[2] * j1[2]) + tc * v1T;
+                            const R jv2 = ((n[0] * j2[0] + n[1] * j2[1]) + n[2] * j2[2]) + tc * v2T;
+                            trial_row(t, ro_cur, sv, yv, cold, cnew, jv1, jv2, alpha, tau, A);
                         }
-                        const R cold = ((n[0] * co[0] + n[1] * co[1]) + n[2] * co[2]) + n[3] - t.margin;
-                        const R cnew = ((n[0] * cn[0] + n[1] * cn[1]) + n[2] * cn[2]) + n[3] - t.margin;
-                        const R tc = (n[0] * cd[0] + n[1] * cd[1]) + n[2] * cd[2];
-                        const R jv1 = ((n[0] * j1[0] + n[1] * j1[1]) + n[2] * j1[2]) + tc * v1[9];
-                        const R jv2 = ((n[0] * j2[0] + n[1] * j2[1]) + n[2] * j2[2]) + tc * v2[9];
-                        trial_row(t, ro_cur, sv, yv, cold, cnew, jv1, jv2, alpha, tau, A);
+#if DDP_GPU
+                        if (++cin == RING_BATCH) {   // batch consumed by every lane: its ring rows take the batch RING_NB further on
+                            __syncwarp();
+                            ring_issue_batch(rq, t, sm, base, cbatch, lane_);
+                            cin = 0;
+                            if (++cbatch == RING_NB) { cbatch = 0; cphase ^= 1; }
+                        }
+#endif
                     }
-                    first_row_load(t, pl, P, g + 1, i, s_n, y_n, n_n);
-                    if ((g & 3) == 3) {   // end of unit g / 4 (see rows_unit): bank its partials, restart the accumulators
-                        acc(lane, 1) += A.lg.total();
-                        acc(lane, 2) += A.e1;
+                    if (g + 1 < 6 && P > 0) load_plane(pl, 0, n_n);   // first plane of the next position group
+                    if ((g & 3) == 3 && g < 15) {   // end of unit g / 4 (see rows_unit): bank its partials, restart the accumulators
+                        if (live) { acc(lane, 1) += A.lg.total(); acc(lane, 2) += A.e1; }
                         if (A.bad) badk(lane, 0) = i;
                         A.lg.lp = R(1); A.lg.lsum = R(0); A.e1 = R(0); A.bad = 0;
                     }
                 }
-                {
-                    const long long ro = (long long)(6 * t.PM + 54) * t.NP + i;
-                    trial_row(t, ro, t.s[ro], t.infeas ? t.y[ro] : R(1), -zo[9] + R(0.3) - t.margin, -zn[9] + R(0.3) - t.margin, -v1[9],
-                              -v2[9], alpha, tau, A);
-                }
                 if (A.bad) badk(lane, 0) = i;
-                {   // stage cost q(x,u), ddp.cpp:1294-1305
-                    R m[9], mu9[9];
+                if (live) {   // stage cost q(x,u), ddp.cpp:1294-1305
+                    R m[9], mu9[9], un[9], tpn[6];
+                    DDP_UNROLL
+                    for (int e = 0; e < 9; e++) un[e] = step_u(zo[e], alpha, vst[e * 32], vst[(9 + e) * 32]);
+                    time_powers(Tn, tpn);
                     rmat<R>(0, tpn, m);
-                    rmat_times_u(m, zn, mu9);
+                    rmat_times_u(m, un, mu9);
                     const R T = tpn[1];
                     const R tterm = time_power == 2 ? R(0.5) * T * w_time * T : R(0.5) * w_time * T;
-                    acc(lane, 0) += R(0.5) * w_snap * dot9(zn, mu9) + tterm;
+                    acc(lane, 0) += R(0.5) * w_snap * dot9(un, mu9) + tterm;
+                    acc(lane, 1) += A.lg.total();
+                    acc(lane, 2) += A.e1;
+                    acc(lane, 3) = rmax(acc(lane, 3), A.cmax);
                 }
-                acc(lane, 1) += A.lg.total();
-                acc(lane, 2) += A.e1;
-                acc(lane, 3) = rmax(acc(lane, 3), A.cmax);
             }
         }
         const int first = warp_min_int(badk, 0, lane_);
         if (first != 0x7fffffff) { fwd_knots += first - base + 1; ok = false; }
         else fwd_knots += nk;
+        if (ok && base + 32 < N) {   // next block: plane counts and the first rows of its ring
+            FOR_LANES(lane) { Pl(lane, 0) = base + 32 + lane < N ? t.nplanes[base + 32 + lane] : 0; }
+            Pw = warp_max_int(Pl, 0, lane_);
+#if DDP_GPU
+            ring_start(rq, t, sm, base + 32, Pw, lane_);
+#endif
+        }
     }
     FOR_LANES(lane) { cp_wait<0>(); }   // nothing of the ring / staging may land after this trial
     WARP_SYNC();
@@ -2143,6 +2268,7 @@ DDP_DEVICE_NOINLINE void gspec_helper_loop(const SolveArgs &A, R *sm, const R *t
     const WsLay wl = ws_layout(A.N, A.PM, A.fcap);
     sm = as_shared(sm);
     if (lane_ == 0) atomicAdd(A.counter + 4, 1u);
+    unsigned idle_ns = DDP_IDLE_NS_MIN;
     while (*(volatile unsigned int *)(A.counter + 3) < (unsigned)A.B) {
         // row units of a trial that another warp of this CTA is running come first: they are short and someone waits for them
         if (ctl != nullptr) {
@@ -2155,7 +2281,7 @@ DDP_DEVICE_NOINLINE void gspec_helper_loop(const SolveArgs &A, R *sm, const R *t
                 job_run_unit(cta_boards + w, u, sm, lane_);
                 if (lane_ == 0) atomicAdd(A.counter + 2, 1u);
             }
-            if (found) continue;
+            if (found) { idle_ns = DDP_IDLE_NS_MIN; continue; }
         }
         // find a board with unclaimed units in the bitmap (start position spread over the helpers), claim one unit
         int bi = -1, unit = -1;
@@ -2198,7 +2324,8 @@ DDP_DEVICE_NOINLINE void gspec_helper_loop(const SolveArgs &A, R *sm, const R *t
                 }
             }
         }
-        if (bi < 0) { __nanosleep(500); continue; }
+        if (bi < 0) { __nanosleep(idle_ns); if (idle_ns < DDP_IDLE_NS_MAX) idle_ns *= 2; continue; }
+        idle_ns = DDP_IDLE_NS_MIN;
         __threadfence();   // acquire: the board and the owner's arrays as of the posting
         GBoard<R> *b = boards + bi;
         Traj<R> t = b->t;

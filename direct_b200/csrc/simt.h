@@ -134,6 +134,18 @@ template <int N> DDP_DEVICE int warp_min_int(const Reg<int, N> &r, int i, int la
     return x;
 #endif
 }
+// Maximum over the warp of element i (int).
+template <int N> DDP_DEVICE int warp_max_int(const Reg<int, N> &r, int i, int lane_) {
+#if DDP_GPU
+    (void)lane_;
+    return __reduce_max_sync(0xffffffffu, r.v[i]);
+#else
+    (void)lane_;
+    int x = r.v[0][i];
+    for (int l = 1; l < 32; l++) if (r.v[l][i] > x) x = r.v[l][i];
+    return x;
+#endif
+}
 template <int N> DDP_DEVICE bool warp_any(const Reg<int, N> &r, int i, int lane_) {
 #if DDP_GPU
     (void)lane_;
@@ -160,6 +172,48 @@ template <int N> DDP_DEVICE void cp_wait() { asm volatile("cp.async.wait_group %
 template <int BYTES> DDP_DEVICE void cp_async(void *smem_dst, const void *gsrc) { memcpy(smem_dst, gsrc, BYTES); }
 DDP_DEVICE void cp_commit() {}
 template <int N> DDP_DEVICE void cp_wait() {}
+#endif
+
+// Bulk asynchronous copies (TMA, cp.async.bulk -> SASS UBLKCP) completing on an mbarrier: ONE lane issues the copy of a whole
+// row / knot tile, the copy engine moves it while the warp computes, and the lanes wait on the barrier's phase parity right
+// before they read the tile from shared memory.  Sizes are multiples of 16 bytes, both addresses 16-byte aligned.
+// The CPU emulation copies at issue time; its waits are no-ops.
+#if DDP_GPU
+DDP_DEVICE void mbar_init(unsigned long long *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+// make barrier initialisations / generic-proxy writes to shared memory visible to the async proxy (the copy engine)
+DDP_DEVICE void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// ... and generic-proxy writes to global memory (slack rows written by st.global that a later bulk copy reads)
+DDP_DEVICE void fence_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+DDP_DEVICE void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+DDP_DEVICE void bulk_g2s(void *smem_dst, const void *gsrc, unsigned bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(smem_dst)),
+                 "l"(__cvta_generic_to_global(gsrc)), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
+                 : "memory");
+}
+DDP_DEVICE void mbar_wait(unsigned long long *bar, unsigned parity) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(a), "r"(parity) : "memory");
+}
+#else
+DDP_DEVICE void mbar_init(unsigned long long *, int) {}
+DDP_DEVICE void fence_async_smem() {}
+DDP_DEVICE void fence_async_all() {}
+DDP_DEVICE void mbar_expect_tx(unsigned long long *, unsigned) {}
+DDP_DEVICE void bulk_g2s(void *smem_dst, const void *gsrc, unsigned bytes, unsigned long long *) { memcpy(smem_dst, gsrc, bytes); }
+DDP_DEVICE void mbar_wait(unsigned long long *, unsigned) {}
 #endif
 
 // Software prefetch of a global line that a later iteration of a row loop will load (no register is tied up).
@@ -223,6 +277,14 @@ DDP_DEVICE float rrsqrt(float x) { return rsqrtf(x); }
 #else
 DDP_DEVICE double rrsqrt(double x) { return 1.0 / sqrt(x); }
 DDP_DEVICE float rrsqrt(float x) { return 1.0f / sqrtf(x); }
+#endif
+// unew = (uold + alpha ku) + Ku dx (ddp.cpp:689/:695).  The line search forms this value in the state recursion AND, to save
+// registers, again in the row phase: one spelling (an explicit fused multiply-add on the GPU) so that both sites give the same bits.
+#if DDP_GPU
+DDP_DEVICE double step_u(double uo, double alpha, double k, double kdx) { return fma(alpha, k, uo) + kdx; }
+DDP_DEVICE float step_u(float uo, float alpha, float k, float kdx) { return fmaf(alpha, k, uo) + kdx; }
+#else
+template <class T> DDP_DEVICE T step_u(T uo, T alpha, T k, T kdx) { return (uo + alpha * k) + kdx; }
 #endif
 DDP_DEVICE double rabs(double x) { return fabs(x); }
 DDP_DEVICE float rabs(float x) { return fabsf(x); }
