@@ -174,7 +174,8 @@ def model_b_report(capi, torch, dev, local_rank, flush, steps, with_cpu):
     import dataclasses
     from direct_b200 import gddp
     B, N = 4096, 100
-    gp = dataclasses.replace(gddp.make_quad_batch(B, N), tol=1e-5)
+    # the start / goal distribution BASELINE.md section 3 states (15-25 m transfers), not the 1.5-3.5 m hops of round 1
+    gp = dataclasses.replace(gddp.make_quad_batch(B, N, workload="stated"), tol=1e-5, iter_max=100)
     solver = capi.Solver(local_rank, "fp32")
     t = {k: torch.from_numpy(getattr(gp, k)).to(dev) for k in ("x0", "xg")}
     o = dict(rtn=torch.zeros(B, dtype=torch.int32, device=dev), iters=torch.zeros(B, dtype=torch.int32, device=dev),
@@ -222,12 +223,14 @@ def model_b_report(capi, torch, dev, local_rank, flush, steps, with_cpu):
     traffic, traffic_src = None, None
     try:   # dram bytes of gddp_pair_kernel per launch, one ncu --set full capture of this workload (profiles/)
         prof = json.load(open(os.path.join(ROOT, "profiles", "latest_ncu_model_b.json")))
-        if prof.get("workload") == f"{B}x{N} quad fp32":
+        if prof.get("workload") == f"{B}x{N} quad fp32 stated":
             traffic, traffic_src = prof["dram_bytes_per_launch"], prof["source"]
     except Exception:
         pass
-    out = {"workload": f"unconstrained DDP, {B} x {N}-knot 12-state/4-input rigid-body quadrotor (explicit Euler, dt 0.05), hover-to-hover "
-                       "transfers of 1.5-3.5 m; model (B) of SURVEY.md 8(d): the reference has no such model, parity unpinned",
+    out = {"workload": f"unconstrained DDP, {B} x {N}-knot 12-state/4-input rigid-body quadrotor (explicit Euler, dt 0.05 -- SURVEY.md 8(d) "
+                       "names RK4; the kernel's Jacobian sparsity is Euler's), start at rest in [-10,10]^2 x [0.5,2.5], goal at rest 15-25 m "
+                       "away (BASELINE.md section 3), iter_max 100; model (B) of SURVEY.md 8(d): the reference has no such model, parity "
+                       "unpinned",
            "dtype": "f32", "value": B / ms * 1e3, "unit": "solves/s", "ms_per_step": ms, "gpu_launches": steps,
            "e2e": {"value": B / e2e_s, "unit": "solves/s", "h2d_bytes_per_step": int(st.h2d_bytes), "d2h_bytes_per_step": int(st.d2h_bytes),
                    "ms_per_step": e2e_s * 1e3},
@@ -323,12 +326,15 @@ def main():
 
     # device-resident inputs / outputs (torch owns the memory; the library gets raw pointers)
     d_in = {k: torch.from_numpy(getattr(pb, k)).to(dev) for k in ("planes", "nplanes", "durations", "x0", "xd")}
-    d_out = dict(rtn=torch.zeros(B, dtype=torch.int32, device=dev), infeas_out=torch.zeros(B, dtype=torch.int32, device=dev),
+    # the four gathered result fields live in ONE packed buffer per rank (views), so that the gather is a single collective
+    packed = D.PackedResults({"poly_time": ((N,), torch.float64), "bez_coeff": ((N, 18), torch.float64), "rtn": ((), torch.int32),
+                              "cost": ((), torch.float64)}, B, B, dev)
+    d_out = dict(rtn=packed.view("rtn"), infeas_out=torch.zeros(B, dtype=torch.int32, device=dev),
                  line_failed_out=torch.zeros(B, dtype=torch.int32, device=dev), iters=torch.zeros(B, dtype=torch.int32, device=dev),
-                 cost=torch.zeros(B, dtype=torch.float64, device=dev), x_final=torch.zeros(B, 9, dtype=torch.float64, device=dev),
+                 cost=packed.view("cost"), x_final=torch.zeros(B, 9, dtype=torch.float64, device=dev),
                  poly_coeff=torch.zeros(B, N, 18, dtype=torch.float64, device=dev),
-                 bez_coeff=torch.zeros(B, N, 18, dtype=torch.float64, device=dev),
-                 poly_time=torch.zeros(B, N, dtype=torch.float64, device=dev), jerk=torch.zeros(B, N, dtype=torch.float64, device=dev),
+                 bez_coeff=packed.view("bez_coeff"),
+                 poly_time=packed.view("poly_time"), jerk=torch.zeros(B, N, dtype=torch.float64, device=dev),
                  stats=torch.zeros(B, 8, dtype=torch.int64, device=dev))
     batch = capi.Batch(B, N, pb.P_max, d_in["planes"].data_ptr(), d_in["nplanes"].data_ptr(), d_in["durations"].data_ptr(),
                        None, d_in["x0"].data_ptr(), d_in["xd"].data_ptr(), None, None, 1, pb.max_vel, pb.max_acc,
@@ -338,9 +344,8 @@ def main():
     counts = [B] * world
 
     def gather():
-        if world > 1:  # gather of the solved trajectories to rank 0 (NCCL), part of the step
-            return D.gather_results({"poly_time": d_out["poly_time"], "bez_coeff": d_out["bez_coeff"],
-                                     "rtn": d_out["rtn"], "cost": d_out["cost"]}, counts)
+        if world > 1:  # gather of the solved trajectories to rank 0 (one NCCL collective into a preallocated buffer), part of the step
+            return packed.gather(counts)
         return None
 
     def device_step():

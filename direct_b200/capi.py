@@ -21,7 +21,7 @@ _lp = C.POINTER(C.c_int64)
 
 class Opts(C.Structure):
     _fields_ = [("device", C.c_int), ("precision", C.c_int), ("warps_per_block", C.c_int),
-                ("blocks_per_sm", C.c_int), ("trace", C.c_int)]
+                ("blocks_per_sm", C.c_int), ("trace", C.c_int), ("ndevices", C.c_int), ("devices", C.POINTER(C.c_int))]
 
 
 class Batch(C.Structure):
@@ -69,7 +69,7 @@ EXPORTS = ["direct_ddp_version", "direct_ddp_create", "direct_ddp_destroy", "dir
            "direct_ddp_solve_two_stage_device", "direct_ddp_time_allocation_device", "direct_ddp_last_stats",
            "direct_ddp_last_trace", "direct_ddp_measure_fma_peak", "direct_ddp_sample", "direct_ddp_sample_device",
            "direct_ddp_corridor_read", "direct_ddp_corridor_write", "direct_ddp_corridor_free", "direct_ddp_replay",
-           "direct_ddp_replay_write", "direct_ddp_sm_clock_hz"]
+           "direct_ddp_replay_write", "direct_ddp_sm_clock_hz", "direct_ddp_device_count"]
 
 _lib = None
 
@@ -111,6 +111,7 @@ def load_library(build_if_missing: bool = True):
                                           C.c_double, C.c_void_p]
         lib.direct_ddp_replay_write.argtypes = [C.c_char_p, C.c_void_p, C.c_int]
         lib.direct_ddp_sm_clock_hz.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+        lib.direct_ddp_device_count.argtypes = [C.c_void_p]
         _lib = lib
     return _lib
 
@@ -151,13 +152,15 @@ def two_stage_opts(stage0=None, stage1=None, time_power=TIME_POWER) -> TwoStage:
 
 
 class Solver:
-    """One libdirect_ddp_b200 handle bound to one GPU."""
+    """One libdirect_ddp_b200 handle bound to one GPU, or (devices=[...]) sharding host-buffer batches over several."""
 
     def __init__(self, device: int = 0, precision: str = "fp64", warps_per_block: int = 0, blocks_per_sm: int = 0,
-                 trace: bool = False):
+                 trace: bool = False, devices=None):
         self.lib = load_library()
         self.h = C.c_void_p()
-        opts = Opts(device, {"fp64": 0, "fp32": 1}[precision], warps_per_block, blocks_per_sm, int(trace))
+        devs = None if devices is None else (C.c_int * len(devices))(*devices)
+        opts = Opts(device if devices is None else devices[0], {"fp64": 0, "fp32": 1}[precision], warps_per_block, blocks_per_sm,
+                    int(trace), 0 if devices is None else len(devices), devs)
         st = self.lib.direct_ddp_create(C.byref(opts), C.byref(self.h))
         if st != 0:
             msg = self.lib.direct_ddp_last_error(self.h).decode() if self.h else "create failed"

@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/direct_ddp.h"
@@ -46,6 +47,7 @@ __global__ void __launch_bounds__(DDP_MAX_THREADS, DDP_MIN_BLOCKS) ipddp_solve_k
         smraw + (((size_t)(360 + wpb * per_warp) * sizeof(R) + 15) & ~(size_t)15));
     ddp::BlockCtl *ctl = reinterpret_cast<ddp::BlockCtl *>(boards + wpb);
     if (lane == 0) { boards[warp].word = 0ull; boards[warp].done = 0; boards[warp].owner_seq = 0; }
+    ddp::ring_init<R>(sm, lane);   // mbarriers of the line search's slack-row ring (ipddp_solver.h "Slack-row ring")
     if (threadIdx.x == 0) { ctl->active_owners = wpb; ctl->jobs_ctr = A.counter + 1; }
     __syncthreads();
     const long long slot = (long long)blockIdx.x * wpb + warp;
@@ -162,6 +164,8 @@ struct direct_ddp_handle_s {
     DevBuf vx[19];  // voxel kernels (voxel.cuh): occupied, inside, candidates, cluster, can_can, can_clu, vertices, result,
                     // claim, loop candidates, conflict rows, loop can_clu, ctl, use, invalid, phase timers, merged map, segment counts, reciprocal table
     int vx_coop_blocks = 0;   // co-resident CTAs of cluster_loop_kernel
+    std::vector<direct_ddp_handle_s *> peers;   // multi-GPU: handles of devices[1..] (owned); this handle is devices[0]
+    bool last_multi = false;                    // the last host-buffer call was sharded over the peers
     const long long *last_stats_dev = nullptr;  // device [B][4] of the last solve (stage 1 / single)
     const long long *last_stats_dev0 = nullptr; // stage 0 when two-stage
     int last_B = 0;
@@ -387,8 +391,8 @@ int download_result(H *h, const direct_ddp_result *host, const direct_ddp_result
     return 0;
 }
 
-int solve_host(H *h, const direct_ddp_batch *in, const direct_ddp_two_stage *ts, direct_ddp_result *out0,
-               direct_ddp_result *out1) {
+int solve_host_one(H *h, const direct_ddp_batch *in, const direct_ddp_two_stage *ts, direct_ddp_result *out0,
+                   direct_ddp_result *out1) {
     int st = validate(h, in);
     if (st) return st;
     if (!out1) { h->err = "result is NULL"; return DIRECT_DDP_ERR_ARG; }
@@ -452,6 +456,65 @@ int solve_host(H *h, const direct_ddp_batch *in, const direct_ddp_two_stage *ts,
     return 0;
 }
 
+// Shard [lo, hi) of a host batch / result: the same struct with every per-trajectory pointer advanced.
+direct_ddp_batch shard_batch(const direct_ddp_batch &in, int lo, int hi) {
+    direct_ddp_batch d = in;
+    const size_t N = (size_t)in.N, PM = (size_t)in.P_max, o = (size_t)lo;
+    d.B = hi - lo;
+    d.planes = in.planes + o * N * PM * 4; d.nplanes = in.nplanes + o * N; d.durations = in.durations + o * N;
+    if (in.seeds) d.seeds = in.seeds + o * N * 3;
+    d.x0 = in.x0 + o * 9; d.xd = in.xd + o * 9;
+    if (in.init_bez) d.init_bez = in.init_bez + o * N * 18;
+    if (in.infeas) d.infeas = in.infeas + o;
+    if (in.nknots) d.nknots = in.nknots + o;
+    return d;
+}
+direct_ddp_result shard_result(const direct_ddp_result &r, int lo, int N) {
+    direct_ddp_result d = r;
+    const size_t o = (size_t)lo, n = (size_t)N;
+#define ADV(f, stride) if (r.f) d.f = r.f + o * (stride)
+    ADV(rtn, 1); ADV(infeas_out, 1); ADV(line_failed_out, 1); ADV(iters, 1); ADV(cost, 1); ADV(x_final, 9);
+    ADV(poly_coeff, n * 18); ADV(bez_coeff, n * 18); ADV(poly_time, n); ADV(jerk, n); ADV(stats, 8);
+#undef ADV
+    return d;
+}
+
+// Host-buffer solve: one device, or the batch sharded over the handle's devices with one host thread per device
+// (contiguous ranges, no collective -- every shard's results go D2H straight into the caller's arrays).
+int solve_host(H *h, const direct_ddp_batch *in, const direct_ddp_two_stage *ts, direct_ddp_result *out0,
+               direct_ddp_result *out1) {
+    h->last_multi = false;
+    const int ndev = 1 + (int)h->peers.size();
+    if (ndev == 1 || !in || in->B < ndev) return solve_host_one(h, in, ts, out0, out1);
+    int st = validate(h, in);
+    if (st) return st;
+    if (!out1) { h->err = "result is NULL"; return DIRECT_DDP_ERR_ARG; }
+    std::vector<direct_ddp_batch> sb(ndev);
+    std::vector<direct_ddp_result> r0(ndev), r1(ndev);
+    std::vector<int> status(ndev, 0);
+    std::vector<std::thread> th;
+    auto run = [&](int k) {
+        H *hk = k == 0 ? h : h->peers[k - 1];
+        status[k] = solve_host_one(hk, &sb[k], ts, (ts && out0) ? &r0[k] : nullptr, &r1[k]);
+    };
+    for (int k = 0; k < ndev; k++) {
+        const int lo = (int)((long long)in->B * k / ndev), hi = (int)((long long)in->B * (k + 1) / ndev);
+        sb[k] = shard_batch(*in, lo, hi);
+        if (ts && out0) r0[k] = shard_result(*out0, lo, in->N);
+        r1[k] = shard_result(*out1, lo, in->N);
+    }
+    for (int k = 1; k < ndev; k++) th.emplace_back(run, k);
+    run(0);
+    for (auto &t : th) t.join();
+    for (int k = 0; k < ndev; k++)
+        if (status[k]) {
+            if (k > 0) h->err = "device " + std::to_string(h->peers[k - 1]->opts.device) + ": " + h->peers[k - 1]->err;
+            return status[k];
+        }
+    h->last_multi = true;
+    return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -464,6 +527,8 @@ int direct_ddp_create(const direct_ddp_opts *opts, direct_ddp_handle *out) {
     H *h = new H();
     memset(&h->opts, 0, sizeof h->opts);
     if (opts) h->opts = *opts;
+    if (h->opts.ndevices < 0 || h->opts.ndevices > 64) { h->err = "ndevices must be in [0, 64]"; *out = h; return DIRECT_DDP_ERR_ARG; }
+    if (h->opts.ndevices > 0 && h->opts.devices) h->opts.device = h->opts.devices[0];
     memset(&h->stats, 0, sizeof h->stats);
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -485,11 +550,35 @@ int direct_ddp_create(const direct_ddp_opts *opts, direct_ddp_handle *out) {
     for (int i = 0; i < 6; i++) cudaEventCreate(&h->ev[i]);
     int st = h->opts.precision == DIRECT_DDP_FP32 ? upload_tables<float>(h) : upload_tables<double>(h);
     *out = h;
-    return st;
+    if (st) return st;
+    // multi-GPU: one ordinary single-device handle per further device
+    const int nd = h->opts.ndevices;
+    const int *devs = h->opts.devices;
+    const int first = h->opts.device;
+    h->opts.ndevices = 0; h->opts.devices = nullptr;   // the caller's array is not kept
+    for (int k = 1; k < nd; k++) {
+        direct_ddp_opts po = h->opts;
+        po.device = devs ? devs[k] : first + k;
+        po.trace = 0;
+        direct_ddp_handle peer = nullptr;
+        const int ps = direct_ddp_create(&po, &peer);
+        if (ps != DIRECT_DDP_OK) {
+            h->err = "device " + std::to_string(po.device) + ": " + (peer ? peer->err : std::string("create failed"));
+            if (peer) direct_ddp_destroy(peer);
+            h->sm_count = 0;   // the handle stays readable for the error text; every solve fails
+            return ps;
+        }
+        h->peers.push_back(peer);
+    }
+    return 0;
 }
+
+int direct_ddp_device_count(direct_ddp_handle h) { return h ? 1 + (int)h->peers.size() : 0; }
 
 void direct_ddp_destroy(direct_ddp_handle h) {
     if (!h) return;
+    for (direct_ddp_handle_s *p : h->peers) direct_ddp_destroy(p);
+    h->peers.clear();
     if (h->sm_count > 0) {
         cudaSetDevice(h->opts.device);
         DevBuf *bufs[] = {&h->planes, &h->nplanes, &h->durations, &h->seeds, &h->x0, &h->xd, &h->init_bez, &h->infeas, &h->nknots,
@@ -616,7 +705,26 @@ int direct_ddp_sm_clock_hz(direct_ddp_handle h, double *hz) {
     return DIRECT_DDP_OK;
 }
 
+static int last_stats_one(direct_ddp_handle h, direct_ddp_stats *out);
 int direct_ddp_last_stats(direct_ddp_handle h, direct_ddp_stats *out) {
+    REQUIRE_DEVICE(h)
+    if (!out) return DIRECT_DDP_ERR_ARG;
+    int st = last_stats_one(h, out);
+    if (st || !h->last_multi) return st;
+    for (direct_ddp_handle_s *p : h->peers) {
+        direct_ddp_stats q;
+        if ((st = last_stats_one(p, &q))) { h->err = p->err; return st; }
+        out->kernel_ms = q.kernel_ms > out->kernel_ms ? q.kernel_ms : out->kernel_ms;
+        out->h2d_ms = q.h2d_ms > out->h2d_ms ? q.h2d_ms : out->h2d_ms;
+        out->d2h_ms = q.d2h_ms > out->d2h_ms ? q.d2h_ms : out->d2h_ms;
+        out->bwd_sweeps += q.bwd_sweeps; out->bwd_knots += q.bwd_knots; out->fwd_trials += q.fwd_trials; out->fwd_knots += q.fwd_knots;
+        out->kernel_launches += q.kernel_launches; out->grid_blocks += q.grid_blocks; out->workspace_slots += q.workspace_slots;
+        out->h2d_bytes += q.h2d_bytes; out->d2h_bytes += q.d2h_bytes; out->coop_jobs += q.coop_jobs; out->helper_units += q.helper_units;
+        out->spec_searches += q.spec_searches; out->spec_trials += q.spec_trials;
+    }
+    return 0;
+}
+static int last_stats_one(direct_ddp_handle h, direct_ddp_stats *out) {
     REQUIRE_DEVICE(h)
     if (!out) return DIRECT_DDP_ERR_ARG;
     if (!h->stats_valid && h->last_stats_dev && h->last_B > 0) {

@@ -141,7 +141,7 @@ struct Lay {
         S1 = 10,    // value-function Hessian as left by the Schur complement, S1[a*10+b] = S[a][b]
         S2 = 100,   // V = (S + S^T)/2 (ddp.cpp:628), V[b*10+a], formed by the writer of S1
         VX = 190,   // V_x (9)
-        MB = 200,   // Cholesky multiplier rows, MB[p*20+r] = L[r][p]  (10 x 20)
+        MB = 200,   // riccati: (x, y') of every lane per pivot round, MB[(kb*20+lane)*2 + {0,1}]  (5 x 20 x 2)
         XT = 400,   // row T of every column, for the T column (20)
         XH = 420,   // fT[p] * (V fT)[p]  (9)
         KC = 430,   // gains of the current knot, KC[p*10+qc], qc 0 = ku, 1..9 = Ku columns
@@ -149,15 +149,18 @@ struct Lay {
         DX = 550,   // rollout broadcast: xnew - xold (9)
         FL = 560,   // filter decision (2)
         FTN = 564,  // riccati: fT (9) and segment time (1) of the knot about to be processed, staged one knot ahead
-        RI = 574,   // riccati: 1/sqrt(pivot) of the ten Cholesky pivots
+        RI = 574,   // (free: the L D L^T pivots need no scale table)
         MSC = 584,  // per-lane 3x3 blocks M_g of the linearisation: MSC[e*32+lane], e < 63.  During the line search
                     // (no linearisation in flight) the same area holds forward_trial's knot ring [0, 480).
-        TOTAL = 584 + 63 * 32,
         // Line search, behind the knot ring [0, 480) and the job partials [512, 1152) of MSC: the slack-row ring of the row
         // phase (RowRing below).  Offsets are multiples of 16 bytes for float and double.
-        RB = 584 + 1152,            // mbarriers of the RING_NB batches (8 bytes each)
         RS = 584 + 1160,            // slack rows s:      RING_ROWS x 32
-        RY = 584 + 1160 + 12 * 32   // dual slack rows y: RING_ROWS x 32   (ends at 584 + 1928 <= TOTAL)
+        RY = 584 + 1160 + 12 * 32,  // dual slack rows y: RING_ROWS x 32   (ends at 584 + 1928 <= RB)
+        // Behind MSC (the linearisation overwrites all of MSC): the ring's mbarriers, initialised once per kernel launch, and
+        // the phase parity each of them completes next (one word, bit b = barrier b).
+        RB = 584 + 63 * 32,         // RING_NB mbarriers, 8 bytes each
+        RP = 584 + 63 * 32 + 6,     // phase word (unsigned), inside the 8 elements reserved here for float and double
+        TOTAL = 584 + 63 * 32 + 8
     };
 };
 enum { RING_BATCH = 4, RING_NB = 3, RING_ROWS = RING_BATCH * RING_NB };
@@ -180,7 +183,7 @@ DDP_HD WsLay ws_layout(int N, int PM, int fcap) {
     w.K = o; o += (long long)N * 100;
     w.kdx = o; o += (long long)N * 10;
     w.aux = o; o += (long long)N * 12;
-    o = (o + 1) & ~1LL;
+    o = (o + 3) & ~3LL;   // H columns are read with 128-bit loads, the row arrays by 16-byte-aligned bulk copies (float: 4 elements)
     w.H = o; o += (long long)N * 400;
     w.s = o; o += (long long)w.MCS * w.NP;
     w.sn = o; o += (long long)w.MCS * w.NP;
@@ -1173,56 +1176,71 @@ template <class R> DDP_DEVICE_NOINLINE bool riccati(Traj<R> &t, R regadd, Reg<R,
                 errl(lane, 0) = e;
             }
         }
-        // ---- ten Cholesky pivots over the u block -----------------------------------------------------------
-        // One rolled loop: after every pivot each lane shifts its column up by one row, so the pivot row is
-        // always element 0 and the loop body has static register indices (ten unrolled copies were 600 SASS
-        // instructions of the v2 kernel's instruction-cache footprint).  Row p + r of the matrix sits in
-        // element r; elements that would belong to rows >= 20 hold don't-care values that are never read.
-        R d = warp_bcast(col, 0, 0, lane_) + regadd;
+        // ---- the ten pivots of the u block, two per round ------------------------------------------------------
+        // Eigen's LLT (ddp.cpp:543/:592) eliminates one column after the other; what the backup needs is the Schur complement
+        // and K = -(Quu + rho I)^-1 [Qu | Qux], and the unit-lower L D L^T of the same ten pivots gives both with the same
+        // stability and without square roots.  The recursion is latency-bound (one warp, profiles/r1h: 400 cycles per pivot in
+        // broadcast -> reciprocal -> multiplier -> shared-memory round trip -> update), so two pivots share a round: the
+        // 2 x 2 pivot block [a b; b c] is broadcast once, 1/a and 1/(a c - b^2) (pivot 2 = det / a) are formed side by side,
+        // every lane takes both elimination steps on its own two entries (l1 = x / a, y' = y - b l1, l2 = y' / pivot2) and
+        // the trailing matrix gets one rank-2 update.  Five rounds instead of ten, same pivots, same failure test
+        // (a pivot <= 0, ddp.cpp:546-551 / :595-600).  After every round each lane shifts its column up by two rows, so
+        // the pivot rows are always elements 0 and 1 and the rolled loop has static register indices.  Row p + r of the
+        // matrix sits in element r; elements that would belong to rows >= 20 hold don't-care values that are never read.
+        //   MB[(kb * 20 + lane) * 2 + {0, 1}] = (x, y') of the lane at round kb   (rows of the eliminated columns times D)
+        //   MSC[(kb * 20 + lane) * 2 + {0, 1}] = (l1, l2)                         (unit-lower L: L[lane][2 kb], L[lane][2 kb + 1])
         DDP_NOUNROLL
-        for (int p = 0; p < 10; p++) {
-            if (d <= R(0)) { ok = false; break; }
-            const R ri = rrsqrt(d);
-            Reg<R, 1> ahead, mreg;
+        for (int kb = 0; kb < 5; kb++) {
+            const int p = 2 * kb;
+            const R a = warp_bcast(col, 0, p, lane_) + regadd;
+            const R b = warp_bcast(col, 1, p, lane_);
+            const R c = warp_bcast(col, 1, p + 1, lane_) + regadd;
+            if (a <= R(0)) { ok = false; break; }
+            const R det = a * c - b * b;   // pivot 2 = c - b^2 / a = det / a
+            if (det <= R(0)) { ok = false; break; }
+            const R ra = rrcp(a), r2 = a * rrcp(det);
+            Reg<R, 2> mreg;
             FOR_LANES(lane) {
-                const R m = (lane == p) ? d * ri : col(lane, 0) * ri;
-                mreg(lane, 0) = m;
-                if (lane < 20) sm[Lay::MB + p * 20 + lane] = m;   // MB[p*20+r] = L[r][p]
-                if (lane == 0) sm[Lay::RI + p] = ri;
-                ahead(lane, 0) = col(lane, 1) - m * m;   // next pivot's diagonal, sent ahead of the update
+                const R x = col(lane, 0);
+                const R l1 = x * ra;
+                const R yp = col(lane, 1) - b * l1;
+                const R l2 = yp * r2;
+                mreg(lane, 0) = l1; mreg(lane, 1) = l2;
+                if (lane < 20) {
+                    sm[Lay::MB + (kb * 20 + lane) * 2] = x; sm[Lay::MB + (kb * 20 + lane) * 2 + 1] = yp;
+                    sm[Lay::MSC + (kb * 20 + lane) * 2] = l1; sm[Lay::MSC + (kb * 20 + lane) * 2 + 1] = l2;
+                }
             }
-            const R dn = warp_bcast(ahead, 0, p + 1, lane_) + regadd;
             WARP_SYNC();
             FOR_LANES(lane) {
-                const R m = mreg(lane, 0);
-                const R *Lp = sm + Lay::MB + p * 20 + p;
+                const R l1 = mreg(lane, 0), l2 = mreg(lane, 1);
+                const R *Xp = sm + Lay::MB + (kb * 20 + p) * 2;   // (x, y') of row p + r at Xp[2 r], Xp[2 r + 1]
                 DDP_UNROLL
-                for (int r = 1; r < 20; r++) col(lane, r - 1) = col(lane, r) - Lp[r] * m;
+                for (int r = 2; r < 20; r++) col(lane, r - 2) = col(lane, r) - (Xp[2 * r] * l1 + Xp[2 * r + 1] * l2);
             }
-            d = dn;
         }
         if (!ok) break;
         // rows 10..19 of the matrix (V_xx block and gradient) now sit in elements 0..9 of lanes 10..19
-        // ---- gains [ku | Ku] = -(L L^T)^-1 [Qu | Qux] ----------------------------------------------------------
+        // ---- gains [ku | Ku] = -(L D L^T)^-1 [Qu | Qux] --------------------------------------------------------
         Reg<R, 10> kx;
         FOR_LANES(lane) {
             if (lane >= 10 && lane < 20) {
-                // column-oriented back-substitution: once k_p is known the nine partial sums below it are updated
-                // independently (dependent chain of 10 instead of 45 FMAs)
+                // this lane's multipliers are D^-1 L^-1 times its right-hand side; L^T k = -(that), column-oriented: once k_q is
+                // known the partial sums above it are updated independently (dependent chain of 10 instead of 45 FMAs)
                 R v[10];
                 DDP_UNROLL
-                for (int p = 0; p < 10; p++) v[p] = sm[Lay::MB + p * 20 + lane];
+                for (int q = 0; q < 10; q++) v[q] = sm[Lay::MSC + ((q >> 1) * 20 + lane) * 2 + (q & 1)];
                 DDP_UNROLL
-                for (int p = 9; p >= 0; p--) {
-                    kx(lane, p) = -(v[p] * sm[Lay::RI + p]);
+                for (int q = 9; q >= 0; q--) {
+                    kx(lane, q) = -v[q];
                     DDP_UNROLL
-                    for (int r = 0; r < p; r++) v[r] += sm[Lay::MB + r * 20 + p] * kx(lane, p);
+                    for (int r = 0; r < q; r++) v[r] += sm[Lay::MSC + ((r >> 1) * 20 + q) * 2 + (r & 1)] * kx(lane, q);   // L[q][r]
                 }
                 const int qc = lane == 19 ? 0 : lane - 9;
                 DDP_UNROLL
-                for (int p = 0; p < 10; p++) {
-                    sm[Lay::KC + p * 10 + qc] = kx(lane, p);
-                    Kout[(long long)i * 100 + p * 10 + qc] = kx(lane, p);
+                for (int q = 0; q < 10; q++) {
+                    sm[Lay::KC + q * 10 + qc] = kx(lane, q);
+                    Kout[(long long)i * 100 + q * 10 + qc] = kx(lane, q);
                 }
             }
         }
@@ -1522,16 +1540,22 @@ template <class R> DDP_DEVICE void ring_issue_batch(RowRing<R> &q, const RowCtx<
         if (q.pg < 6 && ++q.pr == q.Pw) { q.pg++; q.pr = 0; q.pslot = q.pg * t.PM; }
     }
 }
-// Start the ring for the 32-knot block at `base`: barriers re-armed (every copy of the previous block has been consumed),
-// first RING_NB batches in flight.  Called before the block's state recursion so that the rows are there when it ends.
+// Once per kernel launch and warp: the ring's barriers (one arrival each: the issuing lane's expect_tx) and their phase word.
+template <class R> DDP_DEVICE void ring_init(R *sm, int lane_) {
+    if (lane_ < RING_NB) mbar_init(reinterpret_cast<unsigned long long *>(sm + Lay::RB) + lane_, 1);
+    if (lane_ == 0) *reinterpret_cast<unsigned *>(sm + Lay::RP) = 0u;
+    fence_async_smem();
+    __syncwarp();
+}
+// Start the ring for the 32-knot block at `base` (every copy of the previous block has been consumed): first RING_NB batches
+// in flight.  Called before the block's state recursion so that the rows are there when it ends.
 template <class R>
 DDP_DEVICE void ring_start(RowRing<R> &q, const RowCtx<R> &t, R *sm, int base, int Pw, int lane_) {
     q.Pw = Pw; q.issued = 0; q.pr = 0;
     q.pg = Pw > 0 ? 0 : 6; q.pslot = Pw > 0 ? 0 : 6 * t.PM;
     __syncwarp();
-    if (lane_ < RING_NB) mbar_init(reinterpret_cast<unsigned long long *>(sm + Lay::RB) + lane_, 1);
-    fence_async_all();    // the barriers, whatever generic stores last touched the ring area, and the st.global that wrote the slack
-                          // rows (this warp's lanes or, through the job board, helper warps) before the copy engine reads them
+    fence_async_all();    // whatever generic stores last touched the ring area and the st.global that wrote the slack rows (this
+                          // warp's lanes or, through the job board, helper warps) before the copy engine writes / reads them
     __syncwarp();
     DDP_UNROLL
     for (int b = 0; b < RING_NB; b++) ring_issue_batch(q, t, sm, base, b, lane_);
@@ -1731,6 +1755,7 @@ template <class R> DDP_DEVICE_NOINLINE bool forward_trial_solo(Traj<R> &tt_, R a
     int Pw = warp_max_int(Pl, 0, lane_);
 #if DDP_GPU
     RowRing<R> rq;
+    unsigned rphase = *reinterpret_cast<volatile unsigned *>(sm + Lay::RP);   // the barriers live as long as the kernel
     ring_start(rq, t, sm, 0, Pw, lane_);   // the first rows of block 0 travel while its state recursion runs
 #endif
     for (int base = 0; base < N && ok; base += 32) {
@@ -1817,7 +1842,7 @@ template <class R> DDP_DEVICE_NOINLINE bool forward_trial_solo(Traj<R> &tt_, R a
                 R n_n[4] = {R(0), R(0), R(0), R(0)};   // plane of the next row, loaded one row ahead
                 if (P > 0) load_plane(pl, 0, n_n);
 #if DDP_GPU
-                int cbatch = 0, cphase = 0, cin = 0;   // consumer: batch slot, that slot's phase, row in batch
+                int cbatch = 0, cin = 0;   // consumer: batch slot, row in batch; rphase bit b = parity barrier b completes next
 #endif
                 DDP_NOUNROLL
                 for (int g = 0; g < 16; g++) {   // one copy of the row code for all groups (see linearize); g = 15: the time row
@@ -1860,7 +1885,10 @@ template <class R> DDP_DEVICE_NOINLINE bool forward_trial_solo(Traj<R> &tt_, R a
                     for (int r = 0; r < nrw; r++) {
                         const long long ro_cur = (long long)(g < 15 ? row_slot(g, r, t.PM) : 6 * t.PM + 54) * t.NP + i;
 #if DDP_GPU
-                        if (cin == 0) mbar_wait(reinterpret_cast<unsigned long long *>(sm + Lay::RB) + cbatch, (unsigned)cphase);
+                        if (cin == 0) {
+                            mbar_wait(reinterpret_cast<unsigned long long *>(sm + Lay::RB) + cbatch, (rphase >> cbatch) & 1u);
+                            rphase ^= 1u << cbatch;
+                        }
                         const R sv = sm[Lay::RS + (cbatch * RING_BATCH + cin) * 32 + lane];
                         const R yv = t.infeas ? sm[Lay::RY + (cbatch * RING_BATCH + cin) * 32 + lane] : R(1);
 #else
@@ -1884,7 +1912,7 @@ template <class R> DDP_DEVICE_NOINLINE bool forward_trial_solo(Traj<R> &tt_, R a
                             __syncwarp();
                             ring_issue_batch(rq, t, sm, base, cbatch, lane_);
                             cin = 0;
-                            if (++cbatch == RING_NB) { cbatch = 0; cphase ^= 1; }
+                            if (++cbatch == RING_NB) cbatch = 0;
                         }
 #endif
                     }
@@ -1925,6 +1953,10 @@ template <class R> DDP_DEVICE_NOINLINE bool forward_trial_solo(Traj<R> &tt_, R a
     }
     FOR_LANES(lane) { cp_wait<0>(); }   // nothing of the ring / staging may land after this trial
     WARP_SYNC();
+#if DDP_GPU
+    if (lane_ == 0) *reinterpret_cast<volatile unsigned *>(sm + Lay::RP) = rphase;   // every issued batch has been consumed
+    __syncwarp();
+#endif
     tt_.n_fwd_knots += fwd_knots;
 #ifndef DDP_SPEC_PROFILE
     tt_.cyc_seq += cyc_seq;

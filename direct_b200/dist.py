@@ -55,6 +55,46 @@ def gather_results(local: dict[str, torch.Tensor], counts: list[int]) -> dict[st
     return out
 
 
+class PackedResults:
+    """The result fields of one rank in ONE contiguous buffer, so that the gather of the solved trajectories is a single
+    collective into a buffer preallocated on the root: the solver writes straight into the named views (no packing copy),
+    the root reads the gathered fields as per-rank views (no concatenation copy).  Replaces one gather + one torch.cat per
+    field (round 1: four of each, +7 ms per step at 8 GPUs for 0.5 GB over NVLink).
+
+    fields: {name: (per-trajectory shape tuple, torch dtype)}; rows = trajectories of this rank; max_rows = largest shard."""
+
+    def __init__(self, fields: dict, rows: int, max_rows: int, device):
+        self.fields, self.rows, self.max_rows, self.device = fields, rows, max_rows, device
+        self.offsets, off = {}, 0
+        for name, (shape, dtype) in fields.items():
+            nbytes = int(np.prod(shape, dtype=np.int64)) * torch.empty((), dtype=dtype).element_size() * max_rows
+            self.offsets[name] = (off, nbytes)
+            off += (nbytes + 255) // 256 * 256          # every field 256-byte aligned
+        self.nbytes = off
+        self.local = torch.zeros(self.nbytes, dtype=torch.uint8, device=device)
+        self.root = None
+        if dist.is_initialized() and dist.get_rank() == 0:
+            self.root = torch.empty(dist.get_world_size() * self.nbytes, dtype=torch.uint8, device=device)
+
+    def _view(self, buf, name, rows):
+        shape, dtype = self.fields[name]
+        off, nbytes = self.offsets[name]
+        return buf[off:off + nbytes].view(dtype).view((self.max_rows,) + tuple(shape))[:rows]
+
+    def view(self, name: str) -> torch.Tensor:
+        """This rank's tensor of field `name` (rows x shape), a view into the packed buffer."""
+        return self._view(self.local, name, self.rows)
+
+    def gather(self, counts: list[int]):
+        """One collective.  On the root: {name: [tensor of rank 0, tensor of rank 1, ...]} (views), else None."""
+        world = dist.get_world_size()
+        bufs = [self.root[r * self.nbytes:(r + 1) * self.nbytes] for r in range(world)] if self.root is not None else None
+        dist.gather(self.local, bufs, dst=0)
+        if self.root is None:
+            return None
+        return {name: [self._view(bufs[r], name, counts[r]) for r in range(world)] for name in self.fields}
+
+
 def max_over_ranks(value: float, device) -> float:
     t = torch.tensor([value], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)

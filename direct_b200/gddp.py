@@ -38,9 +38,27 @@ class GddpProblem:
                                    u_init=None if self.u_init is None else np.ascontiguousarray(self.u_init[lo:hi]))
 
 
-def make_quad_batch(B: int, N: int = 100, first: int = 0, dt: float = 0.05) -> GddpProblem:
-    """Hover-to-hover transfers: random start pose (small attitude, rates and velocity), goal 1.5-3.5 m away at rest.
-    (With this distribution every one of the first 16384 problems converges in <= 16 iterations in the fp64 oracle.)"""
+def make_quad_batch(B: int, N: int = 100, first: int = 0, dt: float = 0.05, workload: str = "hop") -> GddpProblem:
+    """workload = "hop": hover-to-hover transfers: random start pose (small attitude, rates and velocity), goal 1.5-3.5 m away
+    at rest (every one of the first 16384 problems converges in <= 16 iterations in the fp64 oracle).
+    workload = "stated": the start / goal distribution BASELINE.md section 3 and SURVEY.md 8(d) state for the benchmark: start at
+    rest in [-10, 10]^2 x [0.5, 2.5], goal at rest at radius U(15, 25) m, heading U(0, 2 pi), z ~ U(0.5, 1.8) (the reference's own
+    generator, teach_repeat_planner.cpp:196-200, :215-217).  A 5 s horizon for a 15-25 m transfer: ~98 % of the problems converge,
+    in ~17 iterations (fp64 oracle)."""
+    if workload == "stated":
+        rs = _Stream(np.arange(first, first + B, dtype=np.int64) + (3 << 40))
+        x0 = np.zeros((B, 12)); xg = np.zeros((B, 12))
+        x0[:, 0:3] = np.concatenate([rs.uniform(2, -10.0, 10.0), rs.uniform(1, 0.5, 2.5)], axis=1)
+        th = rs.uniform(1, 0.0, 2.0 * np.pi)[:, 0]
+        rad = rs.uniform(1, 15.0, 25.0)[:, 0]
+        xg[:, 0] = x0[:, 0] + rad * np.cos(th); xg[:, 1] = x0[:, 1] + rad * np.sin(th); xg[:, 2] = rs.uniform(1, 0.5, 1.8)[:, 0]
+        q = np.array([2.0] * 3 + [0.5] * 3 + [10.0] * 3 + [0.2] * 3)
+        qf = np.array([100.0] * 3 + [10.0] * 3 + [50.0] * 3 + [2.0] * 3)
+        r = np.array([1.0, 200.0, 200.0, 200.0])
+        uh = np.array([QUAD_MASS * QUAD_G, 0.0, 0.0, 0.0])
+        return GddpProblem(MODEL_QUAD12, 12, 4, B, N, dt, x0, xg, q, qf, r, uh)
+    if workload != "hop":
+        raise ValueError("workload must be 'hop' or 'stated'")
     rs = _Stream(np.arange(first, first + B, dtype=np.int64) + (1 << 40))
     x0 = np.zeros((B, 12)); xg = np.zeros((B, 12))
     x0[:, 0:3] = np.concatenate([rs.uniform(2, -3.0, 3.0), rs.uniform(1, 1.0, 2.0)], axis=1)

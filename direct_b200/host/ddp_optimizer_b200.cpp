@@ -42,6 +42,7 @@ struct SharedSolver {
     int create_status = 0;
     SharedSolver() {
         direct_ddp_opts o;
+        std::memset(&o, 0, sizeof o);   // fields added to the ABI later (ndevices, devices) default to 'single device'
         o.device = 0; o.precision = DIRECT_DDP_FP64; o.warps_per_block = 0; o.blocks_per_sm = 0; o.trace = 0;
         if (const char *e = std::getenv("DIRECT_DDP_DEVICE")) o.device = std::atoi(e);
         if (const char *e = std::getenv("DIRECT_DDP_PRECISION")) o.precision = (std::atoi(e) == 32) ? DIRECT_DDP_FP32 : DIRECT_DDP_FP64;

@@ -52,6 +52,14 @@ typedef struct direct_ddp_opts {
     int warps_per_block; /* 0 = default (4)                                                        */
     int blocks_per_sm;   /* 0 = as many as shared memory / registers allow                         */
     int trace;           /* !=0: keep a per-iteration trace of trajectory 0 (debug)                */
+    /* Multi-GPU, single host process: with ndevices > 1 every HOST-buffer entry point
+     * (direct_ddp_solve_batch, direct_ddp_solve_two_stage, direct_ddp_replay) shards its batch into ndevices
+     * contiguous ranges [B k / n, B (k + 1) / n), one per device, each driven by its own host thread and stream:
+     * H2D of the shard, solve, D2H of the shard straight into the caller's arrays.  Trajectories are independent, so
+     * there is no collective on the data path (the host is the consumer of the results; nothing is gathered on a GPU).
+     * The *_device entry points keep running on devices[0] (`device` when devices is NULL).  0 or 1 = single device. */
+    int ndevices;
+    const int *devices;  /* [ndevices] CUDA ordinals, or NULL = device, device + 1, ...             */
 } direct_ddp_opts;
 
 /* One batch of B independent problems, all with N polytopes (= knots = polynomial segments).
@@ -138,7 +146,10 @@ typedef struct direct_ddp_trace_row {
 typedef struct direct_ddp_handle_s *direct_ddp_handle;
 
 int direct_ddp_version(void);
-/* Creates a solver bound to one device.  *out is NULL on failure. */
+/* Creates a solver bound to opts->device, or to the opts->ndevices devices of opts->devices.  *out is NULL on failure.
+ * A handle supports ONE call in flight at a time: the asynchronous *_device entry points share the handle's scratch
+ * (workspace, work-queue counter, stage-0 -> stage-1 carry buffers), so a second call must not be enqueued on another
+ * stream before the first has finished; use one handle per concurrent stream. */
 int direct_ddp_create(const direct_ddp_opts *opts, direct_ddp_handle *out);
 void direct_ddp_destroy(direct_ddp_handle h);
 const char *direct_ddp_last_error(direct_ddp_handle h);
@@ -198,7 +209,12 @@ int direct_ddp_replay_write(const char *path, const double *rows, int nrows);
 /* SM clock of the handle's device in Hz (converts the cycle counts of direct_ddp_result::stats into seconds). */
 int direct_ddp_sm_clock_hz(direct_ddp_handle h, double *hz);
 
+/* Statistics of the last call.  After a call that was sharded over several devices: kernel_ms, h2d_ms, d2h_ms are the
+ * maxima over the devices, counters and byte counts the sums, grid_blocks / workspace_slots the sums, block_threads /
+ * smem_bytes_per_block those of devices[0]. */
 int direct_ddp_last_stats(direct_ddp_handle h, direct_ddp_stats *out);
+/* Number of devices the handle shards host-buffer batches over (1 for a single-device handle). */
+int direct_ddp_device_count(direct_ddp_handle h);
 /* Register-resident FMA throughput of the device (TFLOP/s, 2 flops per FMA) for DIRECT_DDP_FP64 or
  * DIRECT_DDP_FP32: the measured denominator of the FMA roofline bench.py reports. */
 int direct_ddp_measure_fma_peak(direct_ddp_handle h, int precision, double *tflops);

@@ -50,6 +50,8 @@ def build(ref: bool = True) -> None:
     if ref and os.path.exists("/root/reference/global_planner/src/ddp_optimizer.cpp") \
             and os.path.exists(os.path.join(_HERE, "ref_driver.cpp")):
         subprocess.check_call(["make", "-s", "-C", _HERE, "ref"])
+        if os.path.exists(os.path.join(_HERE, "bezier_ref_driver.cpp")):
+            subprocess.check_call(["make", "-s", "-C", _HERE, "bezier"])
         if os.path.exists(os.path.join(_HERE, "..", "direct_b200", "libdirect_ddp_b200.so")):
             subprocess.check_call(["make", "-s", "-C", _HERE, "dropin"])
 
@@ -197,6 +199,25 @@ def solve_traced(pb, i=0, cap=512, **kw):
 def max_threads() -> int:
     lib().ipddp_oracle_max_threads.restype = C.c_int
     return int(lib().ipddp_oracle_max_threads())
+
+
+def bezier_ref_available() -> bool:
+    return os.path.exists(os.path.join(_HERE, "_ref", "libbezier_ref.so"))
+
+
+def bezier_sample_ref(bez_coeff, poly_time, S):
+    """The REFERENCE's own Bernstein::getPos / getVel / getAcc (utils/bezier_base.h:77-115, compiled unmodified into
+    oracle/_ref/libbezier_ref.so by `make -C oracle bezier`), scaled like its callers do.  Same shapes as bezier_sample."""
+    lib_ = C.CDLL(os.path.join(_HERE, "_ref", "libbezier_ref.so"))
+    lib_.bezier_ref_sample.argtypes = [C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp]
+    bez = np.ascontiguousarray(bez_coeff, dtype=np.float64)
+    T = np.ascontiguousarray(poly_time, dtype=np.float64)
+    B, N = T.shape
+    pos = np.zeros((B, N, S, 3)); vel = np.zeros_like(pos); acc = np.zeros_like(pos)
+    st = lib_.bezier_ref_sample(B, N, int(S), _p(bez), _p(T), _p(pos), _p(vel), _p(acc))
+    if st:
+        raise RuntimeError(f"bezier_ref_sample failed with status {st}")
+    return pos, vel, acc
 
 
 # ---- §8(f) #3: trajectory sampling, restated from the reference's Bernstein evaluators ---------------------------

@@ -22,7 +22,8 @@ def build(ref: bool = False):
         eng = os.path.join(REF_PG, "src", "cluster_engine.cu")
         if not os.path.exists(REF_SO) or os.path.getmtime(drv) > os.path.getmtime(REF_SO):
             os.makedirs(os.path.dirname(REF_SO), exist_ok=True)
-            subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-shared", "-Xcompiler", "-fPIC", "-w",
+            # -O3 -use_fast_math are the reference's own flags (polyhedron_generator/CMakeLists.txt:19-31); only the arch differs
+            subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-use_fast_math", "-shared", "-Xcompiler", "-fPIC", "-w",
                                    "-I", os.path.join(REF_PG, "include"), drv, eng, "-o", REF_SO])
     return so
 

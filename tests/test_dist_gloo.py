@@ -45,6 +45,17 @@ def _worker(rank, world, port, total, N, q):
                  time=torch.from_numpy(r.poly_time))
     counts = [b - a for a, b in (D.shard_range(total, k, world) for k in range(world))]
     g = D.gather_results(local, counts)
+    # the same through the packed single-collective path (what bench.py uses): fields are views of one buffer per rank
+    pk = D.PackedResults({"rtn": ((), torch.int32), "cost": ((), torch.float64), "bez": ((N, 18), torch.float64),
+                          "time": ((N,), torch.float64)}, hi - lo, max(counts), "cpu")
+    for name, tsr in local.items():
+        pk.view(name).copy_(tsr)
+    gp = pk.gather(counts)
+    if rank == 0:
+        for name in local:
+            assert torch.equal(torch.cat(gp[name], dim=0), g[name]), name
+    else:
+        assert gp is None
     t = D.max_over_ranks(float(rank + 1), "cpu")
     assert t == float(world)
     if rank == 0:

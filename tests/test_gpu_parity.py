@@ -162,9 +162,21 @@ def test_gpu_dropin_translation_unit_matches_reference_fixtures(oracle, name):
     assert rel_err(r1.x_final[:, 0], d["s1_terminal_norm"]) < TOL64       # getTerminalNorm()
 
 
+def test_gpu_bezier_sampling_matches_the_references_own_evaluators(solver):
+    """bezier_sample_kernel against the fixture produced by the reference's own Bernstein::getPos /
+    getVel / getAcc (utils/bezier_base.h:77-115 compiled unmodified, tests/golden/make_bezier_golden.py)."""
+    import os
+    from conftest import GOLDEN
+    d = np.load(os.path.join(GOLDEN, "bezier_ref.npz"))
+    pos, vel, acc = solver.sample(d["bez_coeff"], d["poly_time"], int(d["S"]))
+    for g, name in zip((pos, vel, acc), ("pos", "vel", "acc")):
+        assert rel_err(g, d[name]) < 1e-12, name
+
+
 def test_gpu_bezier_sampling_matches_reference_formulas(solver, oracle):
     """batched Bernstein evaluation of solved trajectories against the numpy restatement of
-    bezier_base.h:77-115; plus the properties the node relies on (segment ends = control points 0 / 5, C0-C2 joins)."""
+    bezier_base.h:77-115 (itself pinned by tests/test_oracle.py against the reference's evaluators); plus the properties the
+    node relies on (segment ends = control points 0 / 5, C0-C2 joins)."""
     pb = make_batch(32, 40, "poly", first=77)
     _, g = solver.solve_two_stage(pb, want_stage0=False)
     S = 9
@@ -237,3 +249,27 @@ def test_gpu_polytopes_with_more_than_32_planes_match_oracle(solver, oracle):
         assert np.array_equal(a.stats[ok, :4], g.stats[ok, :4])
         assert_valid_result(pb, g)
     assert_screened_out_bounded(oracle, pb, ok, (a0, a1), (g0, g1))
+
+
+def test_gpu_multi_device_handle_shards_host_batches(solver):
+    """direct_ddp_opts.devices[]: a handle over several devices shards every host-buffer batch into contiguous
+    ranges, one host thread + stream per device, results D2H straight into the caller's arrays -- same bits as one device.
+    Runs with the devices that are there: two handles on device 0 when the box has a single GPU."""
+    import torch
+    from direct_b200.capi import Solver
+    ndev = torch.cuda.device_count()
+    devices = [0, 1] if ndev >= 2 else [0, 0]
+    pb = make_batch(37, 20, "poly", first=900)          # 37 = 18 + 19: uneven shards
+    a0, a1 = solver.solve_two_stage(pb)
+    m = Solver(0, "fp64", devices=devices)
+    assert m.lib.direct_ddp_device_count(m.h) == 2
+    g0, g1 = m.solve_two_stage(pb)
+    st = m.stats()
+    for a, g in ((a0, g0), (a1, g1)):
+        for f in ("rtn", "iters", "infeas_out", "cost", "poly_coeff", "bez_coeff", "poly_time", "jerk", "x_final"):
+            assert np.array_equal(getattr(a, f), getattr(g, f)), f
+        assert np.array_equal(a.stats[:, :4], g.stats[:, :4])
+    assert st.bwd_knots == int(a0.stats[:, 1].sum() + a1.stats[:, 1].sum()) and st.kernel_launches == 2
+    r = m.solve_batch(pb.slice(0, 1), infeas=1, zero_init=1, **STAGE0)      # B < ndevices: runs on devices[0]
+    assert r.rtn[0] == a0.rtn[0] and np.array_equal(r.poly_coeff[0], a0.poly_coeff[0])
+    m.close()

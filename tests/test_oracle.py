@@ -147,3 +147,20 @@ def test_bezier_sampling_oracle_endpoints_and_derivatives(oracle):
     inner = slice(1, -1)   # central differences; the one-sided end points are only first-order accurate
     assert np.allclose((np.gradient(pos, axis=2) / dt)[:, :, inner], vel[:, :, inner], rtol=0, atol=1e-4 * np.abs(vel).max())
     assert np.allclose((np.gradient(vel, axis=2) / dt)[:, :, inner], acc[:, :, inner], rtol=0, atol=1e-4 * np.abs(acc).max())
+
+
+def test_bezier_restatement_matches_the_references_own_evaluators(oracle):
+    """oracle_py.bezier_sample (numpy) against tests/golden/bezier_ref.npz, the output of the reference's own
+    Bernstein::getPos / getVel / getAcc (utils/bezier_base.h:77-115, compiled unmodified: `make -C oracle bezier`,
+    tests/golden/make_bezier_golden.py), and against that library itself where it is built."""
+    import os
+    from conftest import GOLDEN
+    d = np.load(os.path.join(GOLDEN, "bezier_ref.npz"))
+    S = int(d["S"])
+    got = oracle.bezier_sample(d["bez_coeff"], d["poly_time"], S)
+    for g, name in zip(got, ("pos", "vel", "acc")):
+        assert rel_err(g, d[name]) < 1e-14, name
+    if oracle.bezier_ref_available():
+        live = oracle.bezier_sample_ref(d["bez_coeff"], d["poly_time"], S)
+        for g, name in zip(live, ("pos", "vel", "acc")):
+            assert np.array_equal(g, d[name]), name
