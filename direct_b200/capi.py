@@ -111,7 +111,8 @@ def load_library(build_if_missing: bool = True):
                                           C.c_double, C.c_void_p]
         lib.direct_ddp_replay_write.argtypes = [C.c_char_p, C.c_void_p, C.c_int]
         lib.direct_ddp_sm_clock_hz.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
-        lib.direct_ddp_device_count.argtypes = [C.c_void_p]
+        if hasattr(lib, "direct_ddp_device_count"):   # absent from older builds loaded through DIRECT_DDP_LIB (tuning experiments)
+            lib.direct_ddp_device_count.argtypes = [C.c_void_p]
         _lib = lib
     return _lib
 

@@ -164,6 +164,9 @@ struct Lay {
     };
 };
 enum { RING_BATCH = 4, RING_NB = 3, RING_ROWS = RING_BATCH * RING_NB };
+#ifndef DDP_ROW_RING
+#define DDP_ROW_RING 0   // 1: the line search streams its slack rows through the TMA ring below; measured SLOWER than L1-prefetched global loads, kept for A/B
+#endif
 DDP_HD int smem_elems_per_warp(int /*pm*/) { return Lay::TOTAL; }
 
 // Workspace slot layout (elements of Real).  Row arrays (s, y and their trial copies) are stored
@@ -388,14 +391,19 @@ template <class R> struct RowCtx {
     const double *planes;
     const int32_t *nplanes;
     long long NP;
-    int PM, infeas;
+    int PM, MCS, infeas;
     R mu, margin, max_vel, max_acc;
 };
+// Offset of (row slot, knot i) in a row array.  Layout [block of 32 knots][row slot][32 knots]: lane <-> knot accesses coalesce,
+// the row visited next sits 32 elements further on, and ALL rows of a 32-knot block are contiguous (MCS x 32 elements), so that
+// the line search's bulk copies (RowRing) move any number of consecutive rows with one instruction.
+DDP_DEVICE long long row_ofs(int MCS, int slot, int i) { return ((long long)(i >> 5) * MCS + slot) * 32 + (i & 31); }
+enum { ROW_STRIDE = 32 };   // elements between consecutive row slots of a knot
 template <class R> DDP_DEVICE RowCtx<R> row_ctx(const Traj<R> &t) {
     RowCtx<R> c;
     c.s = as_global(t.s); c.y = as_global(t.y); c.sn = as_global(t.sn); c.yn = as_global(t.yn); c.tab = t.tab;
     c.planes = as_global(t.planes); c.nplanes = as_global(t.nplanes);
-    c.NP = t.NP; c.PM = t.PM; c.infeas = t.infeas; c.mu = t.mu; c.margin = t.margin; c.max_vel = t.max_vel; c.max_acc = t.max_acc;
+    c.NP = t.NP; c.PM = t.PM; c.MCS = t.MCS; c.infeas = t.infeas; c.mu = t.mu; c.margin = t.margin; c.max_vel = t.max_vel; c.max_acc = t.max_acc;
     return c;
 }
 
@@ -411,7 +419,7 @@ template <class R> DDP_DEVICE RowCtx<R> row_global(RowCtx<R> c) {
 template <class R>
 DDP_DEVICE void first_row_load(const RowCtx<R> &t, const double *pl, int P, int g, int i, R &s_n, R &y_n, R *n_n) {
     if (g < 15 && (g >= 6 || P > 0)) {
-        const long long ro = (long long)row_slot(g, 0, t.PM) * t.NP + i;
+        const long long ro = row_ofs(t.MCS, row_slot(g, 0, t.PM), i);
         s_n = t.s[ro];
         if (t.infeas) y_n = t.y[ro];
         if (g < 6) load_plane(pl, 0, n_n);
@@ -573,7 +581,7 @@ template <class R> DDP_DEVICE_NOINLINE void lin_unit(const JobCtx<R> *cp_, int u
                     // instruction fetch and every extra copy of the row body costs more than the latency it hides.
                     R s_n = R(0), y_n = R(1), n_n[4] = {R(0), R(0), R(0), R(0)};
                     if (nr > 0) {
-                        const long long ro = (long long)row_slot(g, 0, t.PM) * t.NP + i;
+                        const long long ro = row_ofs(t.MCS, row_slot(g, 0, t.PM), i);
                         s_n = t.s[ro];
                         if (t.infeas) y_n = t.y[ro];
                         if (g < 6) load_plane(pl, 0, n_n);
@@ -585,9 +593,9 @@ template <class R> DDP_DEVICE_NOINLINE void lin_unit(const JobCtx<R> *cp_, int u
                         if (g < 6) { n[0] = n_n[0]; n[1] = n_n[1]; n[2] = n_n[2]; n[3] = n_n[3]; }
                         else fixed_row(r, lim, n);
                         {
-                            const long long ro = (long long)row_slot(g, r + 1, t.PM) * t.NP + i;
-                            prefetch_l1(t.s + ro + (ROW_PREFETCH - 1) * t.NP);
-                            if (t.infeas) prefetch_l1(t.y + ro + (ROW_PREFETCH - 1) * t.NP);
+                            const long long ro = row_ofs(t.MCS, row_slot(g, r + 1, t.PM), i);
+                            prefetch_l1(t.s + ro + (ROW_PREFETCH - 1) * ROW_STRIDE);
+                            if (t.infeas) prefetch_l1(t.y + ro + (ROW_PREFETCH - 1) * ROW_STRIDE);
                             if (r + 1 < nr) {
                                 s_n = t.s[ro];
                                 if (t.infeas) y_n = t.y[ro];
@@ -618,7 +626,7 @@ template <class R> DDP_DEVICE_NOINLINE void lin_unit(const JobCtx<R> *cp_, int u
                     }
                 }
                 {   // the time row -T + 0.3 <= 0 (ddp.cpp:1279): Jacobian -1 in the T entry only
-                    const long long ro = (long long)(6 * t.PM + 54) * t.NP + i;
+                    const long long ro = row_ofs(t.MCS, 6 * t.PM + 54, i);
                     R Ds, gw;
                     row_weights(t.infeas, t.mu, sgn, -z[9] + R(0.3) - t.margin, t.s[ro], t.infeas ? t.y[ro] : R(1), Ds, gw, emu, ecy);
                     tt += Ds; gt -= gw;
@@ -922,9 +930,9 @@ template <class R> DDP_DEVICE_NOINLINE void linearize_solo(Traj<R> &tt_, Reg<R, 
                         if (g < 6) { n[0] = n_n[0]; n[1] = n_n[1]; n[2] = n_n[2]; n[3] = n_n[3]; }
                         else fixed_row(r, lim, n);
                         {
-                            const long long ro = (long long)row_slot(g, r + 1, t.PM) * t.NP + i;
-                            prefetch_l1(t.s + ro + (ROW_PREFETCH - 1) * t.NP);
-                            if (t.infeas) prefetch_l1(t.y + ro + (ROW_PREFETCH - 1) * t.NP);
+                            const long long ro = row_ofs(t.MCS, row_slot(g, r + 1, t.PM), i);
+                            prefetch_l1(t.s + ro + (ROW_PREFETCH - 1) * ROW_STRIDE);
+                            if (t.infeas) prefetch_l1(t.y + ro + (ROW_PREFETCH - 1) * ROW_STRIDE);
                             if (r + 1 < nr) {
                                 s_n = t.s[ro];
                                 if (t.infeas) y_n = t.y[ro];
@@ -956,7 +964,7 @@ template <class R> DDP_DEVICE_NOINLINE void linearize_solo(Traj<R> &tt_, Reg<R, 
                     }
                 }
                 {   // the time row -T + 0.3 <= 0 (ddp.cpp:1279): Jacobian -1 in the T entry only
-                    const long long ro = (long long)(6 * t.PM + 54) * t.NP + i;
+                    const long long ro = row_ofs(t.MCS, 6 * t.PM + 54, i);
                     R Ds, gw;
                     row_weights(t.infeas, t.mu, sgn, -z[9] + R(0.3) - t.margin, t.s[ro], t.infeas ? t.y[ro] : R(1), Ds, gw, emu, ecy);
                     tt += Ds; gt -= gw;
@@ -1207,8 +1215,8 @@ template <class R> DDP_DEVICE_NOINLINE bool riccati(Traj<R> &t, R regadd, Reg<R,
                 const R l2 = yp * r2;
                 mreg(lane, 0) = l1; mreg(lane, 1) = l2;
                 if (lane < 20) {
-                    sm[Lay::MB + (kb * 20 + lane) * 2] = x; sm[Lay::MB + (kb * 20 + lane) * 2 + 1] = yp;
-                    sm[Lay::MSC + (kb * 20 + lane) * 2] = l1; sm[Lay::MSC + (kb * 20 + lane) * 2 + 1] = l2;
+                    st2(sm + Lay::MB + (kb * 20 + lane) * 2, x, yp);
+                    st2(sm + Lay::MSC + (kb * 20 + lane) * 2, l1, l2);
                 }
             }
             WARP_SYNC();
@@ -1216,7 +1224,10 @@ template <class R> DDP_DEVICE_NOINLINE bool riccati(Traj<R> &t, R regadd, Reg<R,
                 const R l1 = mreg(lane, 0), l2 = mreg(lane, 1);
                 const R *Xp = sm + Lay::MB + (kb * 20 + p) * 2;   // (x, y') of row p + r at Xp[2 r], Xp[2 r + 1]
                 DDP_UNROLL
-                for (int r = 2; r < 20; r++) col(lane, r - 2) = col(lane, r) - (Xp[2 * r] * l1 + Xp[2 * r + 1] * l2);
+                for (int r = 2; r < 20; r++) {
+                    const Pair2<R> xy = ld2(Xp + 2 * r);   // one 128-bit shared load per row
+                    col(lane, r - 2) = col(lane, r) - (xy.x * l1 + xy.y * l2);
+                }
             }
         }
         if (!ok) break;
@@ -1229,12 +1240,19 @@ template <class R> DDP_DEVICE_NOINLINE bool riccati(Traj<R> &t, R regadd, Reg<R,
                 // known the partial sums above it are updated independently (dependent chain of 10 instead of 45 FMAs)
                 R v[10];
                 DDP_UNROLL
-                for (int q = 0; q < 10; q++) v[q] = sm[Lay::MSC + ((q >> 1) * 20 + lane) * 2 + (q & 1)];
+                for (int kb = 0; kb < 5; kb++) {
+                    const Pair2<R> m = ld2(sm + Lay::MSC + (kb * 20 + lane) * 2);
+                    v[2 * kb] = m.x; v[2 * kb + 1] = m.y;
+                }
                 DDP_UNROLL
                 for (int q = 9; q >= 0; q--) {
                     kx(lane, q) = -v[q];
                     DDP_UNROLL
-                    for (int r = 0; r < q; r++) v[r] += sm[Lay::MSC + ((r >> 1) * 20 + q) * 2 + (r & 1)] * kx(lane, q);   // L[q][r]
+                    for (int kb = 0; 2 * kb < q; kb++) {   // L[q][2 kb], L[q][2 kb + 1]: one 128-bit load per round
+                        const Pair2<R> m = ld2(sm + Lay::MSC + (kb * 20 + q) * 2);
+                        v[2 * kb] += m.x * kx(lane, q);
+                        if (2 * kb + 1 < q) v[2 * kb + 1] += m.y * kx(lane, q);
+                    }
                 }
                 const int qc = lane == 19 ? 0 : lane - 9;
                 DDP_UNROLL
@@ -1450,7 +1468,7 @@ DDP_DEVICE_NOINLINE void rows_unit(const JobCtx<R> *cp_, int u0, int u1, int lan
                     }
                     R s_n = R(0), y_n = R(1), n_n[4] = {R(0), R(0), R(0), R(0)};   // one-deep pipeline, see lin_unit
                     if (nr > 0) {
-                        const long long ro = (long long)row_slot(g, 0, t.PM) * t.NP + i;
+                        const long long ro = row_ofs(t.MCS, row_slot(g, 0, t.PM), i);
                         s_n = t.s[ro];
                         if (t.infeas) y_n = t.y[ro];
                         if (g < 6) load_plane(pl, 0, n_n);
@@ -1458,14 +1476,14 @@ DDP_DEVICE_NOINLINE void rows_unit(const JobCtx<R> *cp_, int u0, int u1, int lan
                     DDP_NOUNROLL
                     for (int r = 0; r < nr; r++) {
                         const R sv = s_n, yv = y_n;
-                        const long long ro_cur = (long long)row_slot(g, r, t.PM) * t.NP + i;
+                        const long long ro_cur = row_ofs(t.MCS, row_slot(g, r, t.PM), i);
                         R n[4];
                         if (g < 6) { n[0] = n_n[0]; n[1] = n_n[1]; n[2] = n_n[2]; n[3] = n_n[3]; }
                         else fixed_row(r, lim, n);
-                        prefetch_l1(t.s + ro_cur + ROW_PREFETCH * t.NP);
-                        if (t.infeas) prefetch_l1(t.y + ro_cur + ROW_PREFETCH * t.NP);
+                        prefetch_l1(t.s + ro_cur + ROW_PREFETCH * ROW_STRIDE);
+                        if (t.infeas) prefetch_l1(t.y + ro_cur + ROW_PREFETCH * ROW_STRIDE);
                         if (r + 1 < nr) {
-                            const long long ro = ro_cur + t.NP;
+                            const long long ro = ro_cur + ROW_STRIDE;
                             s_n = t.s[ro];
                             if (t.infeas) y_n = t.y[ro];
                             if (g < 6) load_plane(pl, r + 1, n_n);
@@ -1478,7 +1496,7 @@ DDP_DEVICE_NOINLINE void rows_unit(const JobCtx<R> *cp_, int u0, int u1, int lan
                         trial_row(t, ro_cur, sv, yv, cold, cnew, jv1, jv2, alpha, tau, A);
                     }
                 } else {
-                    const long long ro = (long long)(6 * t.PM + 54) * t.NP + i;
+                    const long long ro = row_ofs(t.MCS, 6 * t.PM + 54, i);
                     trial_row(t, ro, t.s[ro], t.infeas ? t.y[ro] : R(1), -zo[9] + R(0.3) - t.margin, -zn[9] + R(0.3) - t.margin, -v1[9],
                               -v2[9], alpha, tau, A);
                     // stage cost q(x,u), ddp.cpp:1294-1305
@@ -1507,38 +1525,29 @@ DDP_DEVICE_NOINLINE void rows_unit(const JobCtx<R> *cp_, int u0, int u1, int lan
 }
 
 // =============================================================================================
-// Slack-row ring (TMA).  The row phase of a line-search trial walks the 6 P + 55 constraint rows of 32 knots (lane <-> knot)
-// and needs, for every row, the 32 slack values s (and dual slacks y in the infeasible phase) of those knots: one 256-byte
-// line per row and array, [row slot][knot] in the workspace, row slots in visit order.  Loading them with one LDG per lane
-// and row left the loop waiting on global-memory latency (profiles/r1h: 17 % of all stall samples sit on those loads, L1
-// prefetch or not).  Here ONE lane hands whole batches of RING_BATCH rows to the copy engine (cp.async.bulk, completion on an
-// mbarrier) RING_NB batches = RING_ROWS rows ahead of their use; the lanes read the values from shared memory.
-// Everything is warp-uniform: the visit sequence is  (position group g < 6: rows 0 .. Pw-1, Pw = most planes of any of the 32
-// knots) , (6 rows of each velocity / acceleration group) , time row;  lanes whose polytope has fewer planes skip the body.
+// Slack-row ring (TMA).  The row phase of a line-search trial walks the 6 PM + 55 row slots of 32 knots (lane <-> knot)
+// and needs, for every row, the 32 slack values s (and dual slacks y in the infeasible phase) of those knots.  Loading them
+// with one LDG per lane and row left the loop waiting on global-memory latency (profiles/r1h: 17 % of all stall samples sit
+// on those loads, L1 prefetch or not).  The row arrays are laid out [32-knot block][row slot][32] (row_ofs), so the rows of a
+// block are one contiguous strip in visit order: ONE lane hands RING_BATCH consecutive rows to the copy engine with a single
+// cp.async.bulk per array (completion on an mbarrier), RING_NB batches = RING_ROWS rows ahead of their use, and the lanes
+// read the values from shared memory.  Everything is warp-uniform: every slot is streamed, also the unused ones of a
+// polytope with fewer than PM planes (the lanes skip the body there).
 // GPU only: the lane-by-lane CPU emulation reads the rows straight from the workspace (same arithmetic).
 // =============================================================================================
-template <class R> struct RowRing {
-    int Pw;                    // most planes of any knot of the block: 6 Pw + 55 rows in the sequence
-    int pslot, pg, pr, issued; // producer: workspace row slot / position group / row in group of the next row to issue, rows issued
-};
 #if DDP_GPU
-template <class R> DDP_DEVICE void ring_issue_batch(RowRing<R> &q, const RowCtx<R> &t, R *sm, int base, int bslot, int lane_) {
-    const int left = 6 * q.Pw + 55 - q.issued;
-    const int n = left < RING_BATCH ? left : RING_BATCH;
-    if (n <= 0) return;
-    unsigned long long *bar = reinterpret_cast<unsigned long long *>(sm + Lay::RB) + bslot;
-    const unsigned row_bytes = 32u * (unsigned)sizeof(R);
-    if (lane_ == 0) mbar_expect_tx(bar, (unsigned)n * row_bytes * (t.infeas ? 2u : 1u));
-    for (int k = 0; k < n; k++) {
-        if (lane_ == 0) {
-            const long long go = (long long)q.pslot * t.NP + base;
-            bulk_g2s(sm + Lay::RS + (bslot * RING_BATCH + k) * 32, t.s + go, row_bytes, bar);
-            if (t.infeas) bulk_g2s(sm + Lay::RY + (bslot * RING_BATCH + k) * 32, t.y + go, row_bytes, bar);
-        }
-        // next row in visit order: position groups own PM slots each and use Pw of them, the rest is contiguous
-        q.pslot++; q.issued++;
-        if (q.pg < 6 && ++q.pr == q.Pw) { q.pg++; q.pr = 0; q.pslot = q.pg * t.PM; }
-    }
+// Batch number `batch` (rows batch * RING_BATCH ...) of the block at `base` into ring slot batch % RING_NB.
+template <class R> DDP_DEVICE_NOINLINE void ring_issue_batch(const RowCtx<R> &t, R *sm, int base, int batch) {
+    const int first = batch * RING_BATCH;
+    const int n = t.MCS - first < RING_BATCH ? t.MCS - first : RING_BATCH;
+    if (n <= 0 || (threadIdx.x & 31) != 0) return;
+    const int bslot = batch % RING_NB;
+    unsigned long long *bar = reinterpret_cast<unsigned long long *>(as_shared(sm) + Lay::RB) + bslot;
+    const unsigned bytes = (unsigned)n * 32u * (unsigned)sizeof(R);
+    const long long go = row_ofs(t.MCS, first, base);
+    mbar_expect_tx(bar, bytes * (t.infeas ? 2u : 1u));
+    bulk_g2s(as_shared(sm) + Lay::RS + bslot * RING_BATCH * 32, as_global(t.s) + go, bytes, bar);
+    if (t.infeas) bulk_g2s(as_shared(sm) + Lay::RY + bslot * RING_BATCH * 32, as_global(t.y) + go, bytes, bar);
 }
 // Once per kernel launch and warp: the ring's barriers (one arrival each: the issuing lane's expect_tx) and their phase word.
 template <class R> DDP_DEVICE void ring_init(R *sm, int lane_) {
@@ -1549,16 +1558,13 @@ template <class R> DDP_DEVICE void ring_init(R *sm, int lane_) {
 }
 // Start the ring for the 32-knot block at `base` (every copy of the previous block has been consumed): first RING_NB batches
 // in flight.  Called before the block's state recursion so that the rows are there when it ends.
-template <class R>
-DDP_DEVICE void ring_start(RowRing<R> &q, const RowCtx<R> &t, R *sm, int base, int Pw, int lane_) {
-    q.Pw = Pw; q.issued = 0; q.pr = 0;
-    q.pg = Pw > 0 ? 0 : 6; q.pslot = Pw > 0 ? 0 : 6 * t.PM;
+template <class R> DDP_DEVICE void ring_start(const RowCtx<R> &t, R *sm, int base) {
     __syncwarp();
     fence_async_all();    // whatever generic stores last touched the ring area and the st.global that wrote the slack rows (this
                           // warp's lanes or, through the job board, helper warps) before the copy engine writes / reads them
     __syncwarp();
-    DDP_UNROLL
-    for (int b = 0; b < RING_NB; b++) ring_issue_batch(q, t, sm, base, b, lane_);
+    DDP_NOUNROLL
+    for (int b = 0; b < RING_NB; b++) ring_issue_batch(t, sm, base, b);
 }
 #endif
 
@@ -1749,14 +1755,9 @@ template <class R> DDP_DEVICE_NOINLINE bool forward_trial_solo(Traj<R> &tt_, R a
         }
     }
     bool ok = true;
-    // planes of this lane's knot of the block and the most planes of any knot of the block (warp-uniform row sequence)
-    Reg<int, 1> Pl;
-    FOR_LANES(lane) { Pl(lane, 0) = lane < N ? t.nplanes[lane] : 0; }
-    int Pw = warp_max_int(Pl, 0, lane_);
-#if DDP_GPU
-    RowRing<R> rq;
+#if DDP_GPU && DDP_ROW_RING
     unsigned rphase = *reinterpret_cast<volatile unsigned *>(sm + Lay::RP);   // the barriers live as long as the kernel
-    ring_start(rq, t, sm, 0, Pw, lane_);   // the first rows of block 0 travel while its state recursion runs
+    ring_start(t, sm, 0);   // the first rows of block 0 travel while its state recursion runs
 #endif
     for (int base = 0; base < N && ok; base += 32) {
         const int nk = N - base < 32 ? N - base : 32;
@@ -1837,17 +1838,17 @@ template <class R> DDP_DEVICE_NOINLINE bool forward_trial_solo(Traj<R> &tt_, R a
                 const R Tn = step_u(zo[9], alpha, v1T, v2T);   // = xun[9] (ddp.cpp:689/:695, rollout above)
                 TrialAcc<R> A;
                 A.lg.lp = R(1); A.lg.lsum = R(0); A.e1 = R(0); A.bad = 0; A.cmax = R(-INFINITY);
-                const int P = live ? Pl(lane, 0) : 0;
+                const int P = live ? t.nplanes[il] : 0;
                 const double *pl = t.planes + (long long)il * t.PM * 4;
                 R n_n[4] = {R(0), R(0), R(0), R(0)};   // plane of the next row, loaded one row ahead
                 if (P > 0) load_plane(pl, 0, n_n);
-#if DDP_GPU
-                int cbatch = 0, cin = 0;   // consumer: batch slot, row in batch; rphase bit b = parity barrier b completes next
+#if DDP_GPU && DDP_ROW_RING
+                int cbatch = 0, cin = 0;   // consumer: batch number, row in batch; rphase bit b = parity barrier b completes next
 #endif
                 DDP_NOUNROLL
                 for (int g = 0; g < 16; g++) {   // one copy of the row code for all groups (see linearize); g = 15: the time row
                     const int shift = group_shift(g), nr = g < 6 ? P : (g < 15 ? (live ? 6 : 0) : (live ? 1 : 0));
-                    const int nrw = g < 6 ? Pw : (g < 15 ? 6 : 1);
+                    const int nrw = g < 6 ? t.PM : (g < 15 ? 6 : 1);   // warp-uniform: every row slot is visited
                     const R lim = g < 11 ? t.max_vel : t.max_acc;
                     R co[3], cd[3], cn[3], j1[3], j2[3];
                     if (g < 15) {
@@ -1883,15 +1884,23 @@ template <class R> DDP_DEVICE_NOINLINE bool forward_trial_solo(Traj<R> &tt_, R a
                     }
                     DDP_NOUNROLL
                     for (int r = 0; r < nrw; r++) {
-                        const long long ro_cur = (long long)(g < 15 ? row_slot(g, r, t.PM) : 6 * t.PM + 54) * t.NP + i;
-#if DDP_GPU
+                        const long long ro_cur = row_ofs(t.MCS, g < 15 ? row_slot(g, r, t.PM) : 6 * t.PM + 54, i);
+#if DDP_GPU && DDP_ROW_RING
+                        const int cslot = cbatch % RING_NB;
                         if (cin == 0) {
-                            mbar_wait(reinterpret_cast<unsigned long long *>(sm + Lay::RB) + cbatch, (rphase >> cbatch) & 1u);
-                            rphase ^= 1u << cbatch;
-                        }
-                        const R sv = sm[Lay::RS + (cbatch * RING_BATCH + cin) * 32 + lane];
-                        const R yv = t.infeas ? sm[Lay::RY + (cbatch * RING_BATCH + cin) * 32 + lane] : R(1);
+#ifdef DDP_RING_DEBUG
+                            mbar_wait_dbg(reinterpret_cast<unsigned long long *>(sm + Lay::RB) + cslot, (rphase >> cslot) & 1u,
+                                          g * 100 + r, cbatch, base);
 #else
+                            mbar_wait(reinterpret_cast<unsigned long long *>(sm + Lay::RB) + cslot, (rphase >> cslot) & 1u);
+#endif
+                            rphase ^= 1u << cslot;
+                        }
+                        const R sv = sm[Lay::RS + (cslot * RING_BATCH + cin) * 32 + lane];
+                        const R yv = t.infeas ? sm[Lay::RY + (cslot * RING_BATCH + cin) * 32 + lane] : R(1);
+#else
+                        prefetch_l1(t.s + ro_cur + ROW_PREFETCH * ROW_STRIDE);
+                        if (t.infeas) prefetch_l1(t.y + ro_cur + ROW_PREFETCH * ROW_STRIDE);
                         const R sv = r < nr ? t.s[ro_cur] : R(0), yv = (r < nr && t.infeas) ? t.y[ro_cur] : R(1);
 #endif
                         R n[4];
@@ -1907,12 +1916,11 @@ template <class R> DDP_DEVICE_NOINLINE bool forward_trial_solo(Traj<R> &tt_, R a
                             const R jv2 = ((n[0] * j2[0] + n[1] * j2[1]) + n[2] * j2[2]) + tc * v2T;
                             trial_row(t, ro_cur, sv, yv, cold, cnew, jv1, jv2, alpha, tau, A);
                         }
-#if DDP_GPU
+#if DDP_GPU && DDP_ROW_RING
                         if (++cin == RING_BATCH) {   // batch consumed by every lane: its ring rows take the batch RING_NB further on
                             __syncwarp();
-                            ring_issue_batch(rq, t, sm, base, cbatch, lane_);
-                            cin = 0;
-                            if (++cbatch == RING_NB) cbatch = 0;
+                            ring_issue_batch(t, sm, base, cbatch + RING_NB);
+                            cin = 0; cbatch++;
                         }
 #endif
                     }
@@ -1943,17 +1951,13 @@ template <class R> DDP_DEVICE_NOINLINE bool forward_trial_solo(Traj<R> &tt_, R a
         const int first = warp_min_int(badk, 0, lane_);
         if (first != 0x7fffffff) { fwd_knots += first - base + 1; ok = false; }
         else fwd_knots += nk;
-        if (ok && base + 32 < N) {   // next block: plane counts and the first rows of its ring
-            FOR_LANES(lane) { Pl(lane, 0) = base + 32 + lane < N ? t.nplanes[base + 32 + lane] : 0; }
-            Pw = warp_max_int(Pl, 0, lane_);
-#if DDP_GPU
-            ring_start(rq, t, sm, base + 32, Pw, lane_);
+#if DDP_GPU && DDP_ROW_RING
+        if (ok && base + 32 < N) ring_start(t, sm, base + 32);   // the first rows of the next block's ring
 #endif
-        }
     }
     FOR_LANES(lane) { cp_wait<0>(); }   // nothing of the ring / staging may land after this trial
     WARP_SYNC();
-#if DDP_GPU
+#if DDP_GPU && DDP_ROW_RING
     if (lane_ == 0) *reinterpret_cast<volatile unsigned *>(sm + Lay::RP) = rphase;   // every issued batch has been consumed
     __syncwarp();
 #endif
@@ -2057,7 +2061,7 @@ template <class R> DDP_DEVICE_NOINLINE bool scan_constraints(Traj<R> &t, int mod
             int v = 0;
             visit_rows(c_, i, z, [&](int slot, R c) {
                 if (mode == 0) {
-                    if (c_.infeas) { const R yv = c_.y[(long long)slot * c_.NP + i]; lg.mul(yv); e1 += rabs(c + yv); }
+                    if (c_.infeas) { const R yv = c_.y[row_ofs(c_.MCS, slot, i)]; lg.mul(yv); e1 += rabs(c + yv); }
                     else lg.mul(-c);
                 } else if (mode == 1) { if (c >= thresh) v = 1; }
                 else { if (c > thresh) v = 1; }
@@ -2511,8 +2515,8 @@ template <class R> DDP_DEVICE_NOINLINE void solve_one(const SolveArgs &A, int st
             DDP_UNROLL
             for (int e = 0; e < 10; e++) t.xu[(long long)i * 20 + e] = u[e];
             for (int r = 0; r < t.MCS; r++) {
-                t.s[(long long)r * t.NP + i] = R(0.1);   // ddp.cpp:150-151
-                t.y[(long long)r * t.NP + i] = R(0.01);
+                t.s[row_ofs(t.MCS, r, i)] = R(0.1);   // ddp.cpp:150-151
+                t.y[row_ofs(t.MCS, r, i)] = R(0.01);
             }
         }
     }

@@ -214,7 +214,7 @@ def test_gpu_time_allocation_device_matches_reference_rule(solver, oracle):
     step = rng.uniform(0.05, 6.0, size=(B, N + 1, 3)) * rng.choice([-1.0, 1.0], size=(B, N + 1, 3))
     pts = np.cumsum(step, axis=1)
     dev = torch.device("cuda", 0)
-    for mv, ma in ((2.0, 2.0), (3.5, 1.25)):
+    for mv, ma in ((2.0, 2.0), (3.0, 2.5)):
         start, end = np.ascontiguousarray(pts[:, 0]), np.ascontiguousarray(pts[:, N])
         seeds = np.ascontiguousarray(pts[:, :N])
         t = [torch.from_numpy(a).to(dev) for a in (start, end, seeds)]
