@@ -135,6 +135,9 @@ struct SolveArgs {
 // Per-warp shared-memory scratch (elements of Real).  Independent of the number of planes: the
 // knot-parallel phases read planes straight from global memory (each lane its own knot).
 // ---------------------------------------------------------------------------------------------
+#ifndef DDP_CPR_DEPTH
+#define DDP_CPR_DEPTH 4   // 4: 2 x 96.5 KB of shared memory per SM, still the 196 KB carve-out (8 would take the L1 from 60 to 28 KB)
+#endif
 struct Lay {
     enum {
         XD = 0,     // desired terminal state (9)
@@ -160,9 +163,14 @@ struct Lay {
         // the phase parity each of them completes next (one word, bit b = barrier b).
         RB = 584 + 63 * 32,         // RING_NB mbarriers, 8 bytes each
         RP = 584 + 63 * 32 + 6,     // phase word (unsigned), inside the 8 elements reserved here for float and double
-        TOTAL = 584 + 63 * 32 + 8
+        // Slack-row staging of the row loops (cp.async, one element per lane and row): CPR_DEPTH rows of s, then of y.  Outside
+        // MSC because the linearisation fills all of MSC while its row loop runs.  2 x 88.3 KB -> 2 x 96.5 KB per SM at depth 4: the
+        // same shared-memory carve-out (196 KB), so the L1 keeps its size.
+        CR = 584 + 63 * 32 + 8,
+        TOTAL = 584 + 63 * 32 + 8 + 2 * DDP_CPR_DEPTH * 32
     };
 };
+enum { CPR_DEPTH = DDP_CPR_DEPTH };   // rows in flight ahead of the row being processed
 enum { RING_BATCH = 4, RING_NB = 3, RING_ROWS = RING_BATCH * RING_NB };
 #ifndef DDP_ROW_RING
 #define DDP_ROW_RING 0   // 1: the line search streams its slack rows through the TMA ring below; measured SLOWER than L1-prefetched global loads, kept for A/B
@@ -412,6 +420,39 @@ template <class R> DDP_DEVICE RowCtx<R> row_global(RowCtx<R> c) {
     c.s = as_global(c.s); c.y = as_global(c.y); c.sn = as_global(c.sn); c.yn = as_global(c.yn);
     c.planes = as_global(c.planes); c.nplanes = as_global(c.nplanes);
     return c;
+}
+
+// Slack rows of one knot through shared memory by cp.async (LDGSTS), one element per lane and row, CPR_DEPTH rows ahead of their
+// use.  The row slots of a knot are visited in storage order (row_ofs: 32 elements apart), so the row wanted next is always
+// one pointer step away.  Why not registers: every load of a warp that is in flight on the same scoreboard has to land before
+// the oldest can be consumed, so a register pipeline k rows deep exposes the latency of the row issued LAST (measured: 181 ms
+// against 164 ms, profiles/r2g); cp.async completes through its own group counter and costs no scoreboard.  Why not TMA: see
+// RowRing below (an elected lane, a barrier wait and a warp synchronisation per batch; measured slower).  Each lane reads only
+// what it copied itself, so cp.async.wait_group is all the synchronisation there is.
+template <class R> struct RowStream {
+    const R *ps, *py;   // next row to fetch (this lane's knot)
+    R *rs;              // this lane's column of the staging area: rs[d * 32] = s, rs[(CPR_DEPTH + d) * 32] = y of ring slot d
+    int slot, infeas;
+};
+template <class R> DDP_DEVICE void row_stream_fetch(RowStream<R> &q, int d) {
+    cp_async<sizeof(R)>(q.rs + d * 32, q.ps);
+    if (q.infeas) cp_async<sizeof(R)>(q.rs + (CPR_DEPTH + d) * 32, q.py);
+    cp_commit();
+    q.ps += ROW_STRIDE; q.py += ROW_STRIDE;
+}
+template <class R> DDP_DEVICE void row_stream_start(RowStream<R> &q, const RowCtx<R> &t, R *sm, int i, int lane) {
+    q.ps = t.s + row_ofs(t.MCS, 0, i); q.py = t.y + row_ofs(t.MCS, 0, i);
+    q.rs = sm + Lay::CR + lane; q.slot = 0; q.infeas = t.infeas;
+    DDP_UNROLL
+    for (int d = 0; d < CPR_DEPTH; d++) row_stream_fetch(q, d);
+}
+// Slack (and dual slack) of the next row in visit order; refills the slot it frees with the row CPR_DEPTH further on.
+template <class R> DDP_DEVICE void row_stream_next(RowStream<R> &q, R &sv, R &yv) {
+    cp_wait<CPR_DEPTH - 1>();
+    sv = q.rs[q.slot * 32];
+    yv = q.infeas ? q.rs[(CPR_DEPTH + q.slot) * 32] : R(1);
+    row_stream_fetch(q, q.slot);
+    q.slot = q.slot + 1 == CPR_DEPTH ? 0 : q.slot + 1;
 }
 
 // First row of row group g of knot i into the one-deep pipeline registers (slack, dual slack, plane), issued while the
@@ -908,11 +949,16 @@ template <class R> DDP_DEVICE_NOINLINE void linearize_solo(Traj<R> &tt_, Reg<R, 
                 // ---- pass 1: rows -> weights -> per-group blocks.  One rolled loop over the 15 row groups and one over
                 // the rows of a group (a single copy of the row code: the kernel is instruction-fetch bound,
                 // profiles/r1c); the slack of row r+1 is loaded while row r is processed. ------------------------
-                R s_n = R(0), y_n = R(1), n_n[4] = {R(0), R(0), R(0), R(0)};   // pipeline registers, see first_row_load
-                first_row_load(t, pl, P, 0, i, s_n, y_n, n_n);
+                // Slack rows through the cp.async row stream (RowStream): every row slot of the knot is visited in storage order;
+                // the slots a polytope with fewer than PM planes leaves unused are skipped by the body only.  The plane of the
+                // next row is loaded one row ahead.
+                RowStream<R> rows_in;
+                row_stream_start(rows_in, t, smw, i, lane);
+                R n_n[4] = {R(0), R(0), R(0), R(0)};
+                if (P > 0) load_plane(pl, 0, n_n);
                 DDP_NOUNROLL
                 for (int g = 0; g < 15; g++) {
-                    const int shift = group_shift(g), nr = g < 6 ? P : 6;
+                    const int shift = group_shift(g), nr = g < 6 ? P : 6, nrw = g < 6 ? t.PM : 6;
                     const R lim = g < 11 ? t.max_vel : t.max_acc;
                     R b[6], bd[6], cp[3], cd[3];
                     basis_row_rt(tab + g * 6, shift, tp, b);
@@ -920,37 +966,28 @@ template <class R> DDP_DEVICE_NOINLINE void linearize_solo(Traj<R> &tt_, Reg<R, 
                     DDP_UNROLL
                     for (int a = 0; a < 3; a++) { cp[a] = dot_axis<R, 0>(b, z, a); cd[a] = dot_axis<R, 0>(bd, z, a); }
                     R M[6] = {R(0), R(0), R(0), R(0), R(0), R(0)}, wv[3] = {R(0), R(0), R(0)}, gv[3] = {R(0), R(0), R(0)};
-                    // one-deep software pipeline: slack (and plane) of row r+1 are loaded while row r is processed.  Deeper
-                    // pipelines / two-row unrolling were measured slower at full occupancy: the kernel is bound by
-                    // instruction fetch and every extra copy of the row body costs more than the latency it hides.
                     DDP_NOUNROLL
-                    for (int r = 0; r < nr; r++) {
-                        const R sv = s_n, yv = y_n;
-                        R n[4];
-                        if (g < 6) { n[0] = n_n[0]; n[1] = n_n[1]; n[2] = n_n[2]; n[3] = n_n[3]; }
-                        else fixed_row(r, lim, n);
-                        {
-                            const long long ro = row_ofs(t.MCS, row_slot(g, r + 1, t.PM), i);
-                            prefetch_l1(t.s + ro + (ROW_PREFETCH - 1) * ROW_STRIDE);
-                            if (t.infeas) prefetch_l1(t.y + ro + (ROW_PREFETCH - 1) * ROW_STRIDE);
-                            if (r + 1 < nr) {
-                                s_n = t.s[ro];
-                                if (t.infeas) y_n = t.y[ro];
-                                if (g < 6) load_plane(pl, r + 1, n_n);
-                            }
+                    for (int r = 0; r < nrw; r++) {
+                        R sv, yv;
+                        row_stream_next(rows_in, sv, yv);
+                        if (r < nr) {
+                            R n[4];
+                            if (g < 6) { n[0] = n_n[0]; n[1] = n_n[1]; n[2] = n_n[2]; n[3] = n_n[3]; }
+                            else fixed_row(r, lim, n);
+                            if (g < 6 && r + 1 < nr) load_plane(pl, r + 1, n_n);
+                            const R c = ((n[0] * cp[0] + n[1] * cp[1]) + n[2] * cp[2]) + n[3] - t.margin;
+                            const R tc = (n[0] * cd[0] + n[1] * cd[1]) + n[2] * cd[2];
+                            R Ds, gw;
+                            row_weights(t.infeas, t.mu, sgn, c, sv, yv, Ds, gw, emu, ecy);
+                            M[0] += Ds * (n[0] * n[0]); M[1] += Ds * (n[0] * n[1]); M[2] += Ds * (n[0] * n[2]);
+                            M[3] += Ds * (n[1] * n[1]); M[4] += Ds * (n[1] * n[2]); M[5] += Ds * (n[2] * n[2]);
+                            const R dt = Ds * tc, gtc = gw * tc;
+                            wv[0] += dt * n[0]; wv[1] += dt * n[1]; wv[2] += dt * n[2];
+                            gv[0] += gw * n[0]; gv[1] += gw * n[1]; gv[2] += gw * n[2];
+                            tt += dt * tc; gt += gtc;
                         }
-                        const R c = ((n[0] * cp[0] + n[1] * cp[1]) + n[2] * cp[2]) + n[3] - t.margin;
-                        const R tc = (n[0] * cd[0] + n[1] * cd[1]) + n[2] * cd[2];
-                        R Ds, gw;
-                        row_weights(t.infeas, t.mu, sgn, c, sv, yv, Ds, gw, emu, ecy);
-                        M[0] += Ds * (n[0] * n[0]); M[1] += Ds * (n[0] * n[1]); M[2] += Ds * (n[0] * n[2]);
-                        M[3] += Ds * (n[1] * n[1]); M[4] += Ds * (n[1] * n[2]); M[5] += Ds * (n[2] * n[2]);
-                        const R dt = Ds * tc, gtc = gw * tc;
-                        wv[0] += dt * n[0]; wv[1] += dt * n[1]; wv[2] += dt * n[2];
-                        gv[0] += gw * n[0]; gv[1] += gw * n[1]; gv[2] += gw * n[2];
-                        tt += dt * tc; gt += gtc;
                     }
-                    first_row_load(t, pl, P, g + 1, i, s_n, y_n, n_n);
+                    if (g + 1 < 6 && P > 0) load_plane(pl, 0, n_n);   // first plane of the next position group
                     if (g < 6) {
                         DDP_UNROLL
                         for (int e = 0; e < 6; e++) msc[(g * 6 + e) * 32] = M[e];
@@ -963,11 +1000,12 @@ template <class R> DDP_DEVICE_NOINLINE void linearize_solo(Traj<R> &tt_, Reg<R, 
                         for (int a = 0; a < 3; a++) { accT[l * 3 + a] += b[l] * wv[a]; accG[l * 3 + a] += b[l] * gv[a]; }
                     }
                 }
-                {   // the time row -T + 0.3 <= 0 (ddp.cpp:1279): Jacobian -1 in the T entry only
-                    const long long ro = row_ofs(t.MCS, 6 * t.PM + 54, i);
-                    R Ds, gw;
-                    row_weights(t.infeas, t.mu, sgn, -z[9] + R(0.3) - t.margin, t.s[ro], t.infeas ? t.y[ro] : R(1), Ds, gw, emu, ecy);
+                {   // the time row -T + 0.3 <= 0 (ddp.cpp:1279): Jacobian -1 in the T entry only; its slack is the stream's next row
+                    R sv, yv, Ds, gw;
+                    row_stream_next(rows_in, sv, yv);
+                    row_weights(t.infeas, t.mu, sgn, -z[9] + R(0.3) - t.margin, sv, yv, Ds, gw, emu, ecy);
                     tt += Ds; gt -= gw;
+                    cp_wait<0>();   // the stream's look-ahead copies (rows past the block) land before the staging area is reused
                 }
                 errs(lane, 0) = emu; errs(lane, 1) = ecy;
                 // ---- stage cost (ddp.cpp:1338-1368): quu = w [R (x) I, R'u; (R'u)^T, .], qu = w [R u; .] --------
@@ -1844,6 +1882,9 @@ template <class R> DDP_DEVICE_NOINLINE bool forward_trial_solo(Traj<R> &tt_, R a
                 if (P > 0) load_plane(pl, 0, n_n);
 #if DDP_GPU && DDP_ROW_RING
                 int cbatch = 0, cin = 0;   // consumer: batch number, row in batch; rphase bit b = parity barrier b completes next
+#else
+                RowStream<R> rows_in;
+                row_stream_start(rows_in, t, sm, i, lane);
 #endif
                 DDP_NOUNROLL
                 for (int g = 0; g < 16; g++) {   // one copy of the row code for all groups (see linearize); g = 15: the time row
@@ -1899,9 +1940,8 @@ template <class R> DDP_DEVICE_NOINLINE bool forward_trial_solo(Traj<R> &tt_, R a
                         const R sv = sm[Lay::RS + (cslot * RING_BATCH + cin) * 32 + lane];
                         const R yv = t.infeas ? sm[Lay::RY + (cslot * RING_BATCH + cin) * 32 + lane] : R(1);
 #else
-                        prefetch_l1(t.s + ro_cur + ROW_PREFETCH * ROW_STRIDE);
-                        if (t.infeas) prefetch_l1(t.y + ro_cur + ROW_PREFETCH * ROW_STRIDE);
-                        const R sv = r < nr ? t.s[ro_cur] : R(0), yv = (r < nr && t.infeas) ? t.y[ro_cur] : R(1);
+                        R sv, yv;
+                        row_stream_next(rows_in, sv, yv);
 #endif
                         R n[4];
                         if (g < 6) { n[0] = n_n[0]; n[1] = n_n[1]; n[2] = n_n[2]; n[3] = n_n[3]; }
