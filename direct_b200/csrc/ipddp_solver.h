@@ -440,8 +440,8 @@ template <class R> DDP_DEVICE void row_stream_fetch(RowStream<R> &q, int d) {
     cp_commit();
     q.ps += ROW_STRIDE; q.py += ROW_STRIDE;
 }
-template <class R> DDP_DEVICE void row_stream_start(RowStream<R> &q, const RowCtx<R> &t, R *sm, int i, int lane) {
-    q.ps = t.s + row_ofs(t.MCS, 0, i); q.py = t.y + row_ofs(t.MCS, 0, i);
+template <class R> DDP_DEVICE void row_stream_start(RowStream<R> &q, const RowCtx<R> &t, R *sm, int i, int lane, int slot0 = 0) {
+    q.ps = t.s + row_ofs(t.MCS, slot0, i); q.py = t.y + row_ofs(t.MCS, slot0, i);
     q.rs = sm + Lay::CR + lane; q.slot = 0; q.infeas = t.infeas;
     DDP_UNROLL
     for (int d = 0; d < CPR_DEPTH; d++) row_stream_fetch(q, d);
@@ -606,10 +606,17 @@ template <class R> DDP_DEVICE_NOINLINE void lin_unit(const JobCtx<R> *cp_, int u
                 for (int e = 0; e < 18; e++) { accT[e] = R(0); accG[e] = R(0); }
                 // ---- pass 1: rows -> weights -> per-group blocks.  One rolled loop over the 15 row groups and one over
                 // the rows of a group (a single copy of the row code: the kernel is instruction-fetch bound,
-                // profiles/r1c); the slack of row r+1 is loaded while row r is processed. ------------------------
+                // profiles/r1c). ------------------------
+                // Slack rows through the cp.async row stream (RowStream): every row slot of the knot is visited in storage order;
+                // the slots a polytope with fewer than PM planes leaves unused are skipped by the body only.  The plane of the
+                // next row is loaded one row ahead.
+                RowStream<R> rows_in;
+                row_stream_start(rows_in, t, smw, i, lane);
+                R n_n[4] = {R(0), R(0), R(0), R(0)};
+                if (P > 0) load_plane(pl, 0, n_n);
                 DDP_NOUNROLL
                 for (int g = 0; g < 15; g++) {
-                    const int shift = group_shift(g), nr = g < 6 ? P : 6;
+                    const int shift = group_shift(g), nr = g < 6 ? P : 6, nrw = g < 6 ? t.PM : 6;
                     const R lim = g < 11 ? t.max_vel : t.max_acc;
                     R b[6], bd[6], cp[3], cd[3];
                     basis_row_rt(tab + g * 6, shift, tp, b);
@@ -617,43 +624,28 @@ template <class R> DDP_DEVICE_NOINLINE void lin_unit(const JobCtx<R> *cp_, int u
                     DDP_UNROLL
                     for (int a = 0; a < 3; a++) { cp[a] = dot_axis<R, 0>(b, z, a); cd[a] = dot_axis<R, 0>(bd, z, a); }
                     R M[6] = {R(0), R(0), R(0), R(0), R(0), R(0)}, wv[3] = {R(0), R(0), R(0)}, gv[3] = {R(0), R(0), R(0)};
-                    // one-deep software pipeline: slack (and plane) of row r+1 are loaded while row r is processed.  Deeper
-                    // pipelines / two-row unrolling were measured slower at full occupancy: the kernel is bound by
-                    // instruction fetch and every extra copy of the row body costs more than the latency it hides.
-                    R s_n = R(0), y_n = R(1), n_n[4] = {R(0), R(0), R(0), R(0)};
-                    if (nr > 0) {
-                        const long long ro = row_ofs(t.MCS, row_slot(g, 0, t.PM), i);
-                        s_n = t.s[ro];
-                        if (t.infeas) y_n = t.y[ro];
-                        if (g < 6) load_plane(pl, 0, n_n);
-                    }
                     DDP_NOUNROLL
-                    for (int r = 0; r < nr; r++) {
-                        const R sv = s_n, yv = y_n;
-                        R n[4];
-                        if (g < 6) { n[0] = n_n[0]; n[1] = n_n[1]; n[2] = n_n[2]; n[3] = n_n[3]; }
-                        else fixed_row(r, lim, n);
-                        {
-                            const long long ro = row_ofs(t.MCS, row_slot(g, r + 1, t.PM), i);
-                            prefetch_l1(t.s + ro + (ROW_PREFETCH - 1) * ROW_STRIDE);
-                            if (t.infeas) prefetch_l1(t.y + ro + (ROW_PREFETCH - 1) * ROW_STRIDE);
-                            if (r + 1 < nr) {
-                                s_n = t.s[ro];
-                                if (t.infeas) y_n = t.y[ro];
-                                if (g < 6) load_plane(pl, r + 1, n_n);
-                            }
+                    for (int r = 0; r < nrw; r++) {
+                        R sv, yv;
+                        row_stream_next(rows_in, sv, yv);
+                        if (r < nr) {
+                            R n[4];
+                            if (g < 6) { n[0] = n_n[0]; n[1] = n_n[1]; n[2] = n_n[2]; n[3] = n_n[3]; }
+                            else fixed_row(r, lim, n);
+                            if (g < 6 && r + 1 < nr) load_plane(pl, r + 1, n_n);
+                            const R c = ((n[0] * cp[0] + n[1] * cp[1]) + n[2] * cp[2]) + n[3] - t.margin;
+                            const R tc = (n[0] * cd[0] + n[1] * cd[1]) + n[2] * cd[2];
+                            R Ds, gw;
+                            row_weights(t.infeas, t.mu, sgn, c, sv, yv, Ds, gw, emu, ecy);
+                            M[0] += Ds * (n[0] * n[0]); M[1] += Ds * (n[0] * n[1]); M[2] += Ds * (n[0] * n[2]);
+                            M[3] += Ds * (n[1] * n[1]); M[4] += Ds * (n[1] * n[2]); M[5] += Ds * (n[2] * n[2]);
+                            const R dt = Ds * tc, gtc = gw * tc;
+                            wv[0] += dt * n[0]; wv[1] += dt * n[1]; wv[2] += dt * n[2];
+                            gv[0] += gw * n[0]; gv[1] += gw * n[1]; gv[2] += gw * n[2];
+                            tt += dt * tc; gt += gtc;
                         }
-                        const R c = ((n[0] * cp[0] + n[1] * cp[1]) + n[2] * cp[2]) + n[3] - t.margin;
-                        const R tc = (n[0] * cd[0] + n[1] * cd[1]) + n[2] * cd[2];
-                        R Ds, gw;
-                        row_weights(t.infeas, t.mu, sgn, c, sv, yv, Ds, gw, emu, ecy);
-                        M[0] += Ds * (n[0] * n[0]); M[1] += Ds * (n[0] * n[1]); M[2] += Ds * (n[0] * n[2]);
-                        M[3] += Ds * (n[1] * n[1]); M[4] += Ds * (n[1] * n[2]); M[5] += Ds * (n[2] * n[2]);
-                        const R dt = Ds * tc, gtc = gw * tc;
-                        wv[0] += dt * n[0]; wv[1] += dt * n[1]; wv[2] += dt * n[2];
-                        gv[0] += gw * n[0]; gv[1] += gw * n[1]; gv[2] += gw * n[2];
-                        tt += dt * tc; gt += gtc;
                     }
+                    if (g + 1 < 6 && P > 0) load_plane(pl, 0, n_n);   // first plane of the next position group
                     if (g < 6) {
                         DDP_UNROLL
                         for (int e = 0; e < 6; e++) msc[(g * 6 + e) * 32] = M[e];
@@ -666,11 +658,12 @@ template <class R> DDP_DEVICE_NOINLINE void lin_unit(const JobCtx<R> *cp_, int u
                         for (int a = 0; a < 3; a++) { accT[l * 3 + a] += b[l] * wv[a]; accG[l * 3 + a] += b[l] * gv[a]; }
                     }
                 }
-                {   // the time row -T + 0.3 <= 0 (ddp.cpp:1279): Jacobian -1 in the T entry only
-                    const long long ro = row_ofs(t.MCS, 6 * t.PM + 54, i);
-                    R Ds, gw;
-                    row_weights(t.infeas, t.mu, sgn, -z[9] + R(0.3) - t.margin, t.s[ro], t.infeas ? t.y[ro] : R(1), Ds, gw, emu, ecy);
+                {   // the time row -T + 0.3 <= 0 (ddp.cpp:1279): Jacobian -1 in the T entry only; its slack is the stream's next row
+                    R sv, yv, Ds, gw;
+                    row_stream_next(rows_in, sv, yv);
+                    row_weights(t.infeas, t.mu, sgn, -z[9] + R(0.3) - t.margin, sv, yv, Ds, gw, emu, ecy);
                     tt += Ds; gt -= gw;
+                    cp_wait<0>();   // the stream's look-ahead copies (rows past the block) land before the staging area is reused
                 }
                 errs(lane, 0) = emu; errs(lane, 1) = ecy;
                 // ---- stage cost (ddp.cpp:1338-1368): quu = w [R (x) I, R'u; (R'u)^T, .], qu = w [R u; .] --------
@@ -767,7 +760,7 @@ template <class R> DDP_DEVICE_NOINLINE void lin_unit(const JobCtx<R> *cp_, int u
 // ---- job board protocol (GPU only; the CPU emulation runs every unit in the owner) --------------------------------
 // One unit of the line-search rows (defined below): per-lane partials of units u0 .. u1-1 into part / badk.
 template <class R>
-DDP_DEVICE_NOINLINE void rows_unit(const JobCtx<R> *cp_, int u0, int u1, int lane_, Reg<R, 16> &part, Reg<int, 4> &badk);
+DDP_DEVICE_NOINLINE void rows_unit(const JobCtx<R> *cp_, int u0, int u1, int lane_, Reg<R, 16> &part, Reg<int, 4> &badk, R *smw);
 
 #if DDP_GPU
 // Claim the next unit of the job currently posted on `b` (any job when want_seq == 0): returns the unit or -1.
@@ -797,7 +790,7 @@ template <class R> DDP_DEVICE_NOINLINE void job_run_unit(JobBoard<R> *b, int u, 
     } else {
         Reg<R, 16> part;
         Reg<int, 4> badk;
-        rows_unit(&b->ctx, u, u + 1, lane_, part, badk);
+        rows_unit(&b->ctx, u, u + 1, lane_, part, badk, smw);
         DDP_UNROLL
         for (int e = 0; e < 4; e++) {
             if (e == u) {
@@ -888,7 +881,7 @@ template <class R> DDP_DEVICE void run_rows(Traj<R> &t, const JobCtx<R> &ctx, Re
         return;
     }
 #endif
-    rows_unit(&ctx, 0, 4, lane_, part, badk);
+    rows_unit(&ctx, 0, 4, lane_, part, badk, t.sm);
 }
 
 // Linearisation of the whole trajectory as a job of one unit per 32 knots (idle warps of the CTA available).
@@ -1456,8 +1449,9 @@ template <class R> DDP_DEVICE_NOINLINE void stage_knot(R *slot, const R *K, cons
 // part(3u..3u+2) = {stage cost, sum log(barrier argument), |c + y|_1}, badk(u) = this lane's knot if it fails the
 // fraction-to-boundary rule (ddp.cpp:683-687 / :699-703), else 0x7fffffff.
 template <class R>
-DDP_DEVICE_NOINLINE void rows_unit(const JobCtx<R> *cp_, int u0, int u1, int lane_, Reg<R, 16> &part, Reg<int, 4> &badk) {
+DDP_DEVICE_NOINLINE void rows_unit(const JobCtx<R> *cp_, int u0, int u1, int lane_, Reg<R, 16> &part, Reg<int, 4> &badk, R *smw) {
     (void)lane_;
+    smw = as_shared(smw);   // staging area of the warp that RUNS the unit (owner or helper)
     const JobCtx<R> c = *cp_;
     const RowCtx<R> t = row_global(c.row);
     const int N = c.N, time_power = c.time_power;
@@ -1490,10 +1484,15 @@ DDP_DEVICE_NOINLINE void rows_unit(const JobCtx<R> *cp_, int u0, int u1, int lan
             TrialAcc<R> A;
             A.lg.lp = R(1); A.lg.lsum = R(0); A.e1 = R(0); A.bad = 0; A.cmax = R(-INFINITY);
             R q_cost = R(0);
+            // slack rows of the unit's groups through the cp.async row stream (RowStream): all row slots in storage order
+            RowStream<R> rows_in;
+            row_stream_start(rows_in, t, smw, i, lane, row_slot(4 * u0, 0, t.PM));
+            R n_n[4] = {R(0), R(0), R(0), R(0)};   // plane of the next row, loaded one row ahead
+            if (4 * u0 < 6 && P > 0) load_plane(pl, 0, n_n);
             DDP_NOUNROLL
             for (int g = 4 * u0; g < 16 && g < 4 * u1; g++) {   // g = 15: the time row and the stage cost
                 if (g < 15) {   // one copy of the row code for all groups (see lin_unit)
-                    const int shift = group_shift(g), nr = g < 6 ? P : 6;
+                    const int shift = group_shift(g), nr = g < 6 ? P : 6, nrw = g < 6 ? t.PM : 6;
                     const R lim = g < 11 ? t.max_vel : t.max_acc;
                     R b[6], bd[6], bn[6], co[3], cd[3], cn[3], j1[3], j2[3];
                     basis_row_rt(tab + g * 6, shift, tpo, b);
@@ -1504,39 +1503,30 @@ DDP_DEVICE_NOINLINE void rows_unit(const JobCtx<R> *cp_, int u0, int u1, int lan
                         co[a] = dot_axis<R, 0>(b, zo, a); cd[a] = dot_axis<R, 0>(bd, zo, a); cn[a] = dot_axis<R, 0>(bn, zn, a);
                         j1[a] = dot_axis<R, 3>(b, v1, a); j2[a] = dot_axis<R, 0>(b, v2, a);
                     }
-                    R s_n = R(0), y_n = R(1), n_n[4] = {R(0), R(0), R(0), R(0)};   // one-deep pipeline, see lin_unit
-                    if (nr > 0) {
-                        const long long ro = row_ofs(t.MCS, row_slot(g, 0, t.PM), i);
-                        s_n = t.s[ro];
-                        if (t.infeas) y_n = t.y[ro];
-                        if (g < 6) load_plane(pl, 0, n_n);
-                    }
                     DDP_NOUNROLL
-                    for (int r = 0; r < nr; r++) {
-                        const R sv = s_n, yv = y_n;
-                        const long long ro_cur = row_ofs(t.MCS, row_slot(g, r, t.PM), i);
-                        R n[4];
-                        if (g < 6) { n[0] = n_n[0]; n[1] = n_n[1]; n[2] = n_n[2]; n[3] = n_n[3]; }
-                        else fixed_row(r, lim, n);
-                        prefetch_l1(t.s + ro_cur + ROW_PREFETCH * ROW_STRIDE);
-                        if (t.infeas) prefetch_l1(t.y + ro_cur + ROW_PREFETCH * ROW_STRIDE);
-                        if (r + 1 < nr) {
-                            const long long ro = ro_cur + ROW_STRIDE;
-                            s_n = t.s[ro];
-                            if (t.infeas) y_n = t.y[ro];
-                            if (g < 6) load_plane(pl, r + 1, n_n);
+                    for (int r = 0; r < nrw; r++) {
+                        R sv, yv;
+                        row_stream_next(rows_in, sv, yv);
+                        if (r < nr) {
+                            const long long ro_cur = row_ofs(t.MCS, row_slot(g, r, t.PM), i);
+                            R n[4];
+                            if (g < 6) { n[0] = n_n[0]; n[1] = n_n[1]; n[2] = n_n[2]; n[3] = n_n[3]; }
+                            else fixed_row(r, lim, n);
+                            if (g < 6 && r + 1 < nr) load_plane(pl, r + 1, n_n);
+                            const R cold = ((n[0] * co[0] + n[1] * co[1]) + n[2] * co[2]) + n[3] - t.margin;
+                            const R cnew = ((n[0] * cn[0] + n[1] * cn[1]) + n[2] * cn[2]) + n[3] - t.margin;
+                            const R tc = (n[0] * cd[0] + n[1] * cd[1]) + n[2] * cd[2];
+                            const R jv1 = ((n[0] * j1[0] + n[1] * j1[1]) + n[2] * j1[2]) + tc * v1[9];
+                            const R jv2 = ((n[0] * j2[0] + n[1] * j2[1]) + n[2] * j2[2]) + tc * v2[9];
+                            trial_row(t, ro_cur, sv, yv, cold, cnew, jv1, jv2, alpha, tau, A);
                         }
-                        const R cold = ((n[0] * co[0] + n[1] * co[1]) + n[2] * co[2]) + n[3] - t.margin;
-                        const R cnew = ((n[0] * cn[0] + n[1] * cn[1]) + n[2] * cn[2]) + n[3] - t.margin;
-                        const R tc = (n[0] * cd[0] + n[1] * cd[1]) + n[2] * cd[2];
-                        const R jv1 = ((n[0] * j1[0] + n[1] * j1[1]) + n[2] * j1[2]) + tc * v1[9];
-                        const R jv2 = ((n[0] * j2[0] + n[1] * j2[1]) + n[2] * j2[2]) + tc * v2[9];
-                        trial_row(t, ro_cur, sv, yv, cold, cnew, jv1, jv2, alpha, tau, A);
                     }
+                    if (g + 1 < 6 && P > 0) load_plane(pl, 0, n_n);   // first plane of the next position group
                 } else {
                     const long long ro = row_ofs(t.MCS, 6 * t.PM + 54, i);
-                    trial_row(t, ro, t.s[ro], t.infeas ? t.y[ro] : R(1), -zo[9] + R(0.3) - t.margin, -zn[9] + R(0.3) - t.margin, -v1[9],
-                              -v2[9], alpha, tau, A);
+                    R sv, yv;
+                    row_stream_next(rows_in, sv, yv);
+                    trial_row(t, ro, sv, yv, -zo[9] + R(0.3) - t.margin, -zn[9] + R(0.3) - t.margin, -v1[9], -v2[9], alpha, tau, A);
                     // stage cost q(x,u), ddp.cpp:1294-1305
                     R m[9], mu9[9];
                     rmat<R>(0, tpn, m);
@@ -1558,6 +1548,7 @@ DDP_DEVICE_NOINLINE void rows_unit(const JobCtx<R> *cp_, int u0, int u1, int lan
                     A.lg.lp = R(1); A.lg.lsum = R(0); A.e1 = R(0); A.bad = 0; A.cmax = R(-INFINITY);
                 }
             }
+            cp_wait<0>();   // the stream's look-ahead copies land before anybody reuses the staging area
         }
     }
 }
