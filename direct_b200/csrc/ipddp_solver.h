@@ -303,6 +303,24 @@ DDP_DEVICE int row_slot(int g, int r, int PM) { return g < 6 ? g * PM + r : 6 * 
 #define DDP_ROW_PREFETCH 3
 #endif
 enum { ROW_PREFETCH = DDP_ROW_PREFETCH };   // rows ahead
+// Unrolling of the row loops (rows of a knot are independent but for a running product and two maxima, and one row is one
+// long dependent fp64 chain): SOLO = the loops of a warp working alone (the bulk of a batch, eight warps per SM share the
+// instruction cache), COOP = the loops of the job units that only run when warps are idle (the tail of a batch).
+#ifndef DDP_ROW_UNROLL_SOLO
+#define DDP_ROW_UNROLL_SOLO 1
+#endif
+#ifndef DDP_ROW_UNROLL_COOP
+#define DDP_ROW_UNROLL_COOP 1
+#endif
+#define DDP_PRAGMA_(x) _Pragma(#x)
+#define DDP_PRAGMA(x) DDP_PRAGMA_(x)
+#if DDP_GPU
+#define DDP_ROWLOOP_SOLO DDP_PRAGMA(unroll DDP_ROW_UNROLL_SOLO)
+#define DDP_ROWLOOP_COOP DDP_PRAGMA(unroll DDP_ROW_UNROLL_COOP)
+#else
+#define DDP_ROWLOOP_SOLO
+#define DDP_ROWLOOP_COOP
+#endif
 // Direction and offset of a velocity / acceleration row: n = +-e_a, d = -limit (ddp.cpp:1238, :1276).
 template <class R> DDP_DEVICE void fixed_row(int r, R lim, R *n) {
     const int a = r >> 1;
@@ -624,7 +642,7 @@ template <class R> DDP_DEVICE_NOINLINE void lin_unit(const JobCtx<R> *cp_, int u
                     DDP_UNROLL
                     for (int a = 0; a < 3; a++) { cp[a] = dot_axis<R, 0>(b, z, a); cd[a] = dot_axis<R, 0>(bd, z, a); }
                     R M[6] = {R(0), R(0), R(0), R(0), R(0), R(0)}, wv[3] = {R(0), R(0), R(0)}, gv[3] = {R(0), R(0), R(0)};
-                    DDP_NOUNROLL
+                    DDP_ROWLOOP_COOP
                     for (int r = 0; r < nrw; r++) {
                         R sv, yv;
                         row_stream_next(rows_in, sv, yv);
@@ -959,7 +977,7 @@ template <class R> DDP_DEVICE_NOINLINE void linearize_solo(Traj<R> &tt_, Reg<R, 
                     DDP_UNROLL
                     for (int a = 0; a < 3; a++) { cp[a] = dot_axis<R, 0>(b, z, a); cd[a] = dot_axis<R, 0>(bd, z, a); }
                     R M[6] = {R(0), R(0), R(0), R(0), R(0), R(0)}, wv[3] = {R(0), R(0), R(0)}, gv[3] = {R(0), R(0), R(0)};
-                    DDP_NOUNROLL
+                    DDP_ROWLOOP_SOLO
                     for (int r = 0; r < nrw; r++) {
                         R sv, yv;
                         row_stream_next(rows_in, sv, yv);
@@ -1296,20 +1314,28 @@ template <class R> DDP_DEVICE_NOINLINE bool riccati(Traj<R> &t, R regadd, Reg<R,
         // The reference backs up with the UNREGULARISED Quu (ddp.cpp:574/:615, :620-627).  With
         // K = -(Quu+rho I)^-1 Qux that equals the Schur complement above minus rho K^T K (and
         // minus rho K^T k for Vx).
-        if (regadd != R(0)) {
-            WARP_SYNC();
+        FOR_LANES(lane) {
+            if (lane >= 10 && lane < 19) {
+                const int b = lane - 10;
+                DDP_UNROLL
+                for (int a = 0; a < 9; a++) sm[Lay::S1 + a * 10 + b] = col(lane, a);   // S[a][b]
+            }
+            if (lane < 10) sm[Lay::FTN + lane] = pre(lane, 0);
+        }
+        if (regadd != R(0)) {   // column b of rho K^T K (and rho K^T k) off the shared-memory copy, one rolled loop over the rows:
+            WARP_SYNC();        // 30 instructions instead of 190 unrolled ones in a kernel that is instruction-cache bound
             FOR_LANES(lane) {
                 if (lane >= 10 && lane < 19) {
-                    const int qc = lane - 9;
+                    const int b = lane - 10, qc = lane - 9;
                     R kq[10];   // this lane's gain column, re-read from shared memory (keeping kx live across the block spilled it)
                     DDP_UNROLL
                     for (int p = 0; p < 10; p++) kq[p] = sm[Lay::KC + p * 10 + qc];
-                    DDP_UNROLL
+                    DDP_NOUNROLL
                     for (int r = 0; r < 9; r++) {
                         R acc = R(0);
                         DDP_UNROLL
                         for (int p = 0; p < 10; p++) acc += sm[Lay::KC + p * 10 + (r + 1)] * kq[p];
-                        col(lane, r) -= regadd * acc;
+                        sm[Lay::S1 + r * 10 + b] -= regadd * acc;
                     }
                     R acc = R(0);
                     DDP_UNROLL
@@ -1319,20 +1345,14 @@ template <class R> DDP_DEVICE_NOINLINE bool riccati(Traj<R> &t, R regadd, Reg<R,
             }
         }
         FOR_LANES(lane) {
-            if (lane >= 10 && lane < 19) {
-                const int b = lane - 10;
-                DDP_UNROLL
-                for (int a = 0; a < 9; a++) sm[Lay::S1 + a * 10 + b] = col(lane, a);   // S[a][b]
-                sm[Lay::VX + b] = col(lane, 9);
-            }
-            if (lane < 10) sm[Lay::FTN + lane] = pre(lane, 0);
+            if (lane >= 10 && lane < 19) sm[Lay::VX + lane - 10] = col(lane, 9);
         }
         WARP_SYNC();
-        FOR_LANES(lane) {   // V[b][a] = (S[a][b] + S[b][a]) / 2, row b of S1 was written by the other lanes
+        FOR_LANES(lane) {   // V[b][a] = (S[a][b] + S[b][a]) / 2 (ddp.cpp:628)
             if (lane >= 10 && lane < 19) {
                 const int b = lane - 10;
                 DDP_UNROLL
-                for (int a = 0; a < 9; a++) sm[Lay::S2 + b * 10 + a] = R(0.5) * (sm[Lay::S1 + b * 10 + a] + col(lane, a));
+                for (int a = 0; a < 9; a++) sm[Lay::S2 + b * 10 + a] = R(0.5) * (sm[Lay::S1 + b * 10 + a] + sm[Lay::S1 + a * 10 + b]);
             }
         }
         WARP_SYNC();
@@ -1503,7 +1523,7 @@ DDP_DEVICE_NOINLINE void rows_unit(const JobCtx<R> *cp_, int u0, int u1, int lan
                         co[a] = dot_axis<R, 0>(b, zo, a); cd[a] = dot_axis<R, 0>(bd, zo, a); cn[a] = dot_axis<R, 0>(bn, zn, a);
                         j1[a] = dot_axis<R, 3>(b, v1, a); j2[a] = dot_axis<R, 0>(b, v2, a);
                     }
-                    DDP_NOUNROLL
+                    DDP_ROWLOOP_COOP
                     for (int r = 0; r < nrw; r++) {
                         R sv, yv;
                         row_stream_next(rows_in, sv, yv);
@@ -1914,7 +1934,7 @@ template <class R> DDP_DEVICE_NOINLINE bool forward_trial_solo(Traj<R> &tt_, R a
                         co[0] = -zo[9]; cn[0] = -Tn; cd[0] = R(0); j1[0] = -v1T; j2[0] = -v2T;
                         co[1] = co[2] = cn[1] = cn[2] = cd[1] = cd[2] = j1[1] = j1[2] = j2[1] = j2[2] = R(0);
                     }
-                    DDP_NOUNROLL
+                    DDP_ROWLOOP_SOLO
                     for (int r = 0; r < nrw; r++) {
                         const long long ro_cur = row_ofs(t.MCS, g < 15 ? row_slot(g, r, t.PM) : 6 * t.PM + 54, i);
 #if DDP_GPU && DDP_ROW_RING
