@@ -177,6 +177,12 @@ enum { RING_BATCH = 4, RING_NB = 3, RING_ROWS = RING_BATCH * RING_NB };
 #endif
 DDP_HD int smem_elems_per_warp(int /*pm*/) { return Lay::TOTAL; }
 
+// Linearisation record of one knot, what the Riccati recursion reads: the symmetric 20 x 20 matrix Hc packed as its lower triangle,
+// row-major (210), then fT (9) and the segment time (1), padded to a multiple of 16 bytes in float and double.  One record is ONE
+// bulk copy (cp.async.bulk) into the recursion's shared-memory ring; the full square used to cost twice the HBM traffic and
+// ten 128-bit loads per lane and knot.
+enum { HREC = 224 };
+DDP_DEVICE constexpr int hpk(int r, int c) { return r >= c ? r * (r + 1) / 2 + c : c * (c + 1) / 2 + r; }
 // Workspace slot layout (elements of Real).  Row arrays (s, y and their trial copies) are stored
 // [row slot][knot] with the knot index padded to a multiple of 32, so lane <-> knot accesses coalesce.
 // Row slots (row_slot below): corridor row (control point j, plane k) -> j*PM+k; then 6 rows per v / a group; time.
@@ -195,7 +201,7 @@ DDP_HD WsLay ws_layout(int N, int PM, int fcap) {
     w.kdx = o; o += (long long)N * 10;
     w.aux = o; o += (long long)N * 12;
     o = (o + 3) & ~3LL;   // H columns are read with 128-bit loads, the row arrays by 16-byte-aligned bulk copies (float: 4 elements)
-    w.H = o; o += (long long)N * 400;
+    w.H = o; o += (long long)N * HREC;
     w.s = o; o += (long long)w.MCS * w.NP;
     w.sn = o; o += (long long)w.MCS * w.NP;
     w.y = o; o += (long long)w.MCS * w.NP;
@@ -592,7 +598,7 @@ template <class R> DDP_HD int coop_smem_bytes(int warps_per_block) {
 // =============================================================================================
 // Backward pass, knot-parallel part (lane <-> knot): everything of ddp.cpp:476-590 that does not depend
 // on the value function.  Per knot it writes the constraint + stage-cost part of the augmented Hessian
-//   Hc = [ H  g ; g^T . ]  (20 x 20, z order [u(9), T, x(9), gradient])  to t.H and  fT = dx+/dT  to t.aux.
+//   Hc = [ H  g ; g^T . ]  (20 x 20, z order [u(9), T, x(9), gradient]), fT = dx+/dT and the segment time as one record (HREC) of t.H.
 // Returns per-lane maxima of |r| and |c+y| in errs (ddp.cpp:636-637).
 // =============================================================================================
 template <class R> DDP_DEVICE_NOINLINE void lin_unit(const JobCtx<R> *cp_, int u, R *smw, int lane_, Reg<R, 2> &errs) {
@@ -604,7 +610,7 @@ template <class R> DDP_DEVICE_NOINLINE void lin_unit(const JobCtx<R> *cp_, int u
     const R w_snap = c.w_snap, w_time = c.w_time;
     const R *DDP_RESTRICT xu = as_global(c.xu);
     R *DDP_RESTRICT Hout = as_global(c.H);
-    R *DDP_RESTRICT auxout = as_global(c.aux);
+    (void)c.aux;
     const R sgn = t.infeas ? R(1) : R(-1);
     {
         const int base = 32 * (c.base + u);
@@ -698,7 +704,7 @@ template <class R> DDP_DEVICE_NOINLINE void lin_unit(const JobCtx<R> *cp_, int u
                 if (time_power == 2) { quT = w_time * z[9] + R(0.5) * w_snap * uRpu; quuTT = w_time + R(0.5) * w_snap * uRppu; }
                 else { quT = R(0.5) * w_time + R(0.5) * w_snap * uRpu; quuTT = R(0.5) * w_snap * uRppu; }
                 // ---- write row/column T and the gradient -------------------------------------------------------
-                R *Hi = Hout + (long long)i * 400;
+                R *Hi = Hout + (long long)i * HREC;
                 DDP_UNROLL
                 for (int l = 0; l < 6; l++) {
                     DDP_UNROLL
@@ -706,17 +712,18 @@ template <class R> DDP_DEVICE_NOINLINE void lin_unit(const JobCtx<R> *cp_, int u
                         const int r = zidx(l, a);
                         R hT = accT[l * 3 + a], gr = accG[l * 3 + a];
                         if (l >= 3) { hT += w_snap * Rpu[r]; gr += w_snap * Ru[r]; }
-                        Hi[r * 20 + 9] = hT; Hi[9 * 20 + r] = hT;
-                        Hi[r * 20 + 19] = gr; Hi[19 * 20 + r] = gr;
+                        Hi[hpk(r, 9)] = hT;
+                        Hi[hpk(r, 19)] = gr;
                     }
                 }
-                Hi[9 * 20 + 9] = quuTT + tt;
-                Hi[9 * 20 + 19] = quT + gt; Hi[19 * 20 + 9] = quT + gt;
-                Hi[19 * 20 + 19] = R(0);
+                Hi[hpk(9, 9)] = quuTT + tt;
+                Hi[hpk(9, 19)] = quT + gt;
+                Hi[hpk(19, 19)] = R(0);
                 R fT[9];
                 ft_vector(tp, z, fT);
                 DDP_UNROLL
-                for (int q = 0; q < 9; q++) auxout[(long long)i * 12 + q] = fT[q];
+                for (int q = 0; q < 9; q++) Hi[210 + q] = fT[q];
+                Hi[219] = z[9];   // the segment time rides along: the recursion needs nothing else of the iterate
                 // ---- pass 2: H[(l,a),(l',a')] = sum_g beta_g[l] beta_g[l'] M_g[a][a'] ------------------------------
                 {   // same-axis blocks: all 15 groups, plus the stage cost w R (x) I on the u coefficients
                     R h0[21], h1[21], h2[21];
@@ -741,9 +748,9 @@ template <class R> DDP_DEVICE_NOINLINE void lin_unit(const JobCtx<R> *cp_, int u
                             R v0 = h0[e], v1 = h1[e], v2 = h2[e];
                             if (la >= 3) { const R q = w_snap * rm[(la - 3) * 3 + (lb - 3)]; v0 += q; v1 += q; v2 += q; }
                             const int r = zidx(la, 0), c = zidx(lb, 0);
-                            Hi[r * 20 + c] = v0; Hi[c * 20 + r] = v0;
-                            Hi[(r + 1) * 20 + c + 1] = v1; Hi[(c + 1) * 20 + r + 1] = v1;
-                            Hi[(r + 2) * 20 + c + 2] = v2; Hi[(c + 2) * 20 + r + 2] = v2;
+                            Hi[hpk(r, c)] = v0;
+                            Hi[hpk(r + 1, c + 1)] = v1;
+                            Hi[hpk(r + 2, c + 2)] = v2;
                         }
                     }
                 }
@@ -761,12 +768,12 @@ template <class R> DDP_DEVICE_NOINLINE void lin_unit(const JobCtx<R> *cp_, int u
                             const int e = pidx(la, lb);
                             const int ra = zidx(la, 0), rb = zidx(lb, 0);
                             // axes (0,1): entries ((la,0),(lb,1)) and ((lb,0),(la,1)) and their transposes; likewise (0,2), (1,2)
-                            Hi[ra * 20 + rb + 1] = h0[e]; Hi[(rb + 1) * 20 + ra] = h0[e];
-                            Hi[rb * 20 + ra + 1] = h0[e]; Hi[(ra + 1) * 20 + rb] = h0[e];
-                            Hi[ra * 20 + rb + 2] = h1[e]; Hi[(rb + 2) * 20 + ra] = h1[e];
-                            Hi[rb * 20 + ra + 2] = h1[e]; Hi[(ra + 2) * 20 + rb] = h1[e];
-                            Hi[(ra + 1) * 20 + rb + 2] = h2[e]; Hi[(rb + 2) * 20 + ra + 1] = h2[e];
-                            Hi[(rb + 1) * 20 + ra + 2] = h2[e]; Hi[(ra + 2) * 20 + rb + 1] = h2[e];
+                            Hi[hpk(ra, rb + 1)] = h0[e];
+                            Hi[hpk(rb, ra + 1)] = h0[e];
+                            Hi[hpk(ra, rb + 2)] = h1[e];
+                            Hi[hpk(rb, ra + 2)] = h1[e];
+                            Hi[hpk(ra + 1, rb + 2)] = h2[e];
+                            Hi[hpk(rb + 1, ra + 2)] = h2[e];
                         }
                     }
                 }
@@ -937,7 +944,7 @@ template <class R> DDP_DEVICE_NOINLINE void linearize_solo(Traj<R> &tt_, Reg<R, 
     const R w_snap = tt_.w_snap, w_time = tt_.w_time;
     const R *DDP_RESTRICT xu = as_global(tt_.xu);
     R *DDP_RESTRICT Hout = as_global(tt_.H);
-    R *DDP_RESTRICT auxout = as_global(tt_.aux);
+
     R *smw = as_shared(tt_.sm);
     const R *tab = as_shared(t.tab);
     const R sgn = t.infeas ? R(1) : R(-1);
@@ -1033,7 +1040,7 @@ template <class R> DDP_DEVICE_NOINLINE void linearize_solo(Traj<R> &tt_, Reg<R, 
                 if (time_power == 2) { quT = w_time * z[9] + R(0.5) * w_snap * uRpu; quuTT = w_time + R(0.5) * w_snap * uRppu; }
                 else { quT = R(0.5) * w_time + R(0.5) * w_snap * uRpu; quuTT = R(0.5) * w_snap * uRppu; }
                 // ---- write row/column T and the gradient -------------------------------------------------------
-                R *Hi = Hout + (long long)i * 400;
+                R *Hi = Hout + (long long)i * HREC;
                 DDP_UNROLL
                 for (int l = 0; l < 6; l++) {
                     DDP_UNROLL
@@ -1041,17 +1048,18 @@ template <class R> DDP_DEVICE_NOINLINE void linearize_solo(Traj<R> &tt_, Reg<R, 
                         const int r = zidx(l, a);
                         R hT = accT[l * 3 + a], gr = accG[l * 3 + a];
                         if (l >= 3) { hT += w_snap * Rpu[r]; gr += w_snap * Ru[r]; }
-                        Hi[r * 20 + 9] = hT; Hi[9 * 20 + r] = hT;
-                        Hi[r * 20 + 19] = gr; Hi[19 * 20 + r] = gr;
+                        Hi[hpk(r, 9)] = hT;
+                        Hi[hpk(r, 19)] = gr;
                     }
                 }
-                Hi[9 * 20 + 9] = quuTT + tt;
-                Hi[9 * 20 + 19] = quT + gt; Hi[19 * 20 + 9] = quT + gt;
-                Hi[19 * 20 + 19] = R(0);
+                Hi[hpk(9, 9)] = quuTT + tt;
+                Hi[hpk(9, 19)] = quT + gt;
+                Hi[hpk(19, 19)] = R(0);
                 R fT[9];
                 ft_vector(tp, z, fT);
                 DDP_UNROLL
-                for (int q = 0; q < 9; q++) auxout[(long long)i * 12 + q] = fT[q];
+                for (int q = 0; q < 9; q++) Hi[210 + q] = fT[q];
+                Hi[219] = z[9];   // the segment time rides along: the recursion needs nothing else of the iterate
                 // ---- pass 2: H[(l,a),(l',a')] = sum_g beta_g[l] beta_g[l'] M_g[a][a'] ------------------------------
                 {   // same-axis blocks: all 15 groups, plus the stage cost w R (x) I on the u coefficients
                     R h0[21], h1[21], h2[21];
@@ -1076,9 +1084,9 @@ template <class R> DDP_DEVICE_NOINLINE void linearize_solo(Traj<R> &tt_, Reg<R, 
                             R v0 = h0[e], v1 = h1[e], v2 = h2[e];
                             if (la >= 3) { const R q = w_snap * rm[(la - 3) * 3 + (lb - 3)]; v0 += q; v1 += q; v2 += q; }
                             const int r = zidx(la, 0), c = zidx(lb, 0);
-                            Hi[r * 20 + c] = v0; Hi[c * 20 + r] = v0;
-                            Hi[(r + 1) * 20 + c + 1] = v1; Hi[(c + 1) * 20 + r + 1] = v1;
-                            Hi[(r + 2) * 20 + c + 2] = v2; Hi[(c + 2) * 20 + r + 2] = v2;
+                            Hi[hpk(r, c)] = v0;
+                            Hi[hpk(r + 1, c + 1)] = v1;
+                            Hi[hpk(r + 2, c + 2)] = v2;
                         }
                     }
                 }
@@ -1096,12 +1104,12 @@ template <class R> DDP_DEVICE_NOINLINE void linearize_solo(Traj<R> &tt_, Reg<R, 
                             const int e = pidx(la, lb);
                             const int ra = zidx(la, 0), rb = zidx(lb, 0);
                             // axes (0,1): entries ((la,0),(lb,1)) and ((lb,0),(la,1)) and their transposes; likewise (0,2), (1,2)
-                            Hi[ra * 20 + rb + 1] = h0[e]; Hi[(rb + 1) * 20 + ra] = h0[e];
-                            Hi[rb * 20 + ra + 1] = h0[e]; Hi[(ra + 1) * 20 + rb] = h0[e];
-                            Hi[ra * 20 + rb + 2] = h1[e]; Hi[(rb + 2) * 20 + ra] = h1[e];
-                            Hi[rb * 20 + ra + 2] = h1[e]; Hi[(ra + 2) * 20 + rb] = h1[e];
-                            Hi[(ra + 1) * 20 + rb + 2] = h2[e]; Hi[(rb + 2) * 20 + ra + 1] = h2[e];
-                            Hi[(rb + 1) * 20 + ra + 2] = h2[e]; Hi[(ra + 2) * 20 + rb + 1] = h2[e];
+                            Hi[hpk(ra, rb + 1)] = h0[e];
+                            Hi[hpk(rb, ra + 1)] = h0[e];
+                            Hi[hpk(ra, rb + 2)] = h1[e];
+                            Hi[hpk(rb, ra + 2)] = h1[e];
+                            Hi[hpk(ra + 1, rb + 2)] = h2[e];
+                            Hi[hpk(rb + 1, ra + 2)] = h2[e];
                         }
                     }
                 }
@@ -1124,13 +1132,18 @@ template <class R> DDP_DEVICE_NOINLINE bool riccati(Traj<R> &t, R regadd, Reg<R,
     const int N = t.N;
     const R *DDP_RESTRICT Hin = as_global(t.H);
     const R *DDP_RESTRICT xu = as_global(t.xu);
-    const R *DDP_RESTRICT aux = as_global(t.aux);
     R *DDP_RESTRICT Kout = as_global(t.K);
     const R w_terminal = t.w_terminal;
     // terminal value function, ddp.cpp:1318-1323: Vx = P (x_N - x_d), Vxx = P = w_terminal I
-    // Nothing inside the knot loop may touch local memory: a local load shares its scoreboard with the global prefetch
-    // of the next knot's columns and would wait for it (profiles/r1h: 16 % of the recursion).  So the by-reference
-    // error accumulator is kept in a local copy and F/G entries are selected, not indexed, per lane.
+    // Nothing inside the knot loop may touch local memory or wait on a global load: the linearisation records (HREC elements per
+    // knot: packed Hessian, fT, segment time) arrive through a three-deep shared-memory ring filled by the copy engine, one
+    // cp.async.bulk per knot issued by lane 0 three knots ahead, completion on the warp's mbarriers (phase word Lay::RP).
+    // The ring sits in MSC behind the multiplier table [0, 200); MSC is idle while the recursion runs.
+    R *tiles = sm + Lay::MSC + HREC;
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(sm + Lay::RB);
+    unsigned rphase = *reinterpret_cast<volatile unsigned *>(sm + Lay::RP);
+    const unsigned rec_bytes = (unsigned)(HREC * sizeof(R));
+    int issued = 0;   // records handed to the copy engine: record k = knot N-1-k, ring slot k % 3
     Reg<R, 1> errl;
     FOR_LANES(lane) {
         errl(lane, 0) = R(0);
@@ -1138,42 +1151,42 @@ template <class R> DDP_DEVICE_NOINLINE bool riccati(Traj<R> &t, R regadd, Reg<R,
             const R v = (e / 10 == e % 10 && e % 10 < 9) ? w_terminal : R(0);
             sm[Lay::S1 + e] = v; sm[Lay::S2 + e] = v;
         }
-        if (lane < 9) {
-            sm[Lay::VX + lane] = w_terminal * (xu[(long long)N * 20 + 10 + lane] - sm[Lay::XD + lane]);
-            sm[Lay::FTN + lane] = aux[(long long)(N - 1) * 12 + lane];
-        }
-        if (lane == 9) sm[Lay::FTN + 9] = xu[(long long)(N - 1) * 20 + 9];
+        if (lane < 9) sm[Lay::VX + lane] = w_terminal * (xu[(long long)N * 20 + 10 + lane] - sm[Lay::XD + lane]);
+        fence_async_all();   // the records (st.global of this warp or of its helpers) and the last generic stores to MSC before the copies
     }
     WARP_SYNC();
-    Reg<R, 20> col, nxt;
-    Reg<R, 1> pre;   // next knot's fT (lanes 0-8) / segment time (lane 9), loaded one knot ahead
     FOR_LANES(lane) {
-        if (lane < 20) load20(Hin + (long long)(N - 1) * 400 + lane * 20, &nxt(lane, 0));
-        else {
-            DDP_UNROLL
-            for (int r = 0; r < 20; r++) nxt(lane, r) = R(0);
+        if (lane == 0) {
+            for (int k = 0; k < 3 && k < N; k++) {
+                mbar_expect_tx(bars + k, rec_bytes);
+                bulk_g2s(tiles + k * HREC, Hin + (long long)(N - 1 - k) * HREC, rec_bytes, bars + k);
+            }
         }
     }
+    issued = N < 3 ? N : 3;
+    Reg<R, 20> col;
     long long knots = 0;
     bool ok = true;
     for (int i = N - 1; i >= 0; i--) {
+        const int slot = (int)(knots % 3);
         knots++;
-        // uniform per-knot data: segment time, F/G, fT (staged in shared memory by the previous iteration)
+        mbar_wait(bars + slot, (rphase >> slot) & 1u);
+        rphase ^= 1u << slot;
+        const R *tile = tiles + slot * HREC;
+        // uniform per-knot data: segment time, F/G, fT
         R tp[6], fg[18], fT[9];
-        time_powers(sm[Lay::FTN + 9], tp);
+        time_powers(tile[219], tp);
         fg_matrix(tp, fg);
         DDP_UNROLL
-        for (int q = 0; q < 9; q++) fT[q] = sm[Lay::FTN + q];
+        for (int q = 0; q < 9; q++) fT[q] = tile[210 + q];
         FOR_LANES(lane) {
-            DDP_UNROLL
-            for (int r = 0; r < 20; r++) col(lane, r) = nxt(lane, r);
-            pre(lane, 0) = R(0);
-            if (i > 0) {   // prefetch the next knot's column, fT and time while this one is eliminated
-                if (lane < 20) load20(Hin + (long long)(i - 1) * 400 + lane * 20, &nxt(lane, 0));
-                // one load through a selected address: two predicated loads into the same register made the second wait
-                // for the first (write-after-write), a full global-load latency per knot (profiles/r1h)
-                const R *psrc = lane < 9 ? aux + (long long)(i - 1) * 12 + lane : xu + (long long)(i - 1) * 20 + 9;
-                if (lane < 10) pre(lane, 0) = *psrc;
+            if (lane < 20) {   // column `lane` of the symmetric matrix out of its packed lower triangle
+                const int tri = lane * (lane + 1) / 2;
+                DDP_UNROLL
+                for (int r = 0; r < 20; r++) col(lane, r) = tile[r >= lane ? r * (r + 1) / 2 + lane : tri + r];
+            } else {
+                DDP_UNROLL
+                for (int r = 0; r < 20; r++) col(lane, r) = R(0);
             }
             if (lane < 20 && lane != 9) {
                 R tj[9];
@@ -1213,10 +1226,19 @@ template <class R> DDP_DEVICE_NOINLINE bool riccati(Traj<R> &t, R regadd, Reg<R,
                 R acc = R(0);
                 DDP_UNROLL
                 for (int q = 0; q < 9; q++) acc += sm[Lay::S2 + p * 10 + q] * fT[q];
-                sm[Lay::XH + p] = sm[Lay::FTN + p] * acc;   // fT[p]: from shared memory, a dynamic register index would be local memory
+                sm[Lay::XH + p] = tile[210 + p] * acc;   // fT[p]: from shared memory, a dynamic register index would be local memory
             }
         }
         WARP_SYNC();
+        if (issued < N) {   // every lane has taken what it needs of this record: its ring slot gets the record three knots on
+            FOR_LANES(lane) {
+                if (lane == 0) {
+                    mbar_expect_tx(bars + slot, rec_bytes);
+                    bulk_g2s(tiles + slot * HREC, Hin + (long long)(N - 1 - issued) * HREC, rec_bytes, bars + slot);
+                }
+            }
+            issued++;
+        }
         FOR_LANES(lane) {
             if (lane == 9) {   // the T column is the T row of the others (the matrix is symmetric)
                 DDP_UNROLL
@@ -1320,7 +1342,6 @@ template <class R> DDP_DEVICE_NOINLINE bool riccati(Traj<R> &t, R regadd, Reg<R,
                 DDP_UNROLL
                 for (int a = 0; a < 9; a++) sm[Lay::S1 + a * 10 + b] = col(lane, a);   // S[a][b]
             }
-            if (lane < 10) sm[Lay::FTN + lane] = pre(lane, 0);
         }
         if (regadd != R(0)) {   // column b of rho K^T K (and rho K^T k) off the shared-memory copy, one rolled loop over the rows:
             WARP_SYNC();        // 30 instructions instead of 190 unrolled ones in a kernel that is instruction-cache bound
@@ -1357,7 +1378,16 @@ template <class R> DDP_DEVICE_NOINLINE bool riccati(Traj<R> &t, R regadd, Reg<R,
         }
         WARP_SYNC();
     }
-    FOR_LANES(lane) { errq(lane, 0) = errl(lane, 0); }
+    for (long long k = knots; k < issued; k++) {   // a failed factorisation leaves records in flight: they land before MSC is reused
+        const int slot = (int)(k % 3);
+        mbar_wait(bars + slot, (rphase >> slot) & 1u);
+        rphase ^= 1u << slot;
+    }
+    FOR_LANES(lane) {
+        errq(lane, 0) = errl(lane, 0);
+        if (lane == 0) *reinterpret_cast<volatile unsigned *>(sm + Lay::RP) = rphase;
+    }
+    WARP_SYNC();
     t.n_bwd_knots += knots;
     return ok;
 }
