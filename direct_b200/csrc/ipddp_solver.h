@@ -155,13 +155,9 @@ struct Lay {
         RI = 574,   // (free: the L D L^T pivots need no scale table)
         MSC = 584,  // per-lane 3x3 blocks M_g of the linearisation: MSC[e*32+lane], e < 63.  During the line search
                     // (no linearisation in flight) the same area holds forward_trial's knot ring [0, 480).
-        // Line search, behind the knot ring [0, 480) and the job partials [512, 1152) of MSC: the slack-row ring of the row
-        // phase (RowRing below).  Offsets are multiples of 16 bytes for float and double.
-        RS = 584 + 1160,            // slack rows s:      RING_ROWS x 32
-        RY = 584 + 1160 + 12 * 32,  // dual slack rows y: RING_ROWS x 32   (ends at 584 + 1928 <= RB)
-        // Behind MSC (the linearisation overwrites all of MSC): the ring's mbarriers, initialised once per kernel launch, and
-        // the phase parity each of them completes next (one word, bit b = barrier b).
-        RB = 584 + 63 * 32,         // RING_NB mbarriers, 8 bytes each
+        // Behind MSC (the linearisation overwrites all of MSC): the warp's three mbarriers, initialised once per kernel launch,
+        // and the phase parity each of them completes next (one word, bit b = barrier b).
+        RB = 584 + 63 * 32,         // three mbarriers, 8 bytes each
         RP = 584 + 63 * 32 + 6,     // phase word (unsigned), inside the 8 elements reserved here for float and double
         // Slack-row staging of the row loops (cp.async, one element per lane and row): CPR_DEPTH rows of s, then of y.  Outside
         // MSC because the linearisation fills all of MSC while its row loop runs.  2 x 88.3 KB -> 2 x 96.5 KB per SM at depth 4: the
@@ -171,10 +167,6 @@ struct Lay {
     };
 };
 enum { CPR_DEPTH = DDP_CPR_DEPTH };   // rows in flight ahead of the row being processed
-enum { RING_BATCH = 4, RING_NB = 3, RING_ROWS = RING_BATCH * RING_NB };
-#ifndef DDP_ROW_RING
-#define DDP_ROW_RING 0   // 1: the line search streams its slack rows through the TMA ring below; measured SLOWER than L1-prefetched global loads, kept for A/B
-#endif
 DDP_HD int smem_elems_per_warp(int /*pm*/) { return Lay::TOTAL; }
 
 // Linearisation record of one knot, what the Riccati recursion reads: the symmetric 20 x 20 matrix Hc packed as its lower triangle,
@@ -184,7 +176,7 @@ DDP_HD int smem_elems_per_warp(int /*pm*/) { return Lay::TOTAL; }
 enum { HREC = 224 };
 DDP_DEVICE constexpr int hpk(int r, int c) { return r >= c ? r * (r + 1) / 2 + c : c * (c + 1) / 2 + r; }
 // Workspace slot layout (elements of Real).  Row arrays (s, y and their trial copies) are stored
-// [row slot][knot] with the knot index padded to a multiple of 32, so lane <-> knot accesses coalesce.
+// [32-knot block][row slot][32] (row_ofs), so lane <-> knot accesses coalesce and a knot's rows are 32 elements apart.
 // Row slots (row_slot below): corridor row (control point j, plane k) -> j*PM+k; then 6 rows per v / a group; time.
 struct WsLay {
     long long xu, xun, K, kdx, aux, H, s, sn, y, yn, filt, total;
@@ -450,9 +442,11 @@ template <class R> DDP_DEVICE RowCtx<R> row_global(RowCtx<R> c) {
 // use.  The row slots of a knot are visited in storage order (row_ofs: 32 elements apart), so the row wanted next is always
 // one pointer step away.  Why not registers: every load of a warp that is in flight on the same scoreboard has to land before
 // the oldest can be consumed, so a register pipeline k rows deep exposes the latency of the row issued LAST (measured: 181 ms
-// against 164 ms, profiles/r2g); cp.async completes through its own group counter and costs no scoreboard.  Why not TMA: see
-// RowRing below (an elected lane, a barrier wait and a warp synchronisation per batch; measured slower).  Each lane reads only
-// what it copied itself, so cp.async.wait_group is all the synchronisation there is.
+// against 164 ms, profiles/r2g); cp.async completes through its own group counter and costs no scoreboard.  Why not TMA here: a
+// cp.async.bulk ring of 12 rows (one elected lane, an mbarrier wait and a warp synchronisation per batch of 4 rows) was built and
+// measured SLOWER than plain loads (172.8 ms against 164.4 ms at B = 4096, 505 against 461 ms at 16 k; profiles/r2e): its extra
+// code pushed the kernel over the instruction-cache cliff.  Each lane reads only what it copied itself, so cp.async.wait_group
+// is all the synchronisation there is.
 template <class R> struct RowStream {
     const R *ps, *py;   // next row to fetch (this lane's knot)
     R *rs;              // this lane's column of the staging area: rs[d * 32] = s, rs[(CPR_DEPTH + d) * 32] = y of ring slot d
@@ -1483,17 +1477,6 @@ DDP_DEVICE void trial_row(const RowCtx<R> &t, long long ro, R sv, R yv, R cold, 
     }
 }
 
-// cp.async of `n` elements (a multiple of 16 bytes, 16-byte aligned on both sides) by the whole warp.
-template <class R> DDP_DEVICE void warp_copy_async(R *dst, const R *src, int n, int lane) {
-    const int chunks = n * (int)sizeof(R) / 16;
-    for (int c = lane; c < chunks; c += 32) cp_async<16>((char *)dst + 16 * c, (const char *)src + 16 * c);
-}
-// Stage knot i of the line search: gains [ku | Ku] (100) and the old point [u; x] (20).
-template <class R> DDP_DEVICE_NOINLINE void stage_knot(R *slot, const R *K, const R *xu, int i, int lane) {
-    warp_copy_async(slot, K + (long long)i * 100, 100, lane);
-    warp_copy_async(slot + 100, xu + (long long)i * 20, 20, lane);
-}
-
 // Units u0 .. u1-1 of the line-search rows of the 32-knot block c.base (lane <-> knot).  Unit u covers the row
 // groups 4u .. 4u+3; the last one (groups 12-14) also takes the time row and the stage cost.  Per unit and lane:
 // part(3u..3u+2) = {stage cost, sum log(barrier argument), |c + y|_1}, badk(u) = this lane's knot if it fails the
@@ -1603,49 +1586,29 @@ DDP_DEVICE_NOINLINE void rows_unit(const JobCtx<R> *cp_, int u0, int u1, int lan
     }
 }
 
-// =============================================================================================
-// Slack-row ring (TMA).  The row phase of a line-search trial walks the 6 PM + 55 row slots of 32 knots (lane <-> knot)
-// and needs, for every row, the 32 slack values s (and dual slacks y in the infeasible phase) of those knots.  Loading them
-// with one LDG per lane and row left the loop waiting on global-memory latency (profiles/r1h: 17 % of all stall samples sit
-// on those loads, L1 prefetch or not).  The row arrays are laid out [32-knot block][row slot][32] (row_ofs), so the rows of a
-// block are one contiguous strip in visit order: ONE lane hands RING_BATCH consecutive rows to the copy engine with a single
-// cp.async.bulk per array (completion on an mbarrier), RING_NB batches = RING_ROWS rows ahead of their use, and the lanes
-// read the values from shared memory.  Everything is warp-uniform: every slot is streamed, also the unused ones of a
-// polytope with fewer than PM planes (the lanes skip the body there).
-// GPU only: the lane-by-lane CPU emulation reads the rows straight from the workspace (same arithmetic).
-// =============================================================================================
+// Once per kernel launch and warp: the three mbarriers (one arrival each: the issuing lane's expect_tx) that the bulk copies of
+// the warp complete on -- the record ring of the Riccati recursion and the knot ring of the line search, never both at once --
+// and their phase word (bit b = parity barrier b completes next).
 #if DDP_GPU
-// Batch number `batch` (rows batch * RING_BATCH ...) of the block at `base` into ring slot batch % RING_NB.
-template <class R> DDP_DEVICE_NOINLINE void ring_issue_batch(const RowCtx<R> &t, R *sm, int base, int batch) {
-    const int first = batch * RING_BATCH;
-    const int n = t.MCS - first < RING_BATCH ? t.MCS - first : RING_BATCH;
-    if (n <= 0 || (threadIdx.x & 31) != 0) return;
-    const int bslot = batch % RING_NB;
-    unsigned long long *bar = reinterpret_cast<unsigned long long *>(as_shared(sm) + Lay::RB) + bslot;
-    const unsigned bytes = (unsigned)n * 32u * (unsigned)sizeof(R);
-    const long long go = row_ofs(t.MCS, first, base);
-    mbar_expect_tx(bar, bytes * (t.infeas ? 2u : 1u));
-    bulk_g2s(as_shared(sm) + Lay::RS + bslot * RING_BATCH * 32, as_global(t.s) + go, bytes, bar);
-    if (t.infeas) bulk_g2s(as_shared(sm) + Lay::RY + bslot * RING_BATCH * 32, as_global(t.y) + go, bytes, bar);
-}
-// Once per kernel launch and warp: the ring's barriers (one arrival each: the issuing lane's expect_tx) and their phase word.
 template <class R> DDP_DEVICE void ring_init(R *sm, int lane_) {
-    if (lane_ < RING_NB) mbar_init(reinterpret_cast<unsigned long long *>(sm + Lay::RB) + lane_, 1);
+    if (lane_ < 3) mbar_init(reinterpret_cast<unsigned long long *>(sm + Lay::RB) + lane_, 1);
     if (lane_ == 0) *reinterpret_cast<unsigned *>(sm + Lay::RP) = 0u;
     fence_async_smem();
     __syncwarp();
 }
-// Start the ring for the 32-knot block at `base` (every copy of the previous block has been consumed): first RING_NB batches
-// in flight.  Called before the block's state recursion so that the rows are there when it ends.
-template <class R> DDP_DEVICE void ring_start(const RowCtx<R> &t, R *sm, int base) {
-    __syncwarp();
-    fence_async_all();    // whatever generic stores last touched the ring area and the st.global that wrote the slack rows (this
-                          // warp's lanes or, through the job board, helper warps) before the copy engine writes / reads them
-    __syncwarp();
-    DDP_NOUNROLL
-    for (int b = 0; b < RING_NB; b++) ring_issue_batch(t, sm, base, b);
-}
 #endif
+// Knot ring of the line search: the gains [ku | Ku] (100) and the old point [u; x] (20) of knot k as two bulk copies into ring
+// slot k % 3 = [K_k | xu_k], issued by lane 0 two knots ahead of the state recursion.  (Round 1 staged them with sixty 16-byte
+// cp.async per knot spread over the lanes: 5 % of the kernel's issue slots, profiles/r2f.)
+template <class R>
+DDP_DEVICE void knot_issue(R *ring, unsigned long long *bars, const R *K, const R *xu, int k, int lane) {
+    if (lane == 0) {
+        R *slot = ring + (k % 3) * 120;
+        mbar_expect_tx(bars + k % 3, (unsigned)(120 * sizeof(R)));
+        bulk_g2s(slot, K + (long long)k * 100, (unsigned)(100 * sizeof(R)), bars + k % 3);
+        bulk_g2s(slot + 100, xu + (long long)k * 20, (unsigned)(20 * sizeof(R)), bars + k % 3);
+    }
+}
 
 // Closed-loop state / control recursion over knots base .. base+nk-1 of a line-search trial (ddp.cpp:689-697, :1062-1067):
 // lanes 0-9 own u, lanes 10-18 own x.  Out of line on purpose: inside forward_trial the register allocator spilled this
@@ -1656,16 +1619,17 @@ DDP_DEVICE_NOINLINE void rollout_block(R *sm, const R *DDP_RESTRICT xu, R *DDP_R
     sm = as_shared(sm);
     xu = as_global(xu); xun = as_global(xun); Kin = as_global(Kin); kdxo = as_global(kdxo);
     R *ring = sm + Lay::MSC;
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(sm + Lay::RB);
+    unsigned rphase = *reinterpret_cast<volatile unsigned *>(sm + Lay::RP);
     Reg<R, 1> xn, xcur;   // local copy: a by-reference Reg lives in local memory and would be re-read after every store
     FOR_LANES(lane) { xn(lane, 0) = R(0); xcur(lane, 0) = xcur_io(lane, 0); }
         for (int i = base; i < base + nk; i++) {
-            const R *slot = ring + (i & 3) * 120;
-            FOR_LANES(lane) {
-                if (i + 3 < N) stage_knot(ring + ((i + 3) & 3) * 120, Kin, xu, i + 3, lane);
-                cp_commit();
-                cp_wait<3>();
+            const R *slot = ring + (i % 3) * 120;
+            FOR_LANES(lane) {   // knot i + 2 into the slot knot i - 1 left (every lane is past the WARP_SYNC that ended it)
+                if (i + 2 < N) knot_issue(ring, bars, Kin, xu, i + 2, lane);
             }
-            WARP_SYNC();
+            mbar_wait(bars + i % 3, (rphase >> (i % 3)) & 1u);
+            rphase ^= 1u << (i % 3);
             FOR_LANES(lane) {
                 if (lane >= 10 && lane < 19) {
                     const R x = xcur(lane, 0);
@@ -1707,7 +1671,24 @@ DDP_DEVICE_NOINLINE void rollout_block(R *sm, const R *DDP_RESTRICT xu, R *DDP_R
             WARP_SYNC();
             FOR_LANES(lane) { xcur(lane, 0) = xn(lane, 0); }
         }
-    FOR_LANES(lane) { xcur_io(lane, 0) = xcur(lane, 0); }
+    FOR_LANES(lane) {
+        xcur_io(lane, 0) = xcur(lane, 0);
+        if (lane == 0) *reinterpret_cast<volatile unsigned *>(sm + Lay::RP) = rphase;
+    }
+    WARP_SYNC();
+}
+// Knots still in flight when a trial ends (two ahead of the last knot processed, `done` knots processed): they land before the
+// ring area is reused.
+template <class R> DDP_DEVICE void knot_ring_drain(R *sm, int N, int done, int lane_) {
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(sm + Lay::RB);
+    unsigned rphase = *reinterpret_cast<volatile unsigned *>(sm + Lay::RP);
+    const int issued = done + 2 < N ? done + 2 : N;
+    for (int k = done; k < issued; k++) {
+        mbar_wait(bars + k % 3, (rphase >> (k % 3)) & 1u);
+        rphase ^= 1u << (k % 3);
+    }
+    FOR_LANES(lane) { if (lane == 0) *reinterpret_cast<volatile unsigned *>(sm + Lay::RP) = rphase; }
+    WARP_SYNC();
 }
 
 // One line-search trial with step size alpha (ddp.cpp:674-734).  The closed-loop state/control recursion
@@ -1730,23 +1711,25 @@ template <class R> DDP_DEVICE_NOINLINE bool forward_trial_coop(Traj<R> &tt_, R a
     long long fwd_knots = 0, cyc_seq = 0;
     Reg<R, 1> xcur;
     Reg<R, 4> acc;  // per-lane partials: stage cost, log barrier, |c+y|_1, max c
-    // Old point and gains of the next knots stream into a 4-deep shared-memory ring by cp.async, three knots ahead of
-    // the recursion (the MSC scratch of the linearisation is free during the line search): slot = [K_i (100) | xu_i (20)].
+    // Old point and gains of the next knots stream into a three-slot shared-memory ring by bulk copies (knot_issue), two knots
+    // ahead of the recursion (the MSC scratch of the linearisation is free during the line search): slot = [K_i (100) | xu_i (20)].
     R *ring = sm + Lay::MSC;
     FOR_LANES(lane) {
         acc(lane, 0) = R(0); acc(lane, 1) = R(0); acc(lane, 2) = R(0); acc(lane, 3) = R(-INFINITY);
         xcur(lane, 0) = (lane >= 10 && lane < 19) ? xu[lane] : R(0);  // xnew[0] = xold[0]
-        DDP_UNROLL
-        for (int d = 0; d < 3; d++) {
-            if (d < N) stage_knot(ring + (d & 3) * 120, Kin, xu, d, lane);
-            cp_commit();
-        }
+        fence_async_all();   // the gains (Riccati's st.global) and the last generic stores to the ring area before the copy engine
     }
+    WARP_SYNC();
+    FOR_LANES(lane) {
+        for (int d = 0; d < 2 && d < N; d++) knot_issue(ring, reinterpret_cast<unsigned long long *>(sm + Lay::RB), Kin, xu, d, lane);
+    }
+    int knots_done = 0;
     bool ok = true;
     for (int base = 0; base < N && ok; base += 32) {
         const int nk = N - base < 32 ? N - base : 32;
         const long long clk_s = ddp_clock();
         rollout_block(sm, xu, xun, Kin, kdxo, N, base, nk, alpha, lane_, xcur);
+        knots_done = base + nk;
         cyc_seq += ddp_clock() - clk_s;
         // ---- rows of knots base .. base+nk-1, lane <-> knot: four units of row groups (run_job) --------------
         {
@@ -1776,6 +1759,7 @@ template <class R> DDP_DEVICE_NOINLINE bool forward_trial_coop(Traj<R> &tt_, R a
     }
     FOR_LANES(lane) { cp_wait<0>(); }   // nothing of the ring / staging may land after this trial
     WARP_SYNC();
+    knot_ring_drain(sm, N, knots_done, lane_);
     tt_.n_fwd_knots += fwd_knots;
 #ifndef DDP_SPEC_PROFILE
     tt_.cyc_seq += cyc_seq;
@@ -1820,35 +1804,33 @@ template <class R> DDP_DEVICE_NOINLINE bool forward_trial_solo(Traj<R> &tt_, R a
     long long fwd_knots = 0, cyc_seq = 0;
     Reg<R, 1> xcur, xn;
     Reg<R, 4> acc;  // per-lane partials: stage cost, log barrier, |c+y|_1, max c
-    // Old point and gains of the next knots stream into a 4-deep shared-memory ring by cp.async, three knots ahead of
-    // the recursion (the MSC scratch of the linearisation is free during the line search): slot = [K_i (100) | xu_i (20)].
+    // Old point and gains of the next knots stream into a three-slot shared-memory ring by bulk copies (knot_issue), two knots
+    // ahead of the recursion (the MSC scratch of the linearisation is free during the line search): slot = [K_i (100) | xu_i (20)].
     R *ring = sm + Lay::MSC;
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(sm + Lay::RB);
+    unsigned rphase = *reinterpret_cast<volatile unsigned *>(sm + Lay::RP);
     FOR_LANES(lane) {
         acc(lane, 0) = R(0); acc(lane, 1) = R(0); acc(lane, 2) = R(0); acc(lane, 3) = R(-INFINITY);
         xcur(lane, 0) = (lane >= 10 && lane < 19) ? xu[lane] : R(0);  // xnew[0] = xold[0]
         xn(lane, 0) = R(0);
-        DDP_UNROLL
-        for (int d = 0; d < 3; d++) {
-            if (d < N) stage_knot(ring + (d & 3) * 120, Kin, xu, d, lane);
-            cp_commit();
-        }
+        fence_async_all();   // the gains (Riccati's st.global) and the last generic stores to the ring area before the copy engine
     }
+    WARP_SYNC();
+    FOR_LANES(lane) {
+        for (int d = 0; d < 2 && d < N; d++) knot_issue(ring, bars, Kin, xu, d, lane);
+    }
+    int knots_done = 0;
     bool ok = true;
-#if DDP_GPU && DDP_ROW_RING
-    unsigned rphase = *reinterpret_cast<volatile unsigned *>(sm + Lay::RP);   // the barriers live as long as the kernel
-    ring_start(t, sm, 0);   // the first rows of block 0 travel while its state recursion runs
-#endif
     for (int base = 0; base < N && ok; base += 32) {
         const int nk = N - base < 32 ? N - base : 32;
         const long long clk_s = ddp_clock();
         for (int i = base; i < base + nk; i++) {
-            const R *slot = ring + (i & 3) * 120;
-            FOR_LANES(lane) {
-                if (i + 3 < N) stage_knot(ring + ((i + 3) & 3) * 120, Kin, xu, i + 3, lane);
-                cp_commit();
-                cp_wait<3>();
+            const R *slot = ring + (i % 3) * 120;
+            FOR_LANES(lane) {   // knot i + 2 into the slot knot i - 1 left (every lane is past the WARP_SYNC that ended it)
+                if (i + 2 < N) knot_issue(ring, bars, Kin, xu, i + 2, lane);
             }
-            WARP_SYNC();
+            mbar_wait(bars + i % 3, (rphase >> (i % 3)) & 1u);
+            rphase ^= 1u << (i % 3);
             FOR_LANES(lane) {
                 if (lane >= 10 && lane < 19) {
                     const R x = xcur(lane, 0);
@@ -1890,6 +1872,7 @@ template <class R> DDP_DEVICE_NOINLINE bool forward_trial_solo(Traj<R> &tt_, R a
             WARP_SYNC();
             FOR_LANES(lane) { xcur(lane, 0) = xn(lane, 0); }
         }
+        knots_done = base + nk;
         cyc_seq += ddp_clock() - clk_s;
         // ---- rows of knots base .. base+nk-1, lane <-> knot; slack rows from the TMA ring (RowRing) ---------------
         Reg<int, 1> badk;
@@ -1921,12 +1904,8 @@ template <class R> DDP_DEVICE_NOINLINE bool forward_trial_solo(Traj<R> &tt_, R a
                 const double *pl = t.planes + (long long)il * t.PM * 4;
                 R n_n[4] = {R(0), R(0), R(0), R(0)};   // plane of the next row, loaded one row ahead
                 if (P > 0) load_plane(pl, 0, n_n);
-#if DDP_GPU && DDP_ROW_RING
-                int cbatch = 0, cin = 0;   // consumer: batch number, row in batch; rphase bit b = parity barrier b completes next
-#else
                 RowStream<R> rows_in;
                 row_stream_start(rows_in, t, sm, i, lane);
-#endif
                 DDP_NOUNROLL
                 for (int g = 0; g < 16; g++) {   // one copy of the row code for all groups (see linearize); g = 15: the time row
                     const int shift = group_shift(g), nr = g < 6 ? P : (g < 15 ? (live ? 6 : 0) : (live ? 1 : 0));
@@ -1967,23 +1946,8 @@ template <class R> DDP_DEVICE_NOINLINE bool forward_trial_solo(Traj<R> &tt_, R a
                     DDP_ROWLOOP_SOLO
                     for (int r = 0; r < nrw; r++) {
                         const long long ro_cur = row_ofs(t.MCS, g < 15 ? row_slot(g, r, t.PM) : 6 * t.PM + 54, i);
-#if DDP_GPU && DDP_ROW_RING
-                        const int cslot = cbatch % RING_NB;
-                        if (cin == 0) {
-#ifdef DDP_RING_DEBUG
-                            mbar_wait_dbg(reinterpret_cast<unsigned long long *>(sm + Lay::RB) + cslot, (rphase >> cslot) & 1u,
-                                          g * 100 + r, cbatch, base);
-#else
-                            mbar_wait(reinterpret_cast<unsigned long long *>(sm + Lay::RB) + cslot, (rphase >> cslot) & 1u);
-#endif
-                            rphase ^= 1u << cslot;
-                        }
-                        const R sv = sm[Lay::RS + (cslot * RING_BATCH + cin) * 32 + lane];
-                        const R yv = t.infeas ? sm[Lay::RY + (cslot * RING_BATCH + cin) * 32 + lane] : R(1);
-#else
                         R sv, yv;
                         row_stream_next(rows_in, sv, yv);
-#endif
                         R n[4];
                         if (g < 6) { n[0] = n_n[0]; n[1] = n_n[1]; n[2] = n_n[2]; n[3] = n_n[3]; }
                         else if (g < 15) fixed_row(r, lim, n);
@@ -1997,13 +1961,6 @@ template <class R> DDP_DEVICE_NOINLINE bool forward_trial_solo(Traj<R> &tt_, R a
                             const R jv2 = ((n[0] * j2[0] + n[1] * j2[1]) + n[2] * j2[2]) + tc * v2T;
                             trial_row(t, ro_cur, sv, yv, cold, cnew, jv1, jv2, alpha, tau, A);
                         }
-#if DDP_GPU && DDP_ROW_RING
-                        if (++cin == RING_BATCH) {   // batch consumed by every lane: its ring rows take the batch RING_NB further on
-                            __syncwarp();
-                            ring_issue_batch(t, sm, base, cbatch + RING_NB);
-                            cin = 0; cbatch++;
-                        }
-#endif
                     }
                     if (g + 1 < 6 && P > 0) load_plane(pl, 0, n_n);   // first plane of the next position group
                     if ((g & 3) == 3 && g < 15) {   // end of unit g / 4 (see rows_unit): bank its partials, restart the accumulators
@@ -2032,16 +1989,13 @@ template <class R> DDP_DEVICE_NOINLINE bool forward_trial_solo(Traj<R> &tt_, R a
         const int first = warp_min_int(badk, 0, lane_);
         if (first != 0x7fffffff) { fwd_knots += first - base + 1; ok = false; }
         else fwd_knots += nk;
-#if DDP_GPU && DDP_ROW_RING
-        if (ok && base + 32 < N) ring_start(t, sm, base + 32);   // the first rows of the next block's ring
-#endif
     }
-    FOR_LANES(lane) { cp_wait<0>(); }   // nothing of the ring / staging may land after this trial
+    FOR_LANES(lane) {   // nothing of the rings / staging may land after this trial
+        cp_wait<0>();
+        if (lane == 0) *reinterpret_cast<volatile unsigned *>(sm + Lay::RP) = rphase;
+    }
     WARP_SYNC();
-#if DDP_GPU && DDP_ROW_RING
-    if (lane_ == 0) *reinterpret_cast<volatile unsigned *>(sm + Lay::RP) = rphase;   // every issued batch has been consumed
-    __syncwarp();
-#endif
+    knot_ring_drain(sm, N, knots_done, lane_);
     tt_.n_fwd_knots += fwd_knots;
 #ifndef DDP_SPEC_PROFILE
     tt_.cyc_seq += cyc_seq;
