@@ -1346,11 +1346,15 @@ template <class R> DDP_DEVICE_NOINLINE bool riccati(Traj<R> &t, R regadd, Reg<R,
                     DDP_UNROLL
                     for (int p = 0; p < 10; p++) kq[p] = sm[Lay::KC + p * 10 + qc];
                     DDP_NOUNROLL
-                    for (int r = 0; r < 9; r++) {
-                        R acc = R(0);
+                    for (int r = 0; r < 9; r += 3) {   // three rows at a time: three independent ten-term chains in flight
+                        R a0 = R(0), a1 = R(0), a2 = R(0);
                         DDP_UNROLL
-                        for (int p = 0; p < 10; p++) acc += sm[Lay::KC + p * 10 + (r + 1)] * kq[p];
-                        sm[Lay::S1 + r * 10 + b] -= regadd * acc;
+                        for (int p = 0; p < 10; p++) {
+                            const R *kr = sm + Lay::KC + p * 10 + (r + 1);
+                            a0 += kr[0] * kq[p]; a1 += kr[1] * kq[p]; a2 += kr[2] * kq[p];
+                        }
+                        R *sr = sm + Lay::S1 + r * 10 + b;
+                        sr[0] -= regadd * a0; sr[10] -= regadd * a1; sr[20] -= regadd * a2;
                     }
                     R acc = R(0);
                     DDP_UNROLL
