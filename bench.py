@@ -175,7 +175,7 @@ def model_b_report(capi, torch, dev, local_rank, flush, steps, with_cpu):
     from direct_b200 import gddp
     B, N = 4096, 100
     # the start / goal distribution BASELINE.md section 3 states (15-25 m transfers), not the 1.5-3.5 m hops of round 1
-    gp = dataclasses.replace(gddp.make_quad_batch(B, N, workload="stated"), tol=1e-5, iter_max=100)
+    gp = dataclasses.replace(gddp.make_quad_batch(B, N, workload="stated"), tol=1e-5)
     solver = capi.Solver(local_rank, "fp32")
     t = {k: torch.from_numpy(getattr(gp, k)).to(dev) for k in ("x0", "xg")}
     o = dict(rtn=torch.zeros(B, dtype=torch.int32, device=dev), iters=torch.zeros(B, dtype=torch.int32, device=dev),
@@ -229,7 +229,7 @@ def model_b_report(capi, torch, dev, local_rank, flush, steps, with_cpu):
         pass
     out = {"workload": f"unconstrained DDP, {B} x {N}-knot 12-state/4-input rigid-body quadrotor (explicit Euler, dt 0.05 -- SURVEY.md 8(d) "
                        "names RK4; the kernel's Jacobian sparsity is Euler's), start at rest in [-10,10]^2 x [0.5,2.5], goal at rest 15-25 m "
-                       "away (BASELINE.md section 3), iter_max 100; model (B) of SURVEY.md 8(d): the reference has no such model, parity "
+                       "away (BASELINE.md section 3), iter_max 50; model (B) of SURVEY.md 8(d): the reference has no such model, parity "
                        "unpinned",
            "dtype": "f32", "value": B / ms * 1e3, "unit": "solves/s", "ms_per_step": ms, "gpu_launches": steps,
            "e2e": {"value": B / e2e_s, "unit": "solves/s", "h2d_bytes_per_step": int(st.h2d_bytes), "d2h_bytes_per_step": int(st.d2h_bytes),
