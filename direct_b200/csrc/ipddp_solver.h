@@ -1,4 +1,4 @@
-// ipddp_solver.h -- warp-per-trajectory interior-point DDP (IPDDP) solve for sm_100a (v2).
+// ipddp_solver.h -- warp-per-trajectory interior-point DDP (IPDDP) solve for sm_100a.
 //
 // One warp owns one trajectory for its whole solve: setup, initial rollout, the outer barrier loop,
 // backward Riccati/IP sweeps, filter line search and output conversion all run inside one kernel
@@ -15,19 +15,23 @@
 //     values, interior-point weights, the constraint + stage-cost part of the Hessian/gradient of Q),
 //     `evaluate_trial` (slack/dual updates, fraction-to-boundary tests, barrier cost of a line-search
 //     trial), `scan_constraints` (filter reset, feasibility count).  SEQUENTIAL phases (lane <-> matrix
-//     column / state element): `riccati` (dynamics term, ten Cholesky pivots, gains, value backup) and
+//     column / state element): `riccati` (dynamics term, ten pivots in five rounds, gains, value backup) and
 //     the closed-loop state rollout inside `forward_trial`.
 //   * No Jacobian is ever materialised: every constraint row is (basis row beta_g(T)) (x) (direction n)
 //     plus a d/dT entry, so c, J*v, J^T*w and J^T D J come from 15 "row groups" (6 position control
 //     points, 5 velocity, 4 acceleration) and the polytope planes.  J^T D J = sum_g (beta_g beta_g^T) (x) M_g
 //     with 3x3 blocks M_g; only the 126 + 38 distinct entries are formed.
 //   * The 19x19 Hessian of Q in z = [u(10); x(9)] plus the gradient as 20th row/column is held one column
-//     per lane; ten right-looking Cholesky pivots over the u block (pivot broadcast by shuffle, multiplier
-//     row through shared memory, next pivot's diagonal sent ahead of the rank-1 update) leave V_xx, V_x
-//     in the trailing block (a Schur complement); the gains come from one back-substitution per lane.
+//     per lane; the ten pivots of the u block are taken two per round as a unit-lower L D L^T (2 x 2 pivot block
+//     broadcast by shuffle, both reciprocals side by side, multipliers through shared memory, one rank-2 update)
+//     and leave V_xx, V_x in the trailing block (a Schur complement); the gains come from one back-substitution per lane.
 //   * Per-knot state streams through a per-warp workspace slot in global memory (row arrays stored
-//     [row][knot] so lane <-> knot accesses coalesce); c and the slack gains ks,Ks,ky,Ky are recomputed
-//     on the fly instead of being stored.
+//     [32-knot block][row slot][32] so lane <-> knot accesses coalesce and a knot's rows are 32 elements apart); c and the
+//     slack gains ks,Ks,ky,Ky are recomputed on the fly instead of being stored.
+//   * Data movement (round 2): whole tiles travel by bulk copies issued by ONE lane (cp.async.bulk + mbarrier: the
+//     linearisation record of a knot into the Riccati recursion, gains + old point of a knot into the line search's state
+//     recursion); the slack rows of the row loops travel by per-lane cp.async four rows ahead (RowStream).  Neither ties up
+//     a scoreboard or a register; what each costs and what was measured slower is in profiles/r2a_kernel_ab_log.md.
 // Arithmetic is re-associated with respect to the reference (documented in DESIGN.md), so results
 // agree with the oracle to rounding, not bit for bit.
 //
@@ -153,8 +157,9 @@ struct Lay {
         FL = 560,   // filter decision (2)
         FTN = 564,  // riccati: fT (9) and segment time (1) of the knot about to be processed, staged one knot ahead
         RI = 574,   // (free: the L D L^T pivots need no scale table)
-        MSC = 584,  // per-lane 3x3 blocks M_g of the linearisation: MSC[e*32+lane], e < 63.  During the line search
-                    // (no linearisation in flight) the same area holds forward_trial's knot ring [0, 480).
+        MSC = 584,  // per-lane 3x3 blocks M_g of the linearisation: MSC[e*32+lane], e < 63.  While no linearisation is in flight
+                    // the same area holds: Riccati - multiplier table [0, 200) and the record ring [224, 896); line search - knot
+                    // ring [0, 360), job partials / feed-forward staging [512, 1152).
         // Behind MSC (the linearisation overwrites all of MSC): the warp's three mbarriers, initialised once per kernel launch,
         // and the phase parity each of them completes next (one word, bit b = barrier b).
         RB = 584 + 63 * 32,         // three mbarriers, 8 bytes each
@@ -294,13 +299,10 @@ template <class R> DDP_DEVICE void basis_row_rt(const R *tabrow, int sd, const R
 // (six rows each, visited +x,-x,+y,-y,+z,-z like ddp.cpp:1228-1272).
 DDP_DEVICE int group_shift(int g) { return g < 6 ? 0 : (g < 11 ? 1 : 2); }
 // Row slot of row r of group g, in VISIT order (the slot order is internal to the workspace): corridor rows g*PM + k,
-// then the six rows of every velocity / acceleration group, then the time row.  The row visited k rows later therefore
-// sits k*NP elements further on (exactly so for g >= 6 or a full polytope), which is what the row loops prefetch.
+// then the six rows of every velocity / acceleration group, then the time row.  The row loops visit every slot in this
+// order (a polytope with fewer than PM planes skips the body on its unused slots), so the row visited next always sits
+// ROW_STRIDE elements further on (row_ofs), which is what RowStream relies on.
 DDP_DEVICE int row_slot(int g, int r, int PM) { return g < 6 ? g * PM + r : 6 * PM + 6 * (g - 6) + r; }
-#ifndef DDP_ROW_PREFETCH
-#define DDP_ROW_PREFETCH 3
-#endif
-enum { ROW_PREFETCH = DDP_ROW_PREFETCH };   // rows ahead
 // Unrolling of the row loops (rows of a knot are independent but for a running product and two maxima, and one row is one
 // long dependent fp64 chain): SOLO = the loops of a warp working alone (the bulk of a batch, eight warps per SM share the
 // instruction cache), COOP = the loops of the job units that only run when warps are idle (the tail of a batch).
@@ -476,18 +478,6 @@ template <class R> DDP_DEVICE void row_stream_next(RowStream<R> &q, R &sv, R &yv
     yv = q.infeas ? q.rs[(CPR_DEPTH + q.slot) * 32] : R(1);
     row_stream_fetch(q, q.slot);
     q.slot = q.slot + 1 == CPR_DEPTH ? 0 : q.slot + 1;
-}
-
-// First row of row group g of knot i into the one-deep pipeline registers (slack, dual slack, plane), issued while the
-// previous group is being finished so that the group's basis rows are computed under the load latency.
-template <class R>
-DDP_DEVICE void first_row_load(const RowCtx<R> &t, const double *pl, int P, int g, int i, R &s_n, R &y_n, R *n_n) {
-    if (g < 15 && (g >= 6 || P > 0)) {
-        const long long ro = row_ofs(t.MCS, row_slot(g, 0, t.PM), i);
-        s_n = t.s[ro];
-        if (t.infeas) y_n = t.y[ro];
-        if (g < 6) load_plane(pl, 0, n_n);
-    }
 }
 
 // Visit every constraint row of knot i at the point z (constraint VALUES only; computecminvo,

@@ -12,7 +12,6 @@
 #include <math.h>
 #include <stdint.h>
 #include <string.h>
-#include <stdio.h>
 
 #if defined(__CUDACC__) && !defined(DDP_EMULATE)
 #define DDP_GPU 1
@@ -135,18 +134,6 @@ template <int N> DDP_DEVICE int warp_min_int(const Reg<int, N> &r, int i, int la
     return x;
 #endif
 }
-// Maximum over the warp of element i (int).
-template <int N> DDP_DEVICE int warp_max_int(const Reg<int, N> &r, int i, int lane_) {
-#if DDP_GPU
-    (void)lane_;
-    return __reduce_max_sync(0xffffffffu, r.v[i]);
-#else
-    (void)lane_;
-    int x = r.v[0][i];
-    for (int l = 1; l < 32; l++) if (r.v[l][i] > x) x = r.v[l][i];
-    return x;
-#endif
-}
 template <int N> DDP_DEVICE bool warp_any(const Reg<int, N> &r, int i, int lane_) {
 #if DDP_GPU
     (void)lane_;
@@ -196,24 +183,6 @@ DDP_DEVICE void bulk_g2s(void *smem_dst, const void *gsrc, unsigned bytes, unsig
                  "l"(__cvta_generic_to_global(gsrc)), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
                  : "memory");
 }
-#ifdef DDP_RING_DEBUG
-// debug build: a bounded poll that reports where it is stuck and traps instead of hanging the kernel
-DDP_DEVICE void mbar_wait_dbg(unsigned long long *bar, unsigned parity, int tag0, int tag1, int tag2) {
-    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
-    for (long long spin = 0;; spin++) {
-        unsigned ok;
-        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
-                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
-        if (ok) return;
-        if (spin > (1ll << 22)) {
-            if ((threadIdx.x & 31) == 0)
-                printf("RING STUCK block %d warp %d bar@%u parity %u state %016llx tags %d %d %d\n", (int)blockIdx.x, (int)(threadIdx.x >> 5), a,
-                       parity, *(volatile unsigned long long *)bar, tag0, tag1, tag2);
-            __trap();
-        }
-    }
-}
-#endif
 DDP_DEVICE void mbar_wait(unsigned long long *bar, unsigned parity) {
     const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
     asm volatile(
@@ -235,13 +204,6 @@ DDP_DEVICE void bulk_g2s(void *smem_dst, const void *gsrc, unsigned bytes, unsig
 DDP_DEVICE void mbar_wait(unsigned long long *, unsigned) {}
 #endif
 
-// Software prefetch of a global line that a later iteration of a row loop will load (no register is tied up).
-#if DDP_GPU
-DDP_DEVICE void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(__cvta_generic_to_global(p))); }
-#else
-DDP_DEVICE void prefetch_l1(const void *) {}
-#endif
-
 // Two consecutive elements at a 2-element-aligned shared/global address as ONE access (128-bit in fp64, 64-bit in fp32).
 template <class T> struct Pair2 { T x, y; };
 #if DDP_GPU
@@ -252,19 +214,6 @@ DDP_DEVICE void st2(float *p, float a, float b) { *reinterpret_cast<float2 *>(p)
 #else
 template <class T> DDP_DEVICE Pair2<T> ld2(const T *p) { return {p[0], p[1]}; }
 template <class T> DDP_DEVICE void st2(T *p, T a, T b) { p[0] = a; p[1] = b; }
-#endif
-
-// 20 consecutive elements (16-byte aligned) into registers: ten 128-bit loads in fp64 on the GPU.
-template <class T> DDP_DEVICE void load20(const T *p, T *out) {
-    DDP_UNROLL
-    for (int r = 0; r < 20; r++) out[r] = p[r];
-}
-#if DDP_GPU
-template <> DDP_DEVICE void load20<double>(const double *p, double *out) {
-    const double2 *q = reinterpret_cast<const double2 *>(p);
-    DDP_UNROLL
-    for (int r = 0; r < 10; r++) { const double2 v = q[r]; out[2 * r] = v.x; out[2 * r + 1] = v.y; }
-}
 #endif
 
 // log(): called rarely (LogProd) but ~100 SASS instructions per inlined fp64 copy; kept out of line so the hot
