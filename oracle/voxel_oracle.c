@@ -131,6 +131,13 @@ int voxel_oracle_inflate_box(const uint8_t *occ, int nx, int ny, int nz, int32_t
 
 int voxel_oracle_cluster(const uint8_t *occ, const uint8_t *inside, uint8_t *use, uint8_t *invalid, int nx, int ny, int nz,
                          int32_t *cluster_xyz, int cluster_num, int cap, int cand_cap, int itr_cluster_max, int *iters_out) {
+    return voxel_oracle_cluster_hostbuf(occ, inside, use, invalid, nx, ny, nz, cluster_xyz, cluster_num, cap, cand_cap, itr_cluster_max,
+                                        iters_out, NULL);
+}
+
+int voxel_oracle_cluster_hostbuf(const uint8_t *occ, const uint8_t *inside, uint8_t *use, uint8_t *invalid, int nx, int ny, int nz,
+                                 int32_t *cluster_xyz, int cluster_num, int cap, int cand_cap, int itr_cluster_max, int *iters_out,
+                                 uint8_t *host_can_can) {
     const int yz = ny * nz;
     int32_t *active = (int32_t *)malloc(sizeof(int32_t) * 3 * (size_t)(cand_cap > cluster_num ? cand_cap : cluster_num));
     int32_t *cand = (int32_t *)malloc(sizeof(int32_t) * 3 * (size_t)cand_cap);
@@ -158,6 +165,11 @@ int voxel_oracle_cluster(const uint8_t *occ, const uint8_t *inside, uint8_t *use
         if (status) break;
         if (C == 0) break;   /* :652 */
         voxel_oracle_convex_test(occ, inside, ny, nz, cand, C, cluster_xyz, cluster_num, can_can, can_clu);
+        const uint8_t *cc = can_can;
+        if (host_can_can) {   /* the reference's download, :677-682: C (C - 1) / 2 entries, one candidate row short */
+            memcpy(host_can_can, can_can, (size_t)C * ((size_t)C - 1) / 2);
+            cc = host_can_can;
+        }
         memset(accepted, 0, (size_t)C);
         active_num = 0;
         for (int i = 0; i < C; i++) {   /* :693-737 */
@@ -165,7 +177,7 @@ int voxel_oracle_cluster(const uint8_t *occ, const uint8_t *inside, uint8_t *use
             if (!can_clu[i]) convex = 0;
             else {
                 long long bias = (long long)(i + 1) * i / 2;
-                for (int j = 0; j < i; j++) if (!can_can[bias + j] && accepted[j]) { convex = 0; break; }
+                for (int j = 0; j < i; j++) if (!cc[bias + j] && accepted[j]) { convex = 0; break; }
             }
             int x = cand[3 * i], y = cand[3 * i + 1], z = cand[3 * i + 2];
             if (convex) {
@@ -188,6 +200,13 @@ int voxel_oracle_cluster(const uint8_t *occ, const uint8_t *inside, uint8_t *use
 int voxel_oracle_polytope(const uint8_t *occ, int nx, int ny, int nz, const int32_t seed[3], int itr_inflate_max, int itr_cluster_max,
                           int cap, int cand_cap, int32_t *cluster_xyz, int32_t *v, int *iters, uint8_t *inside, uint8_t *use,
                           uint8_t *invalid) {
+    return voxel_oracle_polytope_hostbuf(occ, nx, ny, nz, seed, itr_inflate_max, itr_cluster_max, cap, cand_cap, cluster_xyz, v, iters,
+                                         inside, use, invalid, NULL);
+}
+
+int voxel_oracle_polytope_hostbuf(const uint8_t *occ, int nx, int ny, int nz, const int32_t seed[3], int itr_inflate_max,
+                                  int itr_cluster_max, int cap, int cand_cap, int32_t *cluster_xyz, int32_t *v, int *iters,
+                                  uint8_t *inside, uint8_t *use, uint8_t *invalid, uint8_t *host_can_can) {
     const int yz = ny * nz;
     const size_t cells = (size_t)nx * ny * nz;
     memset(use, 0, cells); memset(invalid, 0, cells); memset(inside, 0, cells);   /* flagClear, :39-45 */
@@ -224,5 +243,6 @@ int voxel_oracle_polytope(const uint8_t *occ, int nx, int ny, int nz, const int3
     }
     for (int i = 0; i < n; i++) inside[cluster_xyz[3 * i] * yz + cluster_xyz[3 * i + 1] * nz + cluster_xyz[3 * i + 2]] = 0;   /* :889-892 */
     if (abs(v[7] - v[1]) == 0 || abs(v[8 + 7] - v[8 + 1]) == 0 || abs(v[16 + 7] - v[16 + 1]) == 0) return n;   /* :911-920 */
-    return voxel_oracle_cluster(occ, inside, use, invalid, nx, ny, nz, cluster_xyz, n, cap, cand_cap, itr_cluster_max, &iters[1]);
+    return voxel_oracle_cluster_hostbuf(occ, inside, use, invalid, nx, ny, nz, cluster_xyz, n, cap, cand_cap, itr_cluster_max, &iters[1],
+                                        host_can_can);
 }

@@ -37,6 +37,18 @@ int voxel_oracle_polytope(const uint8_t *occ, int nx, int ny, int nz, const int3
                           int cap, int cand_cap, int32_t *cluster_xyz, int32_t *vertex_idx, int *iters, uint8_t *inside, uint8_t *use,
                           uint8_t *invalid);
 
+/* The same two functions with the reference's stale read reproduced, for the comparison with its own host loop
+ * (oracle/_ref/libvoxel_server_ref.so): host_can_can [cand_cap (cand_cap + 1) / 2] plays the reference's pinned h_can_can_result, which
+ * lives as long as the generator object: every iteration copies the first C (C - 1) / 2 entries of the kernels' output into it
+ * (cluster_server.cu:677-682) and the acceptance scan reads entry i (i + 1) / 2 + j of it (:700-707), so the row of the LAST candidate
+ * is whatever an earlier iteration or call left there (zeros in a fresh buffer).  NULL = the functions above. */
+int voxel_oracle_cluster_hostbuf(const uint8_t *occ, const uint8_t *inside, uint8_t *use, uint8_t *invalid, int nx, int ny, int nz,
+                                 int32_t *cluster_xyz, int cluster_num, int cap, int cand_cap, int itr_cluster_max, int *iters_out,
+                                 uint8_t *host_can_can);
+int voxel_oracle_polytope_hostbuf(const uint8_t *occ, int nx, int ny, int nz, const int32_t seed[3], int itr_inflate_max,
+                                  int itr_cluster_max, int cap, int cand_cap, int32_t *cluster_xyz, int32_t *vertex_idx, int *iters,
+                                  uint8_t *inside, uint8_t *use, uint8_t *invalid, uint8_t *host_can_can);
+
 #ifdef __cplusplus
 }
 #endif

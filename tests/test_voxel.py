@@ -356,6 +356,34 @@ def test_gpu_polytope_matches_oracle(solver):
         X.polytope(solver, cases[0][0], cases[0][1], 20, 3, 100, 8000)         # cluster capacity below the box's boundary
 
 
+@pytest.mark.gpu
+@pytest.mark.skipif(not V.ref_server_available(), reason="oracle/_ref/libvoxel_server_ref.so (the reference's host loop) did not travel")
+def test_gpu_polytope_against_the_references_own_host_loop(solver):
+    """cudaPolytopeGeneration::polygonGeneration itself (cluster_server.cu:769-966, compiled unmodified with its kernels for sm_100a, ROS
+    reduced to a stopwatch) against the oracle and direct_voxel_polytope.  The reference reads the can_can row of the LAST candidate of
+    every iteration from host bytes its download never wrote; with that stale read reproduced (oracle, host_can_can) the oracle returns
+    the reference's cluster voxel for voxel, call after call on one generator object; without it the oracle is direct_voxel_polytope
+    (test_gpu_polytope_matches_oracle).  So the product and the reference differ by that read and nothing else."""
+    grew = differ = 0
+    cases = [(X.make_map(shape, pillars, mseed, clear=(*cell, 2)), cell, inf, clu) for shape, pillars, mseed, cell, inf, clu in POLY_CASES]
+    cases.append((_slab_map(), (10, 10, 3), 20, 5))
+    for occ, cell, inf, clu in cases:
+        refs, _ = V.ref_server_polytope(occ, cell, inf, clu, reps=3)
+        host = V.reference_host_buffer(10000)
+        for k, ref in enumerate(refs):   # the buffer lives as long as the generator: later calls see what earlier ones left
+            o = V.polytope(occ, cell, inf, clu, 50000, 10000, host_can_can=host)
+            assert np.array_equal(o["cluster"], ref), (occ.shape, cell, k, len(o["cluster"]), len(ref))
+        g = X.polytope(solver, occ, cell, inf, clu, 50000, 10000)
+        assert np.array_equal(g["cluster"], V.polytope(occ, cell, inf, clu, 50000, 10000)["cluster"])
+        grew += g["iters"][1] > 0
+        differ += not np.array_equal(g["cluster"], refs[0])
+        if np.array_equal(g["vertex_idx"], o["vertex_idx"]):   # same box, same initial cluster
+            n0 = len(X.cube_shell(occ.shape, g["vertex_idx"])[2])
+            assert np.array_equal(g["cluster"][:n0], refs[0][:n0])
+    assert grew >= 3       # the cases do run clustering iterations, not only the box
+    assert differ >= 1     # and the stale read is exercised (the corner case loses its last candidate in the reference)
+
+
 def test_closed_form_boundary_rank_of_cube_shell_kernel():
     """cube_shell_kernel (direct_b200/csrc/voxel.cuh) places a boundary voxel of the inflated box at its position in the reference's
     x, y, z scan (cluster_server.cu:848-886) by a closed form instead of a compaction pass.  The same formula, stated here in Python,

@@ -88,6 +88,26 @@ assert np.array_equal(pg["cluster"], clu)
 rep["polytope"] = {"voxels": int(len(pg["cluster"])), "iters": pg["iters"], "device_ms": best, "host_call_ms": wall * 1e3}
 print(f"polytope (polygonGeneration, seed {cell}): {len(pg['cluster'])} voxels, {pg['iters'][0]} inflation + {pg['iters'][1]} clustering iterations: "
       f"{best:.3f} ms on the device, {wall * 1e3:.1f} ms for the host call (map upload, cluster download)")
+# 5. the same call through the reference's own host loop (cluster_server.cu compiled unmodified; inflation on the host, clustering with
+#    per-iteration uploads, two kernels, downloads and the acceptance scan on the host): wall time of polygonGeneration alone
+if V.ref_server_available():
+    import os
+    fd = os.dup(1); dn = os.open(os.devnull, os.O_WRONLY); os.dup2(dn, 1)   # the reference prints a line per call
+    try:
+        refs, rsec = V.ref_server_polytope(occ, cell, 20, a.itr, reps=a.reps)
+    finally:
+        os.dup2(fd, 1); os.close(dn); os.close(fd)
+    host = V.reference_host_buffer(10000)
+    emu = [V.polytope(occ, cell, 20, a.itr, 50000, 10000, host_can_can=host)["cluster"] for _ in refs] if shape[0] * shape[1] * shape[2] <= 200 * 200 * 40 and a.itr <= 3 else None
+    same = bool(np.array_equal(refs[0], pg["cluster"]))
+    rep["polytope"].update({"reference_host_loop_ms": rsec * 1e3, "speedup_device": rsec * 1e3 / best, "speedup_host_call": rsec / wall,
+                            "identical_to_reference_host_loop": same})
+    print(f"   reference's polygonGeneration on the same map and seed: {rsec * 1e3:.2f} ms per call, {len(refs[0])} voxels, "
+          f"{'identical cluster, same order' if same else 'cluster differs (stale last-row read of the reference, DESIGN.md 3.7)'}: "
+          f"{rsec * 1e3 / best:.1f}x the device time, {rsec / wall:.1f}x the host call")
+    if emu is not None:
+        assert all(np.array_equal(e, r) for e, r in zip(emu, refs))
+        print("   = CPU oracle with the reference's stale read reproduced, every call")
 if a.out:
     json.dump(rep, open(a.out, "w"), indent=1)
 s.close()
