@@ -50,7 +50,7 @@ class Stats(C.Structure):
                 ("kernel_launches", C.c_int64), ("grid_blocks", C.c_int), ("block_threads", C.c_int),
                 ("smem_bytes_per_block", C.c_int), ("workspace_slots", C.c_int), ("h2d_bytes", C.c_int64),
                 ("d2h_bytes", C.c_int64), ("coop_jobs", C.c_int64), ("helper_units", C.c_int64),
-                ("spec_searches", C.c_int64), ("spec_trials", C.c_int64)]
+                ("spec_searches", C.c_int64), ("spec_trials", C.c_int64), ("spec_sweeps", C.c_int64), ("spec_sweeps_used", C.c_int64)]
 
 
 class CorridorC(C.Structure):

@@ -261,6 +261,8 @@ template <class R> int launch(H *h, SolveArgs &A, cudaStream_t s) {
         A.coop = (e && atoi(e) == 0) ? 0 : 1;
         e = getenv("DIRECT_DDP_GSPEC");              // tuning knob: 0 disables the speculative line search of the tail
         A.gspec = (e && atoi(e) == 0) ? 0 : A.coop;
+        e = getenv("DIRECT_DDP_SPEC");               // tuning knob: 0 disables the speculative backward sweep of the tail
+        A.spec = (e && atoi(e) == 0) ? 0 : A.coop;
     }
     A.gboards = nullptr; A.gwords = nullptr;
     if (A.gspec) {
@@ -722,6 +724,7 @@ int direct_ddp_last_stats(direct_ddp_handle h, direct_ddp_stats *out) {
         out->kernel_launches += q.kernel_launches; out->grid_blocks += q.grid_blocks; out->workspace_slots += q.workspace_slots;
         out->h2d_bytes += q.h2d_bytes; out->d2h_bytes += q.d2h_bytes; out->coop_jobs += q.coop_jobs; out->helper_units += q.helper_units;
         out->spec_searches += q.spec_searches; out->spec_trials += q.spec_trials;
+        out->spec_sweeps += q.spec_sweeps; out->spec_sweeps_used += q.spec_sweeps_used;
     }
     return 0;
 }
@@ -742,10 +745,11 @@ static int last_stats_one(direct_ddp_handle h, direct_ddp_stats *out) {
             for (int i = 0; i < h->last_B; i++) for (int k = 0; k < 4; k++) tot[k] += tmp[(size_t)i * 8 + k];
         }
         h->stats.bwd_sweeps = tot[0]; h->stats.bwd_knots = tot[1]; h->stats.fwd_trials = tot[2]; h->stats.fwd_knots = tot[3];
-        unsigned int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        unsigned int cnt[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
         CK(cudaMemcpy(cnt, h->counter.p, sizeof cnt, cudaMemcpyDeviceToHost));
         h->stats.coop_jobs = cnt[1]; h->stats.helper_units = cnt[2];
         h->stats.spec_searches = cnt[5]; h->stats.spec_trials = cnt[6];
+        h->stats.spec_sweeps = cnt[7]; h->stats.spec_sweeps_used = cnt[8];
         h->stats_valid = true;
     }
     *out = h->stats;

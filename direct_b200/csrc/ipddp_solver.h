@@ -126,8 +126,10 @@ struct SolveArgs {
     long long ws_stride;
     int fcap;                    // filter capacity per slot
     unsigned int *counter;       // [0] work queue, [1] jobs posted, [2] units run by CTA helpers, [3] trajectories finished,
-                                 // [4] warps of fully idle CTAs, [5] speculative line searches posted, [6] remote trials run
+                                 // [4] warps of fully idle CTAs, [5] speculative line searches posted, [6] remote trials run,
+                                 // [7] speculative backward sweeps claimed, [8] of which used
     int gspec;                   // 1: warps of idle CTAs run line-search trials of the remaining solves ("Speculative line search")
+    int spec;                    // 1: ... and the backward sweep a failing line search would need ("Speculative backward sweep")
     void *gboards;               // GBoard<R>[2 * slots]
     unsigned long long *gwords;  // their claim words, [2 * slots], followed by a bitmap of the boards with unclaimed units
     double *trace;               // optional [cap][12] trace of trajectory 0 (last stage), or NULL
@@ -184,7 +186,7 @@ DDP_DEVICE constexpr int hpk(int r, int c) { return r >= c ? r * (r + 1) / 2 + c
 // [32-knot block][row slot][32] (row_ofs), so lane <-> knot accesses coalesce and a knot's rows are 32 elements apart.
 // Row slots (row_slot below): corridor row (control point j, plane k) -> j*PM+k; then 6 rows per v / a group; time.
 struct WsLay {
-    long long xu, xun, K, kdx, aux, H, s, sn, y, yn, filt, total;
+    long long xu, xun, K, K2, kdx, aux, H, s, sn, y, yn, filt, total;
     int MCS, NP;
 };
 DDP_HD WsLay ws_layout(int N, int PM, int fcap) {
@@ -195,6 +197,7 @@ DDP_HD WsLay ws_layout(int N, int PM, int fcap) {
     w.xu = o; o += (long long)(N + 1) * 20;
     w.xun = o; o += (long long)(N + 1) * 20;
     w.K = o; o += (long long)N * 100;
+    w.K2 = o; o += (long long)N * 100;   // target of a speculative backward sweep ("Speculative backward sweep"); swapped with K when it is used
     w.kdx = o; o += (long long)N * 10;
     w.aux = o; o += (long long)N * 12;
     o = (o + 3) & ~3LL;   // H columns are read with 128-bit loads, the row arrays by 16-byte-aligned bulk copies (float: 4 elements)
@@ -227,7 +230,7 @@ template <class R> struct Traj {
     const int32_t *nplanes;
     R *sm;
     const R *tab;  // [0..89] value table (chosen basis), [90..179] d/dT table
-    R *xu, *xun, *K, *kdx, *aux, *H, *s, *sn, *y, *yn, *filt;
+    R *xu, *xun, *K, *K2, *kdx, *aux, *H, *s, *sn, *y, *yn, *filt;
     int fcap;
     R max_vel, max_acc, w_snap, w_terminal, w_time, margin;
     int time_power, infeas, zero_init, line_init;
@@ -251,6 +254,11 @@ template <class R> struct Traj {
     R *ws_all;                           // workspace of slot 0
     long long ws_stride, off_xun, off_sn, off_yn, off_kdx;
     int gflip, minvo;
+    // speculative backward sweep (see backward_pass)
+    int spec_on;                         // enabled (SolveArgs::spec)
+    int spec_posted;                     // the line search that just failed had its sweep claimed: the next backward pass may take it
+    R spec_regadd;                       // the regularisation it was posted with
+    void *sweep_b;                       // GBoard<R> with a claimed sweep that has not been seen finished yet
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -1115,7 +1123,8 @@ template <class R> DDP_DEVICE_NOINLINE void linearize_solo(Traj<R> &tt_, Reg<R, 
 // [ku | Ku] (ddp.cpp:561-564 / :607-609) and keep the trailing block as Vxx, Vx (ddp.cpp:620-628).
 // Returns false when a pivot is not positive (ddp.cpp:546-551 / :595-600).
 // =============================================================================================
-template <class R> DDP_DEVICE_NOINLINE bool riccati(Traj<R> &t, R regadd, Reg<R, 1> &errq) {
+// `cancel` (speculative sweeps only, global memory): looked at once per knot; set -> the sweep stops like after a failed factorisation.
+template <class R> DDP_DEVICE_NOINLINE bool riccati(Traj<R> &t, R regadd, Reg<R, 1> &errq, const volatile int *cancel = nullptr) {
     const int lane_ = t.lane_;
     R *sm = as_shared(t.sm);
     const int N = t.N;
@@ -1157,6 +1166,7 @@ template <class R> DDP_DEVICE_NOINLINE bool riccati(Traj<R> &t, R regadd, Reg<R,
     long long knots = 0;
     bool ok = true;
     for (int i = N - 1; i >= 0; i--) {
+        if (cancel != nullptr && *cancel != 0) { ok = false; break; }
         const int slot = (int)(knots % 3);
         knots++;
         mbar_wait(bars + slot, (rphase >> slot) & 1u);
@@ -1386,6 +1396,7 @@ template <class R> DDP_DEVICE_NOINLINE bool riccati(Traj<R> &t, R regadd, Reg<R,
 }
 
 // ddp.cpp:440-644.
+template <class R> struct GBoard;
 template <class R> DDP_DEVICE_NOINLINE void backward_pass(Traj<R> &t) {
     const int lane_ = t.lane_;
     const long long clk0 = ddp_clock();
@@ -1399,6 +1410,14 @@ template <class R> DDP_DEVICE_NOINLINE void backward_pass(Traj<R> &t) {
     else if (t.reg > R(24)) t.reg = R(24);
     const R regadd = rpow(t.reg_base, t.reg) - R(1);  // ddp.cpp:529
     Reg<R, 1> errq;
+    bool spec_hit = false;
+#if DDP_GPU
+    if (t.spec_posted) {   // GBoard "Speculative backward sweep": usable iff this pass is the one the failed search anticipated
+        t.spec_posted = 0;
+        spec_hit = t.lin_valid && t.failed && !t.bfailed && regadd == t.spec_regadd;
+        if (!spec_hit && lane_ == 0) *(volatile int *)&((GBoard<R> *)t.sweep_b)->sweep_cancel = 1;
+    }
+#endif
     // The linearisation depends on the iterate and on mu only: a retry after a failed factorisation or after a
     // failed line search (the reference does not relinearise either, ddp.cpp:476) reuses it.
     if (!t.lin_valid) {
@@ -1414,14 +1433,35 @@ template <class R> DDP_DEVICE_NOINLINE void backward_pass(Traj<R> &t) {
     }
     WARP_SYNC();
     const long long clk_r = ddp_clock();
-    const bool ric_ok = riccati(t, regadd, errq);
+    bool ric_ok;
+    R e0;
+#if DDP_GPU
+    if (spec_hit) {   // an idle warp ran exactly this sweep while the search failed
+        GBoard<R> *sb = (GBoard<R> *)t.sweep_b;
+        if (lane_ == 0) {
+            while (*(volatile int *)&sb->sweep_done == 0) __nanosleep(100);
+            atomicAdd(t.gctr + 8, 1u);
+        }
+        __syncwarp();
+        __threadfence();   // acquire: the gains in K2 and the result
+        ric_ok = *(volatile int *)&sb->sweep_ok != 0;
+        e0 = *(volatile R *)&sb->sweep_errq;
+        t.n_bwd_knots += *(volatile long long *)&sb->sweep_knots;
+        R *tmp = t.K; t.K = t.K2; t.K2 = tmp;
+        t.sweep_b = nullptr;
+        __syncwarp();
+    } else
+#endif
+    {
+        ric_ok = riccati(t, regadd, errq);
+        e0 = warp_max(errq, 0, lane_);
+    }
     t.cyc_ric += ddp_clock() - clk_r;
     if (!ric_ok) {
         t.bfailed = 1;
         t.opterr = R(INFINITY);
     } else {
         t.bfailed = 0;
-        const R e0 = warp_max(errq, 0, lane_);
         t.opterr = rmax(rmax(e0, t.infeas ? t.lin_ecy : R(0)), t.lin_emu);  // ddp.cpp:641
     }
     t.cyc_bwd += ddp_clock() - clk0;
@@ -2175,6 +2215,17 @@ template <class R> struct GBoard {
     int retired;        // last generation whose candidates the owner no longer needs
     int claimed_final;  // units that had been claimed when the last search on this board was closed
     struct Res { int ok, slot; long long knots; R cost, costq, logcost, err, cmax; } res[GSPEC_UNITS];
+    // Speculative backward sweep.  When a line search FAILS the next backward pass works on the same linearisation with the
+    // regularisation one step up (ddp.cpp:452-474, :476): everything it needs is known before the search starts, and the Riccati
+    // recursion alone is more than half of an iteration of the solves that are left at the end of a batch.  So a search posted
+    // with sweep = 1 carries one more unit, claimed first: an idle warp runs that sweep into the owner's second gain buffer (K2)
+    // while the trials run, and the owner's next backward pass takes the result (gains by pointer swap, |Qu|_inf, failure flag,
+    // knots visited) - the same function on the same inputs, hence the same bits.  A search that succeeds withdraws the sweep
+    // (sweep_cancel, looked at once per knot); K2 is not handed out again before sweep_done.
+    int sweep;          // 1: unit 0 of this search is the sweep, trial 2^-k is unit k (0: trial 2^-k is unit k - 1)
+    int sweep_cancel, sweep_done, sweep_ok;
+    long long sweep_knots;
+    R sweep_regadd, sweep_errq;
 };
 
 #if DDP_GPU
@@ -2224,11 +2275,18 @@ template <class R> DDP_DEVICE_NOINLINE void forward_pass(Traj<R> &t) {
         const int bidx = t.gindex + t.gflip;
         t.gflip ^= 1;
         int seq = 0;
+        // the sweep the next backward pass needs if this search fails: regularisation of ddp.cpp:452-474 with failed = 1
+        const int want_sweep = (t.spec_on && !t.bfailed) ? 1 : 0;
+        R sweep_reg = t.reg + R(1);
+        if (sweep_reg > R(24)) sweep_reg = R(24);
+        const R sweep_regadd = rpow(t.reg_base, sweep_reg) - R(1);
         __threadfence();   // every lane's part of the iterate and the gains before the board is posted
         __syncwarp();
         if (lane_ == 0) {
             // the previous search on this board may have been closed with units in flight: they are long done
             while (*(volatile int *)&b->done < *(volatile int *)&b->claimed_final) __nanosleep(200);
+            if (t.sweep_b != nullptr)   // a withdrawn sweep may still be writing K2 (for one knot at most), and its board may be this one
+                while (*(volatile int *)&((GBoard<R> *)t.sweep_b)->sweep_done == 0) __nanosleep(100);
             __threadfence();
             GBoard<R> *b0 = (GBoard<R> *)t.gb;
             seq = b0->seq_ctr + 1;
@@ -2236,13 +2294,15 @@ template <class R> DDP_DEVICE_NOINLINE void forward_pass(Traj<R> &t) {
             b->t = t;
             for (int e = 0; e < 9; e++) b->xd[e] = t.sm[Lay::XD + e];
             b->tau = tau; b->done = 0; b->claimed_final = GSPEC_UNITS;
+            b->sweep = want_sweep; b->sweep_cancel = 0; b->sweep_done = 0; b->sweep_regadd = sweep_regadd;
             __threadfence();   // the board before the claim word
-            *(volatile unsigned long long *)w = ((unsigned long long)(unsigned)seq << 32) | ((unsigned long long)GSPEC_UNITS << 16);
+            *(volatile unsigned long long *)w = ((unsigned long long)(unsigned)seq << 32) | ((unsigned long long)(GSPEC_UNITS + want_sweep) << 16);
             __threadfence();
             atomicOr(t.gbits + (bidx >> 5), 1u << (bidx & 31));
             atomicAdd(t.gctr + 5, 1u);
         }
         seq = __shfl_sync(0xffffffffu, seq, 0);
+        t.sweep_b = nullptr;   // (waited for above)
         // the owner's own trial: step 2^0
         t.n_fwd_trials++;
         stepsize = R(1);
@@ -2254,10 +2314,14 @@ template <class R> DDP_DEVICE_NOINLINE void forward_pass(Traj<R> &t) {
 #endif
         if (lane_ == 0) {
             claimed = gspec_close(w);
-            *(volatile int *)&b->claimed_final = claimed;
+            *(volatile int *)&b->claimed_final = claimed > want_sweep ? claimed - want_sweep : 0;   // trials
             atomicAnd(t.gbits + (bidx >> 5), ~(1u << (bidx & 31)));
         }
         claimed = __shfl_sync(0xffffffffu, claimed, 0);
+        if (want_sweep && claimed > 0) {   // unit 0, the sweep, is out
+            t.sweep_b = b; t.spec_regadd = sweep_regadd;
+            claimed--;
+        }
         if (acc0) {
             if (lane_ == 0) { __threadfence(); *(volatile int *)&b->retired = seq; }   // nobody's candidate is needed
             failed = false;
@@ -2312,6 +2376,12 @@ template <class R> DDP_DEVICE_NOINLINE void forward_pass(Traj<R> &t) {
         failed = false;
         break;
     }
+#if DDP_GPU
+    if (t.sweep_b != nullptr) {
+        if (failed) t.spec_posted = 1;   // the next backward pass may be the one the sweep anticipated
+        else if (lane_ == 0) *(volatile int *)&((GBoard<R> *)t.sweep_b)->sweep_cancel = 1;   // nobody needs it
+    }
+#endif
     if (failed) {
         t.failed = 1;
         t.stepsize = R(0);
@@ -2405,6 +2475,26 @@ DDP_DEVICE_NOINLINE void gspec_helper_loop(const SolveArgs &A, R *sm, const R *t
         t.n_fwd_knots = 0; t.cyc_seq = 0;
         if (lane_ < 9) sm[Lay::XD + lane_] = b->xd[lane_];
         __syncwarp();
+        if (b->sweep) {
+            if (unit == 0) {   // the backward sweep this search needs if it fails, into the owner's second gain buffer
+                t.K = t.K2; t.n_bwd_knots = 0;
+                Reg<R, 1> errq;
+                const bool sok = riccati(t, b->sweep_regadd, errq, &b->sweep_cancel);
+                const R e0 = warp_max(errq, 0, lane_);
+                fence_async_all();   // the gains are read by bulk copies of the next trials
+                __threadfence();
+                __syncwarp();
+                if (lane_ == 0) {
+                    b->sweep_ok = sok ? 1 : 0; b->sweep_errq = e0; b->sweep_knots = t.n_bwd_knots;
+                    __threadfence();
+                    *(volatile int *)&b->sweep_done = 1;
+                    atomicAdd(A.counter + 7, 1u);
+                }
+                __syncwarp();
+                continue;
+            }
+            unit--;
+        }
         const int step = unit + 1;
         R alpha = R(1);
         for (int k = 0; k < step; k++) alpha = alpha * R(0.5);
@@ -2446,6 +2536,7 @@ template <class R> DDP_DEVICE_NOINLINE void solve_one(const SolveArgs &A, int st
     t.N = N; t.PM = A.PM; t.NP = wl.NP; t.MCS = wl.MCS; t.lane_ = lane_;
     t.board = board; t.ctl = ctl; t.wpb = wpb;
     t.gb = nullptr; t.gw = nullptr; t.gctr = A.counter; t.gflip = 0; t.minvo = cfg.minvo;
+    t.spec_on = 0; t.spec_posted = 0; t.spec_regadd = R(0); t.sweep_b = nullptr;
 #if DDP_GPU
     if (A.gspec && A.gboards) {
         const long long slot = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -2455,13 +2546,14 @@ template <class R> DDP_DEVICE_NOINLINE void solve_one(const SolveArgs &A, int st
         t.gbits = (unsigned int *)(A.gwords + 2 * (long long)gridDim.x * (blockDim.x >> 5));
         t.ws_all = (R *)A.ws; t.ws_stride = A.ws_stride;
         t.off_xun = wl.xun; t.off_sn = wl.sn; t.off_yn = wl.yn; t.off_kdx = wl.kdx;
+        t.spec_on = A.spec ? 1 : 0;
     }
 #endif
     t.planes = A.planes + (long long)b * NS * A.PM * 4;
     t.nplanes = A.nplanes + (long long)b * NS;
     t.sm = sm;
     t.tab = tabs + (cfg.minvo ? 180 : 0);
-    t.xu = ws + wl.xu; t.xun = ws + wl.xun; t.K = ws + wl.K; t.kdx = ws + wl.kdx; t.aux = ws + wl.aux; t.H = ws + wl.H;
+    t.xu = ws + wl.xu; t.xun = ws + wl.xun; t.K = ws + wl.K; t.K2 = ws + wl.K2; t.kdx = ws + wl.kdx; t.aux = ws + wl.aux; t.H = ws + wl.H;
     t.s = ws + wl.s; t.sn = ws + wl.sn; t.y = ws + wl.y; t.yn = ws + wl.yn;
     t.filt = ws + wl.filt; t.fcap = A.fcap;
     t.max_vel = (R)A.max_vel; t.max_acc = (R)A.max_acc;
@@ -2633,6 +2725,15 @@ template <class R> DDP_DEVICE_NOINLINE void solve_one(const SolveArgs &A, int st
     if (A.trace && b == 0 && (st == 1 || !A.two_stage) && A.trace_len) {
         FOR_LANES(lane) { if (lane == 0) *A.trace_len = trace_n; }
     }
+#if DDP_GPU
+    if (t.sweep_b != nullptr) {   // a sweep of the last search: withdrawn, gone before the workspace is used again
+        if (lane_ == 0) {
+            *(volatile int *)&((GBoard<R> *)t.sweep_b)->sweep_cancel = 1;
+            while (*(volatile int *)&((GBoard<R> *)t.sweep_b)->sweep_done == 0) __nanosleep(100);
+        }
+        __syncwarp();
+    }
+#endif
 
     // ---- outputs (ddp.cpp:418-437), lane <-> knot ---------------------------------------------------------
     const OutPtrs &O = A.out[A.two_stage ? st : 1];

@@ -98,6 +98,32 @@ def test_gpu_full_size_properties(solver):
     assert rel_err(cp[:, :, :, 0], pc[:, :, 0]) < 1e-9
 
 
+def test_gpu_tail_balancing_leaves_every_bit_alone(solver, monkeypatch):
+    """Cooperation inside a CTA, the speculative line search and the speculative backward sweep only change
+    WHO computes a phase: a batch far below the grid (every mechanism active from the start) returns the same bits and the same
+    sweep / trial / knot counters with each of them switched off (tuning knobs DIRECT_DDP_SPEC / _GSPEC / _COOP)."""
+    pb = make_batch(320, 60, "box")
+    ref = None
+    used = {}
+    for knobs in ({}, {"DIRECT_DDP_SPEC": "0"}, {"DIRECT_DDP_GSPEC": "0"}, {"DIRECT_DDP_COOP": "0"}):
+        for k in ("DIRECT_DDP_SPEC", "DIRECT_DDP_GSPEC", "DIRECT_DDP_COOP"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in knobs.items():
+            monkeypatch.setenv(k, v)
+        g0, g1 = solver.solve_two_stage(pb, want_stage0=True)
+        st = solver.stats()
+        used[tuple(knobs)] = (st.helper_units, st.spec_trials, st.spec_sweeps_used)
+        if ref is None:
+            ref = (g0, g1)
+            continue
+        for a, b in zip(ref, (g0, g1)):
+            for f in ("rtn", "iters", "infeas_out") + OUT_FIELDS:
+                assert np.array_equal(getattr(a, f), getattr(b, f)), (knobs, f)
+            assert np.array_equal(a.stats[:, :4], b.stats[:, :4]), knobs
+    assert min(used[()]) > 0, used                                    # all three mechanisms did run in the default configuration
+    assert used[("DIRECT_DDP_SPEC",)][2] == 0 and used[("DIRECT_DDP_GSPEC",)][1] == 0 and used[("DIRECT_DDP_COOP",)] == (0, 0, 0)
+
+
 def test_gpu_full_size_sample_against_oracle(solver, oracle):
     pb = make_batch(4096, 100, "box")
     g0, g = solver.solve_two_stage(pb, want_stage0=True)

@@ -39,7 +39,8 @@ bk = (s0[:, 1] + s1[:, 1]).sum()
 fk = (s0[:, 3] + s1[:, 3]).sum()
 print(f"[{a.tag}] {a.precision} B={a.batch} N={a.knots} {a.kind}: kernel {ms:.1f} ms = {a.batch / ms * 1e3:.0f} solves/s; grid {st.grid_blocks}x{st.block_threads}, "
       f"slots {slots}, smem/block {st.smem_bytes_per_block}")
-print(f"   cooperation: {st.coop_jobs} jobs posted to idle warps, {st.helper_units} units run by helpers")
+print(f"   cooperation: {st.coop_jobs} jobs posted to idle warps, {st.helper_units} units run by helpers; "
+      f"speculative backward sweeps {st.spec_sweeps} posted, {st.spec_sweeps_used} used")
 print(f"   slot busy fraction {tot.sum() / (slots * kcyc):.3f}; longest solve {tot.max() / kcyc:.3f} of the kernel; mean solve {tot.mean() / kcyc:.4f}; "
       f"p50/p90/p99/max Mcycles {np.percentile(tot, 50) / 1e6:.2f}/{np.percentile(tot, 90) / 1e6:.2f}/{np.percentile(tot, 99) / 1e6:.2f}/{tot.max() / 1e6:.2f}")
 print(f"   cycles per backward knot {cyc[:, 0].sum() / bk:.0f} ({bk} knots); per rollout knot {cyc[:, 1].sum() / fk:.0f} ({fk} knots); "
