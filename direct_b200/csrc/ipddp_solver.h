@@ -2205,7 +2205,10 @@ template <class R> DDP_DEVICE bool filter_try(Traj<R> &t, R logcost, R err) {
 // waited for); claimed units always run to completion, and an owner that finds units unclaimed when its own trial is
 // over closes the board and carries on sequentially, so nothing ever waits on a warp that is itself waiting.
 // =============================================================================================
-enum { GSPEC_UNITS = 10, GSPEC_MIN_IDLE = 12 };
+#ifndef DDP_GSPEC_MIN_IDLE
+#define DDP_GSPEC_MIN_IDLE 12   // warps of fully idle CTAs from which on searches are posted (4 and 48 measured: within noise of 12)
+#endif
+enum { GSPEC_UNITS = 10, GSPEC_MIN_IDLE = DDP_GSPEC_MIN_IDLE };
 template <class R> struct GBoard {
     Traj<R> t;          // the owner's view of the trajectory when it posted the search
     R xd[9];            // desired terminal state (lives in the owner's shared memory)
