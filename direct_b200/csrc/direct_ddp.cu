@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(DDP_MAX_THREADS, DDP_MIN_BLOCKS) ipddp_solve_k
     ddp::BlockCtl *ctl = reinterpret_cast<ddp::BlockCtl *>(boards + wpb);
     if (lane == 0) { boards[warp].word = 0ull; boards[warp].done = 0; boards[warp].owner_seq = 0; }
     ddp::ring_init<R>(sm, lane);   // mbarriers of the line search's slack-row ring (ipddp_solver.h "Slack-row ring")
-    if (threadIdx.x == 0) { ctl->active_owners = wpb; ctl->jobs_ctr = A.counter + 1; }
+    if (threadIdx.x == 0) { ctl->active_owners = wpb; ctl->unit_running = 0; ctl->jobs_ctr = A.counter + 1; }
     __syncthreads();
     const long long slot = (long long)blockIdx.x * wpb + warp;
     R *ws = reinterpret_cast<R *>(A.ws) + slot * A.ws_stride;
@@ -266,7 +266,7 @@ template <class R> int launch(H *h, SolveArgs &A, cudaStream_t s) {
     }
     A.gboards = nullptr; A.gwords = nullptr;
     if (A.gspec) {
-        const size_t nb = (size_t)2 * grid * wpb;
+        const size_t nb = (size_t)ddp::GSPEC_BOARDS * grid * wpb;
         if ((st = ensure(h, h->gboards, nb * sizeof(ddp::GBoard<R>)))) return st;
         const size_t wbytes = nb * sizeof(unsigned long long) + ((nb + 31) / 32 + 1) * sizeof(unsigned int);   // words + bitmap
         if ((st = ensure(h, h->gwords, wbytes))) return st;

@@ -130,8 +130,8 @@ struct SolveArgs {
                                  // [7] speculative backward sweeps claimed, [8] of which used
     int gspec;                   // 1: warps of idle CTAs run line-search trials of the remaining solves ("Speculative line search")
     int spec;                    // 1: ... and the backward sweep a failing line search would need ("Speculative backward sweep")
-    void *gboards;               // GBoard<R>[2 * slots]
-    unsigned long long *gwords;  // their claim words, [2 * slots], followed by a bitmap of the boards with unclaimed units
+    void *gboards;               // GBoard<R>[GSPEC_BOARDS * slots]
+    unsigned long long *gwords;  // their claim words, [GSPEC_BOARDS * slots], followed by a bitmap of the boards with unclaimed units
     double *trace;               // optional [cap][12] trace of trajectory 0 (last stage), or NULL
     int trace_cap;
     int *trace_len;
@@ -256,9 +256,9 @@ template <class R> struct Traj {
     int gflip, minvo;
     // speculative backward sweep (see backward_pass)
     int spec_on;                         // enabled (SolveArgs::spec)
-    int spec_posted;                     // the line search that just failed had its sweep claimed: the next backward pass may take it
+    int spec_posted;                     // a sweep is on the slot's third board and has not been closed yet
     R spec_regadd;                       // the regularisation it was posted with
-    void *sweep_b;                       // GBoard<R> with a claimed sweep that has not been seen finished yet
+    void *sweep_b;                       // that board, until the sweep has been taken or seen stopped
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -585,7 +585,7 @@ template <class R> struct JobBoard {
 };
 struct BlockCtl {
     int active_owners;         // warps of the CTA that still pull trajectories from the queue
-    int pad;
+    int unit_running;          // a warp of this (idle) CTA is running a remote line-search unit: the others only serve its rows
     unsigned int *jobs_ctr;    // global counter of posted jobs (statistics)
 };
 template <class R> DDP_HD int coop_smem_bytes(int warps_per_block) {
@@ -1396,7 +1396,11 @@ template <class R> DDP_DEVICE_NOINLINE bool riccati(Traj<R> &t, R regadd, Reg<R,
 }
 
 // ddp.cpp:440-644.
-template <class R> struct GBoard;
+#if DDP_GPU   // "Speculative backward sweep" (GBoard, below)
+template <class R> DDP_DEVICE_NOINLINE bool sweep_resolve(Traj<R> &t, bool want, bool &ok, R &e0);
+template <class R> DDP_DEVICE_NOINLINE void sweep_post(Traj<R> &t, R regadd_next);
+template <class R> DDP_DEVICE bool gspec_ready(const Traj<R> &t);
+#endif
 template <class R> DDP_DEVICE_NOINLINE void backward_pass(Traj<R> &t) {
     const int lane_ = t.lane_;
     const long long clk0 = ddp_clock();
@@ -1410,13 +1414,12 @@ template <class R> DDP_DEVICE_NOINLINE void backward_pass(Traj<R> &t) {
     else if (t.reg > R(24)) t.reg = R(24);
     const R regadd = rpow(t.reg_base, t.reg) - R(1);  // ddp.cpp:529
     Reg<R, 1> errq;
-    bool spec_hit = false;
+    bool spec_hit = false, ric_ok = false;
+    R e0 = R(0);
 #if DDP_GPU
-    if (t.spec_posted) {   // GBoard "Speculative backward sweep": usable iff this pass is the one the failed search anticipated
-        t.spec_posted = 0;
-        spec_hit = t.lin_valid && t.failed && !t.bfailed && regadd == t.spec_regadd;
-        if (!spec_hit && lane_ == 0) *(volatile int *)&((GBoard<R> *)t.sweep_b)->sweep_cancel = 1;
-    }
+    // A sweep posted by the previous backward pass is this pass iff the linearisation is the same and the regularisation is the
+    // one it anticipated (compared bit for bit): a failed search or a failed factorisation in between.  Anything else withdraws it.
+    if (t.spec_posted) spec_hit = sweep_resolve(t, t.lin_valid && regadd == t.spec_regadd, ric_ok, e0);
 #endif
     // The linearisation depends on the iterate and on mu only: a retry after a failed factorisation or after a
     // failed line search (the reference does not relinearise either, ddp.cpp:476) reuses it.
@@ -1433,26 +1436,14 @@ template <class R> DDP_DEVICE_NOINLINE void backward_pass(Traj<R> &t) {
     }
     WARP_SYNC();
     const long long clk_r = ddp_clock();
-    bool ric_ok;
-    R e0;
 #if DDP_GPU
-    if (spec_hit) {   // an idle warp ran exactly this sweep while the search failed
-        GBoard<R> *sb = (GBoard<R> *)t.sweep_b;
-        if (lane_ == 0) {
-            while (*(volatile int *)&sb->sweep_done == 0) __nanosleep(100);
-            atomicAdd(t.gctr + 8, 1u);
-        }
-        __syncwarp();
-        __threadfence();   // acquire: the gains in K2 and the result
-        ric_ok = *(volatile int *)&sb->sweep_ok != 0;
-        e0 = *(volatile R *)&sb->sweep_errq;
-        t.n_bwd_knots += *(volatile long long *)&sb->sweep_knots;
-        R *tmp = t.K; t.K = t.K2; t.K2 = tmp;
-        t.sweep_b = nullptr;
-        __syncwarp();
-    } else
+    if (t.spec_on && gspec_ready(t)) {   // what the next backward pass needs if this one, or the search after it, fails
+        R reg_next = t.reg + R(1);
+        if (reg_next > R(24)) reg_next = R(24);
+        sweep_post(t, rpow(t.reg_base, reg_next) - R(1));
+    }
 #endif
-    {
+    if (!spec_hit) {
         ric_ok = riccati(t, regadd, errq);
         e0 = warp_max(errq, 0, lane_);
     }
@@ -2205,10 +2196,15 @@ template <class R> DDP_DEVICE bool filter_try(Traj<R> &t, R logcost, R err) {
 // waited for); claimed units always run to completion, and an owner that finds units unclaimed when its own trial is
 // over closes the board and carries on sequentially, so nothing ever waits on a warp that is itself waiting.
 // =============================================================================================
+// From this many idle warps on, an idle CTA runs ONE remote unit at a time and keeps its other warps as row helpers of that unit
+// (a trial with three row helpers takes 0.33 Mcycles, alone 0.73): latency of the owner's search instead of trial throughput.
+#ifndef DDP_GSPEC_EXCL_IDLE
+#define DDP_GSPEC_EXCL_IDLE 256
+#endif
 #ifndef DDP_GSPEC_MIN_IDLE
 #define DDP_GSPEC_MIN_IDLE 12   // warps of fully idle CTAs from which on searches are posted (4 and 48 measured: within noise of 12)
 #endif
-enum { GSPEC_UNITS = 10, GSPEC_MIN_IDLE = DDP_GSPEC_MIN_IDLE };
+enum { GSPEC_UNITS = 10, GSPEC_MIN_IDLE = DDP_GSPEC_MIN_IDLE, GSPEC_BOARDS = 3 };   // boards per slot: two for searches, one for sweeps
 template <class R> struct GBoard {
     Traj<R> t;          // the owner's view of the trajectory when it posted the search
     R xd[9];            // desired terminal state (lives in the owner's shared memory)
@@ -2218,14 +2214,15 @@ template <class R> struct GBoard {
     int retired;        // last generation whose candidates the owner no longer needs
     int claimed_final;  // units that had been claimed when the last search on this board was closed
     struct Res { int ok, slot; long long knots; R cost, costq, logcost, err, cmax; } res[GSPEC_UNITS];
-    // Speculative backward sweep.  When a line search FAILS the next backward pass works on the same linearisation with the
-    // regularisation one step up (ddp.cpp:452-474, :476): everything it needs is known before the search starts, and the Riccati
-    // recursion alone is more than half of an iteration of the solves that are left at the end of a batch.  So a search posted
-    // with sweep = 1 carries one more unit, claimed first: an idle warp runs that sweep into the owner's second gain buffer (K2)
-    // while the trials run, and the owner's next backward pass takes the result (gains by pointer swap, |Qu|_inf, failure flag,
-    // knots visited) - the same function on the same inputs, hence the same bits.  A search that succeeds withdraws the sweep
-    // (sweep_cancel, looked at once per knot); K2 is not handed out again before sweep_done.
-    int sweep;          // 1: unit 0 of this search is the sweep, trial 2^-k is unit k (0: trial 2^-k is unit k - 1)
+    // Speculative backward sweep (third board of a slot).  When a line search FAILS, or the factorisation does, the next backward
+    // pass works on the same linearisation with the regularisation one step up (ddp.cpp:452-474, :476, :297-310): everything it
+    // needs exists as soon as the linearisation does, and the Riccati recursion alone is more than half of an iteration of the
+    // solves that are left at the end of a batch.  So the owner posts that sweep (one unit) before it starts its own recursion; a
+    // warp of an idle CTA runs it into the owner's second gain buffer (K2) next to the owner's recursion and search, and a
+    // backward pass that finds the linearisation unchanged and the regularisation it was posted for takes the result (gains by
+    // pointer swap, |Qu|_inf, failure flag, knots visited) - the same function on the same inputs, hence the same bits.  Any other
+    // backward pass withdraws it (sweep_cancel, looked at once per knot); K2 is not handed out again before sweep_done.
+    int sweep;          // 1: this board carries one unit, the sweep (0: a line search, unit k = trial 2^-(k+1))
     int sweep_cancel, sweep_done, sweep_ok;
     long long sweep_knots;
     R sweep_regadd, sweep_errq;
@@ -2278,18 +2275,11 @@ template <class R> DDP_DEVICE_NOINLINE void forward_pass(Traj<R> &t) {
         const int bidx = t.gindex + t.gflip;
         t.gflip ^= 1;
         int seq = 0;
-        // the sweep the next backward pass needs if this search fails: regularisation of ddp.cpp:452-474 with failed = 1
-        const int want_sweep = (t.spec_on && !t.bfailed) ? 1 : 0;
-        R sweep_reg = t.reg + R(1);
-        if (sweep_reg > R(24)) sweep_reg = R(24);
-        const R sweep_regadd = rpow(t.reg_base, sweep_reg) - R(1);
         __threadfence();   // every lane's part of the iterate and the gains before the board is posted
         __syncwarp();
         if (lane_ == 0) {
             // the previous search on this board may have been closed with units in flight: they are long done
             while (*(volatile int *)&b->done < *(volatile int *)&b->claimed_final) __nanosleep(200);
-            if (t.sweep_b != nullptr)   // a withdrawn sweep may still be writing K2 (for one knot at most), and its board may be this one
-                while (*(volatile int *)&((GBoard<R> *)t.sweep_b)->sweep_done == 0) __nanosleep(100);
             __threadfence();
             GBoard<R> *b0 = (GBoard<R> *)t.gb;
             seq = b0->seq_ctr + 1;
@@ -2297,15 +2287,14 @@ template <class R> DDP_DEVICE_NOINLINE void forward_pass(Traj<R> &t) {
             b->t = t;
             for (int e = 0; e < 9; e++) b->xd[e] = t.sm[Lay::XD + e];
             b->tau = tau; b->done = 0; b->claimed_final = GSPEC_UNITS;
-            b->sweep = want_sweep; b->sweep_cancel = 0; b->sweep_done = 0; b->sweep_regadd = sweep_regadd;
+            b->sweep = 0;
             __threadfence();   // the board before the claim word
-            *(volatile unsigned long long *)w = ((unsigned long long)(unsigned)seq << 32) | ((unsigned long long)(GSPEC_UNITS + want_sweep) << 16);
+            *(volatile unsigned long long *)w = ((unsigned long long)(unsigned)seq << 32) | ((unsigned long long)GSPEC_UNITS << 16);
             __threadfence();
             atomicOr(t.gbits + (bidx >> 5), 1u << (bidx & 31));
             atomicAdd(t.gctr + 5, 1u);
         }
         seq = __shfl_sync(0xffffffffu, seq, 0);
-        t.sweep_b = nullptr;   // (waited for above)
         // the owner's own trial: step 2^0
         t.n_fwd_trials++;
         stepsize = R(1);
@@ -2317,14 +2306,10 @@ template <class R> DDP_DEVICE_NOINLINE void forward_pass(Traj<R> &t) {
 #endif
         if (lane_ == 0) {
             claimed = gspec_close(w);
-            *(volatile int *)&b->claimed_final = claimed > want_sweep ? claimed - want_sweep : 0;   // trials
+            *(volatile int *)&b->claimed_final = claimed;
             atomicAnd(t.gbits + (bidx >> 5), ~(1u << (bidx & 31)));
         }
         claimed = __shfl_sync(0xffffffffu, claimed, 0);
-        if (want_sweep && claimed > 0) {   // unit 0, the sweep, is out
-            t.sweep_b = b; t.spec_regadd = sweep_regadd;
-            claimed--;
-        }
         if (acc0) {
             if (lane_ == 0) { __threadfence(); *(volatile int *)&b->retired = seq; }   // nobody's candidate is needed
             failed = false;
@@ -2379,12 +2364,6 @@ template <class R> DDP_DEVICE_NOINLINE void forward_pass(Traj<R> &t) {
         failed = false;
         break;
     }
-#if DDP_GPU
-    if (t.sweep_b != nullptr) {
-        if (failed) t.spec_posted = 1;   // the next backward pass may be the one the sweep anticipated
-        else if (lane_ == 0) *(volatile int *)&((GBoard<R> *)t.sweep_b)->sweep_cancel = 1;   // nobody needs it
-    }
-#endif
     if (failed) {
         t.failed = 1;
         t.stepsize = R(0);
@@ -2402,12 +2381,64 @@ template <class R> DDP_DEVICE_NOINLINE void forward_pass(Traj<R> &t) {
 }
 
 #if DDP_GPU
+// Owner: post the sweep with regularisation regadd_next on the slot's third board (linearisation valid, K2 free or about to be).
+template <class R> DDP_DEVICE_NOINLINE void sweep_post(Traj<R> &t, R regadd_next) {
+    GBoard<R> *sb = (GBoard<R> *)t.gb + 2;
+    unsigned long long *w = t.gw + 2;
+    const int bidx = t.gindex + 2;
+    __threadfence();   // the linearisation records (this warp's or its helpers') before the board
+    __syncwarp();
+    if (t.lane_ == 0) {
+        if (t.sweep_b != nullptr)   // a withdrawn sweep may still be writing K2 (for one knot at most)
+            while (*(volatile int *)&((GBoard<R> *)t.sweep_b)->sweep_done == 0) __nanosleep(100);
+        const int seq = sb->seq_ctr + 1;
+        sb->seq_ctr = seq;
+        sb->t = t;
+        for (int e = 0; e < 9; e++) sb->xd[e] = t.sm[Lay::XD + e];
+        sb->sweep = 1; sb->sweep_cancel = 0; sb->sweep_done = 0; sb->sweep_regadd = regadd_next;
+        __threadfence();   // the board before the claim word
+        *(volatile unsigned long long *)w = ((unsigned long long)(unsigned)seq << 32) | (1ull << 16);
+        __threadfence();
+        atomicOr(t.gbits + (bidx >> 5), 1u << (bidx & 31));
+    }
+    t.sweep_b = sb; t.spec_posted = 1; t.spec_regadd = regadd_next;
+    __syncwarp();
+}
+// Owner: close the posted sweep.  want: take its result if an idle warp claimed it (true: ok / e0 / knots / gains are those of the
+// sweep).  Otherwise, or when nobody claimed it, the caller runs the recursion itself.
+template <class R> DDP_DEVICE_NOINLINE bool sweep_resolve(Traj<R> &t, bool want, bool &ok, R &e0) {
+    GBoard<R> *sb = (GBoard<R> *)t.sweep_b;
+    const int bidx = t.gindex + 2;
+    t.spec_posted = 0;
+    int claimed = 0;
+    if (t.lane_ == 0) {
+        claimed = gspec_close(t.gw + 2);
+        atomicAnd(t.gbits + (bidx >> 5), ~(1u << (bidx & 31)));
+        if (claimed && !want) *(volatile int *)&sb->sweep_cancel = 1;
+        if (claimed && want) {
+            while (*(volatile int *)&sb->sweep_done == 0) __nanosleep(100);
+            atomicAdd(t.gctr + 8, 1u);
+        }
+    }
+    claimed = __shfl_sync(0xffffffffu, claimed, 0);
+    if (!claimed) { t.sweep_b = nullptr; return false; }
+    if (!want) return false;   // t.sweep_b stays set: K2 is not handed out again before that sweep has stopped
+    __threadfence();   // acquire: the gains in K2 and the result
+    ok = *(volatile int *)&sb->sweep_ok != 0;
+    e0 = *(volatile R *)&sb->sweep_errq;
+    t.n_bwd_knots += *(volatile long long *)&sb->sweep_knots;
+    R *tmp = t.K; t.K = t.K2; t.K2 = tmp;
+    t.sweep_b = nullptr;
+    __syncwarp();
+    return true;
+}
+
 // A warp of a fully idle CTA: run line-search trials posted by the remaining solves until every trajectory is finished.
 template <class R>
 DDP_DEVICE_NOINLINE void gspec_helper_loop(const SolveArgs &A, R *sm, const R *tabs, R *ws, int slot, int lane_,
                                            JobBoard<R> *cta_boards, BlockCtl *ctl, int wpb, int me) {
     GBoard<R> *boards = (GBoard<R> *)A.gboards;
-    const int nboards = 2 * (int)(gridDim.x * (blockDim.x >> 5));
+    const int nboards = GSPEC_BOARDS * (int)(gridDim.x * (blockDim.x >> 5));
     const WsLay wl = ws_layout(A.N, A.PM, A.fcap);
     sm = as_shared(sm);
     if (lane_ == 0) atomicAdd(A.counter + 4, 1u);
@@ -2429,6 +2460,14 @@ DDP_DEVICE_NOINLINE void gspec_helper_loop(const SolveArgs &A, R *sm, const R *t
         // find a board with unclaimed units in the bitmap (start position spread over the helpers), claim one unit
         int bi = -1, unit = -1;
         unsigned seq = 0;
+        int excl = 0;   // 1: this warp holds the CTA's right to run a unit (many idle CTAs: one unit per CTA, the rest help with its rows)
+        if (ctl != nullptr && *(volatile unsigned int *)(A.counter + 4) >= (unsigned)DDP_GSPEC_EXCL_IDLE) {
+            int got = 0;
+            if (lane_ == 0) got = atomicCAS(&ctl->unit_running, 0, 1) == 0;
+            got = __shfl_sync(0xffffffffu, got, 0);
+            if (!got) { __nanosleep(DDP_IDLE_NS_MIN); continue; }   // stays close: the running unit posts row jobs every few microseconds
+            excl = 1;
+        }
         {
             const unsigned int *bits = (const unsigned int *)(A.gwords + nboards);
             const int nwords = (nboards + 31) >> 5;
@@ -2467,7 +2506,11 @@ DDP_DEVICE_NOINLINE void gspec_helper_loop(const SolveArgs &A, R *sm, const R *t
                 }
             }
         }
-        if (bi < 0) { __nanosleep(idle_ns); if (idle_ns < DDP_IDLE_NS_MAX) idle_ns *= 2; continue; }
+        if (bi < 0) {
+            if (excl && lane_ == 0) *(volatile int *)&ctl->unit_running = 0;
+            __nanosleep(idle_ns); if (idle_ns < DDP_IDLE_NS_MAX) idle_ns *= 2;
+            continue;
+        }
         idle_ns = DDP_IDLE_NS_MIN;
         __threadfence();   // acquire: the board and the owner's arrays as of the posting
         GBoard<R> *b = boards + bi;
@@ -2479,7 +2522,8 @@ DDP_DEVICE_NOINLINE void gspec_helper_loop(const SolveArgs &A, R *sm, const R *t
         if (lane_ < 9) sm[Lay::XD + lane_] = b->xd[lane_];
         __syncwarp();
         if (b->sweep) {
-            if (unit == 0) {   // the backward sweep this search needs if it fails, into the owner's second gain buffer
+            {   // the backward sweep the owner needs if its iteration fails, into the owner's second gain buffer
+                if (excl && lane_ == 0) *(volatile int *)&ctl->unit_running = 0;   // a sweep posts no row jobs: the CTA may run a trial next to it
                 t.K = t.K2; t.n_bwd_knots = 0;
                 Reg<R, 1> errq;
                 const bool sok = riccati(t, b->sweep_regadd, errq, &b->sweep_cancel);
@@ -2496,7 +2540,6 @@ DDP_DEVICE_NOINLINE void gspec_helper_loop(const SolveArgs &A, R *sm, const R *t
                 __syncwarp();
                 continue;
             }
-            unit--;
         }
         const int step = unit + 1;
         R alpha = R(1);
@@ -2514,6 +2557,7 @@ DDP_DEVICE_NOINLINE void gspec_helper_loop(const SolveArgs &A, R *sm, const R *t
         __syncwarp();
         if (lane_ == 0) {
             atomicAdd(&b->done, 1);
+            if (excl) *(volatile int *)&ctl->unit_running = 0;
             // the candidate stays untouched until the owner has taken it or discarded the search
             if (ok) while (*(volatile int *)&b->retired < (int)seq && *(volatile unsigned int *)(A.counter + 3) < (unsigned)A.B) __nanosleep(500);
         }
@@ -2543,10 +2587,10 @@ template <class R> DDP_DEVICE_NOINLINE void solve_one(const SolveArgs &A, int st
 #if DDP_GPU
     if (A.gspec && A.gboards) {
         const long long slot = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-        t.gb = (GBoard<R> *)A.gboards + 2 * slot;
-        t.gw = A.gwords + 2 * slot;
-        t.gindex = (int)(2 * slot);
-        t.gbits = (unsigned int *)(A.gwords + 2 * (long long)gridDim.x * (blockDim.x >> 5));
+        t.gb = (GBoard<R> *)A.gboards + GSPEC_BOARDS * slot;
+        t.gw = A.gwords + GSPEC_BOARDS * slot;
+        t.gindex = (int)(GSPEC_BOARDS * slot);
+        t.gbits = (unsigned int *)(A.gwords + GSPEC_BOARDS * (long long)gridDim.x * (blockDim.x >> 5));
         t.ws_all = (R *)A.ws; t.ws_stride = A.ws_stride;
         t.off_xun = wl.xun; t.off_sn = wl.sn; t.off_yn = wl.yn; t.off_kdx = wl.kdx;
         t.spec_on = A.spec ? 1 : 0;
@@ -2665,6 +2709,9 @@ template <class R> DDP_DEVICE_NOINLINE void solve_one(const SolveArgs &A, int st
     int iter = 0, bp_no_upd_count = 0, no_upd_count = 0;
     const int bp_no_upd_count_max = 20;
     int trace_n = 0;
+#ifdef DDP_TRACE_CYCLES
+    long long trc[4] = {0, 0, 0, 0};
+#endif
     for (iter = 0; iter < cfg.iter_max; iter++) {
         int n_bwd = 0;
         while (true) {  // ddp.cpp:297-310
@@ -2683,6 +2730,11 @@ template <class R> DDP_DEVICE_NOINLINE void solve_one(const SolveArgs &A, int st
                     tr[0] = t.cost; tr[1] = t.costq; tr[2] = t.logcost; tr[3] = t.err; tr[4] = t.mu; tr[5] = t.reg;
                     tr[6] = t.stepsize; tr[7] = t.opterr; tr[8] = t.step; tr[9] = t.failed; tr[10] = n_bwd;
                     tr[11] = (double)(ddp_clock() - t.cyc_t0);   // SM cycles since the solve began; the host converts with the device's clock
+#ifdef DDP_TRACE_CYCLES   // diagnostic build (tools/timeline.py --cycles): kilo-cycles of this iteration per phase instead of four of the scalars
+                    tr[1] = (double)((t.cyc_bwd - trc[0]) >> 10); tr[2] = (double)((t.cyc_fwd - trc[1]) >> 10);
+                    tr[3] = (double)((t.cyc_ric - trc[2]) >> 10); tr[7] = (double)((t.cyc_seq - trc[3]) >> 10);
+                    trc[0] = t.cyc_bwd; trc[1] = t.cyc_fwd; trc[2] = t.cyc_ric; trc[3] = t.cyc_seq;
+#endif
                 }
             }
             trace_n++;
@@ -2729,12 +2781,13 @@ template <class R> DDP_DEVICE_NOINLINE void solve_one(const SolveArgs &A, int st
         FOR_LANES(lane) { if (lane == 0) *A.trace_len = trace_n; }
     }
 #if DDP_GPU
-    if (t.sweep_b != nullptr) {   // a sweep of the last search: withdrawn, gone before the workspace is used again
-        if (lane_ == 0) {
-            *(volatile int *)&((GBoard<R> *)t.sweep_b)->sweep_cancel = 1;
-            while (*(volatile int *)&((GBoard<R> *)t.sweep_b)->sweep_done == 0) __nanosleep(100);
+    {   // a sweep of the last backward pass: withdrawn, gone before the workspace is used again
+        bool dummy_ok; R dummy_e;
+        if (t.spec_posted) sweep_resolve(t, false, dummy_ok, dummy_e);
+        if (t.sweep_b != nullptr) {
+            if (lane_ == 0) while (*(volatile int *)&((GBoard<R> *)t.sweep_b)->sweep_done == 0) __nanosleep(100);
+            __syncwarp();
         }
-        __syncwarp();
     }
 #endif
 

@@ -9,6 +9,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--first", type=int, default=547)
 ap.add_argument("--batch", type=int, default=4096)
 ap.add_argument("--knots", type=int, default=100)
+ap.add_argument("--cycles", action="store_true", help="library built with -DDDP_TRACE_CYCLES: costq/logcost/err/opterr carry kilo-cycles per phase")
 a = ap.parse_args()
 pb = make_batch(a.batch, a.knots, "box", first=a.first)
 s = Solver(0, "fp64", trace=1)
@@ -18,8 +19,9 @@ for _ in range(2):
 rows = s.trace()
 print(f"kernel {st.kernel_ms:.1f} ms; trajectory 0: stage-1 iterations {g1.iters[0]}, total cycles {(g0.stats[0, 6] + g1.stats[0, 6]) / 1e6:.1f} M; trace rows {len(rows)}")
 prev = 0
-print("iter  t_ms  dt_us step failed n_bwd")
+print("iter  t_ms  dt_us step failed n_bwd" + ("  | kcycles: backward (riccati)  forward (sequential part / wait)" if a.cycles else ""))
 for k, r in enumerate(rows):
-    print(f"{k:4d} {r['t_us'] / 1e3:6.1f} {r['t_us'] - prev:6d} {r['step']:3d} {r['fp_failed']:3d} {r['n_bwd']:3d}")
+    extra = f"  | {r['costq']:6.0f} ({r['err']:5.0f}) {r['logcost']:6.0f} ({r['opterr']:5.0f})" if a.cycles else ""
+    print(f"{k:4d} {r['t_us'] / 1e3:6.1f} {r['t_us'] - prev:6d} {r['step']:3d} {r['fp_failed']:3d} {r['n_bwd']:3d}" + extra)
     prev = r['t_us']
 s.close()
