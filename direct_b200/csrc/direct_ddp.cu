@@ -239,7 +239,15 @@ template <class R> int launch(H *h, SolveArgs &A, cudaStream_t s) {
     if (h->opts.blocks_per_sm > 0 && per_sm > h->opts.blocks_per_sm) per_sm = h->opts.blocks_per_sm;
     long long grid = (long long)per_sm * h->sm_count;
     const long long need = (A.B + wpb - 1) / wpb;
-    if (grid > need) grid = need;
+    if (grid > need) {
+        // A small batch (the node's one corridor at a time) still gets idle CTAs: their warps run its line-search trials and
+        // backward sweeps speculatively (ipddp_solver.h "Speculative line search").  Tuning knob: DIRECT_DDP_MIN_GRID (CTAs).
+        // Measured (profiles/r2w_min_grid.md): one CTA per SM is the best floor - a single hard corridor of 100 knots 113 -> 47 ms.
+        long long min_grid = h->sm_count;
+        if (const char *e = getenv("DIRECT_DDP_MIN_GRID")) min_grid = atoll(e);
+        if (min_grid > grid) min_grid = grid;
+        grid = need > min_grid ? need : min_grid;
+    }
     int max_iter = A.cfg[0].iter_max;
     if (A.two_stage && A.cfg[1].iter_max > max_iter) max_iter = A.cfg[1].iter_max;
     A.fcap = max_iter + 2;
