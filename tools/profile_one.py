@@ -16,8 +16,9 @@ ap.add_argument("--kind", default="box")
 ap.add_argument("--precision", default="fp64")
 ap.add_argument("--launches", type=int, default=2)
 ap.add_argument("--blocks-per-sm", type=int, default=0)
+ap.add_argument("--first", type=int, default=0, help="index of the first trajectory in the generator (547: a hard one)")
 a = ap.parse_args()
-pb = make_batch(a.batch, a.knots, a.kind)
+pb = make_batch(a.batch, a.knots, a.kind, first=a.first)
 s = Solver(0, a.precision, blocks_per_sm=a.blocks_per_sm)
 for _ in range(a.launches):
     _, g = s.solve_two_stage(pb, want_stage0=False)
