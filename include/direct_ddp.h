@@ -18,6 +18,13 @@
  * per-trajectory return code lives in direct_ddp_result::rtn and is never mixed with it.
  * There is no CPU fallback: every solve entry point fails with DIRECT_DDP_ERR_CUDA when no usable
  * sm_100 device is present.
+ *
+ * Environment variables read at every solve (tuning and A/B measurements only; none of them changes a result bit):
+ *   DIRECT_DDP_COOP=0   no cooperation between the warps of a CTA (and none of the two mechanisms below)
+ *   DIRECT_DDP_GSPEC=0  idle CTAs do not run line-search trials of the remaining solves
+ *   DIRECT_DDP_SPEC=0   idle CTAs do not run backward sweeps speculatively
+ *   DIRECT_DDP_MIN_GRID=n   CTAs launched for a small batch (default: one per SM, so that a single corridor has idle CTAs)
+ *   DIRECT_DDP_CARVEOUT=p   shared-memory carve-out hint (percent)
  */
 #ifndef DIRECT_DDP_H_
 #define DIRECT_DDP_H_
