@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define DIRECT_DDP_VERSION 100 /* 0.1.0 */
+#define DIRECT_DDP_VERSION 200 /* 0.2.0: opts.ndevices / devices[], stats.spec_sweeps*, direct_ddp_device_count (round 2) */
 
 enum {
     DIRECT_DDP_OK = 0,

@@ -18,7 +18,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), f"{name} declared in direct_ddp.h but not exported"
     assert set(declared) == set(capi.EXPORTS)
     lib.direct_ddp_version.restype = C.c_int
-    assert lib.direct_ddp_version() == 100
+    assert lib.direct_ddp_version() == 200
 
 
 def test_struct_sizes_match_header():
