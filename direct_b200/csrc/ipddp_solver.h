@@ -2711,6 +2711,10 @@ template <class R> DDP_DEVICE_NOINLINE void solve_one(const SolveArgs &A, int st
     int trace_n = 0;
 #ifdef DDP_TRACE_CYCLES
     long long trc[4] = {0, 0, 0, 0};
+    unsigned long long trace_t0 = 0;
+#if DDP_GPU
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(trace_t0));
+#endif
 #endif
     for (iter = 0; iter < cfg.iter_max; iter++) {
         int n_bwd = 0;
@@ -2805,6 +2809,9 @@ template <class R> DDP_DEVICE_NOINLINE void solve_one(const SolveArgs &A, int st
                 long long *S = O.stats + (long long)b * 8;
                 S[0] = t.n_bwd_sweeps; S[1] = t.n_bwd_knots; S[2] = t.n_fwd_trials; S[3] = t.n_fwd_knots;
                 S[4] = t.cyc_bwd; S[5] = t.cyc_fwd; S[6] = ddp_clock() - t.cyc_t0;
+#if defined(DDP_TRACE_CYCLES) && DDP_GPU   // diagnostic build (tools/tail_who.py): wall-clock start and end of the solve (ns) instead of the phase cycles
+                { unsigned long long now; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now)); S[4] = (long long)trace_t0; S[5] = (long long)now; }
+#endif
                 S[7] = (t.cyc_ric >> 10) | ((t.cyc_seq >> 10) << 32);   // kilo-cycles: Riccati | sequential rollout
             }
         }
