@@ -255,6 +255,9 @@ template <class R> struct Traj {
     long long ws_stride, off_xun, off_sn, off_yn, off_kdx;
     int gflip, minvo;
     // speculative backward sweep (see backward_pass)
+#ifdef DDP_TRACE_CYCLES
+    long long cyc_seg[4];                // diagnostic build: cycles of the recursion per segment of a knot
+#endif
     int spec_on;                         // enabled (SolveArgs::spec)
     int spec_posted;                     // a sweep is on the slot's third board and has not been closed yet
     R spec_regadd;                       // the regularisation it was posted with
@@ -1169,6 +1172,9 @@ template <class R> DDP_DEVICE_NOINLINE bool riccati(Traj<R> &t, R regadd, Reg<R,
         if (cancel != nullptr && *cancel != 0) { ok = false; break; }
         const int slot = (int)(knots % 3);
         knots++;
+#ifdef DDP_TRACE_CYCLES
+        const long long pc0 = ddp_clock();
+#endif
         mbar_wait(bars + slot, (rphase >> slot) & 1u);
         rphase ^= 1u << slot;
         const R *tile = tiles + slot * HREC;
@@ -1248,12 +1254,15 @@ template <class R> DDP_DEVICE_NOINLINE bool riccati(Traj<R> &t, R regadd, Reg<R,
                 col(lane, 9) += hTT;
             }
             if (lane == 19) {   // |Qu|_inf, ddp.cpp:633
-                R e = errl(lane, 0);
+                R m[5];   // a tree instead of a chain of ten (the maximum does not depend on the order)
                 DDP_UNROLL
-                for (int r = 0; r < 10; r++) e = amax(e, rabs(col(lane, r)));
-                errl(lane, 0) = e;
+                for (int r = 0; r < 5; r++) m[r] = amax(rabs(col(lane, 2 * r)), rabs(col(lane, 2 * r + 1)));
+                errl(lane, 0) = amax(amax(errl(lane, 0), m[4]), amax(amax(m[0], m[1]), amax(m[2], m[3])));
             }
         }
+#ifdef DDP_TRACE_CYCLES
+        const long long pc1 = ddp_clock();
+#endif
         // ---- the ten pivots of the u block, two per round ------------------------------------------------------
         // Eigen's LLT (ddp.cpp:543/:592) eliminates one column after the other; what the backup needs is the Schur complement
         // and K = -(Quu + rho I)^-1 [Qu | Qux], and the unit-lower L D L^T of the same ten pivots gives both with the same
@@ -1302,6 +1311,9 @@ template <class R> DDP_DEVICE_NOINLINE bool riccati(Traj<R> &t, R regadd, Reg<R,
         }
         if (!ok) break;
         // rows 10..19 of the matrix (V_xx block and gradient) now sit in elements 0..9 of lanes 10..19
+#ifdef DDP_TRACE_CYCLES
+        const long long pc2 = ddp_clock();
+#endif
         // ---- gains [ku | Ku] = -(L D L^T)^-1 [Qu | Qux] --------------------------------------------------------
         Reg<R, 10> kx;
         FOR_LANES(lane) {
@@ -1332,6 +1344,9 @@ template <class R> DDP_DEVICE_NOINLINE bool riccati(Traj<R> &t, R regadd, Reg<R,
                 }
             }
         }
+#ifdef DDP_TRACE_CYCLES
+        const long long pc3 = ddp_clock();
+#endif
         // The reference backs up with the UNREGULARISED Quu (ddp.cpp:574/:615, :620-627).  With
         // K = -(Quu+rho I)^-1 Qux that equals the Schur complement above minus rho K^T K (and
         // minus rho K^T k for Vx).
@@ -1340,36 +1355,34 @@ template <class R> DDP_DEVICE_NOINLINE bool riccati(Traj<R> &t, R regadd, Reg<R,
                 const int b = lane - 10;
                 DDP_UNROLL
                 for (int a = 0; a < 9; a++) sm[Lay::S1 + a * 10 + b] = col(lane, a);   // S[a][b]
+                sm[Lay::VX + b] = col(lane, 9);
             }
         }
-        if (regadd != R(0)) {   // column b of rho K^T K (and rho K^T k) off the shared-memory copy, one rolled loop over the rows:
-            WARP_SYNC();        // 30 instructions instead of 190 unrolled ones in a kernel that is instruction-cache bound
+        if (regadd != R(0)) {
+            // rho K^T K and rho K^T k off the shared-memory copies, 30 lanes at once: lane < 27 takes rows r .. r+2 of column b of
+            // K^T K (b = lane % 9, r = 3 (lane / 9)), lanes 27 .. 29 three entries each of K^T k; both are sum_p KC[p][c0 + i] KC[p][q],
+            // ten terms in the order of the single-column loop this replaces (one lane per column, three row groups one after the other).
+            WARP_SYNC();
             FOR_LANES(lane) {
-                if (lane >= 10 && lane < 19) {
-                    const int b = lane - 10, qc = lane - 9;
-                    R kq[10];   // this lane's gain column, re-read from shared memory (keeping kx live across the block spilled it)
+                if (lane < 30) {
+                    const int rg = lane / 9;
+                    const int c0 = lane < 27 ? 3 * rg + 1 : 3 * (lane - 27) + 1, q = lane < 27 ? lane - 9 * rg + 1 : 0;
+                    R a0 = R(0), a1 = R(0), a2 = R(0);
                     DDP_UNROLL
-                    for (int p = 0; p < 10; p++) kq[p] = sm[Lay::KC + p * 10 + qc];
-                    DDP_NOUNROLL
-                    for (int r = 0; r < 9; r += 3) {   // three rows at a time: three independent ten-term chains in flight
-                        R a0 = R(0), a1 = R(0), a2 = R(0);
-                        DDP_UNROLL
-                        for (int p = 0; p < 10; p++) {
-                            const R *kr = sm + Lay::KC + p * 10 + (r + 1);
-                            a0 += kr[0] * kq[p]; a1 += kr[1] * kq[p]; a2 += kr[2] * kq[p];
-                        }
-                        R *sr = sm + Lay::S1 + r * 10 + b;
-                        sr[0] -= regadd * a0; sr[10] -= regadd * a1; sr[20] -= regadd * a2;
+                    for (int p = 0; p < 10; p++) {
+                        const R *kr = sm + Lay::KC + p * 10 + c0;
+                        const R kq = sm[Lay::KC + p * 10 + q];
+                        a0 += kr[0] * kq; a1 += kr[1] * kq; a2 += kr[2] * kq;
                     }
-                    R acc = R(0);
-                    DDP_UNROLL
-                    for (int p = 0; p < 10; p++) acc += sm[Lay::KC + p * 10] * kq[p];
-                    col(lane, 9) -= regadd * acc;
+                    if (lane < 27) {
+                        R *sr = sm + Lay::S1 + (c0 - 1) * 10 + (q - 1);
+                        sr[0] -= regadd * a0; sr[10] -= regadd * a1; sr[20] -= regadd * a2;
+                    } else {
+                        R *vr = sm + Lay::VX + (c0 - 1);
+                        vr[0] -= regadd * a0; vr[1] -= regadd * a1; vr[2] -= regadd * a2;
+                    }
                 }
             }
-        }
-        FOR_LANES(lane) {
-            if (lane >= 10 && lane < 19) sm[Lay::VX + lane - 10] = col(lane, 9);
         }
         WARP_SYNC();
         FOR_LANES(lane) {   // V[b][a] = (S[a][b] + S[b][a]) / 2 (ddp.cpp:628)
@@ -1380,6 +1393,9 @@ template <class R> DDP_DEVICE_NOINLINE bool riccati(Traj<R> &t, R regadd, Reg<R,
             }
         }
         WARP_SYNC();
+#ifdef DDP_TRACE_CYCLES   // where a knot of the recursion spends its time: assembly | pivot rounds | gains | backup
+        { const long long pc4 = ddp_clock(); t.cyc_seg[0] += pc1 - pc0; t.cyc_seg[1] += pc2 - pc1; t.cyc_seg[2] += pc3 - pc2; t.cyc_seg[3] += pc4 - pc3; }
+#endif
     }
     for (long long k = knots; k < issued; k++) {   // a failed factorisation leaves records in flight: they land before MSC is reused
         const int slot = (int)(k % 3);
@@ -2611,6 +2627,9 @@ template <class R> DDP_DEVICE_NOINLINE void solve_one(const SolveArgs &A, int st
     t.reg_base = cfg.zero_init ? R(1.6) : R(4.0);      // ddp.cpp:60-61
     t.n_bwd_sweeps = t.n_bwd_knots = t.n_fwd_trials = t.n_fwd_knots = 0;
     t.cyc_bwd = t.cyc_fwd = 0; t.cyc_ric = t.cyc_seq = 0; t.cyc_t0 = ddp_clock();
+#ifdef DDP_TRACE_CYCLES
+    t.cyc_seg[0] = t.cyc_seg[1] = t.cyc_seg[2] = t.cyc_seg[3] = 0;
+#endif
     t.mu = R(0); t.step = 0; t.failed = 0; t.bfailed = 0; t.lin_valid = 0; t.cmax_valid = 0; t.cmax = R(0);
     const bool from_stage0 = (A.two_stage && st == 1);
     int infeas_in;
@@ -2738,6 +2757,8 @@ template <class R> DDP_DEVICE_NOINLINE void solve_one(const SolveArgs &A, int st
                     tr[1] = (double)((t.cyc_bwd - trc[0]) >> 10); tr[2] = (double)((t.cyc_fwd - trc[1]) >> 10);
                     tr[3] = (double)((t.cyc_ric - trc[2]) >> 10); tr[7] = (double)((t.cyc_seq - trc[3]) >> 10);
                     trc[0] = t.cyc_bwd; trc[1] = t.cyc_fwd; trc[2] = t.cyc_ric; trc[3] = t.cyc_seq;
+                    tr[0] = (double)(t.cyc_seg[0] >> 10); tr[4] = (double)(t.cyc_seg[1] >> 10); tr[5] = (double)(t.cyc_seg[2] >> 10); tr[6] = (double)(t.cyc_seg[3] >> 10);
+                    t.cyc_seg[0] = t.cyc_seg[1] = t.cyc_seg[2] = t.cyc_seg[3] = 0;
 #endif
                 }
             }

@@ -21,7 +21,8 @@ print(f"kernel {st.kernel_ms:.1f} ms; trajectory 0: stage-1 iterations {g1.iters
 prev = 0
 print("iter  t_ms  dt_us step failed n_bwd" + ("  | kcycles: backward (riccati)  forward (sequential part / wait)" if a.cycles else ""))
 for k, r in enumerate(rows):
-    extra = f"  | {r['costq']:6.0f} ({r['err']:5.0f}) {r['logcost']:6.0f} ({r['opterr']:5.0f})" if a.cycles else ""
+    extra = (f"  | {r['costq']:6.0f} ({r['err']:5.0f}) {r['logcost']:6.0f} ({r['opterr']:5.0f})"
+             f"  | recursion: assembly {r['cost']:4.0f} rounds {r['mu']:4.0f} gains {r['reg']:4.0f} backup {r['stepsize']:4.0f}") if a.cycles else ""
     print(f"{k:4d} {r['t_us'] / 1e3:6.1f} {r['t_us'] - prev:6d} {r['step']:3d} {r['fp_failed']:3d} {r['n_bwd']:3d}" + extra)
     prev = r['t_us']
 s.close()
