@@ -1193,11 +1193,14 @@ template <class R> DDP_DEVICE_NOINLINE bool riccati(Traj<R> &t, R regadd, Reg<R,
                 DDP_UNROLL
                 for (int r = 0; r < 20; r++) col(lane, r) = R(0);
             }
-            if (lane < 20 && lane != 9) {
+            // Lanes 20 .. 28 ride along for the T-T entry: with tj = row (lane - 20) of V the dot product fT . tj below IS (V fT)[lane - 20],
+            // in the instructions the other lanes need anyway (it used to be a divergent section of its own after this one).
+            if (lane < 29 && lane != 9) {
                 R tj[9];
-                if (lane == 19) {
+                if (lane >= 19) {
+                    const R *src = lane == 19 ? sm + Lay::VX : sm + Lay::S2 + (lane - 20) * 10;
                     DDP_UNROLL
-                    for (int p = 0; p < 9; p++) tj[p] = sm[Lay::VX + p];
+                    for (int p = 0; p < 9; p++) tj[p] = src[p];
                 } else {
                     const int lj = lane < 9 ? 3 + lane / 3 : (lane - 10) / 3, aj = lane < 9 ? lane % 3 : (lane - 10) % 3;
                     R f0 = fg[5], f1 = fg[11], f2 = fg[17];   // column lj of F|G by selects (a dynamic index would go through local memory)
@@ -1214,24 +1217,23 @@ template <class R> DDP_DEVICE_NOINLINE bool riccati(Traj<R> &t, R regadd, Reg<R,
                     // gradient row of this column: (A e_j)^T Vx
                     col(lane, 19) += (f0 * sm[Lay::VX + aj] + f1 * sm[Lay::VX + 3 + aj]) + f2 * sm[Lay::VX + 6 + aj];
                 }
-                DDP_UNROLL
-                for (int l = 0; l < 6; l++) {
+                if (lane < 20) {
                     DDP_UNROLL
-                    for (int a = 0; a < 3; a++)
-                        col(lane, zidx(l, a)) += (fg[l] * tj[a] + fg[6 + l] * tj[3 + a]) + fg[12 + l] * tj[6 + a];
+                    for (int l = 0; l < 6; l++) {
+                        DDP_UNROLL
+                        for (int a = 0; a < 3; a++)
+                            col(lane, zidx(l, a)) += (fg[l] * tj[a] + fg[6 + l] * tj[3 + a]) + fg[12 + l] * tj[6 + a];
+                    }
                 }
                 R hT = R(0);
                 DDP_UNROLL
                 for (int p = 0; p < 9; p++) hT += fT[p] * tj[p];
-                col(lane, 9) += hT;
-                sm[Lay::XT + lane] = col(lane, 9);
-            }
-            if (lane >= 10 && lane < 19) {   // (V fT)[p] for the T-T entry
-                const int p = lane - 10;
-                R acc = R(0);
-                DDP_UNROLL
-                for (int q = 0; q < 9; q++) acc += sm[Lay::S2 + p * 10 + q] * fT[q];
-                sm[Lay::XH + p] = tile[210 + p] * acc;   // fT[p]: from shared memory, a dynamic register index would be local memory
+                if (lane < 20) {
+                    col(lane, 9) += hT;
+                    sm[Lay::XT + lane] = col(lane, 9);
+                } else {
+                    sm[Lay::XH + lane - 20] = tile[210 + lane - 20] * hT;   // fT[p] (V fT)[p]; fT[p] from shared memory: a dynamic register index would be local memory
+                }
             }
         }
         WARP_SYNC();
@@ -1245,20 +1247,22 @@ template <class R> DDP_DEVICE_NOINLINE bool riccati(Traj<R> &t, R regadd, Reg<R,
             issued++;
         }
         FOR_LANES(lane) {
-            if (lane == 9) {   // the T column is the T row of the others (the matrix is symmetric)
-                DDP_UNROLL
-                for (int r = 0; r < 20; r++) if (r != 9) col(lane, r) = sm[Lay::XT + r];
-                R hTT = R(0);
-                DDP_UNROLL
-                for (int p = 0; p < 9; p++) hTT += sm[Lay::XH + p];
-                col(lane, 9) += hTT;
+            // One straight-line block for every lane instead of a section for lane 9 and another for lane 19 (divergent sections run
+            // one after the other and a lone warp pays the full latency of each): everybody forms the T-T sum and its column maxima,
+            // lane 9 and lane 19 keep theirs.
+            R hTT = R(0);
+            DDP_UNROLL
+            for (int p = 0; p < 9; p++) hTT += sm[Lay::XH + p];
+            R m[5];   // |Qu|_inf, ddp.cpp:633: a tree instead of a chain of ten (the maximum does not depend on the order)
+            DDP_UNROLL
+            for (int r = 0; r < 5; r++) m[r] = amax(rabs(col(lane, 2 * r)), rabs(col(lane, 2 * r + 1)));
+            const R e = amax(amax(errl(lane, 0), m[4]), amax(amax(m[0], m[1]), amax(m[2], m[3])));
+            if (lane == 19) errl(lane, 0) = e;
+            DDP_UNROLL
+            for (int r = 0; r < 20; r++) {   // the T column is the T row of the others (the matrix is symmetric)
+                if (r != 9) { const R v = sm[Lay::XT + r]; if (lane == 9) col(lane, r) = v; }
             }
-            if (lane == 19) {   // |Qu|_inf, ddp.cpp:633
-                R m[5];   // a tree instead of a chain of ten (the maximum does not depend on the order)
-                DDP_UNROLL
-                for (int r = 0; r < 5; r++) m[r] = amax(rabs(col(lane, 2 * r)), rabs(col(lane, 2 * r + 1)));
-                errl(lane, 0) = amax(amax(errl(lane, 0), m[4]), amax(amax(m[0], m[1]), amax(m[2], m[3])));
-            }
+            if (lane == 9) col(lane, 9) += hTT;
         }
 #ifdef DDP_TRACE_CYCLES
         const long long pc1 = ddp_clock();
@@ -1276,16 +1280,17 @@ template <class R> DDP_DEVICE_NOINLINE bool riccati(Traj<R> &t, R regadd, Reg<R,
         // matrix sits in element r; elements that would belong to rows >= 20 hold don't-care values that are never read.
         //   MB[(kb * 20 + lane) * 2 + {0, 1}] = (x, y') of the lane at round kb   (rows of the eliminated columns times D)
         //   MSC[(kb * 20 + lane) * 2 + {0, 1}] = (l1, l2)                         (unit-lower L: L[lane][2 kb], L[lane][2 kb + 1])
+        // The pivot block of round kb + 1 is complete as soon as rows p + 2 and p + 3 have had round kb's update, so its broadcast
+        // and the two reciprocals are issued there and run under the other sixteen row updates of round kb (same operations).
+        R pa = warp_bcast(col, 0, 0, lane_) + regadd, pb = warp_bcast(col, 1, 0, lane_), pc = warp_bcast(col, 1, 1, lane_) + regadd;
+        R pdet = pa * pc - pb * pb;   // pivot 2 = c - b^2 / a = det / a
+        R pra = rrcp(pa), pr2 = pa * rrcp(pdet);
         DDP_NOUNROLL
         for (int kb = 0; kb < 5; kb++) {
             const int p = 2 * kb;
-            const R a = warp_bcast(col, 0, p, lane_) + regadd;
-            const R b = warp_bcast(col, 1, p, lane_);
-            const R c = warp_bcast(col, 1, p + 1, lane_) + regadd;
+            const R a = pa, b = pb, det = pdet, ra = pra, r2 = pr2;
             if (a <= R(0)) { ok = false; break; }
-            const R det = a * c - b * b;   // pivot 2 = c - b^2 / a = det / a
             if (det <= R(0)) { ok = false; break; }
-            const R ra = rrcp(a), r2 = a * rrcp(det);
             Reg<R, 2> mreg;
             FOR_LANES(lane) {
                 const R x = col(lane, 0);
@@ -1299,12 +1304,23 @@ template <class R> DDP_DEVICE_NOINLINE bool riccati(Traj<R> &t, R regadd, Reg<R,
                 }
             }
             WARP_SYNC();
+            const R *Xp = sm + Lay::MB + (kb * 20 + p) * 2;   // (x, y') of row p + r at Xp[2 r], Xp[2 r + 1]
             FOR_LANES(lane) {
                 const R l1 = mreg(lane, 0), l2 = mreg(lane, 1);
-                const R *Xp = sm + Lay::MB + (kb * 20 + p) * 2;   // (x, y') of row p + r at Xp[2 r], Xp[2 r + 1]
                 DDP_UNROLL
-                for (int r = 2; r < 20; r++) {
+                for (int r = 2; r < 4; r++) {
                     const Pair2<R> xy = ld2(Xp + 2 * r);   // one 128-bit shared load per row
+                    col(lane, r - 2) = col(lane, r) - (xy.x * l1 + xy.y * l2);
+                }
+            }
+            pa = warp_bcast(col, 0, p + 2, lane_) + regadd; pb = warp_bcast(col, 1, p + 2, lane_); pc = warp_bcast(col, 1, p + 3, lane_) + regadd;
+            pdet = pa * pc - pb * pb;
+            pra = rrcp(pa); pr2 = pa * rrcp(pdet);
+            FOR_LANES(lane) {
+                const R l1 = mreg(lane, 0), l2 = mreg(lane, 1);
+                DDP_UNROLL
+                for (int r = 4; r < 20; r++) {
+                    const Pair2<R> xy = ld2(Xp + 2 * r);
                     col(lane, r - 2) = col(lane, r) - (xy.x * l1 + xy.y * l2);
                 }
             }
@@ -1385,11 +1401,11 @@ template <class R> DDP_DEVICE_NOINLINE bool riccati(Traj<R> &t, R regadd, Reg<R,
             }
         }
         WARP_SYNC();
-        FOR_LANES(lane) {   // V[b][a] = (S[a][b] + S[b][a]) / 2 (ddp.cpp:628)
-            if (lane >= 10 && lane < 19) {
-                const int b = lane - 10;
+        FOR_LANES(lane) {   // V[b][a] = (S[a][b] + S[b][a]) / 2 (ddp.cpp:628), three entries per lane
+            if (lane < 27) {
+                const int b = lane / 3, a0 = 3 * (lane - 3 * b);
                 DDP_UNROLL
-                for (int a = 0; a < 9; a++) sm[Lay::S2 + b * 10 + a] = R(0.5) * (sm[Lay::S1 + b * 10 + a] + sm[Lay::S1 + a * 10 + b]);
+                for (int a = a0; a < a0 + 3; a++) sm[Lay::S2 + b * 10 + a] = R(0.5) * (sm[Lay::S1 + b * 10 + a] + sm[Lay::S1 + a * 10 + b]);
             }
         }
         WARP_SYNC();
