@@ -142,7 +142,7 @@ typedef struct direct_ddp_stats {
     int64_t h2d_bytes, d2h_bytes;
     int64_t coop_jobs, helper_units; /* jobs posted to idle warps of the CTA / units those warps ran (tail balancing) */
     int64_t spec_searches, spec_trials; /* line searches posted to the warps of idle CTAs / trials those warps ran */
-    int64_t spec_sweeps, spec_sweeps_used; /* backward sweeps posted for "this search fails" to idle warps of the CTA / results taken */
+    int64_t spec_sweeps, spec_sweeps_used; /* speculative backward sweeps run by warps of idle CTAs / results taken by their owners */
 } direct_ddp_stats;
 
 typedef struct direct_ddp_trace_row {
