@@ -39,9 +39,10 @@ def test_gpu_matches_reference_fixtures(solver, name):
     assert rel_err(((r1.x_final - pb.xd) ** 2).sum(1), d["s1_terminal_norm"]) < TOL64
 
 
-# horizons around the 32-knot blocks of the knot-parallel phases and around the depth of the bulk-copy rings (2 and 3 knots) included
+# horizons around the 32-knot blocks of the knot-parallel phases and around the depth of the bulk-copy rings (2 and 3 knots) included,
+# and the longest horizon of BASELINE.json's sweep (400 knots)
 @pytest.mark.parametrize("kind,N,B", [("box", 1, 5), ("box", 2, 6), ("box", 3, 6), ("poly", 31, 12), ("box", 32, 12), ("box", 33, 64),
-                                      ("poly", 50, 48), ("box", 64, 10), ("poly", 65, 10), ("box", 96, 12), ("poly", 97, 16), ("poly", 100, 32), ("box", 200, 8)])
+                                      ("poly", 50, 48), ("box", 64, 10), ("poly", 65, 10), ("box", 96, 12), ("poly", 97, 16), ("poly", 100, 32), ("box", 200, 8), ("poly", 400, 6)])
 def test_gpu_two_stage_matches_oracle(solver, oracle, kind, N, B):
     pb = make_batch(B, N, kind, first=2000 + N)
     pert = []
