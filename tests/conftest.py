@@ -32,7 +32,7 @@ def load_golden(name):
     return pb, d
 
 
-GOLDEN_TWO_STAGE = ["box_n5", "poly_n12", "box_n50_single", "poly_n30_minvo", "box_n8_timepower1", "box_n100", "poly40_n10"]
+GOLDEN_TWO_STAGE = ["box_n5", "poly_n12", "box_n50_single", "poly_n30_minvo", "box_n8_timepower1", "box_n100", "poly40_n10", "poly_n200"]
 OUT_FIELDS = ("cost", "poly_coeff", "bez_coeff", "poly_time")
 
 

@@ -31,6 +31,7 @@ CASES = {
     "box_n8_timepower1": (3, 8, "box", 300, {"time_power": 1}),
     "box_n100": (2, 100, "box", 1000, {}),
     "poly40_n10": (3, 10, "poly40", 700, {}),         # polytopes with up to 40 planes (m_c = 6 P + 55 up to 295 rows per knot)
+    "poly_n200": (2, 200, "poly", 4200, {}),           # BASELINE.json configs[3] shape: 200 knots, polyhedral corridor (P <= 14)
 }
 
 
