@@ -2224,7 +2224,7 @@ template <class R> DDP_DEVICE bool filter_try(Traj<R> &t, R logcost, R err) {
 // once whole CTAs are idle their warps run the trials 2^-1 .. 2^-10 of a remaining solve concurrently with the owner's
 // own trial 2^0, each into the candidate buffers of its own (idle) workspace slot.  The owner then walks the results in
 // step order - exactly the decisions of the sequential search - and copies the winning candidate, if any, into its own
-// buffers.  Boards live in global memory (two per slot, used alternately so that a cancelled search never has to be
+// buffers.  Boards live in global memory (two per slot for the searches, used alternately so that a cancelled search never has to be
 // waited for); claimed units always run to completion, and an owner that finds units unclaimed when its own trial is
 // over closes the board and carries on sequentially, so nothing ever waits on a warp that is itself waiting.
 // =============================================================================================
@@ -2241,7 +2241,7 @@ template <class R> struct GBoard {
     Traj<R> t;          // the owner's view of the trajectory when it posted the search
     R xd[9];            // desired terminal state (lives in the owner's shared memory)
     R tau;
-    int seq_ctr;        // generations posted by this slot so far (kept in the first board of the pair; never reset in a launch)
+    int seq_ctr;        // generations posted so far: searches count in the slot's first board, sweeps in its third; never reset in a launch
     int done;           // units finished
     int retired;        // last generation whose candidates the owner no longer needs
     int claimed_final;  // units that had been claimed when the last search on this board was closed
